@@ -1,0 +1,398 @@
+"""CPU oracle for the dNMF fit hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product (dnmf_b200/) never does and fails loudly without its CUDA
+library.  Parity status: PINNED by executing the real reference in the build container
+(tests/test_oracle_vs_reference.py, oracle/make_golden.py -> tests/golden/*.npz); the
+reference itself ships no tests or golden vectors.
+
+Two restatements live here (all file:line citations are relative to /root/reference):
+
+1. `TorchPort` -- the reference's own decomposition, re-stated with the same ATen calls
+   (einsum -> grid_sample(trilinear, zeros, align_corners=True) -> einsum -> mse_loss ->
+   autograd -> torch.optim.Adam over the dense [10,3,T] tensor; Demix/dNMF.py:19-62,181-194)
+   and the fp64 numpy multiplicative update (Demix/dNMF.py:139-149,163-179).  This is the
+   "port" that bench.py times as the CPU baseline and that the GPU parity tests compare with.
+
+2. `closed_form_*` -- the separable closed form the CUDA kernels implement (SURVEY.md F1/F2,
+   Appendix A), in numpy float32 with the exact coordinate op order, plus the integer binning
+   spec (`axis_ranges`, `tile_window`, `bin_tiles`) that the binning kernel must match
+   bit for bit, and `adam_dense` (torch _single_tensor_adam formula, F4).
+"""
+from __future__ import annotations
+
+import math
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+f32 = np.float32
+
+# ------------------------------------------------------------------------------------------------
+# 1. Torch port of the reference decomposition
+# ------------------------------------------------------------------------------------------------
+
+
+def identity_beta(T: int) -> torch.Tensor:
+    """beta[10,3,T]: row 0 zero, rows 1..3 identity, rows 4..9 zero (Demix/dNMF.py:24-26)."""
+    b = torch.zeros(10, 3, T)
+    b[1, 0], b[2, 1], b[3, 2] = 1.0, 1.0, 1.0
+    return b
+
+
+def voxel_basis(sz: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(grid[X,Y,Z,3], phi[X,Y,Z,10]) with phi = [1,x,y,z,x2,y2,z2,xy,xz,yz]
+    (Demix/dNMF.py:22-23,46-51)."""
+    X, Y, Z = (int(s) for s in sz)
+    gx, gy, gz = torch.meshgrid(torch.arange(X), torch.arange(Y), torch.arange(Z), indexing="ij")
+    g = torch.stack((gx, gy, gz), 3).float()
+    x, y, z = g[..., 0:1], g[..., 1:2], g[..., 2:3]
+    phi = torch.cat((torch.ones_like(x), g, g * g, x * y, x * z, y * z), 3)
+    return g, phi
+
+
+def gaussian_volume(grid: torch.Tensor, pos: torch.Tensor, sigma: torch.Tensor) -> torch.Tensor:
+    """A[X,Y,Z,K] = exp(sum_d -(p_d - pos_kd)^2 / sigma_k^2)  (Demix/dNMF.py:39-40)."""
+    d = grid[:, :, :, :, None] - pos.T[None, None, None, :, :]
+    return torch.exp((-(d ** 2) / sigma[None, None, None, None, :] ** 2).sum(3))
+
+
+class TorchPort:
+    """Re-statement of ExponentialFP + DeformableNMF (Demix/dNMF.py:18-194) on CPU torch.
+
+    Layouts are the reference's: beta[10,3,T], C[K,T], frames[B,X,Y,Z]."""
+
+    def __init__(self, sz, K, T, positions=None, shape_std=3.0, C0=None):
+        self.sz = torch.as_tensor(sz).long()
+        self.K, self.T = int(K), int(T)
+        self.grid_id, self.phi = voxel_basis(self.sz.tolist())
+        self.beta = identity_beta(T).requires_grad_(True)
+        self.sigma = torch.ones(K) * shape_std
+        if positions is None:
+            self.pos = 1 + torch.rand(K, 3) * self.sz[None, :]
+        else:
+            self.pos = torch.as_tensor(positions).float()
+        self.A = gaussian_volume(self.grid_id, self.pos, self.sigma)
+        self.C = torch.rand(K, T) if C0 is None else torch.as_tensor(C0).float().clone()
+
+    # -- Demix/dNMF.py:53-58 (reg omitted: detached constant) -------------------------
+    def forward(self, times: Sequence[int], C: Optional[torch.Tensor] = None):
+        C = self.C if C is None else C
+        times = list(times)
+        q = torch.einsum("mnza,abt->mnzbt", self.phi, self.beta[:, :, times])
+        u = 2 * q / (self.sz[None, None, None, :, None] - 1) - 1
+        vol = self.A.permute(3, 2, 1, 0)[None].expand(len(times), -1, -1, -1, -1)
+        A_t = F.grid_sample(vol, u.permute(4, 2, 1, 0, 3), mode="bilinear", padding_mode="zeros",
+                            align_corners=True).permute(0, 1, 4, 3, 2)
+        A_tC = torch.einsum("tkmnz,kt->tmnz", A_t, C[:, times])
+        return A_tC, A_t, u
+
+    # -- Demix/dNMF.py:185-191 --------------------------------------------------------------------
+    def motion_step(self, frames: torch.Tensor, times: Sequence[int], optimizer,
+                    affine: bool = False) -> float:
+        optimizer.zero_grad()
+        A_tC, _, _ = self.forward(times)
+        recon = F.mse_loss(A_tC, frames)
+        recon.backward()
+        if affine:  # "affine" = quadratic rows frozen
+            self.beta.grad[4:] = 0
+        optimizer.step()
+        return float(recon.detach())
+
+    def update_motion(self, batches: Iterable[Tuple[torch.Tensor, Sequence[int]]], optimizer,
+                      epochs: int = 1, affine: bool = False) -> List[float]:
+        losses = []
+        for _ in range(epochs):
+            for frames, times in batches:
+                losses.append(self.motion_step(frames, list(times), optimizer, affine))
+        return losses
+
+    # -- Demix/dNMF.py:69-93 without the NN warp; dense fp64 like the reference -------------------
+    def pushforward(self, batches) -> Tuple[np.ndarray, np.ndarray]:
+        A_list, Y_list = [], []
+        with torch.no_grad():
+            for frames, times in batches:
+                _, A_t, _ = self.forward(list(times))
+                A_list.append(A_t.permute(2, 3, 4, 1, 0).numpy().astype(np.float64))
+                Y_list.append(frames.permute(1, 2, 3, 0).numpy().astype(np.float64))
+        return np.concatenate(A_list, 4), np.concatenate(Y_list, 3)
+
+    # -- Demix/dNMF.py:163-177 --------------------------------------------------------------------
+    def update_footprints(self, batches, gamma_c=1e-2, iter_c=10):
+        A_t, Y = self.pushforward(batches)
+        C = self.C.numpy()
+        Gm, bv = mu_stats_dense(A_t, Y)
+        for _ in range(iter_c):
+            C = mu_sweep(Gm, bv, C, gamma_c)
+        self.C = torch.tensor(C).float()
+        return A_t, Y
+
+
+def mu_stats_dense(A_t: np.ndarray, Y: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """G[k,l,t], b[k,t] in fp64 (Demix/dNMF.py:141-142); hoisting them out of the iteration
+    loop is bit-identical to recomputing them each sweep."""
+    Gm = np.einsum("mnzkt,mnzlt->klt", A_t, A_t)
+    bv = np.einsum("mnzkt,mnzt->kt", A_t, Y)
+    return Gm, bv
+
+
+def mu_sweep(Gm: np.ndarray, bv: np.ndarray, C: np.ndarray, gamma) -> np.ndarray:
+    """One multiplicative update of the traces (Demix/dNMF.py:143-148)."""
+    C1 = bv.copy()
+    C2 = np.einsum("klt,lt->kt", Gm, C)
+    if gamma is not None:
+        nbr = np.hstack((C[:, 0][:, None], C[:, :-1])) + np.hstack((C[:, 1:], C[:, -1][:, None]))
+        C1 = C1 + gamma * nbr
+        C2 = C2 + 2 * gamma * C
+    return C * C1 / (C2 + 1e-32)
+
+
+def log_det_jac(Bm: torch.Tensor, P) -> torch.Tensor:
+    """Diagnostic of Demix/dNMF.py:107-122, including its cross-term index order."""
+    x, y, z = P[0], P[1], P[2]
+    rows = []
+    for c in range(3):
+        rows.append((Bm[1, c] + 2 * Bm[4, c] * x + Bm[7, c] * y + Bm[9, c] * z,
+                     Bm[2, c] + 2 * Bm[5, c] * y + Bm[7, c] * x + Bm[8, c] * z,
+                     Bm[3, c] + 2 * Bm[6, c] * z + Bm[8, c] * y + Bm[9, c] * x))
+    (a, b, c), (d, e, f), (g, h, i) = rows
+    return torch.log(abs(a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g)))
+
+
+# ------------------------------------------------------------------------------------------------
+# 2. Closed form (what the CUDA kernels compute), numpy float32
+# ------------------------------------------------------------------------------------------------
+
+
+def axis_ranges(pos: np.ndarray, sigma: np.ndarray, sz: Sequence[int], cutoff: float) -> np.ndarray:
+    """Integer node ranges [K,3,2] = (lo, hi) of the truncated footprint per axis.
+
+    lo = max(0, ceil(pos - fl(cutoff*sigma))), hi = min(s-1, floor(pos + fl(cutoff*sigma)));
+    cutoff <= 0 means no truncation (lo=0, hi=s-1).  Pure fp32, no FMA: the binning kernel
+    must reproduce this bit for bit."""
+    pos = np.asarray(pos, f32)
+    sigma = np.asarray(sigma, f32)
+    K = pos.shape[0]
+    out = np.zeros((K, 3, 2), np.int32)
+    for d in range(3):
+        s = int(sz[d])
+        if cutoff <= 0 or not math.isfinite(cutoff):
+            out[:, d, 0], out[:, d, 1] = 0, s - 1
+            continue
+        rad = (f32(cutoff) * sigma).astype(f32)
+        lo_f = np.ceil((pos[:, d] - rad).astype(f32))
+        hi_f = np.floor((pos[:, d] + rad).astype(f32))
+        lo_f = np.fmin(np.fmax(lo_f, f32(0)), f32(s))
+        hi_f = np.fmin(np.fmax(hi_f, f32(-1)), f32(s - 1))
+        out[:, d, 0] = lo_f.astype(np.int32)
+        out[:, d, 1] = hi_f.astype(np.int32)
+    return out
+
+
+def axis_tables(pos, sigma, sz, cutoff) -> Tuple[List[np.ndarray], np.ndarray]:
+    """Per axis d: table[K, s_d+3, 2] of (G[i], G[i+1]-G[i]) for i = -2..s_d, with
+    G[i] = exp(-(i-pos)^2/sigma^2) inside [lo,hi] and 0 outside (zero padding of grid_sample
+    + truncation).  Returns (tables, ranges)."""
+    pos = np.asarray(pos, f32)
+    sigma = np.asarray(sigma, f32)
+    rng = axis_ranges(pos, sigma, sz, cutoff)
+    tabs = []
+    for d in range(3):
+        s = int(sz[d])
+        i = np.arange(-2, s + 2, dtype=np.int32)               # nodes -2 .. s+1
+        delta = (i.astype(f32)[None, :] - pos[:, d][:, None]).astype(f32)
+        g = np.exp(-((delta * delta).astype(f32) / (sigma * sigma).astype(f32)[:, None]).astype(f32)).astype(f32)
+        live = (i[None, :] >= rng[:, d, 0][:, None]) & (i[None, :] <= rng[:, d, 1][:, None])
+        g = np.where(live, g, f32(0)).astype(f32)
+        tab = np.stack((g[:, :-1], (g[:, 1:] - g[:, :-1]).astype(f32)), 2)   # i = -2 .. s
+        tabs.append(np.ascontiguousarray(tab))
+    return tabs, rng
+
+
+def sample_coords(beta_t: np.ndarray, sz: Sequence[int]) -> np.ndarray:
+    """Un-normalised sample coordinates ix[3, X, Y, Z] in fp32 with the reference's op order
+    (Demix/dNMF.py:54-55 then ATen grid_sampler unnormalize)."""
+    X, Y, Z = (int(s) for s in sz)
+    x = np.arange(X, dtype=f32)[:, None, None]
+    y = np.arange(Y, dtype=f32)[None, :, None]
+    z = np.arange(Z, dtype=f32)[None, None, :]
+    one = np.ones((X, Y, Z), f32)
+    phi = [one, x * one, y * one, z * one, (x * x) * one, (y * y) * one, (z * z) * one,
+           (x * y) * one, (x * z) * one, (y * z) * one]
+    b = np.asarray(beta_t, f32)
+    out = np.empty((3, X, Y, Z), f32)
+    for d in range(3):
+        q = np.zeros((X, Y, Z), f32)
+        for a in range(10):
+            q = (q + (phi[a] * b[a, d]).astype(f32)).astype(f32)
+        sm1 = f32(int(sz[d]) - 1)
+        u = (((f32(2) * q).astype(f32) / sm1).astype(f32) - f32(1)).astype(f32)
+        out[d] = ((((u + f32(1)).astype(f32)) / f32(2)).astype(f32) * sm1).astype(f32)
+    return out
+
+
+def closed_form_frame(frame: np.ndarray, beta_t: np.ndarray, c_t: np.ndarray, tabs, sz):
+    """One frame: returns (yhat[X,Y,Z] f32, sse float64, dsse_dbeta[10,3] float64) where
+    sse = sum_p (yhat - Y)^2 and dsse_dbeta = 2 * sum_p phi_a r dYhat/dix_b (no 1/(B N))."""
+    X, Y, Z = (int(s) for s in sz)
+    ix = sample_coords(beta_t, sz)
+    i_idx, fr = [], []
+    for d in range(3):
+        s = int(sz[d])
+        c = np.fmin(np.fmax(ix[d], f32(-2)), f32(s))
+        fl = np.floor(c)
+        i_idx.append(fl.astype(np.int32) + 2)
+        fr.append((c - fl).astype(f32))
+    yhat = np.zeros((X, Y, Z), f32)
+    g = [np.zeros((X, Y, Z), f32) for _ in range(3)]
+    K = tabs[0].shape[0]
+    for k in range(K):
+        ck = f32(c_t[k])
+        a, dd = [], []
+        for d in range(3):
+            e = tabs[d][k][i_idx[d]]
+            a.append((e[..., 0] + fr[d] * e[..., 1]).astype(f32))
+            dd.append(e[..., 1])
+        yhat += ck * a[0] * a[1] * a[2]
+        g[0] += ck * dd[0] * a[1] * a[2]
+        g[1] += ck * a[0] * dd[1] * a[2]
+        g[2] += ck * a[0] * a[1] * dd[2]
+    r = (yhat - frame.astype(f32)).astype(f32)
+    sse = float(np.sum(r.astype(np.float64) ** 2))
+    x = np.arange(X, dtype=np.float64)[:, None, None]
+    y = np.arange(Y, dtype=np.float64)[None, :, None]
+    z = np.arange(Z, dtype=np.float64)[None, None, :]
+    one = np.ones((X, Y, Z))
+    phi = [one, x * one, y * one, z * one, x * x * one, y * y * one, z * z * one, x * y * one,
+           x * z * one, y * z * one]
+    grad = np.zeros((10, 3))
+    for b in range(3):
+        h = r.astype(np.float64) * g[b].astype(np.float64)
+        for a_ in range(10):
+            grad[a_, b] = 2.0 * np.sum(phi[a_] * h)
+    return yhat, sse, grad
+
+
+def closed_form_step(frames: np.ndarray, times: Sequence[int], beta: np.ndarray, C: np.ndarray,
+                     tabs, sz) -> Tuple[float, np.ndarray]:
+    """MSE loss and dense gradient [10,3,T] (zero off-batch) of one minibatch
+    (Demix/dNMF.py:187-190; mean over B*N)."""
+    B = len(times)
+    N = int(np.prod([int(s) for s in sz]))
+    grad = np.zeros(beta.shape, np.float64)
+    sse = 0.0
+    for j, t in enumerate(times):
+        _, s, g = closed_form_frame(frames[j], beta[:, :, t], C[:, t], tabs, sz)
+        sse += s
+        grad[:, :, t] += g / (B * N)
+    return sse / (B * N), grad.astype(f32)
+
+
+def adam_dense(p, g, m, v, step: int, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+    """torch.optim.Adam single-tensor formula in fp32 over the WHOLE tensor.
+    Returns (p, m, v) as new float32 arrays; `step` is the 1-based step count."""
+    p, g, m, v = (np.asarray(a, f32) for a in (p, g, m, v))
+    m = (m + f32(1 - b1) * (g - m).astype(f32)).astype(f32)
+    v = ((v * f32(b2)).astype(f32) + (f32(1 - b2) * g).astype(f32) * g).astype(f32)
+    bc1 = 1 - b1 ** step
+    bc2 = 1 - b2 ** step
+    step_size = f32(lr / bc1)
+    denom = ((np.sqrt(v).astype(f32) / f32(math.sqrt(bc2))).astype(f32) + f32(eps)).astype(f32)
+    p = (p - step_size * (m / denom).astype(f32)).astype(f32)
+    return p, m, v
+
+
+def closed_form_mu_stats(frames: np.ndarray, times, beta, tabs, sz):
+    """G[T',K,K], b[T',K] in float64 from the closed-form footprints (A_t values rounded to
+    fp32 first, accumulated in fp64 like Demix/dNMF.py:141-142)."""
+    K = tabs[0].shape[0]
+    Gm = np.zeros((len(times), K, K))
+    bv = np.zeros((len(times), K))
+    for j, t in enumerate(times):
+        ix = sample_coords(beta[:, :, t], sz)
+        a = []
+        for d in range(3):
+            s = int(sz[d])
+            c = np.fmin(np.fmax(ix[d], f32(-2)), f32(s))
+            fl = np.floor(c)
+            e = tabs[d][:, fl.astype(np.int32) + 2]           # [K,X,Y,Z,2]
+            a.append((e[..., 0] + (c - fl).astype(f32)[None] * e[..., 1]).astype(f32))
+        At = ((a[0] * a[1]).astype(f32) * a[2]).astype(f32).reshape(K, -1).astype(np.float64)
+        Gm[j] = At @ At.T
+        bv[j] = At @ frames[j].reshape(-1).astype(np.float64)
+    return Gm, bv
+
+
+# ------------------------------------------------------------------------------------------------
+# 3. Binning spec (integer, bit-exact target for the binning kernel)
+# ------------------------------------------------------------------------------------------------
+
+
+def tile_grid(sz: Sequence[int], tile: Sequence[int]) -> Tuple[int, int, int]:
+    return tuple((int(s) + int(t) - 1) // int(t) for s, t in zip(sz, tile))
+
+
+def tile_window(beta_t: np.ndarray, box_lo: Sequence[int], box_hi: Sequence[int],
+                sz: Sequence[int]) -> np.ndarray:
+    """Conservative window [3,2] = (wlo, whi) of table-entry indices i that voxels of the
+    inclusive box can touch, by fp32 interval arithmetic over the 10 monomials in basis order.
+
+    lo = b0; hi = b0; for a = 1..9: p1 = fl(b_a*mlo_a), p2 = fl(b_a*mhi_a);
+    lo = fl(lo + min(p1,p2)); hi = fl(hi + max(p1,p2)).
+    wlo = floor(clamp(lo, -4, s+4)) - 1, whi = floor(clamp(hi, -4, s+4)) + 1, both clamped
+    to the table domain [-2, s]."""
+    b = np.asarray(beta_t, f32)
+    x0, y0, z0 = (f32(v) for v in box_lo)
+    x1, y1, z1 = (f32(v) for v in box_hi)
+    mlo = [f32(1), x0, y0, z0, f32(x0 * x0), f32(y0 * y0), f32(z0 * z0), f32(x0 * y0), f32(x0 * z0), f32(y0 * z0)]
+    mhi = [f32(1), x1, y1, z1, f32(x1 * x1), f32(y1 * y1), f32(z1 * z1), f32(x1 * y1), f32(x1 * z1), f32(y1 * z1)]
+    win = np.zeros((3, 2), np.int32)
+    with np.errstate(all="ignore"):
+        for d in range(3):
+            lo = f32(b[0, d])
+            hi = f32(b[0, d])
+            for a in range(1, 10):
+                p1 = f32(b[a, d] * mlo[a])
+                p2 = f32(b[a, d] * mhi[a])
+                lo = f32(lo + np.fmin(p1, p2))
+                hi = f32(hi + np.fmax(p1, p2))
+            s = int(sz[d])
+            lo = np.fmin(np.fmax(lo, f32(-4)), f32(s + 4))
+            hi = np.fmin(np.fmax(hi, f32(-4)), f32(s + 4))
+            wlo = int(np.floor(lo)) - 1
+            whi = int(np.floor(hi)) + 1
+            win[d, 0] = min(max(wlo, -2), s)
+            win[d, 1] = min(max(whi, -2), s)
+    return win
+
+
+def bin_tiles(beta: np.ndarray, times: Sequence[int], rng: np.ndarray, sz, tile):
+    """Per (batch slot, tile) sorted neuron lists.  Returns (counts[B*nt], offsets[B*nt+1],
+    ids[total], windows[B*nt,3,2]).  Tile id = (bz*nty + by)*ntx + bx.  Neuron k is listed iff
+    its range is non-empty and, on every axis, lo_k <= whi+1 and hi_k >= wlo."""
+    ntx, nty, ntz = tile_grid(sz, tile)
+    nt = ntx * nty * ntz
+    counts, ids, wins = [], [], []
+    for t in times:
+        for bz in range(ntz):
+            for by in range(nty):
+                for bx in range(ntx):
+                    lo = (bx * tile[0], by * tile[1], bz * tile[2])
+                    hi = tuple(min(lo[d] + tile[d], int(sz[d])) - 1 for d in range(3))
+                    w = tile_window(beta[:, :, t], lo, hi, sz)
+                    ok = np.ones(rng.shape[0], bool)
+                    for d in range(3):
+                        ok &= rng[:, d, 0] <= rng[:, d, 1]
+                        ok &= rng[:, d, 0] <= w[d, 1] + 1
+                        ok &= rng[:, d, 1] >= w[d, 0]
+                    k = np.nonzero(ok)[0].astype(np.int32)
+                    counts.append(len(k))
+                    ids.append(k)
+                    wins.append(w)
+    counts = np.asarray(counts, np.int32)
+    offsets = np.zeros(len(counts) + 1, np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    ids = np.concatenate(ids) if ids else np.zeros(0, np.int32)
+    return counts, offsets, ids, np.asarray(wins, np.int32).reshape(len(times) * nt, 3, 2)

@@ -1,0 +1,112 @@
+"""Generate tests/golden/*.npz by running the REAL reference (/root/reference) on CPU.
+
+Run in the build container only:  python -m oracle.make_golden
+The reference ships no golden vectors; these files pin the oracle and the
+CUDA path to outputs of the reference's own code.  Seeds: np.random.seed(0), torch.manual_seed(0).
+
+  demo_cfg1.npz   demo.py:16-46 configuration (K=10, T=100, 50x50x2, batch 4, Adam lr 1e-5,
+                  shuffle=False): input frames, initial positions, C0, recon loss of each of the
+                  first 250 Adam steps, beta after them, then C after
+                  update_footprints(gamma_c=0, iter_c=50) and after a further
+                  update_footprints(gamma_c=1e-2, iter_c=10); a few frames of A_t / Y_i.
+  random_beta.npz small 3-D case with random quadratic beta (44 % out-of-bounds samples):
+                  forward A_tC, A_t, loss and d loss / d beta from the reference's autograd.
+"""
+import contextlib
+import io
+import os
+import warnings
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch.utils.data import DataLoader
+
+from oracle.ref_shim import load_reference
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def demo_cfg1(ref):
+    np.random.seed(0)
+    torch.manual_seed(0)
+    K, T, B = 10, 100, 4
+    sz = torch.tensor([50, 50, 2])
+    ds = ref.SimulatedVideoDataset(K=K, T=T, sz=sz, shape_std=3, density=.2, bg_snr=-120, motion="gp",
+                                   traces="exp", motion_par={"sigma": [5, 5, .01], "ls": [10, 10, 10]})
+    raw_video = ds.video.clone()
+    loader = DataLoader(ds, batch_size=B, shuffle=False, num_workers=0)
+    dn = ref.DeformableNMF(sz, K, T, positions=ds.positions[:, :, 0])
+    C0 = dn.C.clone()
+    opt = torch.optim.Adam([dn.fp.beta], lr=1e-5)
+    losses = []
+    for _ in range(10):                         # Demix/dNMF.py:185-191, one recon per step
+        for frames, idx in loader:
+            opt.zero_grad()
+            with quiet():
+                A_tC, _, _, _ = dn.fp(idx.tolist(), dn.C)
+            rec = F.mse_loss(A_tC, frames)
+            rec.backward()
+            opt.step()
+            losses.append(float(rec))
+    beta250 = dn.fp.beta.detach().clone()
+    with quiet():
+        A_t, Y_i, Y = dn.update_footprints(loader, B, sz, gamma_c=0, iter_c=50)
+    C_mu0 = dn.C.clone()
+    with quiet():
+        dn.update_footprints(loader, B, sz, gamma_c=1e-2, iter_c=10)
+    C_mu1 = dn.C.clone()
+    frames_all = ds.video.permute(3, 0, 1, 2).contiguous()     # clamped in place by the loader
+    np.savez_compressed(
+        os.path.join(OUT, "demo_cfg1.npz"),
+        sz=sz.numpy(), frames=frames_all.numpy(), raw_frames0=raw_video[:, :, :, 0].numpy(),
+        positions=ds.positions.numpy(), traces=np.asarray(ds.traces), pos0=ds.positions[:, :, 0].numpy(),
+        C0=C0.numpy(), losses=np.asarray(losses), beta250=beta250.numpy(),
+        adam_m=opt.state[dn.fp.beta]["exp_avg"].numpy(), adam_v=opt.state[dn.fp.beta]["exp_avg_sq"].numpy(),
+        C_mu0=C_mu0.numpy(), C_mu1=C_mu1.numpy(),
+        A_t_first4=A_t[..., :4].astype(np.float32), Y_i_first4=Y_i[..., :4].astype(np.float32),
+        Y_first4=Y[..., :4].astype(np.float32))
+    print("demo_cfg1: loss %.6g -> %.6g" % (losses[0], losses[-1]))
+
+
+def random_beta(ref):
+    np.random.seed(1)
+    torch.manual_seed(1)
+    K, T = 5, 6
+    sz = torch.tensor([20, 16, 6])
+    pos = torch.rand(K, 3) * sz[None, :]
+    fp = ref.ExponentialFP(sz, K, T, positions=pos, shape_std=2.5)
+    with torch.no_grad():
+        scale = torch.tensor([2.0, .05, .05, .05, 2e-3, 2e-3, 2e-3, 2e-3, 2e-3, 2e-3])[:, None, None]
+        fp.beta += scale * torch.randn(10, 3, T)
+        fp.beta[:, :, 0] = torch.cat((torch.zeros(1, 3), torch.eye(3), torch.zeros(6, 3)), 0)  # one identity frame
+    C = torch.rand(K, T)
+    frames = torch.rand(T, *sz.tolist())
+    times = list(range(T))
+    with quiet():
+        A_tC, A_t, grid, _ = fp(times, C)
+    loss = F.mse_loss(A_tC, frames)
+    loss.backward()
+    oob = float(((grid.abs() > 1).any(3)).float().mean())
+    np.savez_compressed(
+        os.path.join(OUT, "random_beta.npz"),
+        sz=sz.numpy(), pos=pos.numpy(), sigma=fp.sigma.numpy(), beta=fp.beta.detach().numpy(), C=C.numpy(),
+        frames=frames.numpy(), A_tC=A_tC.detach().numpy(), A_t=A_t.detach().numpy(), loss=float(loss),
+        grad=fp.beta.grad.numpy(), oob_fraction=oob)
+    print("random_beta: loss %.6g, oob %.2f" % (float(loss), oob))
+
+
+def main():
+    warnings.filterwarnings("ignore")
+    os.makedirs(OUT, exist_ok=True)
+    ref, _ = load_reference()
+    demo_cfg1(ref)
+    random_beta(ref)
+
+
+if __name__ == "__main__":
+    main()
