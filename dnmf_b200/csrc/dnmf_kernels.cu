@@ -1,0 +1,1084 @@
+// dnmf_b200 -- hand-written sm_100a kernels of the dNMF fit hot path and their C ABI.
+//
+//   kernel 1a  build_tables_kernel      per-axis truncated Gaussian tables + integer ranges
+//   kernel 1b  bin_count/scan/fill      deterministic neuron-to-tile binning (stand-alone form;
+//                                       the fused kernel runs the same device code in its prologue)
+//   kernel 2   fit_tile_kernel          fused forward + residual + loss + analytic beta-gradient
+//              reduce_partials_kernel   fixed-order second-stage reduction (bit-reproducible)
+//   kernel 3a  adam_kernel              dense Adam over all 30*T deformation coefficients
+//   kernel 3b  mu_* kernels             trace statistics + multiplicative non-negative sweeps
+//
+// Reference lines (Demix/dNMF.py, demo.py) are cited next to each piece; math in SURVEY.md App. A.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/dnmf_b200.h"
+#include "dnmf_device.cuh"
+
+namespace dnmf {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const std::string& s) {
+  g_err = s;
+  return 1;
+}
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" +    \
+                  std::to_string(__LINE__) + ")");                                                \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// kernel 1a: tables.  entry(i) = (G[i], G[i+1]-G[i]) for i = -2..s, G = exp(-(i-pos)^2/sigma^2)
+// inside [lo,hi], 0 outside (zero padding of grid_sample + cutoff).  Demix/dNMF.py:39-40.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gauss_node(int i, float pos, float sigma, int lo, int hi) {
+  if (i < lo || i > hi) return 0.f;
+  float d = __fsub_rn((float)i, pos);
+  float q = __fdiv_rn(__fmul_rn(d, d), __fmul_rn(sigma, sigma));
+  return expf(-q);
+}
+
+__global__ void build_ranges_kernel(const float* __restrict__ pos, const float* __restrict__ sigma,
+                                    int K, int X, int Y, int Z, float cutoff, int* __restrict__ rng) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const int sz[3] = {X, Y, Z};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    int s = sz[d];
+    int lo = 0, hi = s - 1;
+    if (cutoff > 0.f && isfinite(cutoff)) {
+      float rad = __fmul_rn(cutoff, sigma[k]);
+      float lo_f = ceilf(__fsub_rn(pos[k * 3 + d], rad));
+      float hi_f = floorf(__fadd_rn(pos[k * 3 + d], rad));
+      lo_f = fminf(fmaxf(lo_f, 0.f), (float)s);
+      hi_f = fminf(fmaxf(hi_f, -1.f), (float)(s - 1));
+      lo = (int)lo_f;
+      hi = (int)hi_f;
+    }
+    rng[k * 6 + 2 * d] = lo;
+    rng[k * 6 + 2 * d + 1] = hi;
+  }
+}
+
+__global__ void build_tables_kernel(const float* __restrict__ pos, const float* __restrict__ sigma,
+                                    const int* __restrict__ rng, int K, int s, int axis,
+                                    float2* __restrict__ tab) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;  // entry within a neuron's row, i = e - 2
+  int k = blockIdx.y;
+  if (e >= s + 3) return;
+  int i = e - 2;
+  int lo = rng[k * 6 + 2 * axis], hi = rng[k * 6 + 2 * axis + 1];
+  float p = pos[k * 3 + axis], sg = sigma[k];
+  float g0 = gauss_node(i, p, sg, lo, hi);
+  float g1 = gauss_node(i + 1, p, sg, lo, hi);
+  tab[(size_t)k * (s + 3) + e] = make_float2(g0, __fsub_rn(g1, g0));
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 1b: stand-alone binning (count -> exclusive scan -> fill), one warp per (frame, tile).
+// ------------------------------------------------------------------------------------------------
+struct Geom {
+  int X, Y, Z, K, T;
+  int tx, ty, tz, ntx, nty, ntz;
+};
+
+__device__ __forceinline__ void tile_box(const Geom& g, int tile, int& x0, int& y0, int& z0, int& x1,
+                                         int& y1, int& z1) {
+  int bx = tile % g.ntx;
+  int by = (tile / g.ntx) % g.nty;
+  int bz = tile / (g.ntx * g.nty);
+  x0 = bx * g.tx;
+  y0 = by * g.ty;
+  z0 = bz * g.tz;
+  x1 = min(x0 + g.tx, g.X) - 1;
+  y1 = min(y0 + g.ty, g.Y) - 1;
+  z1 = min(z0 + g.tz, g.Z) - 1;
+}
+
+template <bool FILL>
+__global__ void bin_tiles_kernel(Geom g, const float* __restrict__ beta, const int* __restrict__ frame_ids,
+                                 int B, const int* __restrict__ rng, int* __restrict__ counts,
+                                 const long long* __restrict__ offsets, int* __restrict__ windows,
+                                 int* __restrict__ ids, long long ids_capacity) {
+  const int lane = threadIdx.x & 31;
+  const int nt = g.ntx * g.nty * g.ntz;
+  const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= (long long)B * nt) return;
+  const int b = (int)(item / nt), tile = (int)(item - (long long)b * nt);
+  const int t = frame_ids[b];
+  int x0, y0, z0, x1, y1, z1;
+  tile_box(g, tile, x0, y0, z0, x1, y1, z1);
+  int wlo[3], whi[3];
+  const int sz[3] = {g.X, g.Y, g.Z};
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    tile_window_axis(beta + (size_t)d * g.T + t, 3 * g.T, (float)x0, (float)y0, (float)z0, (float)x1,
+                     (float)y1, (float)z1, sz[d], wlo[d], whi[d]);
+  long long base = FILL ? offsets[item] : 0;
+  int cnt = 0;
+  for (int k0 = 0; k0 < g.K; k0 += 32) {
+    int k = k0 + lane;
+    bool ok = (k < g.K) && neuron_in_window(rng + (size_t)k * 6, wlo, whi);
+    unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (FILL && ok) {
+      long long pos = base + cnt + __popc(m & ((1u << lane) - 1u));
+      if (pos < ids_capacity) ids[pos] = k;
+    }
+    cnt += __popc(m);
+  }
+  if (!FILL && lane == 0) {
+    counts[item] = cnt;
+    if (windows) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        windows[item * 6 + 2 * d] = wlo[d];
+        windows[item * 6 + 2 * d + 1] = whi[d];
+      }
+    }
+  }
+}
+
+// Single-block exclusive scan of n int counts into n+1 int64 offsets; also the maximum count.
+__global__ void scan_counts_kernel(const int* __restrict__ counts, long long n, long long* __restrict__ offsets,
+                                   int* __restrict__ max_out) {
+  __shared__ long long s_sum[1024];
+  __shared__ int s_max[1024];
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const long long per = (n + nth - 1) / nth;
+  const long long i0 = min(n, per * tid), i1 = min(n, i0 + per);
+  long long acc = 0;
+  int mx = 0;
+  for (long long i = i0; i < i1; ++i) {
+    acc += counts[i];
+    mx = max(mx, counts[i]);
+  }
+  s_sum[tid] = acc;
+  s_max[tid] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    long long run = 0;
+    int m = 0;
+    for (int i = 0; i < nth; ++i) {
+      long long v = s_sum[i];
+      s_sum[i] = run;
+      run += v;
+      m = max(m, s_max[i]);
+    }
+    offsets[n] = run;
+    if (max_out) *max_out = m;
+  }
+  __syncthreads();
+  long long run = s_sum[tid];
+  for (long long i = i0; i < i1; ++i) {
+    offsets[i] = run;
+    run += counts[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 2: fused forward / residual / loss / analytic gradient.
+//
+// One CTA = NWX*NWY warps = one spatial tile (8*NWX) x (4*NWY) x tz of one frame.  The frame is
+// read ONCE from HBM (coalesced runs of ty*Z floats staged in shared memory).  Prologue: beta_t ->
+// conservative sample window -> neuron list (ascending k, ballot compaction) -> the listed neurons'
+// table slices staged in shared memory with C[k,t] folded into the x slice.  Main loop: each lane
+// owns one (x,y) column and marches along z; per (voxel, neuron) pair 3 LDS.64 + 10 FP32 ops give
+// Yhat and dYhat/dix (no N x K footprint matrix, no transcendental).  The 30 gradient entries are
+// accumulated as z-moments per lane, expanded with the lane's (x,y) monomials, then reduced
+// warp-shuffle -> block -> per-CTA partial; a second kernel sums partials in fixed order.
+// Math: Demix/dNMF.py:54-58 + F.mse_loss (:188) + autograd of grid_sample wrt grid.
+// ------------------------------------------------------------------------------------------------
+struct FitParams {
+  const float* frames;
+  const int* frame_ids;
+  const float* beta;
+  const float* C;
+  const float2* tab0;
+  const float2* tab1;
+  const float2* tab2;
+  const int* rng;
+  float* partials;
+  float* yhat;
+  int frames_are_batch;
+  int X, Y, Z, K, T;
+  int tz, ntx, nty, ntz;
+  int cap, wmax0, wmax1, wmax2;
+  int full_depth;
+};
+
+struct FitSmem {
+  int tab_f2;    // float2 count of the staged-table region
+  int y_f;       // float count of the Y tile
+  int list_u16;  // uint16 count of the list
+  size_t bytes;
+};
+
+static FitSmem fit_smem_layout(int nw, int tx, int ty, int tz, int cap, int wsum, int K) {
+  FitSmem s;
+  s.tab_f2 = cap * wsum;
+  s.y_f = tx * ty * tz + 4;
+  s.list_u16 = (K + 7) & ~7;
+  s.bytes = (size_t)s.tab_f2 * 8 + (size_t)s.y_f * 4 + (size_t)nw * kNumPartials * 4 + 64 * 4 +
+            (size_t)s.list_u16 * 2;
+  return s;
+}
+
+__device__ __forceinline__ void pair_accumulate(float2 ex, float2 ey, float2 ez, float f0, float f1,
+                                                float f2, float& yh, float& g0, float& g1, float& g2) {
+  float ca0 = fmaf(f0, ex.y, ex.x);
+  float a1 = fmaf(f1, ey.y, ey.x);
+  float a2 = fmaf(f2, ez.y, ez.x);
+  float t12 = a1 * a2;
+  yh = fmaf(ca0, t12, yh);
+  g0 = fmaf(ex.y, t12, g0);
+  g1 = fmaf(ca0 * a2, ey.y, g1);
+  g2 = fmaf(ca0 * a1, ez.y, g2);
+}
+
+template <int NWX, int NWY, bool WRITE_YHAT>
+__global__ void __launch_bounds__(32 * NWX * NWY) fit_tile_kernel(const __grid_constant__ FitParams p) {
+  constexpr int NW = NWX * NWY;
+  constexpr int TX = kWarpX * NWX, TY = kWarpY * NWY;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int wsum = p.wmax0 + p.wmax1 + p.wmax2;
+  float2* sTab = reinterpret_cast<float2*>(smem_raw);
+  float* sY = reinterpret_cast<float*>(sTab + (size_t)p.cap * wsum);
+  const int zs = p.full_depth ? p.Z : p.tz;  // smem z-stride between y rows
+  const int RS = TY * zs;                    // smem stride between x rows
+  float* sRed = sY + (TX * TY * p.tz + 4);
+  float* sBeta = sRed + NW * kNumPartials;   // 32 floats
+  int* sInt = reinterpret_cast<int*>(sBeta + 32);  // 32 ints: win[6], cnt[NW], L
+  unsigned short* sList = reinterpret_cast<unsigned short*>(sInt + 32);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nt = p.ntx * p.nty * p.ntz;
+  const int b = blockIdx.x / nt, tile = blockIdx.x - b * nt;
+  const int bx = tile % p.ntx, by = (tile / p.ntx) % p.nty, bz = tile / (p.ntx * p.nty);
+  const int t = p.frame_ids[b];
+  const int x0 = bx * TX, y0 = by * TY, z0 = bz * p.tz;
+  const int nx = min(TX, p.X - x0), ny = min(TY, p.Y - y0), nz = min(p.tz, p.Z - z0);
+  const float* __restrict__ frame = p.frames + (size_t)(p.frames_are_batch ? b : t) * ((size_t)p.X * p.Y * p.Z);
+
+  if (tid < 30) sBeta[tid] = p.beta[(size_t)tid * p.T + t];
+
+  // ---- stream the tile of the frame into shared memory (each voxel read once from HBM) ----
+  if (!WRITE_YHAT) {
+    if (p.full_depth) {
+      const int run = ny * p.Z;
+      for (int lx = warp; lx < nx; lx += NW) {
+        const float* src = frame + ((size_t)(x0 + lx) * p.Y + y0) * p.Z;
+        for (int e = lane; e < run; e += 32) sY[lx * RS + e] = __ldg(src + e);
+      }
+    } else {
+      for (int row = warp; row < nx * TY; row += NW) {
+        int lx = row / TY, ly = row - lx * TY;
+        if (ly < ny) {
+          const float* src = frame + ((size_t)(x0 + lx) * p.Y + (y0 + ly)) * p.Z + z0;
+          for (int e = lane; e < nz; e += 32) sY[lx * RS + ly * zs + e] = __ldg(src + e);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- conservative window of this tile under beta_t (same code as the binning kernel) ----
+  if (tid < 3) {
+    const int s = tid == 0 ? p.X : (tid == 1 ? p.Y : p.Z);
+    int wlo, whi;
+    tile_window_axis(sBeta + tid, 3, (float)x0, (float)y0, (float)z0, (float)(x0 + nx - 1),
+                     (float)(y0 + ny - 1), (float)(z0 + nz - 1), s, wlo, whi);
+    sInt[tid] = wlo;
+    sInt[3 + tid] = whi;
+  }
+  __syncthreads();
+  int wlo[3], whi[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    wlo[d] = sInt[d];
+    whi[d] = sInt[3 + d];
+  }
+
+  // ---- neuron list: ascending k, two-pass ballot compaction across the CTA's warps ----
+  const int per = ((p.K + NW * 32 - 1) / (NW * 32)) * 32;
+  const int kb = warp * per;
+  {
+    int cnt = 0;
+    for (int k0 = kb; k0 < kb + per; k0 += 32) {
+      int k = k0 + lane;
+      bool ok = (k < p.K) && neuron_in_window(p.rng + (size_t)k * 6, wlo, whi);
+      cnt += __popc(__ballot_sync(0xffffffffu, ok));
+    }
+    if (lane == 0) sInt[8 + warp] = cnt;
+  }
+  __syncthreads();
+  int L = 0;
+  {
+    int off = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      int c = sInt[8 + w];
+      if (w < warp) off += c;
+      L += c;
+    }
+    for (int k0 = kb; k0 < kb + per; k0 += 32) {
+      int k = k0 + lane;
+      bool ok = (k < p.K) && neuron_in_window(p.rng + (size_t)k * 6, wlo, whi);
+      unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) sList[off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
+      off += __popc(m);
+    }
+  }
+  __syncthreads();
+
+  // ---- stage table slices of the first nst listed neurons; C[k,t] folded into the x slice ----
+  const int W0 = whi[0] - wlo[0] + 1, W1 = whi[1] - wlo[1] + 1, W2 = whi[2] - wlo[2] + 1;
+  const bool fits = (W0 <= p.wmax0) && (W1 <= p.wmax1) && (W2 <= p.wmax2);
+  const int nst = fits ? min(L, p.cap) : 0;
+  const int sX3 = p.X + 3, sY3 = p.Y + 3, sZ3 = p.Z + 3;
+  for (int j = warp; j < nst; j += NW) {
+    const int k = sList[j];
+    const float ck = __ldg(p.C + (size_t)k * p.T + t);
+    float2* dst = sTab + (size_t)j * wsum;
+    for (int e = lane; e < W0 + W1 + W2; e += 32) {
+      if (e < W0) {
+        float2 v = __ldg(p.tab0 + (size_t)k * sX3 + (wlo[0] + 2 + e));
+        dst[e] = make_float2(v.x * ck, v.y * ck);
+      } else if (e < W0 + W1) {
+        int e1 = e - W0;
+        dst[p.wmax0 + e1] = __ldg(p.tab1 + (size_t)k * sY3 + (wlo[1] + 2 + e1));
+      } else {
+        int e2 = e - W0 - W1;
+        dst[p.wmax0 + p.wmax1 + e2] = __ldg(p.tab2 + (size_t)k * sZ3 + (wlo[2] + 2 + e2));
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- main loop: one (x,y) column per lane, march along z ----
+  const int lx = (warp % NWX) * kWarpX + (lane & 7);
+  const int ly = (warp / NWX) * kWarpY + (lane >> 3);
+  const int gx = x0 + lx, gy = y0 + ly;
+  const bool valid = (gx < p.X) && (gy < p.Y);
+  const float xf = (float)gx, yf = (float)gy;
+  float c0[3], c1[3], c2[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float v = sBeta[d];
+    v = fmaf(sBeta[3 + d], xf, v);
+    v = fmaf(sBeta[6 + d], yf, v);
+    v = fmaf(sBeta[12 + d], xf * xf, v);
+    v = fmaf(sBeta[15 + d], yf * yf, v);
+    v = fmaf(sBeta[21 + d], xf * yf, v);
+    c0[d] = v;
+    c1[d] = fmaf(sBeta[27 + d], yf, fmaf(sBeta[24 + d], xf, sBeta[9 + d]));
+    c2[d] = sBeta[18 + d];
+  }
+  const float sm1x = (float)(p.X - 1), sm1y = (float)(p.Y - 1), sm1z = (float)(p.Z - 1);
+  float S0[3] = {0.f, 0.f, 0.f}, S1[3] = {0.f, 0.f, 0.f}, S2[3] = {0.f, 0.f, 0.f};
+  float sse = 0.f;
+  const int ybase = min(lx, TX - 1) * RS + min(ly, TY - 1) * zs;
+
+  for (int zz = 0; zz < nz; ++zz) {
+    const float zf = (float)(z0 + zz);
+    int i0, i1, i2;
+    float f0, f1, f2;
+    split_coord(sample_coord(fmaf(zf, fmaf(zf, c2[0], c1[0]), c0[0]), sm1x), p.X, i0, f0);
+    split_coord(sample_coord(fmaf(zf, fmaf(zf, c2[1], c1[1]), c0[1]), sm1y), p.Y, i1, f1);
+    split_coord(sample_coord(fmaf(zf, fmaf(zf, c2[2], c1[2]), c0[2]), sm1z), p.Z, i2, f2);
+    i0 = min(max(i0, wlo[0]), whi[0]);
+    i1 = min(max(i1, wlo[1]), whi[1]);
+    i2 = min(max(i2, wlo[2]), whi[2]);
+    float yh = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    {
+      const float2* px = sTab + (i0 - wlo[0]);
+      const float2* py = sTab + p.wmax0 + (i1 - wlo[1]);
+      const float2* pz = sTab + p.wmax0 + p.wmax1 + (i2 - wlo[2]);
+#pragma unroll 4
+      for (int j = 0; j < nst; ++j) {
+        pair_accumulate(px[(size_t)j * wsum], py[(size_t)j * wsum], pz[(size_t)j * wsum], f0, f1, f2,
+                        yh, g0, g1, g2);
+      }
+    }
+    for (int j = nst; j < L; ++j) {  // overflow slots: straight from the L2-resident tables
+      const int k = sList[j];
+      const float ck = __ldg(p.C + (size_t)k * p.T + t);
+      float2 ex = __ldg(p.tab0 + (size_t)k * sX3 + (i0 + 2));
+      float2 ey = __ldg(p.tab1 + (size_t)k * sY3 + (i1 + 2));
+      float2 ez = __ldg(p.tab2 + (size_t)k * sZ3 + (i2 + 2));
+      ex.x *= ck;
+      ex.y *= ck;
+      pair_accumulate(ex, ey, ez, f0, f1, f2, yh, g0, g1, g2);
+    }
+    const float yv = sY[ybase + zz];
+    if (WRITE_YHAT) sY[ybase + zz] = yh;
+    const float r = valid ? (yh - yv) : 0.f;
+    sse = fmaf(r, r, sse);
+    const float h0 = r * g0, h1 = r * g1, h2 = r * g2;
+    const float zf2 = zf * zf;
+    S0[0] += h0;
+    S0[1] += h1;
+    S0[2] += h2;
+    S1[0] = fmaf(zf, h0, S1[0]);
+    S1[1] = fmaf(zf, h1, S1[1]);
+    S1[2] = fmaf(zf, h2, S1[2]);
+    S2[0] = fmaf(zf2, h0, S2[0]);
+    S2[1] = fmaf(zf2, h1, S2[1]);
+    S2[2] = fmaf(zf2, h2, S2[2]);
+  }
+
+  // ---- expand z-moments with this lane's (x,y) monomials, reduce warp -> CTA -> partial ----
+  {
+    auto emit = [&](int a, float coef, const float* S) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        float v = warp_sum(coef * S[d]);
+        if (lane == 0) sRed[warp * kNumPartials + a * 3 + d] = v;
+      }
+    };
+    emit(0, 1.f, S0);
+    emit(1, xf, S0);
+    emit(2, yf, S0);
+    emit(3, 1.f, S1);
+    emit(4, xf * xf, S0);
+    emit(5, yf * yf, S0);
+    emit(6, 1.f, S2);
+    emit(7, xf * yf, S0);
+    emit(8, xf, S1);
+    emit(9, yf, S1);
+    float v = warp_sum(sse);
+    if (lane == 0) {
+      sRed[warp * kNumPartials + 30] = v;
+      sRed[warp * kNumPartials + 31] = 0.f;
+    }
+  }
+  __syncthreads();
+  if (tid < kNumPartials) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) v += sRed[w * kNumPartials + tid];
+    p.partials[(size_t)blockIdx.x * kNumPartials + tid] = v;
+  }
+  if (WRITE_YHAT) {
+    float* out = p.yhat + (size_t)b * ((size_t)p.X * p.Y * p.Z);
+    if (p.full_depth) {
+      const int run = ny * p.Z;
+      for (int lxx = warp; lxx < nx; lxx += NW) {
+        float* dst = out + ((size_t)(x0 + lxx) * p.Y + y0) * p.Z;
+        for (int e = lane; e < run; e += 32) dst[e] = sY[lxx * RS + e];
+      }
+    } else {
+      for (int row = warp; row < nx * TY; row += NW) {
+        int lxx = row / TY, lyy = row - lxx * TY;
+        if (lyy < ny) {
+          float* dst = out + ((size_t)(x0 + lxx) * p.Y + (y0 + lyy)) * p.Z + z0;
+          for (int e = lane; e < nz; e += 32) dst[e] = sY[lxx * RS + lyy * zs + e];
+        }
+      }
+    }
+  }
+}
+
+// Second stage: per frame, sum the CTA partials in a fixed order (double), scale by 2/(B_global*N),
+// write the frame's gradient column and its sum of squared residuals.  grid = B, block = 256.
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, const int* __restrict__ frame_ids,
+                                       int nt, int T, double grad_scale, float* __restrict__ grad,
+                                       double* __restrict__ sse_out) {
+  __shared__ double s[8][kNumPartials];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* src = partials + (size_t)b * nt * kNumPartials;
+  double acc = 0.0;
+  for (int i = warp; i < nt; i += 8) acc += (double)src[(size_t)i * kNumPartials + lane];
+  s[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += s[w][lane];
+    const int t = frame_ids[b];
+    if (lane < 30) grad[(size_t)lane * T + t] = (float)(v * grad_scale);
+    if (lane == 30) sse_out[b] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 3a: dense Adam, torch _single_tensor_adam formula in fp32; block 0 also
+// reduces the batch loss.  grad is consumed and zeroed so the dense buffer stays all-zero
+// outside the next batch.
+// ------------------------------------------------------------------------------------------------
+struct AdamParams {
+  float w1;         // 1 - beta1
+  float b2;         // beta2
+  float w2;         // 1 - beta2
+  float step_size;  // lr / (1 - beta1^step)
+  float bc2_sqrt;   // sqrt(1 - beta2^step)
+  float eps;
+};
+
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int n, int row_len, int affine, AdamParams a,
+                            const double* __restrict__ sse, int B, double loss_scale,
+                            double* __restrict__ loss_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float gi = g[i];
+    g[i] = 0.f;
+    if (affine && (i / row_len) >= 4) gi = 0.f;
+    float mi = m[i], vi = v[i];
+    mi = fmaf(a.w1, __fsub_rn(gi, mi), mi);
+    vi = __fadd_rn(__fmul_rn(vi, a.b2), __fmul_rn(__fmul_rn(a.w2, gi), gi));
+    float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), a.bc2_sqrt), a.eps);
+    p[i] = __fsub_rn(p[i], __fmul_rn(a.step_size, __fdiv_rn(mi, denom)));
+    m[i] = mi;
+    v[i] = vi;
+  }
+  if (blockIdx.x == 0 && loss_out != nullptr && threadIdx.x < 32) {
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < B; j += 32) acc += sse[j];
+    acc = warp_sum_d(acc);
+    if (threadIdx.x == 0) *loss_out = acc * loss_scale;
+  }
+}
+
+__global__ void clamp_negative_kernel(float* __restrict__ x, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) x[i] = fmaxf(x[i], 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense forward for the small-problem API outputs of ExponentialFP.forward (A_t, grid):
+// one thread per (frame, voxel), all K neurons through the global tables.  Not a hot path.
+// ------------------------------------------------------------------------------------------------
+__global__ void dense_forward_kernel(Geom g, const int* __restrict__ frame_ids, int B,
+                                     const float* __restrict__ beta, const float2* __restrict__ tab0,
+                                     const float2* __restrict__ tab1, const float2* __restrict__ tab2,
+                                     float* __restrict__ At, float* __restrict__ grid) {
+  const size_t N = (size_t)g.X * g.Y * g.Z;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * B) return;
+  const int b = (int)(idx / N);
+  const size_t v = idx - (size_t)b * N;
+  const int z = (int)(v % g.Z), y = (int)((v / g.Z) % g.Y), x = (int)(v / ((size_t)g.Z * g.Y));
+  const int t = frame_ids[b];
+  const float xf = (float)x, yf = (float)y, zf = (float)z;
+  const float phi[kBasis] = {1.f, xf, yf, zf, xf * xf, yf * yf, zf * zf, xf * yf, xf * zf, yf * zf};
+  const int sz[3] = {g.X, g.Y, g.Z};
+  int ii[3];
+  float ff[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float q = 0.f;
+#pragma unroll
+    for (int a = 0; a < kBasis; ++a) q = __fadd_rn(q, __fmul_rn(phi[a], beta[((size_t)a * 3 + d) * g.T + t]));
+    const float sm1 = (float)(sz[d] - 1);
+    if (grid) {
+      float u = sm1 == 0.f ? 0.f : __fsub_rn(__fdiv_rn(__fmul_rn(2.f, q), sm1), 1.f);
+      grid[(v * 3 + d) * B + b] = u;
+    }
+    split_coord(sample_coord(q, sm1), sz[d], ii[d], ff[d]);
+  }
+  if (At) {
+    for (int k = 0; k < g.K; ++k) {
+      float2 ex = tab0[(size_t)k * (g.X + 3) + ii[0] + 2];
+      float2 ey = tab1[(size_t)k * (g.Y + 3) + ii[1] + 2];
+      float2 ez = tab2[(size_t)k * (g.Z + 3) + ii[2] + 2];
+      float a = fmaf(ff[0], ex.y, ex.x) * (fmaf(ff[1], ey.y, ey.x) * fmaf(ff[2], ez.y, ez.x));
+      At[((size_t)b * g.K + k) * N + v] = a;
+    }
+  }
+}
+
+}  // namespace dnmf
+
+// ================================================================================================
+// host side: context + C ABI
+// ================================================================================================
+using namespace dnmf;
+
+struct dnmf_ctx {
+  int X = 0, Y = 0, Z = 0, K = 0, T = 0, device = 0;
+  size_t N = 0;
+  int num_sms = 148;
+  int max_smem_optin = 0;
+  // footprints
+  float *d_pos = nullptr, *d_sigma = nullptr;
+  int* d_rng = nullptr;
+  float2* d_tab[3] = {nullptr, nullptr, nullptr};
+  bool have_footprints = false;
+  float cutoff = 0.f;
+  // tiling
+  int nwx = 1, nwy = 1, tz = 0, cap = 0, user_cap = 0;
+  int tx = 8, ty = 4, ntx = 0, nty = 0, ntz = 0;
+  int wmax[3] = {0, 0, 0};
+  int lmax_identity = 0;
+  size_t fit_smem = 0;
+  // video
+  float* d_video = nullptr;
+  // scratch
+  float* d_partials = nullptr;
+  size_t partials_cap = 0;
+  float* d_grad = nullptr;  // [10][3][T]
+  double* d_sse = nullptr;
+  size_t sse_cap = 0;
+  float* d_batch = nullptr;
+  size_t batch_cap = 0;
+  int* d_ids = nullptr;
+  size_t ids_cap = 0;
+  double* d_loss = nullptr;
+  int* d_tmp_counts = nullptr;
+  size_t tmp_counts_cap = 0;
+  long long* d_tmp_offsets = nullptr;
+  int* d_tmp_max = nullptr;
+  float* d_identity_beta = nullptr;
+  // mu statistics
+  double* d_G = nullptr;  // [T][K][K]
+  double* d_b = nullptr;  // [T][K]
+  double* d_Cd[2] = {nullptr, nullptr};  // traces in fp64 during the sweeps, [T][K]
+  int cd_cur = 0;
+  int mu_capM = 0;
+  unsigned long long* d_keys = nullptr;
+  size_t keys_cap = 0;
+  int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+static Geom geom_of(const dnmf_ctx* c) {
+  Geom g;
+  g.X = c->X;
+  g.Y = c->Y;
+  g.Z = c->Z;
+  g.K = c->K;
+  g.T = c->T;
+  g.tx = c->tx;
+  g.ty = c->ty;
+  g.tz = c->tz;
+  g.ntx = c->ntx;
+  g.nty = c->nty;
+  g.ntz = c->ntz;
+  return g;
+}
+
+template <typename T>
+static int ensure(T** ptr, size_t* cap, size_t need) {
+  if (*cap >= need && *ptr) return 0;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr;
+  size_t want = need + need / 4;
+  CU(cudaMalloc((void**)ptr, want * sizeof(T)));
+  *cap = want;
+  return 0;
+}
+
+extern "C" int dnmf_abi_version(void) { return DNMF_ABI_VERSION; }
+extern "C" const char* dnmf_last_error(void) { return g_err.c_str(); }
+
+extern "C" int dnmf_create(dnmf_ctx** out, int X, int Y, int Z, int K, int T, int device) {
+  if (!out) return fail("dnmf_create: out is NULL");
+  if (X < 1 || Y < 1 || Z < 1 || K < 1 || T < 1) return fail("dnmf_create: sizes must be positive");
+  if (K > 65535) return fail("dnmf_create: K > 65535 not supported (uint16 neuron lists)");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(std::string("dnmf_create: no CUDA device (") + cudaGetErrorString(e) +
+                "); this library has no CPU fallback");
+  CU(cudaSetDevice(device));
+  dnmf_ctx* c = new dnmf_ctx();
+  c->X = X;
+  c->Y = Y;
+  c->Z = Z;
+  c->K = K;
+  c->T = T;
+  c->device = device;
+  c->N = (size_t)X * Y * Z;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  c->num_sms = prop.multiProcessorCount;
+  c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  CU(cudaMalloc((void**)&c->d_pos, (size_t)K * 3 * sizeof(float)));
+  CU(cudaMalloc((void**)&c->d_sigma, (size_t)K * sizeof(float)));
+  CU(cudaMalloc((void**)&c->d_rng, (size_t)K * 6 * sizeof(int)));
+  const int s[3] = {X, Y, Z};
+  for (int d = 0; d < 3; ++d) CU(cudaMalloc((void**)&c->d_tab[d], (size_t)K * (s[d] + 3) * sizeof(float2)));
+  CU(cudaMalloc((void**)&c->d_grad, (size_t)30 * T * sizeof(float)));
+  CU(cudaMemset(c->d_grad, 0, (size_t)30 * T * sizeof(float)));
+  CU(cudaMalloc((void**)&c->d_loss, sizeof(double)));
+  CU(cudaMalloc((void**)&c->d_tmp_max, sizeof(int)));
+  CU(cudaMalloc((void**)&c->d_identity_beta, 30 * sizeof(float)));
+  float idb[30];
+  memset(idb, 0, sizeof(idb));
+  idb[1 * 3 + 0] = idb[2 * 3 + 1] = idb[3 * 3 + 2] = 1.f;
+  CU(cudaMemcpy(c->d_identity_beta, idb, sizeof(idb), cudaMemcpyHostToDevice));
+  *out = c;
+  return 0;
+}
+
+extern "C" void dnmf_destroy(dnmf_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  void* ptrs[] = {c->d_pos,     c->d_sigma, c->d_rng,        c->d_tab[0],      c->d_tab[1],
+                  c->d_tab[2],  c->d_video, c->d_partials,   c->d_grad,        c->d_sse,
+                  c->d_batch,   c->d_ids,   c->d_loss,       c->d_tmp_counts,  c->d_tmp_offsets,
+                  c->d_tmp_max, c->d_G,     c->d_b,          c->d_identity_beta,
+                  c->d_Cd[0],   c->d_Cd[1], c->d_keys};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete c;
+}
+
+// ---- tiling -----------------------------------------------------------------------------------
+static int configure_tiling(dnmf_ctx* c, cudaStream_t st);
+
+extern "C" int dnmf_set_tiling(dnmf_ctx* c, int warps_x, int warps_y, int tz, int slot_capacity) {
+  if (!c) return fail("dnmf_set_tiling: ctx is NULL");
+  const bool ok = (warps_x == 1 && warps_y == 1) || (warps_x == 2 && warps_y == 1) ||
+                  (warps_x == 2 && warps_y == 2) || (warps_x == 2 && warps_y == 4);
+  if (!ok) return fail("dnmf_set_tiling: supported warp layouts are 1x1, 2x1, 2x2, 2x4");
+  if (tz < 0) return fail("dnmf_set_tiling: tz must be >= 0");
+  c->nwx = warps_x;
+  c->nwy = warps_y;
+  c->tz = tz;
+  c->user_cap = slot_capacity;
+  CU(cudaSetDevice(c->device));
+  if (c->have_footprints) return configure_tiling(c, 0);
+  return 0;
+}
+
+extern "C" int dnmf_get_tiling(dnmf_ctx* c, int32_t* out) {
+  if (!c || !out) return fail("dnmf_get_tiling: NULL argument");
+  int32_t v[9] = {c->tx, c->ty, c->tz, c->ntx, c->nty, c->ntz, c->nwx, c->nwy, c->cap};
+  memcpy(out, v, sizeof(v));
+  return 0;
+}
+
+static int run_bin_count(dnmf_ctx* c, const float* beta, int beta_T, const int* ids, int B, int* counts,
+                         int* windows, cudaStream_t st) {
+  Geom g = geom_of(c);
+  g.T = beta_T;
+  const long long items = (long long)B * g.ntx * g.nty * g.ntz;
+  const int wpb = 8;
+  bin_tiles_kernel<false><<<(unsigned)((items + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+      g, beta, ids, B, c->d_rng, counts, nullptr, windows, nullptr, 0);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static int configure_tiling(dnmf_ctx* c, cudaStream_t st) {
+  c->tx = kWarpX * c->nwx;
+  c->ty = kWarpY * c->nwy;
+  if (c->tz <= 0 || c->tz > c->Z) c->tz = std::min(c->Z, 32);
+  c->ntx = (c->X + c->tx - 1) / c->tx;
+  c->nty = (c->Y + c->ty - 1) / c->ty;
+  c->ntz = (c->Z + c->tz - 1) / c->tz;
+  const int margin = 4;
+  c->wmax[0] = std::min(c->tx + 2 + margin, c->X + 3);
+  c->wmax[1] = std::min(c->ty + 2 + margin, c->Y + 3);
+  c->wmax[2] = std::min(c->tz + 2 + margin, c->Z + 3);
+  // longest list at identity deformation -> staged-slot capacity
+  const int nt = c->ntx * c->nty * c->ntz;
+  if (ensure(&c->d_tmp_counts, &c->tmp_counts_cap, (size_t)nt)) return 1;
+  if (c->d_tmp_offsets) cudaFree(c->d_tmp_offsets);
+  CU(cudaMalloc((void**)&c->d_tmp_offsets, ((size_t)nt + 1) * sizeof(long long)));
+  int zero = 0;
+  int* d_zero = nullptr;
+  CU(cudaMalloc((void**)&d_zero, sizeof(int)));
+  CU(cudaMemcpyAsync(d_zero, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+  if (run_bin_count(c, c->d_identity_beta, 1, d_zero, 1, c->d_tmp_counts, nullptr, st)) return 1;
+  scan_counts_kernel<<<1, 1024, 0, st>>>(c->d_tmp_counts, nt, c->d_tmp_offsets, c->d_tmp_max);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(&c->lmax_identity, c->d_tmp_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  cudaFree(d_zero);
+  int cap = c->user_cap > 0 ? c->user_cap : c->lmax_identity + c->lmax_identity / 4 + 2;
+  cap = std::max(1, std::min(cap, c->K));
+  const int wsum = c->wmax[0] + c->wmax[1] + c->wmax[2];
+  const int nw = c->nwx * c->nwy;
+  // keep at least ~2 CTAs per SM worth of shared memory when possible
+  const size_t budget = std::min<size_t>((size_t)c->max_smem_optin, (size_t)100 * 1024);
+  while (cap > 1 && fit_smem_layout(nw, c->tx, c->ty, c->tz, cap, wsum, c->K).bytes > budget) --cap;
+  c->cap = cap;
+  c->fit_smem = fit_smem_layout(nw, c->tx, c->ty, c->tz, cap, wsum, c->K).bytes;
+  if (c->fit_smem > (size_t)c->max_smem_optin)
+    return fail("configure_tiling: tile does not fit in shared memory; use a smaller tz");
+  return 0;
+}
+
+// ---- footprints ---------------------------------------------------------------------------------
+extern "C" int dnmf_set_footprints(dnmf_ctx* c, const float* pos_host, const float* sigma_host,
+                                   float cutoff, void* stream) {
+  if (!c || !pos_host || !sigma_host) return fail("dnmf_set_footprints: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(c->d_pos, pos_host, (size_t)c->K * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(c->d_sigma, sigma_host, (size_t)c->K * sizeof(float), cudaMemcpyHostToDevice, st));
+  c->cutoff = cutoff;
+  build_ranges_kernel<<<(c->K + 127) / 128, 128, 0, st>>>(c->d_pos, c->d_sigma, c->K, c->X, c->Y, c->Z,
+                                                          cutoff, c->d_rng);
+  CU(cudaGetLastError());
+  const int s[3] = {c->X, c->Y, c->Z};
+  for (int d = 0; d < 3; ++d) {
+    dim3 grid((s[d] + 3 + 127) / 128, c->K);
+    build_tables_kernel<<<grid, 128, 0, st>>>(c->d_pos, c->d_sigma, c->d_rng, c->K, s[d], d, c->d_tab[d]);
+    CU(cudaGetLastError());
+  }
+  c->have_footprints = true;
+  c->mu_capM = 0;
+  c->counters[3]++;
+  return configure_tiling(c, st);
+}
+
+extern "C" int dnmf_get_ranges(dnmf_ctx* c, int32_t* out) {
+  if (!c || !out) return fail("dnmf_get_ranges: NULL argument");
+  if (!c->have_footprints) return fail("dnmf_get_ranges: call dnmf_set_footprints first");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpy(out, c->d_rng, (size_t)c->K * 6 * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int dnmf_get_table(dnmf_ctx* c, int axis, float* out) {
+  if (!c || !out || axis < 0 || axis > 2) return fail("dnmf_get_table: bad argument");
+  if (!c->have_footprints) return fail("dnmf_get_table: call dnmf_set_footprints first");
+  const int s[3] = {c->X, c->Y, c->Z};
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpy(out, c->d_tab[axis], (size_t)c->K * (s[axis] + 3) * sizeof(float2), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ---- video --------------------------------------------------------------------------------------
+extern "C" int dnmf_upload_frames(dnmf_ctx* c, const float* frames_host, int t0, int n, int clamp_negative,
+                                  void* stream) {
+  if (!c || !frames_host) return fail("dnmf_upload_frames: NULL argument");
+  if (t0 < 0 || n < 0 || t0 + n > c->T) return fail("dnmf_upload_frames: frame range outside [0,T)");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaSetDevice(c->device));
+  if (!c->d_video) CU(cudaMalloc((void**)&c->d_video, c->N * (size_t)c->T * sizeof(float)));
+  float* dst = c->d_video + (size_t)t0 * c->N;
+  CU(cudaMemcpyAsync(dst, frames_host, c->N * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (clamp_negative && n > 0) {
+    clamp_negative_kernel<<<c->num_sms * 8, 256, 0, st>>>(dst, c->N * (size_t)n);
+    CU(cudaGetLastError());
+  }
+  return 0;
+}
+
+extern "C" int dnmf_video_devptr(dnmf_ctx* c, float** out) {
+  if (!c || !out) return fail("dnmf_video_devptr: NULL argument");
+  CU(cudaSetDevice(c->device));
+  if (!c->d_video) CU(cudaMalloc((void**)&c->d_video, c->N * (size_t)c->T * sizeof(float)));
+  *out = c->d_video;
+  return 0;
+}
+
+// ---- stand-alone binning ---------------------------------------------------------------------------
+extern "C" int dnmf_bin_tiles(dnmf_ctx* c, const float* beta_dev, const int32_t* frame_ids_dev, int B,
+                              int32_t* counts_dev, int64_t* offsets_dev, int32_t* windows_dev,
+                              int32_t* ids_dev, int64_t ids_capacity, int64_t* total_host, void* stream) {
+  if (!c || !beta_dev || !frame_ids_dev || !counts_dev || !offsets_dev)
+    return fail("dnmf_bin_tiles: NULL argument");
+  if (!c->have_footprints) return fail("dnmf_bin_tiles: call dnmf_set_footprints first");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaSetDevice(c->device));
+  const long long items = (long long)B * c->ntx * c->nty * c->ntz;
+  if (run_bin_count(c, beta_dev, c->T, frame_ids_dev, B, counts_dev, windows_dev, st)) return 1;
+  scan_counts_kernel<<<1, 1024, 0, st>>>(counts_dev, items, (long long*)offsets_dev, nullptr);
+  CU(cudaGetLastError());
+  if (ids_dev && ids_capacity > 0) {
+    Geom g = geom_of(c);
+    const int wpb = 8;
+    bin_tiles_kernel<true><<<(unsigned)((items + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+        g, beta_dev, frame_ids_dev, B, c->d_rng, counts_dev, (const long long*)offsets_dev, nullptr, ids_dev,
+        ids_capacity);
+    CU(cudaGetLastError());
+  }
+  if (total_host) {
+    long long tot = 0;
+    CU(cudaMemcpyAsync(&tot, offsets_dev + items, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *total_host = tot;
+  }
+  c->counters[2]++;
+  return 0;
+}
+
+// ---- fused step -----------------------------------------------------------------------------------
+template <int NWX, int NWY, bool WY_>
+static int launch_fit(const FitParams& p, int grid, size_t smem, cudaStream_t st) {
+  auto kern = fit_tile_kernel<NWX, NWY, WY_>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  kern<<<grid, 32 * NWX * NWY, smem, st>>>(p);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <bool WY_>
+static int dispatch_fit(dnmf_ctx* c, const FitParams& p, int grid, cudaStream_t st) {
+  const size_t smem = c->fit_smem;
+  if (c->nwx == 1 && c->nwy == 1) return launch_fit<1, 1, WY_>(p, grid, smem, st);
+  if (c->nwx == 2 && c->nwy == 1) return launch_fit<2, 1, WY_>(p, grid, smem, st);
+  if (c->nwx == 2 && c->nwy == 2) return launch_fit<2, 2, WY_>(p, grid, smem, st);
+  if (c->nwx == 2 && c->nwy == 4) return launch_fit<2, 4, WY_>(p, grid, smem, st);
+  return fail("dispatch_fit: unsupported warp layout");
+}
+
+static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, const int32_t* ids, int B,
+                           const float* beta, const float* C) {
+  if (!c->have_footprints) return fail("fit: call dnmf_set_footprints first");
+  if (!frames_dev && !c->d_video) return fail("fit: no resident video (dnmf_upload_frames) and frames_dev is NULL");
+  if ((long long)B * c->ntx * c->nty * c->ntz > 2147483647LL) return fail("fit: too many tiles in one launch");
+  p.frames = frames_dev ? frames_dev : c->d_video;
+  p.frames_are_batch = frames_dev ? 1 : 0;
+  p.frame_ids = ids;
+  p.beta = beta;
+  p.C = C;
+  p.tab0 = c->d_tab[0];
+  p.tab1 = c->d_tab[1];
+  p.tab2 = c->d_tab[2];
+  p.rng = c->d_rng;
+  p.X = c->X;
+  p.Y = c->Y;
+  p.Z = c->Z;
+  p.K = c->K;
+  p.T = c->T;
+  p.tz = c->tz;
+  p.ntx = c->ntx;
+  p.nty = c->nty;
+  p.ntz = c->ntz;
+  p.cap = c->cap;
+  p.wmax0 = c->wmax[0];
+  p.wmax1 = c->wmax[1];
+  p.wmax2 = c->wmax[2];
+  p.full_depth = (c->tz == c->Z) ? 1 : 0;
+  p.yhat = nullptr;
+  const size_t need = (size_t)B * c->ntx * c->nty * c->ntz * kNumPartials;
+  if (ensure(&c->d_partials, &c->partials_cap, need)) return 1;
+  p.partials = c->d_partials;
+  return 0;
+}
+
+extern "C" int dnmf_loss_grad(dnmf_ctx* c, const float* frames_dev, const int32_t* frame_ids_dev, int B,
+                              int B_global, const float* beta_dev, const float* C_dev, float* grad_dev,
+                              double* sse_dev, void* stream) {
+  if (!c || !frame_ids_dev || !beta_dev || !C_dev || !grad_dev || !sse_dev)
+    return fail("dnmf_loss_grad: NULL argument");
+  if (B < 1 || B_global < B) return fail("dnmf_loss_grad: need 1 <= B <= B_global");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaSetDevice(c->device));
+  FitParams p;
+  if (fill_fit_params(c, p, frames_dev, frame_ids_dev, B, beta_dev, C_dev)) return 1;
+  const int nt = c->ntx * c->nty * c->ntz;
+  if (dispatch_fit<false>(c, p, B * nt, st)) return 1;
+  const double scale = 2.0 / ((double)B_global * (double)c->N);
+  reduce_partials_kernel<<<B, 256, 0, st>>>(c->d_partials, frame_ids_dev, nt, c->T, scale, grad_dev, sse_dev);
+  CU(cudaGetLastError());
+  c->counters[0] += 1;  // fused launches
+  c->counters[1] += 1;  // reduce launches
+  return 0;
+}
+
+extern "C" int dnmf_adam_step(dnmf_ctx* c, float* beta_dev, float* grad_dev, float* m_dev, float* v_dev,
+                              double lr, double beta1, double beta2, double eps, int64_t step, int affine,
+                              const double* sse_dev, int B, int B_global, double* loss_dev, void* stream) {
+  if (!c || !beta_dev || !grad_dev || !m_dev || !v_dev) return fail("dnmf_adam_step: NULL argument");
+  if (step < 1) return fail("dnmf_adam_step: step is 1-based");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaSetDevice(c->device));
+  AdamParams a;
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  a.w1 = (float)(1.0 - beta1);
+  a.b2 = (float)beta2;
+  a.w2 = (float)(1.0 - beta2);
+  a.step_size = (float)(lr / bc1);
+  a.bc2_sqrt = (float)sqrt(bc2);
+  a.eps = (float)eps;
+  const int n = 30 * c->T;
+  const double loss_scale = 1.0 / ((double)(B_global > 0 ? B_global : 1) * (double)c->N);
+  adam_kernel<<<(n + 255) / 256, 256, 0, st>>>(beta_dev, grad_dev, m_dev, v_dev, n, 3 * c->T, affine, a,
+                                               sse_dev, B, loss_scale, (sse_dev && loss_dev) ? loss_dev : nullptr);
+  CU(cudaGetLastError());
+  c->counters[4] += 1;
+  return 0;
+}
+
+extern "C" int dnmf_motion_step(dnmf_ctx* c, const float* frames_dev, const int32_t* frame_ids_dev, int B,
+                                int B_global, float* beta_dev, float* m_dev, float* v_dev, const float* C_dev,
+                                double lr, double beta1, double beta2, double eps, int64_t step, int affine,
+                                double* loss_dev, void* stream) {
+  if (!c) return fail("dnmf_motion_step: ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  if (ensure(&c->d_sse, &c->sse_cap, (size_t)B)) return 1;
+  if (dnmf_loss_grad(c, frames_dev, frame_ids_dev, B, B_global, beta_dev, C_dev, c->d_grad, c->d_sse, stream))
+    return 1;
+  return dnmf_adam_step(c, beta_dev, c->d_grad, m_dev, v_dev, lr, beta1, beta2, eps, step, affine, c->d_sse, B,
+                        B_global, loss_dev, stream);
+}
+
+extern "C" int dnmf_motion_step_host(dnmf_ctx* c, const float* frames_host, const int32_t* frame_ids_host,
+                                     int B, int B_global, float* beta_dev, float* m_dev, float* v_dev,
+                                     const float* C_dev, double lr, double beta1, double beta2, double eps,
+                                     int64_t step, int affine, double* loss_host, void* stream) {
+  if (!c || !frames_host || !frame_ids_host) return fail("dnmf_motion_step_host: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaSetDevice(c->device));
+  if (ensure(&c->d_batch, &c->batch_cap, (size_t)B * c->N)) return 1;
+  if (ensure(&c->d_ids, &c->ids_cap, (size_t)B)) return 1;
+  CU(cudaMemcpyAsync(c->d_batch, frames_host, (size_t)B * c->N * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(c->d_ids, frame_ids_host, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (dnmf_motion_step(c, c->d_batch, c->d_ids, B, B_global, beta_dev, m_dev, v_dev, C_dev, lr, beta1, beta2,
+                       eps, step, affine, c->d_loss, stream))
+    return 1;
+  if (loss_host) {
+    CU(cudaMemcpyAsync(loss_host, c->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+extern "C" int dnmf_forward(dnmf_ctx* c, const int32_t* frame_ids_dev, int B, const float* beta_dev,
+                            const float* C_dev, float* AtC_dev, float* At_dev, float* grid_dev, void* stream) {
+  if (!c || !frame_ids_dev || !beta_dev || !C_dev) return fail("dnmf_forward: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaSetDevice(c->device));
+  if (AtC_dev) {
+    // Yhat does not depend on the video: the WRITE_YHAT instantiation never reads `frames`.
+    FitParams p;
+    if (fill_fit_params(c, p, AtC_dev, frame_ids_dev, B, beta_dev, C_dev)) return 1;
+    p.yhat = AtC_dev;
+    if (dispatch_fit<true>(c, p, B * c->ntx * c->nty * c->ntz, st)) return 1;
+    c->counters[0] += 1;
+  }
+  if (At_dev || grid_dev) {
+    if (!c->have_footprints) return fail("dnmf_forward: call dnmf_set_footprints first");
+    const size_t total = c->N * (size_t)B;
+    dense_forward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        geom_of(c), frame_ids_dev, B, beta_dev, c->d_tab[0], c->d_tab[1], c->d_tab[2], At_dev, grid_dev);
+    CU(cudaGetLastError());
+    c->counters[5] += 1;
+  }
+  return 0;
+}
+
+extern "C" int dnmf_get_counters(dnmf_ctx* c, int64_t* out) {
+  if (!c || !out) return fail("dnmf_get_counters: NULL argument");
+  memcpy(out, c->counters, sizeof(c->counters));
+  return 0;
+}
+
+// ---- trace update + registered video --------------------------------------------------------------
+#include "dnmf_mu.inc.cu"

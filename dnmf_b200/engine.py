@@ -1,0 +1,246 @@
+"""Thin torch-tensor front end of the C ABI (include/dnmf_b200.h).
+
+torch is used only for device memory, streams and tensor hand-off: every method turns tensors
+into raw pointers and calls the CUDA library through ctypes.  Nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_dev(t: torch.Tensor, dtype, name: str, device=None):
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise _lib.DnmfError("%s must be a contiguous CUDA %s tensor" % (name, dtype))
+    if device is not None and t.device != device:
+        raise _lib.DnmfError("%s is on %s, engine is on %s" % (name, t.device, device))
+
+
+class Engine:
+    """One GPU's slab: T local frames of an X*Y*Z volume with K neurons."""
+
+    def __init__(self, sz: Sequence[int], K: int, T: int, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.DnmfError("dnmf_b200 needs a CUDA device: there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.X, self.Y, self.Z = (int(s) for s in sz)
+        self.K, self.T = int(K), int(T)
+        self.N = self.X * self.Y * self.Z
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.dnmf_create(ctypes.byref(h), self.X, self.Y, self.Z, self.K, self.T,
+                                        self.device.index), "dnmf_create")
+        self._h = h
+        self._has_video = False
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.dnmf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return _stream_ptr(self.device)
+
+    # -- footprints / tiling ----------------------------------------------------------------------
+    def set_footprints(self, pos, sigma, cutoff: float):
+        pos = np.ascontiguousarray(torch.as_tensor(pos).detach().cpu().numpy(), np.float32)
+        sigma = np.ascontiguousarray(torch.as_tensor(sigma).detach().cpu().numpy(), np.float32)
+        if pos.shape != (self.K, 3) or sigma.shape != (self.K,):
+            raise _lib.DnmfError("positions must be [K,3] and sigma [K]")
+        _lib.check(self.lib.dnmf_set_footprints(self._h, pos.ctypes.data_as(ctypes.c_void_p),
+                                                sigma.ctypes.data_as(ctypes.c_void_p), float(cutoff), self.stream),
+                   "dnmf_set_footprints")
+
+    def ranges(self) -> np.ndarray:
+        out = np.zeros((self.K, 3, 2), np.int32)
+        _lib.check(self.lib.dnmf_get_ranges(self._h, out.ctypes.data_as(ctypes.c_void_p)), "dnmf_get_ranges")
+        return out
+
+    def table(self, axis: int) -> np.ndarray:
+        s = (self.X, self.Y, self.Z)[axis]
+        out = np.zeros((self.K, s + 3, 2), np.float32)
+        _lib.check(self.lib.dnmf_get_table(self._h, axis, out.ctypes.data_as(ctypes.c_void_p)), "dnmf_get_table")
+        return out
+
+    def set_tiling(self, warps_x: int = 1, warps_y: int = 1, tz: int = 0, slot_capacity: int = 0):
+        _lib.check(self.lib.dnmf_set_tiling(self._h, warps_x, warps_y, tz, slot_capacity), "dnmf_set_tiling")
+
+    def tiling(self) -> dict:
+        out = np.zeros(9, np.int32)
+        _lib.check(self.lib.dnmf_get_tiling(self._h, out.ctypes.data_as(ctypes.c_void_p)), "dnmf_get_tiling")
+        keys = ("tx", "ty", "tz", "ntx", "nty", "ntz", "warps_x", "warps_y", "cap")
+        return dict(zip(keys, (int(v) for v in out)))
+
+    # -- video ------------------------------------------------------------------------------------
+    def upload_frames(self, frames: torch.Tensor, t0: int = 0, clamp_negative: bool = True):
+        """frames: host float32 [n,X,Y,Z] (pinned memory makes the copy asynchronous)."""
+        if frames.is_cuda:
+            vid = self.video()
+            vid[t0:t0 + frames.shape[0]].copy_(frames.clamp(min=0) if clamp_negative else frames)
+        else:
+            frames = frames.contiguous().float()
+            _lib.check(self.lib.dnmf_upload_frames(self._h, _ptr(frames), int(t0), int(frames.shape[0]),
+                                                   int(clamp_negative), self.stream), "dnmf_upload_frames")
+            torch.cuda.current_stream(self.device).synchronize()
+        self._has_video = True
+
+    def video(self) -> torch.Tensor:
+        """Zero-copy torch view [T,X,Y,Z] of the resident slab."""
+        p = ctypes.c_void_p()
+        _lib.check(self.lib.dnmf_video_devptr(self._h, ctypes.byref(p)), "dnmf_video_devptr")
+
+        class _Arr:
+            pass
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": (self.T, self.X, self.Y, self.Z), "typestr": "<f4",
+                                      "data": (p.value, False), "version": 2}
+        self._has_video = True
+        return torch.as_tensor(a, device=self.device)
+
+    # -- kernels ----------------------------------------------------------------------------------
+    def bin_tiles(self, beta: torch.Tensor, frame_ids: torch.Tensor):
+        """Stand-alone binning.  Returns (counts, offsets, ids, windows) as numpy arrays."""
+        _check_dev(beta, torch.float32, "beta")
+        ids32 = frame_ids.to(self.device, torch.int32).contiguous()
+        B = int(ids32.numel())
+        tl = self.tiling()
+        nt = tl["ntx"] * tl["nty"] * tl["ntz"]
+        counts = torch.zeros(B * nt, dtype=torch.int32, device=self.device)
+        offsets = torch.zeros(B * nt + 1, dtype=torch.int64, device=self.device)
+        windows = torch.zeros(B * nt, 3, 2, dtype=torch.int32, device=self.device)
+        total = ctypes.c_int64(0)
+        _lib.check(self.lib.dnmf_bin_tiles(self._h, _ptr(beta), _ptr(ids32), B, _ptr(counts), _ptr(offsets),
+                                           _ptr(windows), None, 0, ctypes.byref(total), self.stream), "dnmf_bin_tiles")
+        ids = torch.zeros(max(1, total.value), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.dnmf_bin_tiles(self._h, _ptr(beta), _ptr(ids32), B, _ptr(counts), _ptr(offsets),
+                                           _ptr(windows), _ptr(ids), int(ids.numel()), ctypes.byref(total),
+                                           self.stream), "dnmf_bin_tiles")
+        return (counts.cpu().numpy(), offsets.cpu().numpy(), ids[:total.value].cpu().numpy(), windows.cpu().numpy())
+
+    def loss_grad(self, frame_ids: torch.Tensor, beta: torch.Tensor, C: torch.Tensor,
+                  frames: Optional[torch.Tensor] = None, B_global: Optional[int] = None
+                  ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Returns (grad[10,3,T] float32 with only the batch columns non-zero, sse[B] float64)."""
+        _check_dev(beta, torch.float32, "beta")
+        _check_dev(C, torch.float32, "C")
+        ids32 = frame_ids.to(self.device, torch.int32).contiguous()
+        B = int(ids32.numel())
+        if frames is not None:
+            _check_dev(frames, torch.float32, "frames")
+        grad = torch.zeros(10, 3, self.T, dtype=torch.float32, device=self.device)
+        sse = torch.zeros(B, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.dnmf_loss_grad(self._h, _ptr(frames), _ptr(ids32), B, int(B_global or B), _ptr(beta),
+                                           _ptr(C), _ptr(grad), _ptr(sse), self.stream), "dnmf_loss_grad")
+        return grad, sse
+
+    def adam_step(self, beta, grad, m, v, lr, betas, eps, step, affine=False):
+        for t, n in ((beta, "beta"), (grad, "grad"), (m, "exp_avg"), (v, "exp_avg_sq")):
+            _check_dev(t, torch.float32, n)
+        _lib.check(self.lib.dnmf_adam_step(self._h, _ptr(beta), _ptr(grad), _ptr(m), _ptr(v), float(lr),
+                                           float(betas[0]), float(betas[1]), float(eps), int(step), int(affine),
+                                           None, 0, 0, None, self.stream), "dnmf_adam_step")
+
+    def motion_step(self, frame_ids32: torch.Tensor, beta, m, v, C, lr, betas, eps, step, affine=False,
+                    frames: Optional[torch.Tensor] = None, B_global: Optional[int] = None,
+                    loss_out: Optional[torch.Tensor] = None):
+        """Device-resident step (frames=None reads the resident slab).  loss_out: float64 CUDA scalar."""
+        B = int(frame_ids32.numel())
+        _lib.check(self.lib.dnmf_motion_step(self._h, _ptr(frames), _ptr(frame_ids32), B, int(B_global or B),
+                                             _ptr(beta), _ptr(m), _ptr(v), _ptr(C), float(lr), float(betas[0]),
+                                             float(betas[1]), float(eps), int(step), int(affine), _ptr(loss_out),
+                                             self.stream), "dnmf_motion_step")
+
+    def motion_step_host(self, frames_host: torch.Tensor, ids_host: torch.Tensor, beta, m, v, C, lr, betas, eps,
+                         step, affine=False, B_global: Optional[int] = None) -> float:
+        """End-to-end step from HOST buffers (H2D copy + kernels + loss read-back)."""
+        B = int(ids_host.numel())
+        loss = ctypes.c_double(0.0)
+        _lib.check(self.lib.dnmf_motion_step_host(self._h, _ptr(frames_host), _ptr(ids_host), B, int(B_global or B),
+                                                  _ptr(beta), _ptr(m), _ptr(v), _ptr(C), float(lr), float(betas[0]),
+                                                  float(betas[1]), float(eps), int(step), int(affine),
+                                                  ctypes.byref(loss), self.stream), "dnmf_motion_step_host")
+        return loss.value
+
+    def forward(self, frame_ids: torch.Tensor, beta, C, want_At=False, want_grid=False):
+        _check_dev(beta, torch.float32, "beta")
+        _check_dev(C, torch.float32, "C")
+        ids32 = frame_ids.to(self.device, torch.int32).contiguous()
+        B = int(ids32.numel())
+        AtC = torch.empty(B, self.X, self.Y, self.Z, dtype=torch.float32, device=self.device)
+        At = torch.empty(B, self.K, self.X, self.Y, self.Z, dtype=torch.float32, device=self.device) if want_At else None
+        grid = torch.empty(self.X, self.Y, self.Z, 3, B, dtype=torch.float32, device=self.device) if want_grid else None
+        _lib.check(self.lib.dnmf_forward(self._h, _ptr(ids32), B, _ptr(beta), _ptr(C), _ptr(AtC), _ptr(At),
+                                         _ptr(grid), self.stream), "dnmf_forward")
+        return AtC, At, grid
+
+    def mu_stats(self, frame_ids: torch.Tensor, beta, frames: Optional[torch.Tensor] = None):
+        ids32 = frame_ids.to(self.device, torch.int32).contiguous()
+        if frames is not None:
+            _check_dev(frames, torch.float32, "frames")
+        _lib.check(self.lib.dnmf_mu_stats(self._h, _ptr(frames), _ptr(ids32), int(ids32.numel()), _ptr(beta),
+                                          self.stream), "dnmf_mu_stats")
+
+    def get_mu_stats(self, t: int):
+        G = np.zeros((self.K, self.K))
+        b = np.zeros(self.K)
+        _lib.check(self.lib.dnmf_get_mu_stats(self._h, int(t), G.ctypes.data_as(ctypes.c_void_p),
+                                              b.ctypes.data_as(ctypes.c_void_p)), "dnmf_get_mu_stats")
+        return G, b
+
+    def mu_sweeps(self, C: torch.Tensor, gamma, iters: int):
+        _check_dev(C, torch.float32, "C")
+        _lib.check(self.lib.dnmf_mu_sweeps(self._h, _ptr(C), float(gamma or 0.0), int(gamma is not None), int(iters),
+                                           self.stream), "dnmf_mu_sweeps")
+
+    def mu_begin(self, C):
+        _lib.check(self.lib.dnmf_mu_begin(self._h, _ptr(C), self.stream), "dnmf_mu_begin")
+
+    def mu_sweep(self, gamma, halo_prev=None, halo_next=None):
+        _lib.check(self.lib.dnmf_mu_sweep(self._h, float(gamma or 0.0), int(gamma is not None), _ptr(halo_prev),
+                                          _ptr(halo_next), self.stream), "dnmf_mu_sweep")
+
+    def mu_boundary(self):
+        first = torch.empty(self.K, dtype=torch.float64, device=self.device)
+        last = torch.empty(self.K, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.dnmf_mu_boundary(self._h, _ptr(first), _ptr(last), self.stream), "dnmf_mu_boundary")
+        return first, last
+
+    def mu_end(self, C):
+        _lib.check(self.lib.dnmf_mu_end(self._h, _ptr(C), self.stream), "dnmf_mu_end")
+
+    def iwarp(self, frame_ids: torch.Tensor, beta, frames: Optional[torch.Tensor] = None) -> torch.Tensor:
+        ids32 = frame_ids.to(self.device, torch.int32).contiguous()
+        B = int(ids32.numel())
+        out = torch.empty(B, self.X, self.Y, self.Z, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.dnmf_iwarp(self._h, _ptr(frames), _ptr(ids32), B, _ptr(beta), _ptr(out), self.stream),
+                   "dnmf_iwarp")
+        return out
+
+    def counters(self) -> dict:
+        out = np.zeros(8, np.int64)
+        _lib.check(self.lib.dnmf_get_counters(self._h, out.ctypes.data_as(ctypes.c_void_p)), "dnmf_get_counters")
+        keys = ("fit_launches", "reduce_launches", "bin_calls", "table_builds", "adam_launches",
+                "dense_forward_launches", "mu_stats_launches", "mu_sweep_launches")
+        return dict(zip(keys, (int(v) for v in out)))

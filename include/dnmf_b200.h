@@ -1,0 +1,131 @@
+/*
+ * dnmf_b200 -- C ABI of the B200-native dNMF fit hot path.
+ *
+ * The reference (mathdiane/dNMF) is pure Python and has no FFI; the boundary it exposes is the
+ * class surface of Demix/dNMF.py (ExponentialFP / DeformableNMF).  Each entry point below names
+ * the reference code it replaces (file:line relative to the reference tree).  The Python host
+ * layer in dnmf_b200/model.py binds these with ctypes (see INTEGRATION.md for the stub a
+ * reference maintainer would add).
+ *
+ * Conventions
+ *   - every call returns 0 on success, non-zero on failure; dnmf_last_error() gives the text.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - "_dev" pointers are device pointers, "_host" pointers are host pointers.
+ *   - layouts are the reference's own: beta[10][3][T], C[K][T] (T innermost), frames
+ *     [n][X][Y][Z] (Z innermost, what the reference's DataLoader yields, Demix/dNMF.py:214).
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef DNMF_B200_H
+#define DNMF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dnmf_ctx dnmf_ctx;
+
+#define DNMF_ABI_VERSION 1
+
+int dnmf_abi_version(void);
+const char* dnmf_last_error(void);
+
+/* Context for one GPU's slab of T frames of an X*Y*Z volume with K neurons.
+ * Replaces the constructor state of ExponentialFP.__init__ (Demix/dNMF.py:19-43): voxel grid,
+ * basis and the dense Gaussian volume A are never materialised. */
+int dnmf_create(dnmf_ctx** out, int X, int Y, int Z, int K, int T, int device);
+void dnmf_destroy(dnmf_ctx* ctx);
+
+/* Kernel 1a: per-axis truncated Gaussian tables and integer node ranges from positions/sigma
+ * (Demix/dNMF.py:29-40).  cutoff <= 0 disables truncation.  pos_host[K][3], sigma_host[K]. */
+int dnmf_set_footprints(dnmf_ctx* ctx, const float* pos_host, const float* sigma_host, float cutoff,
+                        void* stream);
+int dnmf_get_ranges(dnmf_ctx* ctx, int32_t* ranges_host /* [K][3][2] */);
+int dnmf_get_table(dnmf_ctx* ctx, int axis, float* table_host /* [K][s_axis+3][2] */);
+
+/* Launch geometry of the fused kernel: warps per CTA along x and y (warp footprint is 8x4 voxels),
+ * tile depth tz (0 = whole Z), staged-slot capacity (0 = automatic). */
+int dnmf_set_tiling(dnmf_ctx* ctx, int warps_x, int warps_y, int tz, int slot_capacity);
+int dnmf_get_tiling(dnmf_ctx* ctx, int32_t* out /* tx,ty,tz,ntx,nty,ntz,warps_x,warps_y,cap */);
+
+/* Resident video slab [T][X][Y][Z] on the device (ingest of SimulatedVideoDataset.video,
+ * Demix/dNMF.py:203,214-215; negative values are clamped to 0 like __getitem__ does). */
+int dnmf_upload_frames(dnmf_ctx* ctx, const float* frames_host, int t0, int n, int clamp_negative,
+                       void* stream);
+int dnmf_video_devptr(dnmf_ctx* ctx, float** out_dev);
+
+/* Kernel 1b (stand-alone form): deterministic neuron-to-tile binning for B frames; the fused
+ * kernel runs the same device code in its prologue.  Outputs are device arrays:
+ * counts[B*nt], offsets[B*nt+1] (int64), windows[B*nt][3][2], ids[ids_capacity]; the total list
+ * length is returned through total_host (ids beyond ids_capacity are not written). */
+int dnmf_bin_tiles(dnmf_ctx* ctx, const float* beta_dev, const int32_t* frame_ids_dev, int B,
+                   int32_t* counts_dev, int64_t* offsets_dev, int32_t* windows_dev, int32_t* ids_dev,
+                   int64_t ids_capacity, int64_t* total_host, void* stream);
+
+/* Kernel 2: fused forward + loss + analytic beta gradient of one minibatch
+ * (ExponentialFP.forward + F.mse_loss + backward, Demix/dNMF.py:54-58,187-190).
+ * frames_dev == NULL reads the resident slab by frame id, else frames_dev is [B][X][Y][Z].
+ * grad_dev[10][3][T] receives the columns of the batch frames (scaled by 2/(B_global*N));
+ * sse_dev[B] (double) receives each frame's sum of squared residuals. */
+int dnmf_loss_grad(dnmf_ctx* ctx, const float* frames_dev, const int32_t* frame_ids_dev, int B,
+                   int B_global, const float* beta_dev, const float* C_dev, float* grad_dev,
+                   double* sse_dev, void* stream);
+
+/* Kernel 3a: dense Adam over all 30*T entries (torch.optim.Adam step at Demix/dNMF.py:191,
+ * demo.py:42).  `step` is the 1-based step count; affine != 0 freezes rows 4..9.  grad_dev is
+ * consumed and reset to zero.  loss_dev (optional) receives sum(sse[0..B)) / (B_global*N). */
+int dnmf_adam_step(dnmf_ctx* ctx, float* beta_dev, float* grad_dev, float* m_dev, float* v_dev,
+                   double lr, double beta1, double beta2, double eps, int64_t step, int affine,
+                   const double* sse_dev, int B, int B_global, double* loss_dev, void* stream);
+
+/* One iteration of DeformableNMF.update_motion's inner loop (Demix/dNMF.py:186-191):
+ * dnmf_loss_grad into the context's gradient buffer followed by dnmf_adam_step. */
+int dnmf_motion_step(dnmf_ctx* ctx, const float* frames_dev, const int32_t* frame_ids_dev, int B,
+                     int B_global, float* beta_dev, float* m_dev, float* v_dev, const float* C_dev,
+                     double lr, double beta1, double beta2, double eps, int64_t step, int affine,
+                     double* loss_dev, void* stream);
+
+/* Same, with HOST buffers: copies frames_host[B][X][Y][Z] and the ids to the device, runs the
+ * step and copies the loss back (synchronises the stream).  This is the end-to-end call. */
+int dnmf_motion_step_host(dnmf_ctx* ctx, const float* frames_host, const int32_t* frame_ids_host,
+                          int B, int B_global, float* beta_dev, float* m_dev, float* v_dev,
+                          const float* C_dev, double lr, double beta1, double beta2, double eps,
+                          int64_t step, int affine, double* loss_host, void* stream);
+
+/* ExponentialFP.forward outputs (Demix/dNMF.py:54-62): A_tC[B][X][Y][Z]; optionally the dense
+ * A_t[B][K][X][Y][Z] and the normalised grid[X][Y][Z][3][B] (small problems only). */
+int dnmf_forward(dnmf_ctx* ctx, const int32_t* frame_ids_dev, int B, const float* beta_dev,
+                 const float* C_dev, float* AtC_dev, float* At_dev, float* grid_dev, void* stream);
+
+/* Kernel 3b: sufficient statistics of the trace update for B frames
+ * (G_t = A_t^T A_t, b_t = A_t^T Y_t, Demix/dNMF.py:141-142; hoisted out of the sweep loop, which
+ * is bit-identical in the reference) accumulated in fp64 into the context. */
+int dnmf_mu_stats(dnmf_ctx* ctx, const float* frames_dev, const int32_t* frame_ids_dev, int B,
+                  const float* beta_dev, void* stream);
+int dnmf_get_mu_stats(dnmf_ctx* ctx, int t, double* G_host /* [K][K] */, double* b_host /* [K] */);
+
+/* Multiplicative sweeps C <- C (b + g nbr) / (G C + 2 g C + 1e-32) over all T frames in fp64
+ * (Demix/dNMF.py:143-148,172-173); use_gamma == 0 reproduces gamma=None.
+ * dnmf_mu_sweeps = begin + iters * sweep + end.  The split form lets a multi-GPU caller exchange
+ * the boundary trace columns between sweeps: halo_prev/next_dev (double[K]) replace the
+ * edge-replicated neighbours of the first/last local frame when non-NULL. */
+int dnmf_mu_begin(dnmf_ctx* ctx, const float* C_dev, void* stream);
+int dnmf_mu_sweep(dnmf_ctx* ctx, double gamma, int use_gamma, const double* halo_prev_dev,
+                  const double* halo_next_dev, void* stream);
+int dnmf_mu_boundary(dnmf_ctx* ctx, double* first_dev, double* last_dev, void* stream);
+int dnmf_mu_end(dnmf_ctx* ctx, float* C_dev, void* stream);
+int dnmf_mu_sweeps(dnmf_ctx* ctx, float* C_dev, double gamma, int use_gamma, int iters, void* stream);
+
+/* Nearest-neighbour registered video Y_i of ExponentialFP.spatial_pushforward / image_iwarp
+ * (Demix/dNMF.py:81-83,90-103) for B frames: out[B][X][Y][Z]. */
+int dnmf_iwarp(dnmf_ctx* ctx, const float* frames_dev, const int32_t* frame_ids_dev, int B,
+               const float* beta_dev, float* out_dev, void* stream);
+
+/* Counters for bench accounting: number of fused-kernel launches etc. since creation. */
+int dnmf_get_counters(dnmf_ctx* ctx, int64_t* out /* [8] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DNMF_B200_H */
