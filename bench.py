@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Benchmark of the dNMF fit hot path (BASELINE.json metric: frame-iterations/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg2]
+
+One "step" = one Adam iteration of DeformableNMF.update_motion over a batch of B frames
+(default B = all T frames of the rank's slab); one frame-iteration = forward +
+loss + beta-gradient + Adam for one frame.  N > 1 is launched by torchrun (one rank per GPU); frames
+are sharded (weak scaling: every rank owns T frames) and the only collective is an 8-byte loss
+all-reduce per step.  The JSON line carries `value` (inputs resident in HBM), `e2e` (host buffers
+through the public API, H2D inside the timed region), `roofline`, `cpu_baseline` and `clocks`.
+
+`--impl reference` times the reference's CPU torch path (the oracle's TorchPort, which is
+bit-identical to /root/reference's code -- tests/test_oracle.py) on the host cores, on the same
+workload shape.  It is the only place besides cpu_baseline where bench.py executes oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (X, Y, Z, K, T per GPU, model sigma, simulator shape_std, deformation)
+    "cfg1": dict(sz=(50, 50, 2), K=10, T=100, sigma=3.0, shape_std=3.0, deformation="quadratic",
+                 desc="demo.py: 50x50x2, K=10, T=100, quadratic"),
+    "cfg2": dict(sz=(256, 128, 21), K=150, T=1000, sigma=3.0, shape_std=3.0, deformation="affine",
+                 desc="single-GPU synthetic volume 256x128x21, K=150, T=1000, affine"),
+    "cfg3": dict(sz=(512, 256, 32), K=300, T=625, sigma=3.0, shape_std=3.0, deformation="quadratic",
+                 desc="whole-brain 512x256x32, K=300, T=5000 over 8 GPUs (625 per GPU), quadratic"),
+    "cfg4": dict(sz=(256, 128, 21), K=1000, T=250, sigma=6.0, shape_std=18.0, deformation="quadratic",
+                 desc="dense stress 256x128x21, K=1000, sigma=6, T=2000 over 8 GPUs (250 per GPU)"),
+}
+CUTOFF = 3.5
+LR = 1e-5
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default: the config's T)")
+    ap.add_argument("--batch", type=int, default=0, help="frames per step and GPU (default: all T)")
+    ap.add_argument("--tiling", default="", help="warps_x,warps_y,tz,cap override")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames per reference step (default 4; 1 for --impl reference)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference / CPU arm (oracle port of the reference's torch path)
+# ------------------------------------------------------------------------------------------------
+def make_cpu_workload(cfg, frames, seed=0):
+    from dnmf_b200.simulate import generate_video
+    vid, positions, _ = generate_video(cfg["K"], frames, cfg["sz"], cfg["shape_std"], .2, -120, "exp", "gp",
+                                       {"sigma": [5, 5, .01], "ls": [10, 10, 10]}, seed=seed, device="cpu",
+                                       frame_major=True)
+    return vid.clamp_(min=0).contiguous(), positions[:, :, 0].contiguous()
+
+
+def time_reference(cfg, frames_per_step, steps, warmup):
+    """Times the reference's CPU torch path (oracle.TorchPort) for `steps` Adam steps."""
+    from oracle.dnmf_oracle import TorchPort
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    B = frames_per_step
+    T = B * (steps + warmup)
+    vid, pos0 = make_cpu_workload(cfg, T)
+    port = TorchPort(cfg["sz"], cfg["K"], T, positions=pos0, shape_std=cfg["sigma"])
+    opt = torch.optim.Adam([port.beta], lr=LR)
+    affine = cfg["deformation"] == "affine"
+    times = []
+    for s in range(steps + warmup):
+        ids = list(range(s * B, (s + 1) * B))
+        t0 = time.perf_counter()
+        port.motion_step(vid[ids], ids, opt, affine)
+        times.append(time.perf_counter() - t0)
+    timed = times[warmup:]
+    return B * len(timed) / sum(timed), sum(timed) / len(timed) * 1e3, cores
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.cpu_frames or 1
+    value, ms, cores = time_reference(cfg, B, args.steps, args.warmup)
+    sample = "%d frame(s) of the %s volume per Adam step through the reference's CPU torch path" % (B, args.config)
+    line = {"impl": "reference", "metric": "frame-iterations/s", "value": value, "unit": "frame-iterations/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["desc"], "frames_per_step": B, "lr": LR},
+            "cpu_baseline": {"value": value, "unit": "frame-iterations/s", "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "frame-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args, cfg):
+    import torch.distributed as dist
+    from dnmf_b200 import DeformableNMF, _lib
+    from dnmf_b200.simulate import generate_video
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world != args.gpus:
+        raise SystemExit("--gpus %d needs torchrun with %d ranks (WORLD_SIZE=%d)" % (args.gpus, args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    sz, K = cfg["sz"], cfg["K"]
+    T = args.frames or cfg["T"]
+    B = args.batch or T
+    N = int(np.prod(sz))
+    torch.manual_seed(1234 + rank)
+
+    # synthetic slab of this rank, generated on the GPU (frame-major), then resident in the context
+    vid, positions, _ = generate_video(K, T, sz, cfg["shape_std"], .2, -120, "exp", "gp",
+                                       {"sigma": [5, 5, .01], "ls": [10, 10, 10]}, seed=100 + rank, device=dev,
+                                       frame_major=True)
+    vid.clamp_(min=0)
+    tiling = tuple(int(v) for v in args.tiling.split(",")) if args.tiling else None
+    dn = DeformableNMF(sz, K, T, positions=positions[:, :, 0], cutoff=CUTOFF, deformation=cfg["deformation"],
+                       shape_std=cfg["sigma"], device=dev, tiling=tiling, verbose=False, frame_offset=rank * T,
+                       global_batch_scale=world)
+    eng = dn.fp.engine
+    dn.attach_video(vid, layout="TXYZ")
+    host_frames = None
+    if not args.no_e2e:
+        host_frames = torch.empty((T,) + tuple(sz), dtype=torch.float32, pin_memory=True)
+        host_frames.copy_(vid)
+    del vid
+    torch.cuda.empty_cache()
+
+    opt = torch.optim.Adam([dn.fp.beta], lr=LR)
+    _, st = dn._adam_state(opt)
+    beta = dn.fp.beta.detach()
+    ids_all = torch.arange(T, dtype=torch.int32, device=dev)
+    batches = [ids_all[i:i + B] for i in range(0, T - B + 1, B)]
+    loss_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+    step_no = [0]
+
+    def one_step(i):
+        ids = batches[i % len(batches)]
+        step_no[0] += 1
+        eng.motion_step(ids, beta, st["exp_avg"], st["exp_avg_sq"], dn.C, LR, (0.9, 0.999), 1e-8, step_no[0],
+                        dn.affine, frames=None, B_global=B * world, loss_out=loss_dev)
+        if world > 1:
+            dist.all_reduce(loss_dev)      # 8 bytes: the only collective of the reference-parity path
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    c0 = eng.counters()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # the timed region must be long enough for nvidia-smi to sample clocks: repeat the K steps if short
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        one_step(args.warmup + i)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    c1 = eng.counters()
+    # keep the GPU under the same load a little longer so the clock sampler sees it (not timed)
+    t_end = time.time() + 1.5
+    while rank == 0 and time.time() < t_end:
+        one_step(0)
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    st["step"].fill_(step_no[0])
+    barrier()
+    t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_total = float(t_ms)
+    frame_iters = B * args.steps * world
+    value = frame_iters / (ms_total * 1e-3)
+    final_loss = float(loss_dev)
+
+    # ---- end to end: public API, host (pinned) frames, H2D + loss read-back inside the timed region ----
+    e2e = None
+    if host_frames is not None:
+        Be = min(B, T)
+        host_batches = [(host_frames[i:i + Be], torch.arange(i, i + Be, dtype=torch.int32))
+                        for i in range(0, T - Be + 1, Be)]
+        dn._video_resident = False
+
+        class Loader:
+            def __init__(self, items):
+                self.items = items
+
+            def __iter__(self):
+                return iter(self.items)
+
+            def __len__(self):
+                return len(self.items)
+
+        nb = len(host_batches)
+        dn.update_motion(Loader([host_batches[i % nb] for i in range(max(1, min(args.warmup, 2)))]), opt, epochs=1)
+        barrier()
+        steps_e = args.steps
+        loader = Loader([host_batches[i % nb] for i in range(steps_e)])
+        ev0.record()
+        dn.update_motion(loader, opt, epochs=1)          # each step ends with a D2H read of the loss
+        ev1.record()
+        barrier()
+        t_e = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": Be * steps_e * world / (float(t_e) * 1e-3), "unit": "frame-iterations/s",
+               "h2d_bytes_per_step": Be * N * 4 + Be * 4, "d2h_bytes_per_step": 8,
+               "api": "DeformableNMF.update_motion(host loader, torch.optim.Adam) -> dnmf_motion_step_host"}
+        dn._video_resident = True
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fit_tile_kernel), timed live with CUDA events ----
+    ids = batches[0]
+    grad_scratch = torch.zeros(10, 3, T, dtype=torch.float32, device=dev)
+    sse = torch.zeros(B, dtype=torch.float64, device=dev)
+    lib = eng.lib
+    import ctypes
+
+    def fit_only():
+        _lib.check(lib.dnmf_loss_grad(eng._h, None, ctypes.c_void_p(ids.data_ptr()), B, B,
+                                      ctypes.c_void_p(beta.data_ptr()), ctypes.c_void_p(dn.C.data_ptr()),
+                                      ctypes.c_void_p(grad_scratch.data_ptr()), ctypes.c_void_p(sse.data_ptr()),
+                                      eng.stream), "dnmf_loss_grad")
+    for _ in range(3):
+        fit_only()
+    torch.cuda.synchronize()
+    reps = max(5, args.steps)
+    ev0.record()
+    for _ in range(reps):
+        fit_only()
+    ev1.record()
+    torch.cuda.synchronize()
+    fit_ms = ev0.elapsed_time(ev1) / reps            # fused kernel + its (tiny) second-stage reduction
+
+    rng = eng.ranges()
+    ext = np.minimum(rng[:, :, 1] - rng[:, :, 0] + 2, np.asarray(sz)[None, :]).clip(min=0)
+    k_eff = float(ext.prod(1).sum()) / N                       # true in-cutoff (voxel, neuron) pairs per voxel
+    counts, _, _, _ = eng.bin_tiles(beta, ids[:1])
+    tl = eng.tiling()
+    listed = float((counts.astype(np.float64) * tl["tx"] * tl["ty"] * tl["tz"]).sum()) / N
+    flops_per_frame = N * (144.0 + 25.0 * k_eff)
+    bytes_per_frame = 4.0 * N
+    peak_fp32 = ctypes.c_double(0.0)
+    _lib.check(lib.dnmf_measure_fp32_peak(local, 5, ctypes.byref(peak_fp32)), "dnmf_measure_fp32_peak")
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach_tf = flops_per_frame * B / (fit_ms * 1e-3) * 1e-12
+    ach_gbs = bytes_per_frame * B / (fit_ms * 1e-3) * 1e-9
+    roofline = {"bound": "fp32", "achieved": ach_tf, "peak": peak_fp32.value, "unit": "TFLOP/s",
+                "frac": ach_tf / peak_fp32.value if peak_fp32.value else None, "traffic": None,
+                "kernel": "fit_tile_kernel", "kernel_ms_per_launch": fit_ms, "frames_per_launch": B,
+                "flops_per_frame_iter": flops_per_frame, "k_eff_in_cutoff_pairs_per_voxel": k_eff,
+                "listed_pairs_per_voxel": listed,
+                "peak_source": "dnmf_measure_fp32_peak (FFMA microbenchmark, measured live in this run)",
+                "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                        "bytes_per_frame_iter": bytes_per_frame,
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        Bc = args.cpu_frames or 4
+        v, ms, cores = time_reference(cfg, Bc, 2, 1)
+        cpu_baseline = {"value": v, "unit": "frame-iterations/s", "cores": cores, "kind": "port",
+                        "sample": "2 Adam steps of %d frames of the %s volume (after 1 warm-up) through the "
+                                  "oracle's torch port of the reference CPU path" % (Bc, args.config),
+                        "ms_per_step": ms}
+
+    launches = sum(c1[k] - c0[k] for k in ("fit_launches", "reduce_launches", "adam_launches"))
+    line = {"metric": "frame-iterations/s", "value": value, "unit": "frame-iterations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["desc"], "name": args.config, "frames_per_gpu": T, "frames_per_step_per_gpu": B,
+                       "cutoff_sigma": CUTOFF, "lr": LR, "tiling": tl,
+                       "l2": "inputs (%.2f GB per step) larger than L2" % (B * N * 4 / 1e9)},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "final_loss": final_loss}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_b200(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

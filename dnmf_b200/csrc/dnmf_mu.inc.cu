@@ -589,3 +589,54 @@ extern "C" int dnmf_iwarp(dnmf_ctx* c, const float* frames_dev, const int32_t* f
   CU(cudaGetLastError());
   return 0;
 }
+
+// ---- FP32 peak microbenchmark (roofline denominator for the FP32-bound fused kernel) ---------------
+namespace dnmf {
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f,
+        x6 = x0 + 6.f, x7 = x0 + 7.f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = fmaf(x0, a, b);
+      x1 = fmaf(x1, a, b);
+      x2 = fmaf(x2, a, b);
+      x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b);
+      x5 = fmaf(x5, a, b);
+      x6 = fmaf(x6, a, b);
+      x7 = fmaf(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+}  // namespace dnmf
+
+extern "C" int dnmf_measure_fp32_peak(int device, int repeats, double* tflops_out) {
+  if (!tflops_out) return fail("dnmf_measure_fp32_peak: NULL argument");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  float* d = nullptr;
+  CU(cudaMalloc((void**)&d, (size_t)blocks * threads * sizeof(float)));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int r = 0; r < repeats + 2; ++r) {
+    CU(cudaEventRecord(e0, 0));
+    fp32_peak_kernel<<<blocks, threads>>>(d, iters, 0.999f, 1e-3f);
+    CU(cudaEventRecord(e1, 0));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+    if (r >= 2) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops_out = best;
+  return 0;
+}

@@ -1,0 +1,371 @@
+"""Host-side mirror of the reference's class surface (Demix/dNMF.py) on top of the CUDA library.
+
+Same names, constructor arguments, entry points and returned values as the reference:
+
+    ExponentialFP(sz, K, T, positions=None, shape_std=3)           Demix/dNMF.py:18-122
+        .beta [10,3,T] leaf tensor, .A [X,Y,Z,K], .pos, .sigma, .sz, forward(times, C)
+    DeformableNMF(sz, K, T, positions=None)                         Demix/dNMF.py:124-194
+        .fp, .C [K,T], update_motion(dataloader, optimizer, gamma, epochs),
+        update_footprints(testloader, batch_size, sz, gamma_c, gamma_a, iter_c),
+        static update_temporal / update_spatial
+
+All arithmetic of the hot path runs in the CUDA kernels behind include/dnmf_b200.h; torch is used
+for device memory, streams and tensor hand-off.  Extra keyword-only arguments (cutoff, deformation,
+tiling, frame sharding) default to the reference's behaviour.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ._lib import DnmfError
+from .engine import Engine
+
+DEFAULT_CUTOFF = 3.5          # per-axis box cutoff in units of sigma (1e-7 loss error)
+DENSE_LIMIT_BYTES = 2 << 30   # largest dense A_t / pushforward array materialised on request
+
+
+def _as_size(sz) -> list:
+    return [int(v) for v in (sz.tolist() if torch.is_tensor(sz) else sz)]
+
+
+class ExponentialFP(nn.Module):
+    """Gaussian footprints resampled through a per-frame quadratic deformation
+    (reference: Demix/dNMF.py:18-122)."""
+
+    def __init__(self, sz, K, T, positions=None, shape_std=3, *, cutoff: float = DEFAULT_CUTOFF,
+                 device=None, tiling: Optional[Sequence[int]] = None):
+        super().__init__()
+        size = _as_size(sz)
+        self.engine = Engine(size, K, T, device)
+        dev = self.engine.device
+        self.K, self.T = int(K), int(T)
+        self.cutoff = float(cutoff)
+        # identity deformation per frame (Demix/dNMF.py:24-27); leaf tensor handed to the caller's optimiser
+        beta = torch.zeros(10, 3, T, device=dev)
+        beta[1, 0], beta[2, 1], beta[3, 2] = 1.0, 1.0, 1.0
+        self.beta = beta.requires_grad_(True)
+        self.sigma = (torch.ones(K) * shape_std).to(dev)                       # :29
+        if positions is None:
+            self.pos = (1 + torch.rand(K, 3) * torch.tensor(size)[None, :]).to(dev)   # :31
+        else:
+            self.pos = torch.as_tensor(positions).float().to(dev)              # :33
+        self.sz = torch.as_tensor(size).to(dev)
+        if tiling is not None:
+            self.engine.set_tiling(*tiling)
+        self.engine.set_footprints(self.pos, self.sigma, self.cutoff)
+        self._A = None
+
+    def set_footprints(self, positions=None, sigma=None, cutoff: Optional[float] = None):
+        """Rebuild the per-axis tables after changing positions / widths / cutoff."""
+        if positions is not None:
+            self.pos = torch.as_tensor(positions).float().to(self.engine.device)
+        if sigma is not None:
+            self.sigma = torch.as_tensor(sigma).float().to(self.engine.device)
+        if cutoff is not None:
+            self.cutoff = float(cutoff)
+        self.engine.set_footprints(self.pos, self.sigma, self.cutoff)
+        self._A = None
+
+    @property
+    def flow_id(self) -> torch.Tensor:
+        """Integer voxel coordinates [X,Y,Z,3] (Demix/dNMF.py:22), built on demand."""
+        X, Y, Z = self.sz.tolist()
+        dev = self.engine.device
+        g = torch.meshgrid(torch.arange(X, device=dev), torch.arange(Y, device=dev), torch.arange(Z, device=dev),
+                           indexing="ij")
+        return torch.stack(g, 3).float()
+
+    @property
+    def transformed(self) -> torch.Tensor:
+        return ExponentialFP.quadratic_basis(self.flow_id)
+
+    @property
+    def A(self) -> torch.Tensor:
+        """Dense (untruncated) Gaussian volume [X,Y,Z,K] of Demix/dNMF.py:39-40.  The kernels never
+        need it; it is materialised lazily for callers that read `fp.A` (demo.py:61)."""
+        if self._A is None:
+            X, Y, Z = self.sz.tolist()
+            if X * Y * Z * self.K * 4 > DENSE_LIMIT_BYTES:
+                raise DnmfError("fp.A would need %.1f GB; read the per-axis tables instead"
+                                % (X * Y * Z * self.K * 4 / 2 ** 30))
+            ax = [torch.arange(n, device=self.engine.device, dtype=torch.float32) for n in (X, Y, Z)]
+            e = [-(ax[d][:, None] - self.pos[:, d][None, :]) ** 2 / self.sigma[None, :] ** 2 for d in range(3)]
+            self._A = torch.exp(e[0][:, None, None, :] + e[1][None, :, None, :] + e[2][None, None, :, :])
+        return self._A
+
+    @staticmethod
+    def quadratic_basis(P: torch.Tensor) -> torch.Tensor:
+        """[..., 3] -> [..., 10] = [1,x,y,z,x2,y2,z2,xy,xz,yz] (Demix/dNMF.py:46-51)."""
+        x, y, z = P[..., 0:1], P[..., 1:2], P[..., 2:3]
+        return torch.cat((torch.ones_like(x), P, P * P, x * y, x * z, y * z), -1)
+
+    def forward(self, times, C, want_dense: Optional[bool] = None):
+        """Returns (A_tC[B,X,Y,Z], A_t[B,K,X,Y,Z], grid[X,Y,Z,3,B], reg[B]) like Demix/dNMF.py:53-62.
+        The dense A_t / grid are produced only while they fit DENSE_LIMIT_BYTES (else None)."""
+        times = [int(t) for t in (times.tolist() if hasattr(times, "tolist") else times)]
+        B = len(times)
+        X, Y, Z = self.sz.tolist()
+        if want_dense is None:
+            want_dense = B * self.K * X * Y * Z * 4 <= DENSE_LIMIT_BYTES
+        C = torch.as_tensor(C).float().to(self.engine.device).contiguous()
+        ids = torch.tensor(times, dtype=torch.int32)
+        with torch.no_grad():
+            AtC, At, grid = self.engine.forward(ids, self.beta.detach(), C, want_At=want_dense, want_grid=want_dense)
+        reg = self.regularizer_values(times)
+        return AtC, At, grid, reg
+
+    def regularizer_values(self, times) -> torch.Tensor:
+        """The detached diagnostic of Demix/dNMF.py:60-61 (log-det-Jacobian at two corners), on the CPU
+        like the reference's torch.tensor([...]) (it carries no gradient)."""
+        b = self.beta.detach()[:, :, list(times)].cpu()
+        hi = (self.sz - 1).cpu().float()
+        lo = torch.zeros(3)
+        return torch.stack([ExponentialFP.log_det_jac(b[:, :, j], hi) ** 2 +
+                            ExponentialFP.log_det_jac(b[:, :, j], lo) ** 2 for j in range(b.shape[2])])
+
+    @staticmethod
+    def log_det_jac(B, P):
+        """log|det J| at point P with the reference's own cross-term indexing (Demix/dNMF.py:107-122)."""
+        x, y, z = P[0], P[1], P[2]
+        r = [(B[1, c] + 2 * B[4, c] * x + B[7, c] * y + B[9, c] * z,
+              B[2, c] + 2 * B[5, c] * y + B[7, c] * x + B[8, c] * z,
+              B[3, c] + 2 * B[6, c] * z + B[8, c] * y + B[9, c] * x) for c in range(3)]
+        (a, b, c), (d, e, f), (g, h, i) = r
+        return torch.log(abs(a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g)))
+
+    @staticmethod
+    def spatial_pushforward(dl, batch_size, sz, device, model):
+        """Dense outputs of Demix/dNMF.py:69-93: (A_t[X,Y,Z,K,T'] f64, Y_i[X,Y,Z,T'] f64, Y[X,Y,Z,T'] f64)
+        as numpy arrays, computed on the GPU batch by batch."""
+        size = _as_size(sz)
+        n = len(dl) * batch_size
+        K = model.C.shape[0]
+        need = size[0] * size[1] * size[2] * K * n * 8
+        if need > 8 * DENSE_LIMIT_BYTES:
+            raise DnmfError("spatial_pushforward would materialise %.1f GB; use update_footprints(dense=False)"
+                            % (need / 2 ** 30))
+        A_t = np.zeros((size[0], size[1], size[2], K, n))
+        Y_i = np.zeros((size[0], size[1], size[2], n))
+        Y = np.zeros((size[0], size[1], size[2], n))
+        eng = model.fp.engine
+        beta = model.fp.beta.detach()
+        for bi, data in enumerate(dl):
+            frames = data[0].float()
+            ids = torch.as_tensor(data[1]).to(torch.int32)
+            fd = frames.to(eng.device).contiguous()
+            _, At, _ = eng.forward(ids, beta, model.C, want_At=True)
+            yi = eng.iwarp(ids, beta, frames=fd)
+            s = slice(bi * batch_size, bi * batch_size + fd.shape[0])
+            A_t[..., s] = At.permute(2, 3, 4, 1, 0).double().cpu().numpy()
+            Y[..., s] = fd.permute(1, 2, 3, 0).double().cpu().numpy()
+            Y_i[..., s] = yi.permute(1, 2, 3, 0).double().cpu().numpy()
+        return A_t, Y_i, Y
+
+
+class DeformableNMF:
+    """dNMF fit: Adam on the per-frame deformation + multiplicative updates of the traces
+    (reference: Demix/dNMF.py:124-194)."""
+
+    def __init__(self, sz, K, T, positions=None, *, cutoff: float = DEFAULT_CUTOFF, deformation: str = "quadratic",
+                 shape_std=3, device=None, tiling=None, verbose: bool = True, frame_offset: int = 0,
+                 global_batch_scale: int = 1):
+        if deformation not in ("quadratic", "affine"):
+            raise ValueError("deformation must be 'quadratic' or 'affine'")
+        self.SpatialModel = ExponentialFP
+        self.fp = ExponentialFP(sz=sz, K=K, T=T, positions=positions, shape_std=shape_std, cutoff=cutoff,
+                                device=device, tiling=tiling)
+        dev = self.fp.engine.device
+        self.C = torch.rand((K, T)).to(dev)                                     # Demix/dNMF.py:130
+        size = _as_size(sz)
+        self.A = torch.rand((K, size[0], size[1])).to(dev)                      # :131 (unused, kept for parity)
+        self._positions = None if positions is None else torch.as_tensor(positions).float()
+        self._size = size
+        self._D = None
+        self.affine = deformation == "affine"
+        self.verbose = verbose
+        self.frame_offset = int(frame_offset)        # first global frame id of this rank's slab
+        self.global_batch_scale = int(global_batch_scale)   # world size when every rank steps a local batch
+        self.loss_history = []                       # python floats / CUDA scalars, one per Adam step
+        self._loss_buf = None
+        self._video_resident = False
+
+    # distance penalty of Demix/dNMF.py:133-135, only used by the (disabled) update_spatial: lazy
+    @property
+    def D(self):
+        if self._positions is None:
+            return None
+        if self._D is None:
+            X, Y, Z = self._size
+            dev = self.fp.engine.device
+            g = torch.stack(torch.meshgrid(torch.arange(X, device=dev), torch.arange(Y, device=dev),
+                                           torch.arange(Z, device=dev), indexing="ij"), 3).reshape(-1, 3).double()
+            d = torch.cdist(g, self._positions.to(dev).double())
+            self._D = (1 - torch.exp(-.01 * d)).reshape(X, Y, Z, -1).cpu().numpy()
+        return self._D
+
+    # -- resident video (extension: keeps the frames in HBM so steps only send frame ids) ----------
+    def attach_video(self, video: torch.Tensor, layout: str = "XYZT"):
+        """Upload this rank's frames once.  layout 'XYZT' is SimulatedVideoDataset.video
+        (Demix/dNMF.py:203), 'TXYZ' is frame-major."""
+        if layout == "XYZT":
+            frames = video.permute(3, 0, 1, 2)
+        elif layout == "TXYZ":
+            frames = video
+        else:
+            raise ValueError("layout must be 'XYZT' or 'TXYZ'")
+        if frames.shape[0] != self.fp.T:
+            raise DnmfError("video has %d frames, model has T=%d" % (frames.shape[0], self.fp.T))
+        self.fp.engine.upload_frames(frames.float().contiguous(), 0, clamp_negative=True)
+        self._video_resident = True
+
+    # -- Adam state shared with the caller's optimiser ---------------------------------------------
+    def _adam_state(self, optimizer):
+        if not isinstance(optimizer, torch.optim.Adam) or type(optimizer) is not torch.optim.Adam:
+            raise DnmfError("update_motion supports torch.optim.Adam only (demo.py:42), got %s" % type(optimizer).__name__)
+        group = None
+        for g in optimizer.param_groups:
+            if any(p is self.fp.beta for p in g["params"]):
+                group = g
+        if group is None:
+            raise DnmfError("the optimiser does not own dnmf.fp.beta")
+        if group.get("weight_decay", 0) != 0 or group.get("amsgrad", False) or group.get("maximize", False):
+            raise DnmfError("weight_decay / amsgrad / maximize are not supported by the device Adam kernel")
+        st = optimizer.state[self.fp.beta]
+        if len(st) == 0:
+            st["step"] = torch.tensor(0.0)
+            st["exp_avg"] = torch.zeros_like(self.fp.beta, memory_format=torch.preserve_format)
+            st["exp_avg_sq"] = torch.zeros_like(self.fp.beta, memory_format=torch.preserve_format)
+        return group, st
+
+    def update_motion(self, dataloader, optimizer, gamma=0, epochs=20):
+        """Demix/dNMF.py:181-194.  Each batch: fused forward/backward kernel + dense device Adam.
+        `gamma` multiplies a detached constant in the reference and does not change
+        the updates; it is accepted for signature compatibility."""
+        eng = self.fp.engine
+        group, st = self._adam_state(optimizer)
+        beta = self.fp.beta.detach()
+        for epoch in range(1, epochs + 1):
+            if self.verbose:
+                print("Epoch " + str(epoch))
+            self.fp.train()
+            for batch_idx, data in enumerate(dataloader):
+                ids = torch.as_tensor(data[1]).to(torch.int32)
+                step = int(st["step"]) + 1
+                lr, betas, eps = group["lr"], group["betas"], group["eps"]
+                if self._video_resident:
+                    if self._loss_buf is None:
+                        self._loss_buf = torch.zeros(1024, dtype=torch.float64, device=eng.device)
+                    slot = self._loss_buf[(step - 1) % 1024:(step - 1) % 1024 + 1]
+                    eng.motion_step(ids.to(eng.device), beta, st["exp_avg"], st["exp_avg_sq"], self.C, lr, betas, eps,
+                                    step, self.affine, frames=None, B_global=ids.numel() * self.global_batch_scale,
+                                    loss_out=slot)
+                    loss = slot
+                else:
+                    frames = data[0]
+                    if frames.is_cuda:
+                        fd = frames.float().contiguous()
+                        slot = torch.zeros(1, dtype=torch.float64, device=eng.device)
+                        eng.motion_step(ids.to(eng.device), beta, st["exp_avg"], st["exp_avg_sq"], self.C, lr, betas,
+                                        eps, step, self.affine, frames=fd,
+                                        B_global=ids.numel() * self.global_batch_scale, loss_out=slot)
+                        loss = slot
+                    else:
+                        fh = frames.float().contiguous()   # clamping at 0 is the dataset's job (Demix/dNMF.py:215)
+                        loss = eng.motion_step_host(fh, ids.contiguous(), beta, st["exp_avg"], st["exp_avg_sq"],
+                                                    self.C, lr, betas, eps, step, self.affine,
+                                                    B_global=ids.numel() * self.global_batch_scale)
+                st["step"] += 1
+                self.loss_history.append(loss if isinstance(loss, float) else loss.clone())
+                if self.verbose and batch_idx % 10 == 0:
+                    print("Recon: " + str(float(loss)))
+                    print("Reg: " + str(self.fp.regularizer_values(ids.tolist())))
+
+    def losses(self) -> np.ndarray:
+        """Per-step reconstruction losses recorded by update_motion (one device sync)."""
+        return np.asarray([float(l) for l in self.loss_history])
+
+    # -- traces -------------------------------------------------------------------------------------
+    @staticmethod
+    def update_temporal(A_t, C, Y, gamma=None):
+        """Stand-alone multiplicative update on dense arrays (Demix/dNMF.py:139-149), fp64 on the GPU."""
+        dev = torch.device("cuda")
+        A = torch.as_tensor(A_t, dtype=torch.float64, device=dev)
+        Cd = torch.as_tensor(C, dtype=torch.float64, device=dev)
+        Yd = torch.as_tensor(Y, dtype=torch.float64, device=dev)
+        A_ts = torch.einsum("mnzkt,mnzlt->klt", A, A)
+        C1 = torch.einsum("mnzkt,mnzt->kt", A, Yd)
+        C2 = torch.einsum("klt,lt->kt", A_ts, Cd)
+        if gamma is not None:
+            reg = torch.cat((Cd[:, :1], Cd[:, :-1]), 1) + torch.cat((Cd[:, 1:], Cd[:, -1:]), 1)
+            C1 = C1 + gamma * reg
+            C2 = C2 + 2 * gamma * Cd
+        return (Cd * C1 / (C2 + 1e-32)).cpu().numpy()
+
+    @staticmethod
+    def update_spatial(A, C, Y_i, D=None, gamma=None):
+        """Non-parametric footprint update of Demix/dNMF.py:151-160 (never called by the reference's
+        fit loop, :174), fp64 on the GPU."""
+        dev = torch.device("cuda")
+        Ad = torch.as_tensor(A, dtype=torch.float64, device=dev)
+        Cd = torch.as_tensor(C, dtype=torch.float64, device=dev)
+        Yd = torch.as_tensor(Y_i, dtype=torch.float64, device=dev)
+        C_s = torch.einsum("kt,pt->kp", Cd, Cd)
+        A1 = torch.einsum("mnt,kt->mnk", Yd, Cd)
+        A2 = torch.einsum("mnk,kp->mnp", Ad, C_s)
+        if D is not None:
+            A2 = A2 + gamma * torch.as_tensor(D, dtype=torch.float64, device=dev)
+        return (Ad * A1 / (A2 + 1e-32)).cpu().numpy()
+
+    def update_traces(self, testloader=None, gamma_c=1e-2, iter_c=10, halo_exchange=None):
+        """Device-only trace update: statistics kernel over all frames, then iter_c sweeps.
+        `halo_exchange(first, last) -> (prev, next)` lets a multi-GPU caller swap boundary columns."""
+        eng = self.fp.engine
+        beta = self.fp.beta.detach()
+        if self._video_resident and testloader is None:
+            ids = torch.arange(self.fp.T, dtype=torch.int32)
+            step = 256
+            for i in range(0, self.fp.T, step):
+                eng.mu_stats(ids[i:i + step], beta)
+        else:
+            for data in testloader:
+                ids = torch.as_tensor(data[1]).to(torch.int32)
+                fd = data[0].float().to(eng.device).contiguous()
+                eng.mu_stats(ids, beta, frames=fd)
+        if halo_exchange is None:
+            eng.mu_sweeps(self.C, gamma_c, iter_c)
+        else:
+            eng.mu_begin(self.C)
+            for _ in range(iter_c):
+                first, last = eng.mu_boundary()
+                prev, nxt = halo_exchange(first, last)
+                eng.mu_sweep(gamma_c, prev, nxt)
+            eng.mu_end(self.C)
+
+    def update_footprints(self, testloader, batch_size, sz, gamma_c=1e-2, gamma_a=1e0, iter_c=10, dense=None):
+        """Demix/dNMF.py:163-179: pushforward, then iter_c multiplicative updates of C.
+        Returns (A_t, Y_i, Y) as numpy fp64 arrays like the reference while they fit in memory
+        (dense=None decides by size; dense=False skips them and returns (None, None, None))."""
+        size = _as_size(sz)
+        n = len(testloader) * batch_size
+        if dense is None:
+            dense = size[0] * size[1] * size[2] * self.C.shape[0] * n * 8 <= 8 * DENSE_LIMIT_BYTES
+        out = (None, None, None)
+        if dense:
+            with torch.no_grad():
+                out = self.SpatialModel.spatial_pushforward(testloader, batch_size, sz, self.fp.engine.device, self)
+        self.update_traces(testloader, gamma_c=gamma_c, iter_c=iter_c)
+        return out
+
+    def fit(self, dataloader, testloader, optimizer, batch_size, sz, outer=5, epochs=10, iter_c=50, gamma=1,
+            gamma_c=0, dense=False):
+        """The schedule of demo.py:44-46."""
+        out = None
+        for _ in range(outer):
+            self.update_motion(dataloader, optimizer, gamma=gamma, epochs=epochs)
+            out = self.update_footprints(testloader, batch_size, sz, gamma_c=gamma_c, iter_c=iter_c, dense=dense)
+        return out

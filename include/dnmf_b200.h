@@ -122,6 +122,10 @@ int dnmf_mu_sweeps(dnmf_ctx* ctx, float* C_dev, double gamma, int use_gamma, int
 int dnmf_iwarp(dnmf_ctx* ctx, const float* frames_dev, const int32_t* frame_ids_dev, int B,
                const float* beta_dev, float* out_dev, void* stream);
 
+/* FFMA microbenchmark: best-of-`repeats` dense FP32 throughput of the device in TFLOP/s (FMA = 2);
+ * the roofline denominator for the FP32-bound fused kernel (MEASURED_PEAKS.json has no FP32 entry). */
+int dnmf_measure_fp32_peak(int device, int repeats, double* tflops_out);
+
 /* Counters for bench accounting: number of fused-kernel launches etc. since creation. */
 int dnmf_get_counters(dnmf_ctx* ctx, int64_t* out /* [8] */);
 

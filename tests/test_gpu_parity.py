@@ -121,3 +121,85 @@ def test_adam_matches_torch():
         np.testing.assert_allclose(dp.cpu().numpy(), ref_p.detach().numpy(), rtol=2e-6, atol=1e-9)
     np.testing.assert_allclose(m.cpu().numpy(), opt.state[ref_p]["exp_avg"].numpy(), rtol=2e-6, atol=1e-12)
     np.testing.assert_allclose(v.cpu().numpy(), opt.state[ref_p]["exp_avg_sq"].numpy(), rtol=2e-6, atol=1e-14)
+
+
+def _demo_model(g, cutoff, resident, tiling=None):
+    from dnmf_b200 import DeformableNMF
+    sz = g["sz"].tolist()
+    K, T = g["C0"].shape
+    dn = DeformableNMF(sz, K, T, positions=torch.tensor(g["pos0"]), cutoff=cutoff, verbose=False, tiling=tiling)
+    dn.C = torch.tensor(g["C0"]).cuda()
+    if resident:
+        dn.attach_video(torch.tensor(g["frames"]), layout="TXYZ")
+    return dn
+
+
+@pytest.mark.parametrize("cutoff,resident", [(0.0, False), (3.5, True), (3.5, False)])
+def test_demo_trajectory_vs_reference(golden_demo, cutoff, resident):
+    """demo.py:41-46 schedule, first 250 Adam steps (shuffle=False, batch 4, lr 1e-5) then the trace
+    updates, against the REAL reference's recorded outputs (tests/golden/demo_cfg1.npz)."""
+    from torch.utils.data import DataLoader
+    from dnmf_b200 import FrameDataset
+    g = golden_demo
+    dn = _demo_model(g, cutoff, resident)
+    loader = DataLoader(FrameDataset(torch.tensor(g["frames"])), batch_size=4, shuffle=False)
+    opt = torch.optim.Adam([dn.fp.beta], lr=1e-5)
+    dn.update_motion(loader, opt, gamma=1, epochs=10)
+    losses = dn.losses()
+    ref = g["losses"]
+    assert losses.shape == ref.shape
+    rel = np.abs(losses - ref) / ref
+    assert rel.max() < 1e-4, rel.max()                     # north_star: loss per iteration <= 1e-4 relative
+    beta = dn.fp.beta.detach().cpu()
+    # deformation field tau_t(p) over all voxels and frames, <= 1e-3 px
+    _, phi = O.voxel_basis(g["sz"].tolist())
+    q_new = torch.einsum("mnza,abt->mnzbt", phi, beta)
+    q_ref = torch.einsum("mnza,abt->mnzbt", phi, torch.tensor(g["beta250"]))
+    assert float((q_new - q_ref).abs().max()) < 1e-3
+    st = opt.state[dn.fp.beta]
+    assert int(st["step"]) == 250
+    m = st["exp_avg"].cpu().numpy()
+    assert np.abs(m - g["adam_m"]).max() <= 1e-3 * np.abs(g["adam_m"]).max()
+    # traces: update_footprints(gamma_c=0, iter_c=50) then (gamma_c=1e-2, iter_c=10)
+    dn.update_footprints(loader, 4, g["sz"].tolist(), gamma_c=0, iter_c=50, dense=False)
+    C = dn.C.cpu().numpy()
+    assert np.abs(C - g["C_mu0"]).max() / np.abs(g["C_mu0"]).max() < 1e-3
+    dn.update_footprints(loader, 4, g["sz"].tolist(), gamma_c=1e-2, iter_c=10, dense=False)
+    C = dn.C.cpu().numpy()
+    assert np.abs(C - g["C_mu1"]).max() / np.abs(g["C_mu1"]).max() < 1e-3
+
+
+def test_mu_stats_vs_closed_form(golden_random):
+    g = golden_random
+    sz = g["sz"].tolist()
+    T = g["beta"].shape[2]
+    e = _engine(sz, 5, T, g["pos"], g["sigma"], 0.0)
+    beta = torch.tensor(g["beta"]).cuda()
+    frames = torch.tensor(g["frames"]).cuda()
+    e.mu_stats(torch.arange(T), beta, frames=frames)
+    tabs, _ = O.axis_tables(g["pos"], g["sigma"], sz, 0.0)
+    Gm, bv = O.closed_form_mu_stats(g["frames"], list(range(T)), g["beta"], tabs, sz)
+    for t in range(T):
+        G, b = e.get_mu_stats(t)
+        np.testing.assert_allclose(G, Gm[t], rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(b, bv[t], rtol=2e-5, atol=1e-6)
+    # and against the reference's dense A_t
+    A = g["A_t"].astype(np.float64).reshape(T, 5, -1)
+    for t in range(T):
+        G, b = e.get_mu_stats(t)
+        np.testing.assert_allclose(G, A[t] @ A[t].T, rtol=1e-4, atol=1e-5)
+
+
+def test_update_footprints_dense_outputs(golden_demo):
+    """A_t / Y returned by update_footprints match the reference's dense arrays (first 4 frames)."""
+    from torch.utils.data import DataLoader
+    from dnmf_b200 import FrameDataset
+    g = golden_demo
+    dn = _demo_model(g, 0.0, False)
+    dn.fp.beta.data.copy_(torch.tensor(g["beta250"]))
+    frames = torch.tensor(g["frames"][:8])
+    loader = DataLoader(FrameDataset(frames), batch_size=4, shuffle=False)
+    A_t, Y_i, Y = dn.update_footprints(loader, 4, g["sz"].tolist(), gamma_c=0, iter_c=1)
+    assert A_t.shape == (50, 50, 2, 10, 8) and Y.shape == (50, 50, 2, 8) and Y_i.shape == Y.shape
+    np.testing.assert_allclose(A_t[..., :4], g["A_t_first4"], atol=3e-6)
+    np.testing.assert_allclose(Y[..., :4], g["Y_first4"], atol=0)
