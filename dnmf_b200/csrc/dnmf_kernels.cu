@@ -192,14 +192,17 @@ __global__ void scan_counts_kernel(const int* __restrict__ counts, long long n, 
 // ------------------------------------------------------------------------------------------------
 // kernel 2: fused forward / residual / loss / analytic gradient.
 //
-// One CTA = NWX*NWY warps = one spatial tile (8*NWX) x (4*NWY) x tz of one frame.  The frame is
-// read ONCE from HBM (coalesced runs of ty*Z floats staged in shared memory).  Prologue: beta_t ->
-// conservative sample window -> neuron list (ascending k, ballot compaction) -> the listed neurons'
-// table slices staged in shared memory with C[k,t] folded into the x slice.  Main loop: each lane
-// owns one (x,y) column and marches along z; per (voxel, neuron) pair 3 LDS.64 + 10 FP32 ops give
-// Yhat and dYhat/dix (no N x K footprint matrix, no transcendental).  The 30 gradient entries are
-// accumulated as z-moments per lane, expanded with the lane's (x,y) monomials, then reduced
-// warp-shuffle -> block -> per-CTA partial; a second kernel sums partials in fixed order.
+// One CTA = NWX*NWY warps = one spatial tile (8*NWX) x (4*NWY) x tz of one frame.  The frame tile is
+// read ONCE from HBM: one bulk async copy (TMA, cp.async.bulk + mbarrier) per contiguous run of
+// ty*Z floats, landing in shared memory while the prologue runs.  Prologue: beta_t -> conservative
+// sample window -> neuron list (ascending k, ballot compaction) -> the listed neurons' table slices
+// staged in shared memory, entry-major [entry][slot] so that consecutive slots are adjacent (one
+// LDS.128 serves two neurons, slot offsets are immediates) with C[k,t] folded into the x slice.
+// Main loop: each lane owns one (x,y) column and marches along z; per (voxel, neuron) pair
+// 1.5 LDS + 10 FP32 ops give Yhat and dYhat/dix (no N x K footprint matrix, no transcendental).
+// The 30 gradient entries are accumulated as z-moments per lane, expanded with the lane's (x,y)
+// monomials and reduced with a transposing butterfly (31 shuffles for 32 values) -> CTA partial;
+// a second kernel sums partials in fixed order (bit-reproducible).
 // Math: Demix/dNMF.py:54-58 + F.mse_loss (:188) + autograd of grid_sample wrt grid.
 // ------------------------------------------------------------------------------------------------
 struct FitParams {
@@ -216,8 +219,12 @@ struct FitParams {
   int frames_are_batch;
   int X, Y, Z, K, T;
   int tz, ntx, nty, ntz;
-  int cap, wmax0, wmax1, wmax2;
+  int cap;  // staged slot capacity, even
+  int wmax0, wmax1, wmax2;
   int full_depth;
+  int bulk_ok;   // tile rows may be fetched with cp.async.bulk (16 B alignment holds)
+  int fast_div;  // exact 3-instruction division verified for all three axes
+  float rcp0, rcp1, rcp2;
 };
 
 struct FitSmem {
@@ -232,42 +239,91 @@ static FitSmem fit_smem_layout(int nw, int tx, int ty, int tz, int cap, int wsum
   s.tab_f2 = cap * wsum;
   s.y_f = tx * ty * tz + 4;
   s.list_u16 = (K + 7) & ~7;
-  s.bytes = (size_t)s.tab_f2 * 8 + (size_t)s.y_f * 4 + (size_t)nw * kNumPartials * 4 + 64 * 4 +
+  s.bytes = (size_t)s.tab_f2 * 8 + (size_t)s.y_f * 4 + (size_t)nw * kNumPartials * 4 + 64 * 4 + 16 +
             (size_t)s.list_u16 * 2;
   return s;
 }
 
-__device__ __forceinline__ void pair_accumulate(float2 ex, float2 ey, float2 ez, float f0, float f1,
-                                                float f2, float& yh, float& g0, float& g1, float& g2) {
-  float ca0 = fmaf(f0, ex.y, ex.x);
-  float a1 = fmaf(f1, ey.y, ey.x);
-  float a2 = fmaf(f2, ez.y, ez.x);
-  float t12 = a1 * a2;
+// un-normalised sample coordinate, fast exact-division form (see verify_coord_kernel)
+__device__ __forceinline__ float sample_coord_fast(float q, float sm1, float rcp) {
+  const float x = __fadd_rn(q, q);
+  const float q0 = __fmul_rn(x, rcp);
+  const float r = __fmaf_rn(-q0, sm1, x);
+  const float v = __fmaf_rn(r, rcp, q0);
+  const float u = __fsub_rn(v, 1.f);
+  return __fmul_rn(__fmul_rn(__fadd_rn(u, 1.f), 0.5f), sm1);
+}
+
+// Exhaustive check over all 2^32 float bit patterns that the fast form equals the reference op
+// sequence (true division) for this axis size; the fast path is enabled only when no pattern differs.
+__global__ void verify_coord_kernel(float sm1, float rcp, unsigned long long* __restrict__ mismatches) {
+  const unsigned base = (blockIdx.x * blockDim.x + threadIdx.x) * 256u;
+  unsigned bad = 0;
+  for (unsigned i = 0; i < 256u; ++i) {
+    const unsigned bits = base + i;
+    if (((bits >> 23) & 0xffu) >= 253u) continue;  // |q| >= 2^126, inf, NaN: 2q overflows, reference is UB there
+    const float q = __uint_as_float(bits);
+    const float a = sample_coord(q, sm1);
+    const float b = sample_coord_fast(q, sm1, rcp);
+    const bool same = (__float_as_uint(a) == __float_as_uint(b)) || (isnan(a) && isnan(b));
+    bad += same ? 0u : 1u;
+  }
+  if (bad) atomicAdd(mismatches, (unsigned long long)bad);
+}
+
+__device__ __forceinline__ void pair_accumulate(float ex_g, float ex_d, float ey_g, float ey_d, float ez_g,
+                                                float ez_d, float f0, float f1, float f2, float& yh,
+                                                float& g0, float& g1, float& g2) {
+  const float ca0 = fmaf(f0, ex_d, ex_g);
+  const float a1 = fmaf(f1, ey_d, ey_g);
+  const float a2 = fmaf(f2, ez_d, ez_g);
+  const float t12 = a1 * a2;
   yh = fmaf(ca0, t12, yh);
-  g0 = fmaf(ex.y, t12, g0);
-  g1 = fmaf(ca0 * a2, ey.y, g1);
-  g2 = fmaf(ca0 * a1, ez.y, g2);
+  g0 = fmaf(ex_d, t12, g0);
+  g1 = fmaf(ca0 * a2, ey_d, g1);
+  g2 = fmaf(ca0 * a1, ez_d, g2);
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// Sum 32 per-lane values across the warp with 31 shuffles: afterwards lane l holds the total of v[l].
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
 }
 
 template <int NWX, int NWY, bool WRITE_YHAT>
-__global__ void __launch_bounds__(32 * NWX * NWY) fit_tile_kernel(const __grid_constant__ FitParams p) {
+__global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? 20 : 1) fit_tile_kernel(const __grid_constant__ FitParams p) {
   constexpr int NW = NWX * NWY;
   constexpr int TX = kWarpX * NWX, TY = kWarpY * NWY;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int wsum = p.wmax0 + p.wmax1 + p.wmax2;
-  float2* sTab = reinterpret_cast<float2*>(smem_raw);
-  float* sY = reinterpret_cast<float*>(sTab + (size_t)p.cap * wsum);
+  const int CAP = p.cap;
+  float2* sTab = reinterpret_cast<float2*>(smem_raw);  // [entry][slot], slot stride 8 B
+  float* sY = reinterpret_cast<float*>(sTab + (size_t)CAP * wsum);
   const int zs = p.full_depth ? p.Z : p.tz;  // smem z-stride between y rows
   const int RS = TY * zs;                    // smem stride between x rows
   float* sRed = sY + (TX * TY * p.tz + 4);
-  float* sBeta = sRed + NW * kNumPartials;   // 32 floats
-  int* sInt = reinterpret_cast<int*>(sBeta + 32);  // 32 ints: win[6], cnt[NW], L
-  unsigned short* sList = reinterpret_cast<unsigned short*>(sInt + 32);
+  float* sBeta = sRed + NW * kNumPartials;          // 32 floats
+  int* sInt = reinterpret_cast<int*>(sBeta + 32);   // 32 ints: win[6], cnt[NW]
+  unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sInt + 32);  // 16 B
+  unsigned short* sList = reinterpret_cast<unsigned short*>(sBar + 2);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nt = p.ntx * p.nty * p.ntz;
-  const int b = blockIdx.x / nt, tile = blockIdx.x - b * nt;
-  const int bx = tile % p.ntx, by = (tile / p.ntx) % p.nty, bz = tile / (p.ntx * p.nty);
+  // grid = (ntx, nty, B*ntz): no integer division on the common ntz == 1 path
+  const int bx = blockIdx.x, by = blockIdx.y;
+  const int b = p.ntz == 1 ? (int)blockIdx.z : (int)blockIdx.z / p.ntz;
+  const int bz = p.ntz == 1 ? 0 : (int)blockIdx.z - b * p.ntz;
+  const unsigned cta_linear = ((unsigned)blockIdx.z * gridDim.y + by) * gridDim.x + bx;  // = (b*ntz+bz, by, bx)
   const int t = p.frame_ids[b];
   const int x0 = bx * TX, y0 = by * TY, z0 = bz * p.tz;
   const int nx = min(TX, p.X - x0), ny = min(TY, p.Y - y0), nz = min(p.tz, p.Z - z0);
@@ -276,9 +332,28 @@ __global__ void __launch_bounds__(32 * NWX * NWY) fit_tile_kernel(const __grid_c
   if (tid < 30) sBeta[tid] = p.beta[(size_t)tid * p.T + t];
 
   // ---- stream the tile of the frame into shared memory (each voxel read once from HBM) ----
+  bool bulk = false;
   if (!WRITE_YHAT) {
-    if (p.full_depth) {
-      const int run = ny * p.Z;
+    const int run = ny * p.Z;
+    bulk = p.bulk_ok && p.full_depth && ((run & 3) == 0);
+    if (bulk) {
+      const unsigned bar = smem_u32(sBar);
+      if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nx * run * 4)
+                     : "memory");
+      }
+      __syncthreads();
+      if (tid < nx) {
+        const float* src = frame + ((size_t)(x0 + tid) * p.Y + y0) * p.Z;
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(sY + tid * RS)),
+            "l"(src), "r"(run * 4), "r"(bar)
+            : "memory");
+      }
+    } else if (p.full_depth) {
       for (int lx = warp; lx < nx; lx += NW) {
         const float* src = frame + ((size_t)(x0 + lx) * p.Y + y0) * p.Z;
         for (int e = lane; e < run; e += 32) sY[lx * RS + e] = __ldg(src + e);
@@ -312,58 +387,84 @@ __global__ void __launch_bounds__(32 * NWX * NWY) fit_tile_kernel(const __grid_c
     whi[d] = sInt[3 + d];
   }
 
-  // ---- neuron list: ascending k, two-pass ballot compaction across the CTA's warps ----
-  const int per = ((p.K + NW * 32 - 1) / (NW * 32)) * 32;
-  const int kb = warp * per;
-  {
+  // ---- neuron list: ascending k, ballot compaction (single pass for one warp, two passes else) ----
+  int L = 0;
+  if (NW == 1) {
+    for (int k0 = 0; k0 < p.K; k0 += 32) {
+      const int k = k0 + lane;
+      const bool ok = (k < p.K) && neuron_in_window(p.rng + (size_t)k * 6, wlo, whi);
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) sList[L + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
+      L += __popc(m);
+    }
+    __syncwarp();
+  } else {
+    const int per = ((p.K + NW * 32 - 1) / (NW * 32)) * 32;
+    const int kb = warp * per;
     int cnt = 0;
     for (int k0 = kb; k0 < kb + per; k0 += 32) {
-      int k = k0 + lane;
-      bool ok = (k < p.K) && neuron_in_window(p.rng + (size_t)k * 6, wlo, whi);
+      const int k = k0 + lane;
+      const bool ok = (k < p.K) && neuron_in_window(p.rng + (size_t)k * 6, wlo, whi);
       cnt += __popc(__ballot_sync(0xffffffffu, ok));
     }
     if (lane == 0) sInt[8 + warp] = cnt;
-  }
-  __syncthreads();
-  int L = 0;
-  {
+    __syncthreads();
     int off = 0;
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
-      int c = sInt[8 + w];
+      const int c = sInt[8 + w];
       if (w < warp) off += c;
       L += c;
     }
     for (int k0 = kb; k0 < kb + per; k0 += 32) {
-      int k = k0 + lane;
-      bool ok = (k < p.K) && neuron_in_window(p.rng + (size_t)k * 6, wlo, whi);
-      unsigned m = __ballot_sync(0xffffffffu, ok);
+      const int k = k0 + lane;
+      const bool ok = (k < p.K) && neuron_in_window(p.rng + (size_t)k * 6, wlo, whi);
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
       if (ok) sList[off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
       off += __popc(m);
     }
+    __syncthreads();
   }
-  __syncthreads();
 
   // ---- stage table slices of the first nst listed neurons; C[k,t] folded into the x slice ----
   const int W0 = whi[0] - wlo[0] + 1, W1 = whi[1] - wlo[1] + 1, W2 = whi[2] - wlo[2] + 1;
   const bool fits = (W0 <= p.wmax0) && (W1 <= p.wmax1) && (W2 <= p.wmax2);
-  const int nst = fits ? min(L, p.cap) : 0;
+  const int nst = fits ? min(L, CAP) : 0;
+  const int nst2 = (nst + 1) & ~1;  // slots are consumed in pairs; an odd tail slot is zero-filled
   const int sX3 = p.X + 3, sY3 = p.Y + 3, sZ3 = p.Z + 3;
-  for (int j = warp; j < nst; j += NW) {
-    const int k = sList[j];
-    const float ck = __ldg(p.C + (size_t)k * p.T + t);
-    float2* dst = sTab + (size_t)j * wsum;
-    for (int e = lane; e < W0 + W1 + W2; e += 32) {
+  {
+    const int Wt = W0 + W1 + W2;
+    for (int e = tid; e < Wt; e += 32 * NW) {
+      // this thread owns table entry e of every slot: resolve its axis once
+      const float2* src;
+      int row, dst_e;
+      bool isx = false;
       if (e < W0) {
-        float2 v = __ldg(p.tab0 + (size_t)k * sX3 + (wlo[0] + 2 + e));
-        dst[e] = make_float2(v.x * ck, v.y * ck);
+        src = p.tab0 + (wlo[0] + 2 + e);
+        row = sX3;
+        dst_e = e;
+        isx = true;
       } else if (e < W0 + W1) {
-        int e1 = e - W0;
-        dst[p.wmax0 + e1] = __ldg(p.tab1 + (size_t)k * sY3 + (wlo[1] + 2 + e1));
+        src = p.tab1 + (wlo[1] + 2 + (e - W0));
+        row = sY3;
+        dst_e = p.wmax0 + (e - W0);
       } else {
-        int e2 = e - W0 - W1;
-        dst[p.wmax0 + p.wmax1 + e2] = __ldg(p.tab2 + (size_t)k * sZ3 + (wlo[2] + 2 + e2));
+        src = p.tab2 + (wlo[2] + 2 + (e - W0 - W1));
+        row = sZ3;
+        dst_e = p.wmax0 + p.wmax1 + (e - W0 - W1);
       }
+      float2* dst = sTab + (size_t)dst_e * CAP;
+      for (int j = 0; j < nst; ++j) {
+        const int k = sList[j];
+        float2 v = __ldg(src + (size_t)k * row);
+        if (isx) {
+          const float ck = __ldg(p.C + (size_t)k * p.T + t);
+          v.x *= ck;
+          v.y *= ck;
+        }
+        dst[j] = v;
+      }
+      if (nst2 > nst) dst[nst] = make_float2(0.f, 0.f);
     }
   }
   __syncthreads();
@@ -388,43 +489,82 @@ __global__ void __launch_bounds__(32 * NWX * NWY) fit_tile_kernel(const __grid_c
     c2[d] = sBeta[18 + d];
   }
   const float sm1x = (float)(p.X - 1), sm1y = (float)(p.Y - 1), sm1z = (float)(p.Z - 1);
+  const float rcpx = p.rcp0, rcpy = p.rcp1, rcpz = p.rcp2;
   float S0[3] = {0.f, 0.f, 0.f}, S1[3] = {0.f, 0.f, 0.f}, S2[3] = {0.f, 0.f, 0.f};
   float sse = 0.f;
-  const int ybase = min(lx, TX - 1) * RS + min(ly, TY - 1) * zs;
+  const float* yptr = sY + lx * RS + ly * zs;
+  const bool fast = p.fast_div != 0;
+  // shared-memory byte addresses of the three slice regions; one table entry = CAP slots of 8 B
+  const unsigned strideB = (unsigned)CAP * 8u;
+  const unsigned baseX = smem_u32(sTab);
+  const unsigned baseY = baseX + (unsigned)p.wmax0 * strideB;
+  const unsigned baseZ = baseY + (unsigned)p.wmax1 * strideB;
+  const int W0m1 = W0 - 1, W1m1 = W1 - 1, W2m1 = W2 - 1;
+  const int wl0 = wlo[0], wl1 = wlo[1], wl2 = wlo[2];
+  const int nhalf = nst2 >> 1;
+  const bool has_overflow = L > nst;
 
-  for (int zz = 0; zz < nz; ++zz) {
-    const float zf = (float)(z0 + zz);
-    int i0, i1, i2;
-    float f0, f1, f2;
-    split_coord(sample_coord(fmaf(zf, fmaf(zf, c2[0], c1[0]), c0[0]), sm1x), p.X, i0, f0);
-    split_coord(sample_coord(fmaf(zf, fmaf(zf, c2[1], c1[1]), c0[1]), sm1y), p.Y, i1, f1);
-    split_coord(sample_coord(fmaf(zf, fmaf(zf, c2[2], c1[2]), c0[2]), sm1z), p.Z, i2, f2);
-    i0 = min(max(i0, wlo[0]), whi[0]);
-    i1 = min(max(i1, wlo[1]), whi[1]);
-    i2 = min(max(i2, wlo[2]), whi[2]);
+  if (bulk) {  // wait for the bulk copies of the Y tile (phase 0 of the mbarrier)
+    const unsigned bar = smem_u32(sBar);
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(0)
+          : "memory");
+    }
+  }
+
+  float zf = (float)z0;
+  for (int zz = 0; zz < nz; ++zz, zf += 1.f) {
+    const float q0 = fmaf(zf, fmaf(zf, c2[0], c1[0]), c0[0]);
+    const float q1 = fmaf(zf, fmaf(zf, c2[1], c1[1]), c0[1]);
+    const float q2 = fmaf(zf, fmaf(zf, c2[2], c1[2]), c0[2]);
+    float ix0, ix1, ix2;
+    if (fast) {
+      ix0 = sample_coord_fast(q0, sm1x, rcpx);
+      ix1 = sample_coord_fast(q1, sm1y, rcpy);
+      ix2 = sample_coord_fast(q2, sm1z, rcpz);
+    } else {
+      ix0 = sample_coord(q0, sm1x);
+      ix1 = sample_coord(q1, sm1y);
+      ix2 = sample_coord(q2, sm1z);
+    }
+    // floor / fraction.  The clamp to the (conservative) window bounds every table access; samples
+    // below / above the table domain [-2, s] land on its first / last entry, which are zero, so no
+    // float clamp is needed.
+    const int i0 = __float2int_rd(ix0), i1 = __float2int_rd(ix1), i2 = __float2int_rd(ix2);
+    const float f0 = ix0 - (float)i0, f1 = ix1 - (float)i1, f2 = ix2 - (float)i2;
+    const unsigned o0 = (unsigned)min(max(i0 - wl0, 0), W0m1);
+    const unsigned o1 = (unsigned)min(max(i1 - wl1, 0), W1m1);
+    const unsigned o2 = (unsigned)min(max(i2 - wl2, 0), W2m1);
     float yh = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
     {
-      const float2* px = sTab + (i0 - wlo[0]);
-      const float2* py = sTab + p.wmax0 + (i1 - wlo[1]);
-      const float2* pz = sTab + p.wmax0 + p.wmax1 + (i2 - wlo[2]);
-#pragma unroll 4
-      for (int j = 0; j < nst; ++j) {
-        pair_accumulate(px[(size_t)j * wsum], py[(size_t)j * wsum], pz[(size_t)j * wsum], f0, f1, f2,
-                        yh, g0, g1, g2);
+      unsigned ax = o0 * strideB + baseX, ay = o1 * strideB + baseY, az = o2 * strideB + baseZ;
+#pragma unroll 1
+      for (int j = 0; j < nhalf; ++j, ax += 16u, ay += 16u, az += 16u) {
+        float4 ex, ey, ez;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ex.x), "=f"(ex.y), "=f"(ex.z), "=f"(ex.w) : "r"(ax));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ey.x), "=f"(ey.y), "=f"(ey.z), "=f"(ey.w) : "r"(ay));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ez.x), "=f"(ez.y), "=f"(ez.z), "=f"(ez.w) : "r"(az));
+        pair_accumulate(ex.x, ex.y, ey.x, ey.y, ez.x, ez.y, f0, f1, f2, yh, g0, g1, g2);
+        pair_accumulate(ex.z, ex.w, ey.z, ey.w, ez.z, ez.w, f0, f1, f2, yh, g0, g1, g2);
       }
     }
-    for (int j = nst; j < L; ++j) {  // overflow slots: straight from the L2-resident tables
-      const int k = sList[j];
-      const float ck = __ldg(p.C + (size_t)k * p.T + t);
-      float2 ex = __ldg(p.tab0 + (size_t)k * sX3 + (i0 + 2));
-      float2 ey = __ldg(p.tab1 + (size_t)k * sY3 + (i1 + 2));
-      float2 ez = __ldg(p.tab2 + (size_t)k * sZ3 + (i2 + 2));
-      ex.x *= ck;
-      ex.y *= ck;
-      pair_accumulate(ex, ey, ez, f0, f1, f2, yh, g0, g1, g2);
+    if (has_overflow) {  // slots beyond the staged capacity: straight from the L2-resident tables
+      const int j0 = o0 + wl0 + 2, j1 = o1 + wl1 + 2, j2 = o2 + wl2 + 2;
+      for (int j = nst; j < L; ++j) {
+        const int k = sList[j];
+        const float ck = __ldg(p.C + (size_t)k * p.T + t);
+        const float2 ex = __ldg(p.tab0 + (size_t)k * sX3 + j0);
+        const float2 ey = __ldg(p.tab1 + (size_t)k * sY3 + j1);
+        const float2 ez = __ldg(p.tab2 + (size_t)k * sZ3 + j2);
+        pair_accumulate(ex.x * ck, ex.y * ck, ey.x, ey.y, ez.x, ez.y, f0, f1, f2, yh, g0, g1, g2);
+      }
     }
-    const float yv = sY[ybase + zz];
-    if (WRITE_YHAT) sY[ybase + zz] = yh;
+    const float yv = yptr[zz];
+    if (WRITE_YHAT) sY[lx * RS + ly * zs + zz] = yh;
     const float r = valid ? (yh - yv) : 0.f;
     sse = fmaf(r, r, sse);
     const float h0 = r * g0, h1 = r * g1, h2 = r * g2;
@@ -440,39 +580,43 @@ __global__ void __launch_bounds__(32 * NWX * NWY) fit_tile_kernel(const __grid_c
     S2[2] = fmaf(zf2, h2, S2[2]);
   }
 
-  // ---- expand z-moments with this lane's (x,y) monomials, reduce warp -> CTA -> partial ----
+  // ---- expand z-moments with this lane's (x,y) monomials, transposing warp reduction ----
   {
-    auto emit = [&](int a, float coef, const float* S) {
+    float v[32];
+    const float xx = xf * xf, yy = yf * yf, xy = xf * yf;
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        float v = warp_sum(coef * S[d]);
-        if (lane == 0) sRed[warp * kNumPartials + a * 3 + d] = v;
-      }
-    };
-    emit(0, 1.f, S0);
-    emit(1, xf, S0);
-    emit(2, yf, S0);
-    emit(3, 1.f, S1);
-    emit(4, xf * xf, S0);
-    emit(5, yf * yf, S0);
-    emit(6, 1.f, S2);
-    emit(7, xf * yf, S0);
-    emit(8, xf, S1);
-    emit(9, yf, S1);
-    float v = warp_sum(sse);
-    if (lane == 0) {
-      sRed[warp * kNumPartials + 30] = v;
-      sRed[warp * kNumPartials + 31] = 0.f;
+    for (int d = 0; d < 3; ++d) {
+      v[0 * 3 + d] = S0[d];
+      v[1 * 3 + d] = xf * S0[d];
+      v[2 * 3 + d] = yf * S0[d];
+      v[3 * 3 + d] = S1[d];
+      v[4 * 3 + d] = xx * S0[d];
+      v[5 * 3 + d] = yy * S0[d];
+      v[6 * 3 + d] = S2[d];
+      v[7 * 3 + d] = xy * S0[d];
+      v[8 * 3 + d] = xf * S1[d];
+      v[9 * 3 + d] = yf * S1[d];
+    }
+    v[30] = sse;
+    v[31] = 0.f;
+    const float tot = warp_transpose_sum(v, lane);
+    if (NW == 1) {
+      p.partials[(size_t)cta_linear * kNumPartials + lane] = tot;
+    } else {
+      sRed[warp * kNumPartials + lane] = tot;
     }
   }
-  __syncthreads();
-  if (tid < kNumPartials) {
-    float v = 0.f;
+  if (NW > 1) {
+    __syncthreads();
+    if (tid < kNumPartials) {
+      float v = 0.f;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) v += sRed[w * kNumPartials + tid];
-    p.partials[(size_t)blockIdx.x * kNumPartials + tid] = v;
+      for (int w = 0; w < NW; ++w) v += sRed[w * kNumPartials + tid];
+      p.partials[(size_t)cta_linear * kNumPartials + tid] = v;
+    }
   }
   if (WRITE_YHAT) {
+    __syncthreads();
     float* out = p.yhat + (size_t)b * ((size_t)p.X * p.Y * p.Z);
     if (p.full_depth) {
       const int run = ny * p.Z;
@@ -626,6 +770,8 @@ struct dnmf_ctx {
   int wmax[3] = {0, 0, 0};
   int lmax_identity = 0;
   size_t fit_smem = 0;
+  int fast_div = 0;
+  float rcp[3] = {0.f, 0.f, 0.f};
   // video
   float* d_video = nullptr;
   // scratch
@@ -721,6 +867,38 @@ extern "C" int dnmf_create(dnmf_ctx** out, int X, int Y, int Z, int K, int T, in
   memset(idb, 0, sizeof(idb));
   idb[1 * 3 + 0] = idb[2 * 3 + 1] = idb[3 * 3 + 2] = 1.f;
   CU(cudaMemcpy(c->d_identity_beta, idb, sizeof(idb), cudaMemcpyHostToDevice));
+  // enable the 3-instruction exact division only after an exhaustive device-side proof per axis size
+  {
+    static std::mutex mu;
+    static std::vector<std::pair<int, int>> proven;  // (s-1, ok)
+    std::lock_guard<std::mutex> lock(mu);
+    unsigned long long* d_bad = nullptr;
+    CU(cudaMalloc((void**)&d_bad, sizeof(unsigned long long)));
+    int all_ok = 1;
+    for (int d = 0; d < 3; ++d) {
+      const int sm1 = s[d] - 1;
+      c->rcp[d] = sm1 > 0 ? (float)(1.0 / (double)sm1) : 0.f;
+      int ok = -1;
+      for (auto& pr : proven)
+        if (pr.first == sm1) ok = pr.second;
+      if (ok < 0) {
+        if (sm1 <= 0) {
+          ok = 0;
+        } else {
+          CU(cudaMemset(d_bad, 0, sizeof(unsigned long long)));
+          verify_coord_kernel<<<65536, 256>>>((float)sm1, c->rcp[d], d_bad);
+          CU(cudaGetLastError());
+          unsigned long long bad = 1;
+          CU(cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost));
+          ok = bad == 0 ? 1 : 0;
+        }
+        proven.push_back({sm1, ok});
+      }
+      all_ok = all_ok && ok;
+    }
+    cudaFree(d_bad);
+    c->fast_div = all_ok;
+  }
   *out = c;
   return 0;
 }
@@ -782,7 +960,7 @@ static int configure_tiling(dnmf_ctx* c, cudaStream_t st) {
   c->ntx = (c->X + c->tx - 1) / c->tx;
   c->nty = (c->Y + c->ty - 1) / c->ty;
   c->ntz = (c->Z + c->tz - 1) / c->tz;
-  const int margin = 4;
+  const int margin = 2;
   c->wmax[0] = std::min(c->tx + 2 + margin, c->X + 3);
   c->wmax[1] = std::min(c->ty + 2 + margin, c->Y + 3);
   c->wmax[2] = std::min(c->tz + 2 + margin, c->Z + 3);
@@ -802,12 +980,15 @@ static int configure_tiling(dnmf_ctx* c, cudaStream_t st) {
   CU(cudaStreamSynchronize(st));
   cudaFree(d_zero);
   int cap = c->user_cap > 0 ? c->user_cap : c->lmax_identity + c->lmax_identity / 4 + 2;
-  cap = std::max(1, std::min(cap, c->K));
+  cap = std::max(2, std::min(cap, c->K + 1));
+  cap = (cap + 1) & ~1;               // slots are consumed in pairs (LDS.128)
+  if ((cap & 3) == 0) cap += 2;       // slot-row stride = 2 (mod 4) float2: spreads entries over banks
   const int wsum = c->wmax[0] + c->wmax[1] + c->wmax[2];
   const int nw = c->nwx * c->nwy;
   // keep at least ~2 CTAs per SM worth of shared memory when possible
   const size_t budget = std::min<size_t>((size_t)c->max_smem_optin, (size_t)100 * 1024);
-  while (cap > 1 && fit_smem_layout(nw, c->tx, c->ty, c->tz, cap, wsum, c->K).bytes > budget) --cap;
+  while (cap > 2 && fit_smem_layout(nw, c->tx, c->ty, c->tz, cap, wsum, c->K).bytes > budget) cap -= 4;
+  if (cap < 2) cap = 2;
   c->cap = cap;
   c->fit_smem = fit_smem_layout(nw, c->tx, c->ty, c->tz, cap, wsum, c->K).bytes;
   if (c->fit_smem > (size_t)c->max_smem_optin)
@@ -914,25 +1095,39 @@ extern "C" int dnmf_bin_tiles(dnmf_ctx* c, const float* beta_dev, const int32_t*
 
 // ---- fused step -----------------------------------------------------------------------------------
 template <int NWX, int NWY, bool WY_>
-static int launch_fit(const FitParams& p, int grid, size_t smem, cudaStream_t st) {
+static int launch_fit(const FitParams& p0, int B, size_t smem, cudaStream_t st) {
   auto kern = fit_tile_kernel<NWX, NWY, WY_>;
   static size_t configured = 0;
   if (smem > configured) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  kern<<<grid, 32 * NWX * NWY, smem, st>>>(p);
-  CU(cudaGetLastError());
+  // grid = (ntx, nty, frames*ntz); gridDim.z <= 65535, so very large batches go out in chunks
+  const int maxB = std::max(1, 65535 / p0.ntz);
+  const size_t N = (size_t)p0.X * p0.Y * p0.Z;
+  const size_t nt = (size_t)p0.ntx * p0.nty * p0.ntz;
+  for (int b0 = 0; b0 < B; b0 += maxB) {
+    const int nb = std::min(maxB, B - b0);
+    FitParams p = p0;
+    p.frame_ids = p0.frame_ids + b0;
+    p.partials = p0.partials + (size_t)b0 * nt * kNumPartials;
+    if (p0.frames_are_batch) p.frames = p0.frames + (size_t)b0 * N;
+    if (p0.yhat) p.yhat = p0.yhat + (size_t)b0 * N;
+    dim3 grid((unsigned)p0.ntx, (unsigned)p0.nty, (unsigned)(nb * p0.ntz));
+    kern<<<grid, 32 * NWX * NWY, smem, st>>>(p);
+    CU(cudaGetLastError());
+  }
   return 0;
 }
 
 template <bool WY_>
-static int dispatch_fit(dnmf_ctx* c, const FitParams& p, int grid, cudaStream_t st) {
+static int dispatch_fit(dnmf_ctx* c, const FitParams& p, int B, cudaStream_t st) {
   const size_t smem = c->fit_smem;
-  if (c->nwx == 1 && c->nwy == 1) return launch_fit<1, 1, WY_>(p, grid, smem, st);
-  if (c->nwx == 2 && c->nwy == 1) return launch_fit<2, 1, WY_>(p, grid, smem, st);
-  if (c->nwx == 2 && c->nwy == 2) return launch_fit<2, 2, WY_>(p, grid, smem, st);
-  if (c->nwx == 2 && c->nwy == 4) return launch_fit<2, 4, WY_>(p, grid, smem, st);
+  if (c->nty > 65535) return fail("dispatch_fit: more than 65535 tiles along y");
+  if (c->nwx == 1 && c->nwy == 1) return launch_fit<1, 1, WY_>(p, B, smem, st);
+  if (c->nwx == 2 && c->nwy == 1) return launch_fit<2, 1, WY_>(p, B, smem, st);
+  if (c->nwx == 2 && c->nwy == 2) return launch_fit<2, 2, WY_>(p, B, smem, st);
+  if (c->nwx == 2 && c->nwy == 4) return launch_fit<2, 4, WY_>(p, B, smem, st);
   return fail("dispatch_fit: unsupported warp layout");
 }
 
@@ -964,6 +1159,12 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
   p.wmax1 = c->wmax[1];
   p.wmax2 = c->wmax[2];
   p.full_depth = (c->tz == c->Z) ? 1 : 0;
+  p.bulk_ok = (((uintptr_t)p.frames & 15) == 0) && (((size_t)c->Y * c->Z) % 4 == 0) &&
+              (((size_t)c->ty * c->Z) % 4 == 0);
+  p.fast_div = c->fast_div;
+  p.rcp0 = c->rcp[0];
+  p.rcp1 = c->rcp[1];
+  p.rcp2 = c->rcp[2];
   p.yhat = nullptr;
   const size_t need = (size_t)B * c->ntx * c->nty * c->ntz * kNumPartials;
   if (ensure(&c->d_partials, &c->partials_cap, need)) return 1;
@@ -982,7 +1183,7 @@ extern "C" int dnmf_loss_grad(dnmf_ctx* c, const float* frames_dev, const int32_
   FitParams p;
   if (fill_fit_params(c, p, frames_dev, frame_ids_dev, B, beta_dev, C_dev)) return 1;
   const int nt = c->ntx * c->nty * c->ntz;
-  if (dispatch_fit<false>(c, p, B * nt, st)) return 1;
+  if (dispatch_fit<false>(c, p, B, st)) return 1;
   const double scale = 2.0 / ((double)B_global * (double)c->N);
   reduce_partials_kernel<<<B, 256, 0, st>>>(c->d_partials, frame_ids_dev, nt, c->T, scale, grad_dev, sse_dev);
   CU(cudaGetLastError());
@@ -1060,7 +1261,7 @@ extern "C" int dnmf_forward(dnmf_ctx* c, const int32_t* frame_ids_dev, int B, co
     FitParams p;
     if (fill_fit_params(c, p, AtC_dev, frame_ids_dev, B, beta_dev, C_dev)) return 1;
     p.yhat = AtC_dev;
-    if (dispatch_fit<true>(c, p, B * c->ntx * c->nty * c->ntz, st)) return 1;
+    if (dispatch_fit<true>(c, p, B, st)) return 1;
     c->counters[0] += 1;
   }
   if (At_dev || grid_dev) {
