@@ -3,7 +3,7 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this module; the product (dnmf_b200/) never does and fails loudly without its CUDA
 library.  Parity status: PINNED by executing the real reference in the build container
-(tests/test_oracle_vs_reference.py, oracle/make_golden.py -> tests/golden/*.npz); the
+(tests/test_oracle.py, oracle/make_golden.py -> tests/golden/*.npz); the
 reference itself ships no tests or golden vectors.
 
 Two restatements live here (all file:line citations are relative to /root/reference):
@@ -228,6 +228,11 @@ def sample_coords(beta_t: np.ndarray, sz: Sequence[int]) -> np.ndarray:
         for a in range(10):
             q = (q + (phi[a] * b[a, d]).astype(f32)).astype(f32)
         sm1 = f32(int(sz[d]) - 1)
+        if int(sz[d]) == 1:
+            # The reference divides by s-1 = 0 here (NaN everywhere).  The CUDA path
+            # documents a deviation for singleton axes: the sample coordinate is q itself.
+            out[d] = q
+            continue
         u = (((f32(2) * q).astype(f32) / sm1).astype(f32) - f32(1)).astype(f32)
         out[d] = ((((u + f32(1)).astype(f32)) / f32(2)).astype(f32) * sm1).astype(f32)
     return out

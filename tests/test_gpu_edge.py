@@ -1,0 +1,260 @@
+"""GPU edge cases and size-independent properties of the CUDA path (through the C ABI)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dnmf_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _case(sz, K, T, seed, sigma=2.5, beta_scale=1.0):
+    rng = np.random.default_rng(seed)
+    pos = (rng.random((K, 3)) * np.asarray(sz)).astype(np.float32)
+    sig = np.full(K, sigma, np.float32)
+    g = torch.Generator().manual_seed(seed)
+    s = torch.tensor([1.0, .02, .02, .02, 5e-4, 5e-4, 5e-4, 5e-4, 5e-4, 5e-4])[:, None, None] * beta_scale
+    beta = O.identity_beta(T) + s * torch.randn(10, 3, T, generator=g)
+    beta[:, :, 0] = O.identity_beta(1)[:, :, 0]
+    C = torch.rand(K, T, generator=g)
+    frames = torch.rand(T, *sz, generator=g)
+    return pos, sig, beta, C, frames
+
+
+def _check(sz, K, T, seed, cutoff, tiling, sigma=2.5, beta_scale=1.0, tol=3e-5):
+    from dnmf_b200.engine import Engine
+    pos, sig, beta, C, frames = _case(sz, K, T, seed, sigma, beta_scale)
+    e = Engine(sz, K, T)
+    e.set_tiling(*tiling)
+    e.set_footprints(pos, sig, cutoff)
+    grad, sse = e.loss_grad(torch.arange(T), beta.cuda(), C.cuda(), frames=frames.cuda())
+    tabs, _ = O.axis_tables(pos, sig, sz, cutoff)
+    loss, gref = O.closed_form_step(frames.numpy(), list(range(T)), beta.numpy(), C.numpy(), tabs, sz)
+    N = int(np.prod(sz))
+    assert abs(float(sse.sum()) / (T * N) - loss) <= 1e-5 * loss
+    err = np.abs(grad.cpu().numpy() - gref).max() / np.abs(gref).max()
+    assert err < tol, err
+    return e
+
+
+@pytest.mark.parametrize("sz", [[13, 7, 5], [8, 4, 1], [33, 9, 2], [17, 30, 11], [50, 50, 2]])
+@pytest.mark.parametrize("tiling", [(1, 1, 0, 0), (2, 2, 0, 0)])
+def test_ragged_sizes(sz, tiling):
+    """volumes that do not divide into tiles, odd depths (no bulk-copy alignment), singleton z."""
+    _check(sz, 4, 3, seed=sum(sz), cutoff=3.5, tiling=tiling)
+
+
+def test_depth_chunked_tiles():
+    _check([20, 12, 40], 6, 2, seed=5, cutoff=3.0, tiling=(1, 1, 16, 0))
+    _check([20, 12, 40], 6, 2, seed=5, cutoff=3.0, tiling=(2, 1, 7, 0))
+
+
+def test_list_longer_than_staged_capacity():
+    """more listed neurons than staged slots: the overflow path through the global tables."""
+    e = _check([24, 16, 6], 40, 2, seed=9, cutoff=0.0, tiling=(1, 1, 0, 4), sigma=4.0)
+    assert e.tiling()["cap"] <= 6
+    _check([24, 16, 6], 40, 2, seed=9, cutoff=0.0, tiling=(2, 4, 0, 8), sigma=4.0)
+
+
+def test_window_wider_than_staged_slices():
+    """a strong deformation makes the tile window outgrow the staged slices: global-table path."""
+    _check([24, 16, 6], 8, 3, seed=11, cutoff=3.5, tiling=(1, 1, 0, 0), beta_scale=8.0, tol=1e-4)
+
+
+def test_neurons_outside_volume_and_empty_ranges():
+    from dnmf_b200.engine import Engine
+    sz = [16, 12, 4]
+    pos = np.array([[-40., 5., 1.], [8., 6., 2.], [100., 100., 100.]], np.float32)
+    sig = np.full(3, 2.0, np.float32)
+    e = Engine(sz, 3, 2)
+    e.set_footprints(pos, sig, 3.0)
+    rng = e.ranges()
+    assert np.array_equal(rng, O.axis_ranges(pos, sig, sz, 3.0))
+    assert rng[0, 0, 0] > rng[0, 0, 1] and rng[2, 1, 0] > rng[2, 1, 1]       # empty ranges
+    beta = O.identity_beta(2).cuda()
+    counts, offsets, ids, _ = e.bin_tiles(beta, torch.arange(2))
+    assert set(ids.tolist()) <= {1}
+    C = torch.ones(3, 2).cuda()
+    frames = torch.rand(2, *sz)
+    grad, sse = e.loss_grad(torch.arange(2), beta, C, frames=frames.cuda())
+    tabs, _ = O.axis_tables(pos, sig, sz, 3.0)
+    loss, gref = O.closed_form_step(frames.numpy(), [0, 1], beta.cpu().numpy(), C.cpu().numpy(), tabs, sz)
+    assert abs(float(sse.sum()) / (2 * 768) - loss) <= 1e-6 * loss
+
+
+def test_affine_freezes_quadratic_rows():
+    from dnmf_b200.engine import Engine
+    e = Engine([8, 8, 2], 2, 3)
+    p = O.identity_beta(3).cuda()
+    g = torch.ones(10, 3, 3).cuda()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    e.adam_step(p, g, m, v, 1e-2, (0.9, 0.999), 1e-8, 1, affine=True)
+    d = (p - O.identity_beta(3).cuda()).abs()
+    assert float(d[4:].max()) == 0.0 and float(d[:4].min()) > 0.0
+    assert float(m[4:].abs().max()) == 0.0 and float(v[4:].abs().max()) == 0.0
+
+
+def test_bitwise_reproducible_and_frame_order_independent():
+    """fixed-order reductions: same inputs -> identical bits; a frame's gradient does not depend on
+    which other frames share its batch or on its slot."""
+    from dnmf_b200.engine import Engine
+    sz, K, T = [40, 24, 9], 12, 6
+    pos, sig, beta, C, frames = _case(sz, K, T, 21)
+    e = Engine(sz, K, T)
+    e.set_footprints(pos, sig, 3.5)
+    e.upload_frames(frames, clamp_negative=False)
+    b, c = beta.cuda(), C.cuda()
+    g1, s1 = e.loss_grad(torch.arange(T), b, c)
+    g2, s2 = e.loss_grad(torch.arange(T), b, c)
+    assert torch.equal(g1, g2) and torch.equal(s1, s2)
+    perm = torch.tensor([4, 1, 5])
+    g3, s3 = e.loss_grad(perm, b, c, B_global=T)
+    assert torch.equal(g3[:, :, perm], g1[:, :, perm]) and torch.equal(s3, s1[perm])
+    assert float(g3[:, :, [0, 2, 3]].abs().max()) == 0.0
+
+
+def test_forward_is_linear_in_traces_and_zero_for_zero_traces():
+    from dnmf_b200.engine import Engine
+    sz, K, T = [32, 20, 7], 9, 2
+    pos, sig, beta, C, _ = _case(sz, K, T, 33)
+    e = Engine(sz, K, T)
+    e.set_footprints(pos, sig, 3.5)
+    b = beta.cuda()
+    y1, _, _ = e.forward(torch.arange(T), b, C.cuda())
+    y2, _, _ = e.forward(torch.arange(T), b, (2 * C).cuda())
+    y0, _, _ = e.forward(torch.arange(T), b, torch.zeros_like(C).cuda())
+    assert float(y0.abs().max()) == 0.0
+    np.testing.assert_allclose(y2.cpu().numpy(), 2 * y1.cpu().numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_perfect_model_has_zero_loss_and_gradient():
+    """Y := model output  =>  sse == 0 and gradient == 0 exactly (encode -> decode round trip)."""
+    from dnmf_b200.engine import Engine
+    sz, K, T = [32, 20, 7], 9, 3
+    pos, sig, beta, C, _ = _case(sz, K, T, 35)
+    e = Engine(sz, K, T)
+    e.set_footprints(pos, sig, 3.5)
+    b, c = beta.cuda(), C.cuda()
+    y, _, _ = e.forward(torch.arange(T), b, c)
+    grad, sse = e.loss_grad(torch.arange(T), b, c, frames=y.contiguous())
+    assert float(sse.abs().max()) == 0.0 and float(grad.abs().max()) == 0.0
+
+
+def test_iwarp_matches_scipy_nearest():
+    """registered video Y_i (Demix/dNMF.py:81-83,95-103) against scipy's NearestNDInterpolator on a
+    deformation without exact ties."""
+    import scipy.interpolate
+    from dnmf_b200.engine import Engine
+    sz, K, T = [18, 14, 5], 3, 2
+    pos, sig, beta, C, frames = _case(sz, K, T, 41, beta_scale=0.7)
+    beta[:, :, 0] = beta[:, :, 1] * 1.01
+    e = Engine(sz, K, T)
+    e.set_footprints(pos, sig, 3.5)
+    out = e.iwarp(torch.arange(T), beta.cuda(), frames=frames.cuda()).cpu().numpy()
+    grid = np.array(np.where(np.ones(sz))).T
+    for t in range(T):
+        u = O.sample_coords  # noqa: F841  (coordinates below follow the reference: scale by sz, not sz-1)
+        _, phi = O.voxel_basis(sz)
+        q = torch.einsum("mnza,ab->mnzb", phi, beta[:, :, t])
+        un = 2 * q / (torch.tensor(sz) - 1) - 1
+        f = ((un + 1) / 2) * torch.tensor(sz).float()
+        interp = scipy.interpolate.NearestNDInterpolator(f.reshape(-1, 3).numpy(), frames[t].reshape(-1).numpy())
+        ref = interp(grid).reshape(sz)
+        agree = (out[t] == ref).mean()
+        assert agree > 0.995, agree
+
+
+def test_full_size_cfg2_properties():
+    """BASELINE.json config 2 shape (256x128x21, K=150): determinism, perfect-model round trip and the
+    zero-trace checksum at full size (the oracle is too slow here, properties are size-independent)."""
+    from dnmf_b200.engine import Engine
+    sz, K, T = [256, 128, 21], 150, 4
+    pos, sig, beta, C, _ = _case(sz, K, T, 51, sigma=3.0, beta_scale=0.2)
+    e = Engine(sz, K, T)
+    e.set_footprints(pos, sig, 3.5)
+    b, c = beta.cuda(), C.cuda()
+    y, _, _ = e.forward(torch.arange(T), b, c)
+    assert torch.isfinite(y).all() and float(y.max()) > 0
+    g0, s0 = e.loss_grad(torch.arange(T), b, c, frames=y.contiguous())
+    assert float(s0.abs().max()) == 0.0 and float(g0.abs().max()) == 0.0
+    frames = (y * 1.1).contiguous()
+    g1, s1 = e.loss_grad(torch.arange(T), b, c, frames=frames)
+    g2, s2 = e.loss_grad(torch.arange(T), b, c, frames=frames)
+    assert torch.equal(g1, g2) and torch.equal(s1, s2)
+    # sse of Y = 1.1*Yhat is 0.01 * sum(Yhat^2): checksum of checksums
+    ref = 0.01 * (y.double() ** 2).sum(dim=(1, 2, 3))
+    np.testing.assert_allclose(s1.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4)
+    # a slice of the full-size volume against the oracle's closed form (one frame, one x-slab)
+    tabs, _ = O.axis_tables(pos, sig, sz, 3.5)
+    yh, _, _ = O.closed_form_frame(np.zeros(sz, np.float32), beta[:, :, 1].numpy(), C[:, 1].numpy(), tabs, sz)
+    # q is a 10-term fp32 sum of magnitude ~255: summation order (Horner+FMA here, sequential in the
+    # oracle, MKL bmm in the reference) moves samples by a few ulp(255) = 3e-5 px -> up to ~1e-5 in A_tC
+    np.testing.assert_allclose(y[1].cpu().numpy(), yh, atol=3e-5)
+
+
+def test_two_rank_frame_sharding_matches_single_rank(tmp_path):
+    """2 processes on ONE GPU, each owning half the frames (B_global = all frames): the concatenated
+    beta and the all-reduced loss equal the single-process result bit for bit."""
+    worker = tmp_path / "w.py"
+    worker.write_text(r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from dnmf_b200.engine import Engine
+from dnmf_b200.sharding import frame_slab, allreduce_loss
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+torch.cuda.set_device(0)
+d = np.load(sys.argv[2])
+sz, K, T = d["sz"].tolist(), int(d["K"]), int(d["T"])
+start, count = frame_slab(T, world, rank)
+e = Engine(sz, K, count)
+e.set_footprints(d["pos"], d["sig"], 3.5)
+e.upload_frames(torch.tensor(d["frames"][start:start + count]), clamp_negative=False)
+beta = torch.tensor(d["beta"][:, :, start:start + count]).contiguous().cuda()
+C = torch.tensor(d["C"][:, start:start + count]).contiguous().cuda()
+m, v = torch.zeros_like(beta), torch.zeros_like(beta)
+loss = torch.zeros(1, dtype=torch.float64, device="cuda")
+ids = torch.arange(count, dtype=torch.int32, device="cuda")
+losses = []
+for step in range(1, 4):
+    e.motion_step(ids, beta, m, v, C, 1e-3, (0.9, 0.999), 1e-8, step, False, B_global=T, loss_out=loss)
+    l = loss.cpu().clone()
+    allreduce_loss(l)
+    losses.append(float(l))
+np.savez(sys.argv[3] + "_%d.npz" % rank, beta=beta.cpu().numpy(), losses=np.asarray(losses), start=start)
+dist.destroy_process_group()
+''')
+    from dnmf_b200.engine import Engine
+    sz, K, T = [24, 16, 5], 5, 6
+    pos, sig, beta, C, frames = _case(sz, K, T, 61)
+    data = tmp_path / "data.npz"
+    np.savez(data, sz=np.asarray(sz), K=K, T=T, pos=pos, sig=sig, beta=beta.numpy(), C=C.numpy(), frames=frames.numpy())
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(worker), ROOT, str(data),
+                          str(tmp_path / "out")], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    e = Engine(sz, K, T)
+    e.set_footprints(pos, sig, 3.5)
+    e.upload_frames(frames, clamp_negative=False)
+    b, c = beta.clone().cuda(), C.cuda()
+    m, v = torch.zeros_like(b), torch.zeros_like(b)
+    loss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ids = torch.arange(T, dtype=torch.int32, device="cuda")
+    ref_losses = []
+    for step in range(1, 4):
+        e.motion_step(ids, b, m, v, c, 1e-3, (0.9, 0.999), 1e-8, step, False, B_global=T, loss_out=loss)
+        ref_losses.append(float(loss))
+    parts = [np.load(str(tmp_path / "out") + "_%d.npz" % r) for r in range(2)]
+    got = np.concatenate([p["beta"] for p in parts], 2)
+    assert np.array_equal(got, b.cpu().numpy())
+    np.testing.assert_allclose(parts[0]["losses"], ref_losses, rtol=1e-12)
