@@ -144,7 +144,7 @@ def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = args.cpu_frames or 1
+    B = args.cpu_frames or 4
     value, ms, cores = time_reference(cfg, B, args.steps, args.warmup)
     sample = "%d frame(s) of the %s volume per Adam step through the reference's CPU torch path" % (B, args.config)
     line = {"impl": "reference", "metric": "frame-iterations/s", "value": value, "unit": "frame-iterations/s",
