@@ -239,6 +239,7 @@ def run_b200(args, cfg):
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     c1 = eng.counters()
+    final_loss = float(loss_dev)
     # keep the GPU under the same load a little longer so the clock sampler sees it (not timed)
     t_end = time.time() + 1.5
     while rank == 0 and time.time() < t_end:
@@ -253,7 +254,6 @@ def run_b200(args, cfg):
     ms_total = float(t_ms)
     frame_iters = B * args.steps * world
     value = frame_iters / (ms_total * 1e-3)
-    final_loss = float(loss_dev)
 
     # ---- end to end: public API, host (pinned) frames, H2D + loss read-back inside the timed region ----
     e2e = None
@@ -337,8 +337,17 @@ def run_b200(args, cfg):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     ach_tf = flops_per_frame * B / (fit_ms * 1e-3) * 1e-12
     ach_gbs = bytes_per_frame * B / (fit_ms * 1e-3) * 1e-9
+    traffic, traffic_src = None, None
+    try:   # DRAM bytes per frame of fit_tile_kernel from the committed `ncu --set full` capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "fit_tile_traffic.json")))
+        if tj.get("config") == args.config:
+            traffic, traffic_src = tj["dram_bytes_per_frame"] * B, tj["source"]
+    except Exception:
+        pass
     roofline = {"bound": "fp32", "achieved": ach_tf, "peak": peak_fp32.value, "unit": "TFLOP/s",
-                "frac": ach_tf / peak_fp32.value if peak_fp32.value else None, "traffic": None,
+                "frac": ach_tf / peak_fp32.value if peak_fp32.value else None, "traffic": traffic,
+                "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": bytes_per_frame * B,
                 "kernel": "fit_tile_kernel", "kernel_ms_per_launch": fit_ms, "frames_per_launch": B,
                 "flops_per_frame_iter": flops_per_frame, "k_eff_in_cutoff_pairs_per_voxel": k_eff,
                 "listed_pairs_per_voxel": listed,
