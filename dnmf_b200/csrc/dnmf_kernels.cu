@@ -113,7 +113,7 @@ template <bool FILL>
 __global__ void bin_tiles_kernel(Geom g, const float* __restrict__ beta, const int* __restrict__ frame_ids,
                                  int B, const int* __restrict__ rng, int* __restrict__ counts,
                                  const long long* __restrict__ offsets, int* __restrict__ windows,
-                                 int* __restrict__ ids, long long ids_capacity) {
+                                 int* __restrict__ ids, long long ids_capacity, int expand) {
   const int lane = threadIdx.x & 31;
   const int nt = g.ntx * g.nty * g.ntz;
   const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -128,6 +128,11 @@ __global__ void bin_tiles_kernel(Geom g, const float* __restrict__ beta, const i
   for (int d = 0; d < 3; ++d)
     tile_window_axis(beta + (size_t)d * g.T + t, 3 * g.T, (float)x0, (float)y0, (float)z0, (float)x1,
                      (float)y1, (float)z1, sz[d], wlo[d], whi[d]);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {  // expand > 0 only when building the static candidate lists
+    wlo[d] -= expand;
+    whi[d] += expand;
+  }
   long long base = FILL ? offsets[item] : 0;
   int cnt = 0;
   for (int k0 = 0; k0 < g.K; k0 += 32) {
@@ -225,6 +230,9 @@ struct FitParams {
   int bulk_ok;   // tile rows may be fetched with cp.async.bulk (16 B alignment holds)
   int fast_div;  // exact 3-instruction division verified for all three axes
   float rcp0, rcp1, rcp2;
+  const long long* cand_off;  // static per-tile candidate lists (identity windows expanded by cand_expand)
+  const int* cand_ids;
+  int cand_expand;
 };
 
 struct FitSmem {
@@ -286,6 +294,25 @@ __device__ __forceinline__ void pair_accumulate(float ex_g, float ex_d, float ey
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// Loop-invariant values the compiler would otherwise rematerialise inside the hot loop (constant-bank
+// reloads, int->float conversions, address arithmetic): routing them through an opaque move pins
+// them in a register.
+__device__ __forceinline__ float pin(float v) {
+  float r;
+  asm volatile("mov.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ unsigned pin(unsigned v) {
+  unsigned r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ int pin(int v) {
+  int r;
+  asm volatile("mov.s32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+
 // Sum 32 per-lane values across the warp with 31 shuffles: afterwards lane l holds the total of v[l].
 __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 #pragma unroll
@@ -301,7 +328,7 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int NWX, int NWY, bool WRITE_YHAT>
+template <int NWX, int NWY, bool WRITE_YHAT, bool FAST_DIV>
 __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? 20 : 1) fit_tile_kernel(const __grid_constant__ FitParams p) {
   constexpr int NW = NWX * NWY;
   constexpr int TX = kWarpX * NWX, TY = kWarpY * NWY;
@@ -387,50 +414,70 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? 20 : 1) fit
     whi[d] = sInt[3 + d];
   }
 
-  // ---- neuron list: ascending k, ballot compaction (single pass for one warp, two passes else) ----
+  // ---- neuron list: ascending k, ballot compaction (single pass for one warp, two passes else).
+  // Candidates come from the static per-tile lists when the window stays inside the expanded identity
+  // window they were built for (the usual case), else from a scan over all K neurons.
   int L = 0;
-  if (NW == 1) {
-    for (int k0 = 0; k0 < p.K; k0 += 32) {
-      const int k = k0 + lane;
-      const bool ok = (k < p.K) && neuron_in_window(p.rng + (size_t)k * 6, wlo, whi);
-      const unsigned m = __ballot_sync(0xffffffffu, ok);
-      if (ok) sList[L + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
-      L += __popc(m);
+  {
+    const int* __restrict__ cand = nullptr;
+    int r0 = 0, r1 = p.K;
+    if (p.cand_off != nullptr) {
+      const int e = p.cand_expand;
+      const bool inside = wlo[0] >= max(x0 - 1, -2) - e && whi[0] <= min(x0 + nx, p.X) + e &&
+                          wlo[1] >= max(y0 - 1, -2) - e && whi[1] <= min(y0 + ny, p.Y) + e &&
+                          wlo[2] >= max(z0 - 1, -2) - e && whi[2] <= min(z0 + nz, p.Z) + e;
+      if (inside) {
+        const int tile = (bz * p.nty + by) * p.ntx + bx;
+        cand = p.cand_ids;
+        r0 = (int)p.cand_off[tile];
+        r1 = (int)p.cand_off[tile + 1];
+      }
     }
-    __syncwarp();
-  } else {
-    const int per = ((p.K + NW * 32 - 1) / (NW * 32)) * 32;
-    const int kb = warp * per;
-    int cnt = 0;
-    for (int k0 = kb; k0 < kb + per; k0 += 32) {
-      const int k = k0 + lane;
-      const bool ok = (k < p.K) && neuron_in_window(p.rng + (size_t)k * 6, wlo, whi);
-      cnt += __popc(__ballot_sync(0xffffffffu, ok));
-    }
-    if (lane == 0) sInt[8 + warp] = cnt;
-    __syncthreads();
-    int off = 0;
+    if (NW == 1) {
+      for (int c0i = r0; c0i < r1; c0i += 32) {
+        const int idx = c0i + lane;
+        const int k = idx < r1 ? (cand ? cand[idx] : idx) : -1;
+        const bool ok = (k >= 0) && neuron_in_window(p.rng + (size_t)k * 6, wlo, whi);
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) sList[L + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
+        L += __popc(m);
+      }
+      __syncwarp();
+    } else {
+      const int per = ((r1 - r0 + NW * 32 - 1) / (NW * 32)) * 32;
+      const int kb = r0 + warp * per;
+      int cnt = 0;
+      for (int c0i = kb; c0i < kb + per; c0i += 32) {
+        const int idx = c0i + lane;
+        const int k = idx < r1 ? (cand ? cand[idx] : idx) : -1;
+        const bool ok = (k >= 0) && neuron_in_window(p.rng + (size_t)k * 6, wlo, whi);
+        cnt += __popc(__ballot_sync(0xffffffffu, ok));
+      }
+      if (lane == 0) sInt[8 + warp] = cnt;
+      __syncthreads();
+      int off = 0;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      const int c = sInt[8 + w];
-      if (w < warp) off += c;
-      L += c;
+      for (int w = 0; w < NW; ++w) {
+        const int c = sInt[8 + w];
+        if (w < warp) off += c;
+        L += c;
+      }
+      for (int c0i = kb; c0i < kb + per; c0i += 32) {
+        const int idx = c0i + lane;
+        const int k = idx < r1 ? (cand ? cand[idx] : idx) : -1;
+        const bool ok = (k >= 0) && neuron_in_window(p.rng + (size_t)k * 6, wlo, whi);
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) sList[off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
+        off += __popc(m);
+      }
+      __syncthreads();
     }
-    for (int k0 = kb; k0 < kb + per; k0 += 32) {
-      const int k = k0 + lane;
-      const bool ok = (k < p.K) && neuron_in_window(p.rng + (size_t)k * 6, wlo, whi);
-      const unsigned m = __ballot_sync(0xffffffffu, ok);
-      if (ok) sList[off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
-      off += __popc(m);
-    }
-    __syncthreads();
   }
 
   // ---- stage table slices of the first nst listed neurons; C[k,t] folded into the x slice ----
   const int W0 = whi[0] - wlo[0] + 1, W1 = whi[1] - wlo[1] + 1, W2 = whi[2] - wlo[2] + 1;
   const bool fits = (W0 <= p.wmax0) && (W1 <= p.wmax1) && (W2 <= p.wmax2);
   const int nst = fits ? min(L, CAP) : 0;
-  const int nst2 = (nst + 1) & ~1;  // slots are consumed in pairs; an odd tail slot is zero-filled
   const int sX3 = p.X + 3, sY3 = p.Y + 3, sZ3 = p.Z + 3;
   {
     const int Wt = W0 + W1 + W2;
@@ -464,7 +511,6 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? 20 : 1) fit
         }
         dst[j] = v;
       }
-      if (nst2 > nst) dst[nst] = make_float2(0.f, 0.f);
     }
   }
   __syncthreads();
@@ -488,20 +534,19 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? 20 : 1) fit
     c1[d] = fmaf(sBeta[27 + d], yf, fmaf(sBeta[24 + d], xf, sBeta[9 + d]));
     c2[d] = sBeta[18 + d];
   }
-  const float sm1x = (float)(p.X - 1), sm1y = (float)(p.Y - 1), sm1z = (float)(p.Z - 1);
-  const float rcpx = p.rcp0, rcpy = p.rcp1, rcpz = p.rcp2;
+  const float sm1x = pin((float)(p.X - 1)), sm1y = pin((float)(p.Y - 1)), sm1z = pin((float)(p.Z - 1));
+  const float rcpx = pin(p.rcp0), rcpy = pin(p.rcp1), rcpz = pin(p.rcp2);
   float S0[3] = {0.f, 0.f, 0.f}, S1[3] = {0.f, 0.f, 0.f}, S2[3] = {0.f, 0.f, 0.f};
   float sse = 0.f;
-  const float* yptr = sY + lx * RS + ly * zs;
-  const bool fast = p.fast_div != 0;
+  unsigned yaddr = smem_u32(sY + lx * RS + ly * zs);  // walks the lane's column of the Y tile, 4 B per z step
   // shared-memory byte addresses of the three slice regions; one table entry = CAP slots of 8 B
-  const unsigned strideB = (unsigned)CAP * 8u;
-  const unsigned baseX = smem_u32(sTab);
-  const unsigned baseY = baseX + (unsigned)p.wmax0 * strideB;
-  const unsigned baseZ = baseY + (unsigned)p.wmax1 * strideB;
-  const int W0m1 = W0 - 1, W1m1 = W1 - 1, W2m1 = W2 - 1;
-  const int wl0 = wlo[0], wl1 = wlo[1], wl2 = wlo[2];
-  const int nhalf = nst2 >> 1;
+  const unsigned strideB = pin((unsigned)CAP * 8u);
+  const unsigned baseX = pin(smem_u32(sTab));
+  const unsigned baseY = pin(baseX + (unsigned)p.wmax0 * strideB);
+  const unsigned baseZ = pin(baseY + (unsigned)p.wmax1 * strideB);
+  const int W0m1 = pin(W0 - 1), W1m1 = pin(W1 - 1), W2m1 = pin(W2 - 1);
+  const int wl0 = pin(wlo[0]), wl1 = pin(wlo[1]), wl2 = pin(wlo[2]);
+  const int nquad = nst >> 2;
   const bool has_overflow = L > nst;
 
   if (bulk) {  // wait for the bulk copies of the Y tile (phase 0 of the mbarrier)
@@ -517,12 +562,12 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? 20 : 1) fit
   }
 
   float zf = (float)z0;
-  for (int zz = 0; zz < nz; ++zz, zf += 1.f) {
+  for (int zz = 0; zz < nz; ++zz, zf += 1.f, yaddr += 4u) {
     const float q0 = fmaf(zf, fmaf(zf, c2[0], c1[0]), c0[0]);
     const float q1 = fmaf(zf, fmaf(zf, c2[1], c1[1]), c0[1]);
     const float q2 = fmaf(zf, fmaf(zf, c2[2], c1[2]), c0[2]);
     float ix0, ix1, ix2;
-    if (fast) {
+    if (FAST_DIV) {
       ix0 = sample_coord_fast(q0, sm1x, rcpx);
       ix1 = sample_coord_fast(q1, sm1y, rcpy);
       ix2 = sample_coord_fast(q2, sm1z, rcpz);
@@ -542,15 +587,43 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? 20 : 1) fit
     float yh = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
     {
       unsigned ax = o0 * strideB + baseX, ay = o1 * strideB + baseY, az = o2 * strideB + baseZ;
+#define DNMF_LDS4(v, addr, off) \
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+" #off "];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr))
+#define DNMF_LDS2(v, addr, off) asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+" #off "];" : "=f"(v.x), "=f"(v.y) : "r"(addr))
 #pragma unroll 1
-      for (int j = 0; j < nhalf; ++j, ax += 16u, ay += 16u, az += 16u) {
-        float4 ex, ey, ez;
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ex.x), "=f"(ex.y), "=f"(ex.z), "=f"(ex.w) : "r"(ax));
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ey.x), "=f"(ey.y), "=f"(ey.z), "=f"(ey.w) : "r"(ay));
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ez.x), "=f"(ez.y), "=f"(ez.z), "=f"(ez.w) : "r"(az));
+      for (int j = 0; j < nquad; ++j, ax += 32u, ay += 32u, az += 32u) {  // four neurons per iteration
+        float4 ex, ey, ez, fx, fy, fz;
+        DNMF_LDS4(ex, ax, 0);
+        DNMF_LDS4(ey, ay, 0);
+        DNMF_LDS4(ez, az, 0);
+        DNMF_LDS4(fx, ax, 16);
+        DNMF_LDS4(fy, ay, 16);
+        DNMF_LDS4(fz, az, 16);
         pair_accumulate(ex.x, ex.y, ey.x, ey.y, ez.x, ez.y, f0, f1, f2, yh, g0, g1, g2);
         pair_accumulate(ex.z, ex.w, ey.z, ey.w, ez.z, ez.w, f0, f1, f2, yh, g0, g1, g2);
+        pair_accumulate(fx.x, fx.y, fy.x, fy.y, fz.x, fz.y, f0, f1, f2, yh, g0, g1, g2);
+        pair_accumulate(fx.z, fx.w, fy.z, fy.w, fz.z, fz.w, f0, f1, f2, yh, g0, g1, g2);
       }
+      if (nst & 2) {
+        float4 ex, ey, ez;
+        DNMF_LDS4(ex, ax, 0);
+        DNMF_LDS4(ey, ay, 0);
+        DNMF_LDS4(ez, az, 0);
+        pair_accumulate(ex.x, ex.y, ey.x, ey.y, ez.x, ez.y, f0, f1, f2, yh, g0, g1, g2);
+        pair_accumulate(ex.z, ex.w, ey.z, ey.w, ez.z, ez.w, f0, f1, f2, yh, g0, g1, g2);
+        ax += 16u;
+        ay += 16u;
+        az += 16u;
+      }
+      if (nst & 1) {
+        float2 ex, ey, ez;
+        DNMF_LDS2(ex, ax, 0);
+        DNMF_LDS2(ey, ay, 0);
+        DNMF_LDS2(ez, az, 0);
+        pair_accumulate(ex.x, ex.y, ey.x, ey.y, ez.x, ez.y, f0, f1, f2, yh, g0, g1, g2);
+      }
+#undef DNMF_LDS4
+#undef DNMF_LDS2
     }
     if (has_overflow) {  // slots beyond the staged capacity: straight from the L2-resident tables
       const int j0 = o0 + wl0 + 2, j1 = o1 + wl1 + 2, j2 = o2 + wl2 + 2;
@@ -563,8 +636,9 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? 20 : 1) fit
         pair_accumulate(ex.x * ck, ex.y * ck, ey.x, ey.y, ez.x, ez.y, f0, f1, f2, yh, g0, g1, g2);
       }
     }
-    const float yv = yptr[zz];
-    if (WRITE_YHAT) sY[lx * RS + ly * zs + zz] = yh;
+    float yv;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(yv) : "r"(yaddr));
+    if (WRITE_YHAT) asm volatile("st.shared.f32 [%0], %1;" ::"r"(yaddr), "f"(yh) : "memory");
     const float r = valid ? (yh - yv) : 0.f;
     sse = fmaf(r, r, sse);
     const float h0 = r * g0, h1 = r * g1, h2 = r * g2;
@@ -772,6 +846,9 @@ struct dnmf_ctx {
   size_t fit_smem = 0;
   int fast_div = 0;
   float rcp[3] = {0.f, 0.f, 0.f};
+  long long* d_cand_off = nullptr;  // static candidate lists per tile (identity windows +- cand_expand)
+  int* d_cand_ids = nullptr;
+  int cand_expand = 6;
   // video
   float* d_video = nullptr;
   // scratch
@@ -910,7 +987,7 @@ extern "C" void dnmf_destroy(dnmf_ctx* c) {
                   c->d_tab[2],  c->d_video, c->d_partials,   c->d_grad,        c->d_sse,
                   c->d_batch,   c->d_ids,   c->d_loss,       c->d_tmp_counts,  c->d_tmp_offsets,
                   c->d_tmp_max, c->d_G,     c->d_b,          c->d_identity_beta,
-                  c->d_Cd[0],   c->d_Cd[1], c->d_keys};
+                  c->d_Cd[0],   c->d_Cd[1], c->d_keys,       c->d_cand_off,    c->d_cand_ids};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete c;
@@ -942,13 +1019,13 @@ extern "C" int dnmf_get_tiling(dnmf_ctx* c, int32_t* out) {
 }
 
 static int run_bin_count(dnmf_ctx* c, const float* beta, int beta_T, const int* ids, int B, int* counts,
-                         int* windows, cudaStream_t st) {
+                         int* windows, cudaStream_t st, int expand = 0) {
   Geom g = geom_of(c);
   g.T = beta_T;
   const long long items = (long long)B * g.ntx * g.nty * g.ntz;
   const int wpb = 8;
   bin_tiles_kernel<false><<<(unsigned)((items + wpb - 1) / wpb), wpb * 32, 0, st>>>(
-      g, beta, ids, B, c->d_rng, counts, nullptr, windows, nullptr, 0);
+      g, beta, ids, B, c->d_rng, counts, nullptr, windows, nullptr, 0, expand);
   CU(cudaGetLastError());
   return 0;
 }
@@ -978,6 +1055,29 @@ static int configure_tiling(dnmf_ctx* c, cudaStream_t st) {
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(&c->lmax_identity, c->d_tmp_max, sizeof(int), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  // static candidate lists: identity windows expanded by cand_expand nodes on every side
+  {
+    if (c->d_cand_off) cudaFree(c->d_cand_off);
+    if (c->d_cand_ids) cudaFree(c->d_cand_ids);
+    c->d_cand_off = nullptr;
+    c->d_cand_ids = nullptr;
+    CU(cudaMalloc((void**)&c->d_cand_off, ((size_t)nt + 1) * sizeof(long long)));
+    if (run_bin_count(c, c->d_identity_beta, 1, d_zero, 1, c->d_tmp_counts, nullptr, st, c->cand_expand)) return 1;
+    scan_counts_kernel<<<1, 1024, 0, st>>>(c->d_tmp_counts, nt, c->d_cand_off, nullptr);
+    CU(cudaGetLastError());
+    long long total = 0;
+    CU(cudaMemcpyAsync(&total, c->d_cand_off + nt, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMalloc((void**)&c->d_cand_ids, (size_t)std::max<long long>(total, 1) * sizeof(int)));
+    Geom g1 = geom_of(c);
+    g1.T = 1;
+    const int wpb = 8;
+    bin_tiles_kernel<true><<<(unsigned)((nt + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+        g1, c->d_identity_beta, d_zero, 1, c->d_rng, c->d_tmp_counts, c->d_cand_off, nullptr, c->d_cand_ids, total,
+        c->cand_expand);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+  }
   cudaFree(d_zero);
   int cap = c->user_cap > 0 ? c->user_cap : c->lmax_identity + c->lmax_identity / 4 + 2;
   cap = std::max(2, std::min(cap, c->K + 1));
@@ -1080,7 +1180,7 @@ extern "C" int dnmf_bin_tiles(dnmf_ctx* c, const float* beta_dev, const int32_t*
     const int wpb = 8;
     bin_tiles_kernel<true><<<(unsigned)((items + wpb - 1) / wpb), wpb * 32, 0, st>>>(
         g, beta_dev, frame_ids_dev, B, c->d_rng, counts_dev, (const long long*)offsets_dev, nullptr, ids_dev,
-        ids_capacity);
+        ids_capacity, 0);
     CU(cudaGetLastError());
   }
   if (total_host) {
@@ -1094,9 +1194,9 @@ extern "C" int dnmf_bin_tiles(dnmf_ctx* c, const float* beta_dev, const int32_t*
 }
 
 // ---- fused step -----------------------------------------------------------------------------------
-template <int NWX, int NWY, bool WY_>
+template <int NWX, int NWY, bool WY_, bool FD_>
 static int launch_fit(const FitParams& p0, int B, size_t smem, cudaStream_t st) {
-  auto kern = fit_tile_kernel<NWX, NWY, WY_>;
+  auto kern = fit_tile_kernel<NWX, NWY, WY_, FD_>;
   static size_t configured = 0;
   if (smem > configured) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1124,10 +1224,15 @@ template <bool WY_>
 static int dispatch_fit(dnmf_ctx* c, const FitParams& p, int B, cudaStream_t st) {
   const size_t smem = c->fit_smem;
   if (c->nty > 65535) return fail("dispatch_fit: more than 65535 tiles along y");
-  if (c->nwx == 1 && c->nwy == 1) return launch_fit<1, 1, WY_>(p, B, smem, st);
-  if (c->nwx == 2 && c->nwy == 1) return launch_fit<2, 1, WY_>(p, B, smem, st);
-  if (c->nwx == 2 && c->nwy == 2) return launch_fit<2, 2, WY_>(p, B, smem, st);
-  if (c->nwx == 2 && c->nwy == 4) return launch_fit<2, 4, WY_>(p, B, smem, st);
+  const bool fd = c->fast_div != 0;
+#define DNMF_DISPATCH(a, b)                                                  \
+  if (c->nwx == a && c->nwy == b)                                            \
+    return fd ? launch_fit<a, b, WY_, true>(p, B, smem, st) : launch_fit<a, b, WY_, false>(p, B, smem, st);
+  DNMF_DISPATCH(1, 1)
+  DNMF_DISPATCH(2, 1)
+  DNMF_DISPATCH(2, 2)
+  DNMF_DISPATCH(2, 4)
+#undef DNMF_DISPATCH
   return fail("dispatch_fit: unsupported warp layout");
 }
 
@@ -1165,6 +1270,9 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
   p.rcp0 = c->rcp[0];
   p.rcp1 = c->rcp[1];
   p.rcp2 = c->rcp[2];
+  p.cand_off = c->d_cand_off;
+  p.cand_ids = c->d_cand_ids;
+  p.cand_expand = c->cand_expand;
   p.yhat = nullptr;
   const size_t need = (size_t)B * c->ntx * c->nty * c->ntz * kNumPartials;
   if (ensure(&c->d_partials, &c->partials_cap, need)) return 1;
