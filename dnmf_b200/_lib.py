@@ -5,7 +5,7 @@ import re
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libdnmf_b200.so")
+LIB_PATH = os.environ.get("DNMF_B200_LIB") or os.path.join(_HERE, "_C", "libdnmf_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dnmf_b200.h")
 
 _lib = None

@@ -22,6 +22,10 @@
 #include "../../include/dnmf_b200.h"
 #include "dnmf_device.cuh"
 
+#ifndef DNMF_MINB
+#define DNMF_MINB 22  // resident single-warp CTAs per SM the fused kernel is compiled for (register budget)
+#endif
+
 namespace dnmf {
 
 // ------------------------------------------------------------------------------------------------
@@ -292,6 +296,21 @@ __device__ __forceinline__ void pair_accumulate(float ex_g, float ex_d, float ey
   g2 = fmaf(ca0 * a1, ez_d, g2);
 }
 
+// Two neurons at once with Blackwell's packed FP32x2 instructions (FFMA2 / FMUL2: two IEEE fp32
+// results per lane per issue slot).  Operands are (slot j, slot j+1) pairs straight out of one LDS.128.
+__device__ __forceinline__ void pair2_accumulate(float2 exG, float2 exD, float2 eyG, float2 eyD, float2 ezG,
+                                                 float2 ezD, float2 f0, float2 f1, float2 f2, float2& yh,
+                                                 float2& g0, float2& g1, float2& g2) {
+  const float2 ca0 = __ffma2_rn(f0, exD, exG);
+  const float2 a1 = __ffma2_rn(f1, eyD, eyG);
+  const float2 a2 = __ffma2_rn(f2, ezD, ezG);
+  const float2 t12 = __fmul2_rn(a1, a2);
+  yh = __ffma2_rn(ca0, t12, yh);
+  g0 = __ffma2_rn(exD, t12, g0);
+  g1 = __ffma2_rn(__fmul2_rn(ca0, a2), eyD, g1);
+  g2 = __ffma2_rn(__fmul2_rn(ca0, a1), ezD, g2);
+}
+
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 // Loop-invariant values the compiler would otherwise rematerialise inside the hot loop (constant-bank
@@ -329,7 +348,7 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 }
 
 template <int NWX, int NWY, bool WRITE_YHAT, bool FAST_DIV>
-__global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? 20 : 1) fit_tile_kernel(const __grid_constant__ FitParams p) {
+__global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB : 1) fit_tile_kernel(const __grid_constant__ FitParams p) {
   constexpr int NW = NWX * NWY;
   constexpr int TX = kWarpX * NWX, TY = kWarpY * NWY;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -500,7 +519,8 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? 20 : 1) fit
         row = sZ3;
         dst_e = p.wmax0 + p.wmax1 + (e - W0 - W1);
       }
-      float2* dst = sTab + (size_t)dst_e * CAP;
+      // slots j, j+1 share one float4 = (G_j, G_j+1, D_j, D_j+1): packed operands for FFMA2
+      float* dst = reinterpret_cast<float*>(sTab + (size_t)dst_e * CAP);
       for (int j = 0; j < nst; ++j) {
         const int k = sList[j];
         float2 v = __ldg(src + (size_t)k * row);
@@ -509,7 +529,9 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? 20 : 1) fit
           v.x *= ck;
           v.y *= ck;
         }
-        dst[j] = v;
+        float* d4 = dst + (j >> 1) * 4 + (j & 1);
+        d4[0] = v.x;
+        d4[2] = v.y;
       }
     }
   }
@@ -584,12 +606,13 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? 20 : 1) fit
     const unsigned o0 = (unsigned)min(max(i0 - wl0, 0), W0m1);
     const unsigned o1 = (unsigned)min(max(i1 - wl1, 0), W1m1);
     const unsigned o2 = (unsigned)min(max(i2 - wl2, 0), W2m1);
-    float yh = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    float yh, g0, g1, g2;
     {
       unsigned ax = o0 * strideB + baseX, ay = o1 * strideB + baseY, az = o2 * strideB + baseZ;
+      const float2 ff0 = make_float2(f0, f0), ff1 = make_float2(f1, f1), ff2 = make_float2(f2, f2);
+      float2 yh2 = make_float2(0.f, 0.f), g02 = yh2, g12 = yh2, g22 = yh2;
 #define DNMF_LDS4(v, addr, off) \
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+" #off "];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr))
-#define DNMF_LDS2(v, addr, off) asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+" #off "];" : "=f"(v.x), "=f"(v.y) : "r"(addr))
 #pragma unroll 1
       for (int j = 0; j < nquad; ++j, ax += 32u, ay += 32u, az += 32u) {  // four neurons per iteration
         float4 ex, ey, ez, fx, fy, fz;
@@ -599,31 +622,37 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? 20 : 1) fit
         DNMF_LDS4(fx, ax, 16);
         DNMF_LDS4(fy, ay, 16);
         DNMF_LDS4(fz, az, 16);
-        pair_accumulate(ex.x, ex.y, ey.x, ey.y, ez.x, ez.y, f0, f1, f2, yh, g0, g1, g2);
-        pair_accumulate(ex.z, ex.w, ey.z, ey.w, ez.z, ez.w, f0, f1, f2, yh, g0, g1, g2);
-        pair_accumulate(fx.x, fx.y, fy.x, fy.y, fz.x, fz.y, f0, f1, f2, yh, g0, g1, g2);
-        pair_accumulate(fx.z, fx.w, fy.z, fy.w, fz.z, fz.w, f0, f1, f2, yh, g0, g1, g2);
+        pair2_accumulate(make_float2(ex.x, ex.y), make_float2(ex.z, ex.w), make_float2(ey.x, ey.y),
+                         make_float2(ey.z, ey.w), make_float2(ez.x, ez.y), make_float2(ez.z, ez.w), ff0, ff1, ff2,
+                         yh2, g02, g12, g22);
+        pair2_accumulate(make_float2(fx.x, fx.y), make_float2(fx.z, fx.w), make_float2(fy.x, fy.y),
+                         make_float2(fy.z, fy.w), make_float2(fz.x, fz.y), make_float2(fz.z, fz.w), ff0, ff1, ff2,
+                         yh2, g02, g12, g22);
       }
       if (nst & 2) {
         float4 ex, ey, ez;
         DNMF_LDS4(ex, ax, 0);
         DNMF_LDS4(ey, ay, 0);
         DNMF_LDS4(ez, az, 0);
-        pair_accumulate(ex.x, ex.y, ey.x, ey.y, ez.x, ez.y, f0, f1, f2, yh, g0, g1, g2);
-        pair_accumulate(ex.z, ex.w, ey.z, ey.w, ez.z, ez.w, f0, f1, f2, yh, g0, g1, g2);
+        pair2_accumulate(make_float2(ex.x, ex.y), make_float2(ex.z, ex.w), make_float2(ey.x, ey.y),
+                         make_float2(ey.z, ey.w), make_float2(ez.x, ez.y), make_float2(ez.z, ez.w), ff0, ff1, ff2,
+                         yh2, g02, g12, g22);
         ax += 16u;
         ay += 16u;
         az += 16u;
       }
-      if (nst & 1) {
-        float2 ex, ey, ez;
-        DNMF_LDS2(ex, ax, 0);
-        DNMF_LDS2(ey, ay, 0);
-        DNMF_LDS2(ez, az, 0);
-        pair_accumulate(ex.x, ex.y, ey.x, ey.y, ez.x, ez.y, f0, f1, f2, yh, g0, g1, g2);
+      yh = yh2.x + yh2.y;
+      g0 = g02.x + g02.y;
+      g1 = g12.x + g12.y;
+      g2 = g22.x + g22.y;
+      if (nst & 1) {  // odd tail slot: lanes (x, z) of its float4 hold (G, D)
+        float4 ex, ey, ez;
+        DNMF_LDS4(ex, ax, 0);
+        DNMF_LDS4(ey, ay, 0);
+        DNMF_LDS4(ez, az, 0);
+        pair_accumulate(ex.x, ex.z, ey.x, ey.z, ez.x, ez.z, f0, f1, f2, yh, g0, g1, g2);
       }
 #undef DNMF_LDS4
-#undef DNMF_LDS2
     }
     if (has_overflow) {  // slots beyond the staged capacity: straight from the L2-resident tables
       const int j0 = o0 + wl0 + 2, j1 = o1 + wl1 + 2, j2 = o2 + wl2 + 2;
