@@ -322,7 +322,9 @@ def run_b200(args, cfg):
     rng = eng.ranges()
     ext = np.minimum(rng[:, :, 1] - rng[:, :, 0] + 2, np.asarray(sz)[None, :]).clip(min=0)
     k_eff = float(ext.prod(1).sum()) / N                       # true in-cutoff (voxel, neuron) pairs per voxel
-    counts, _, _, _ = eng.bin_tiles(beta, ids[:1])
+    beta_id = torch.zeros(10, 3, T, device=dev)
+    beta_id[1, 0], beta_id[2, 1], beta_id[3, 2] = 1.0, 1.0, 1.0
+    counts, _, _, _ = eng.bin_tiles(beta_id, ids[:1])           # list lengths at the identity deformation
     tl = eng.tiling()
     listed = float((counts.astype(np.float64) * tl["tx"] * tl["ty"] * tl["tz"]).sum()) / N
     flops_per_frame = N * (144.0 + 25.0 * k_eff)

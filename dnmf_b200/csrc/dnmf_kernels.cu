@@ -869,6 +869,7 @@ struct dnmf_ctx {
   float cutoff = 0.f;
   // tiling
   int nwx = 1, nwy = 1, tz = 0, cap = 0, user_cap = 0;
+  bool auto_tiling = true;  // until dnmf_set_tiling is called: pick the warp layout from the list lengths
   int tx = 8, ty = 4, ntx = 0, nty = 0, ntz = 0;
   int wmax[3] = {0, 0, 0};
   int lmax_identity = 0;
@@ -1035,6 +1036,7 @@ extern "C" int dnmf_set_tiling(dnmf_ctx* c, int warps_x, int warps_y, int tz, in
   c->nwy = warps_y;
   c->tz = tz;
   c->user_cap = slot_capacity;
+  c->auto_tiling = false;
   CU(cudaSetDevice(c->device));
   if (c->have_footprints) return configure_tiling(c, 0);
   return 0;
@@ -1059,7 +1061,36 @@ static int run_bin_count(dnmf_ctx* c, const float* beta, int beta_T, const int* 
   return 0;
 }
 
+static int configure_tiling_fixed(dnmf_ctx* c, cudaStream_t st);
+
+// Short lists (cfg1-3: a handful of neurons per tile) want the smallest CTA footprint (one warp, tightest
+// lists); dense configurations (cfg4: ~100 neurons per tile) want several warps sharing one staged copy
+// of the table slices, or shared memory caps occupancy at a few warps per SM.
 static int configure_tiling(dnmf_ctx* c, cudaStream_t st) {
+  if (!c->auto_tiling) return configure_tiling_fixed(c, st);
+  static const int layouts[4][2] = {{1, 1}, {2, 1}, {2, 2}, {2, 4}};
+  int best = 0;
+  double best_per_warp = 1e30;
+  for (int i = 0; i < 4; ++i) {
+    c->nwx = layouts[i][0];
+    c->nwy = layouts[i][1];
+    if (configure_tiling_fixed(c, st)) return 1;
+    const double per_warp = (double)c->fit_smem / (c->nwx * c->nwy);
+    if (per_warp < best_per_warp) {
+      best_per_warp = per_warp;
+      best = i;
+    }
+    if (per_warp <= 11.0 * 1024) {
+      best = i;
+      break;
+    }
+  }
+  c->nwx = layouts[best][0];
+  c->nwy = layouts[best][1];
+  return configure_tiling_fixed(c, st);
+}
+
+static int configure_tiling_fixed(dnmf_ctx* c, cudaStream_t st) {
   c->tx = kWarpX * c->nwx;
   c->ty = kWarpY * c->nwy;
   if (c->tz <= 0 || c->tz > c->Z) c->tz = std::min(c->Z, 32);
@@ -1115,7 +1146,7 @@ static int configure_tiling(dnmf_ctx* c, cudaStream_t st) {
   const int wsum = c->wmax[0] + c->wmax[1] + c->wmax[2];
   const int nw = c->nwx * c->nwy;
   // keep at least ~2 CTAs per SM worth of shared memory when possible
-  const size_t budget = std::min<size_t>((size_t)c->max_smem_optin, (size_t)100 * 1024);
+  const size_t budget = std::min<size_t>((size_t)c->max_smem_optin, (size_t)113 * 1024);
   while (cap > 2 && fit_smem_layout(nw, c->tx, c->ty, c->tz, cap, wsum, c->K).bytes > budget) cap -= 4;
   if (cap < 2) cap = 2;
   c->cap = cap;

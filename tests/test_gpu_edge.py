@@ -258,3 +258,27 @@ dist.destroy_process_group()
     got = np.concatenate([p["beta"] for p in parts], 2)
     assert np.array_equal(got, b.cpu().numpy())
     np.testing.assert_allclose(parts[0]["losses"], ref_losses, rtol=1e-12)
+
+
+def test_binning_large_k_bit_exact():
+    """config-4-like density: K=1000 wide footprints on a 64x32x21 sub-volume."""
+    from dnmf_b200.engine import Engine
+    rng = np.random.default_rng(4)
+    sz, K, T = [64, 32, 21], 1000, 2
+    pos = (rng.random((K, 3)) * np.asarray(sz) * 1.2 - 0.1 * np.asarray(sz)).astype(np.float32)
+    sig = np.full(K, 6.0, np.float32)
+    e = Engine(sz, K, T)
+    e.set_footprints(pos, sig, 3.5)
+    _, _, beta, _, _ = _case(sz, 2, T, 77, beta_scale=0.5)
+    counts, offsets, ids, wins = e.bin_tiles(beta.cuda(), torch.arange(T))
+    tl = e.tiling()
+    rc, ro, ri, rw = O.bin_tiles(beta.numpy(), [0, 1], e.ranges(), sz, (tl["tx"], tl["ty"], tl["tz"]))
+    assert np.array_equal(wins, rw) and np.array_equal(counts, rc)
+    assert np.array_equal(offsets, ro) and np.array_equal(ids, ri)
+    assert counts.max() > 200
+
+
+@pytest.mark.parametrize("tiling", [(1, 1, 0, 0), (2, 4, 0, 0)])
+def test_dense_neurons_loss_grad(tiling):
+    """many overlapping wide footprints (long lists, staged + overflow slots) against the closed form."""
+    _check([40, 24, 6], 120, 2, seed=13, cutoff=3.5, tiling=tiling, sigma=5.0, tol=5e-5)
