@@ -347,10 +347,12 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int NWX, int NWY, bool WRITE_YHAT, bool FAST_DIV>
+// SUB = y-adjacent 8x4 sub-tiles processed one after the other by each warp: they share the tile
+// prologue (window, list, staging, TMA) and the reduction epilogue.
+template <int NWX, int NWY, int SUB, bool WRITE_YHAT, bool FAST_DIV>
 __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB : 1) fit_tile_kernel(const __grid_constant__ FitParams p) {
   constexpr int NW = NWX * NWY;
-  constexpr int TX = kWarpX * NWX, TY = kWarpY * NWY;
+  constexpr int TX = kWarpX * NWX, TY = kWarpY * NWY * SUB;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int wsum = p.wmax0 + p.wmax1 + p.wmax2;
   const int CAP = p.cap;
@@ -537,30 +539,15 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
   }
   __syncthreads();
 
-  // ---- main loop: one (x,y) column per lane, march along z ----
+  // ---- main loop: one (x,y) column per lane (per sub-tile), march along z ----
   const int lx = (warp % NWX) * kWarpX + (lane & 7);
-  const int ly = (warp / NWX) * kWarpY + (lane >> 3);
-  const int gx = x0 + lx, gy = y0 + ly;
-  const bool valid = (gx < p.X) && (gy < p.Y);
-  const float xf = (float)gx, yf = (float)gy;
-  float c0[3], c1[3], c2[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    float v = sBeta[d];
-    v = fmaf(sBeta[3 + d], xf, v);
-    v = fmaf(sBeta[6 + d], yf, v);
-    v = fmaf(sBeta[12 + d], xf * xf, v);
-    v = fmaf(sBeta[15 + d], yf * yf, v);
-    v = fmaf(sBeta[21 + d], xf * yf, v);
-    c0[d] = v;
-    c1[d] = fmaf(sBeta[27 + d], yf, fmaf(sBeta[24 + d], xf, sBeta[9 + d]));
-    c2[d] = sBeta[18 + d];
-  }
+  const int ly0 = (warp / NWX) * (kWarpY * SUB) + (lane >> 3);
+  const int gx = x0 + lx;
+  const float xf = (float)gx;
   const float sm1x = pin((float)(p.X - 1)), sm1y = pin((float)(p.Y - 1)), sm1z = pin((float)(p.Z - 1));
   const float rcpx = pin(p.rcp0), rcpy = pin(p.rcp1), rcpz = pin(p.rcp2);
-  float S0[3] = {0.f, 0.f, 0.f}, S1[3] = {0.f, 0.f, 0.f}, S2[3] = {0.f, 0.f, 0.f};
+  float S0[SUB][3], S1[SUB][3], S2[3] = {0.f, 0.f, 0.f};
   float sse = 0.f;
-  unsigned yaddr = smem_u32(sY + lx * RS + ly * zs);  // walks the lane's column of the Y tile, 4 B per z step
   // shared-memory byte addresses of the three slice regions; one table entry = CAP slots of 8 B
   const unsigned strideB = pin((unsigned)CAP * 8u);
   const unsigned baseX = pin(smem_u32(sTab));
@@ -583,6 +570,28 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
     }
   }
 
+#pragma unroll
+  for (int h = 0; h < SUB; ++h) {
+  const int ly = ly0 + h * kWarpY;
+  const int gy = y0 + ly;
+  const bool valid = (gx < p.X) && (gy < p.Y);
+  const float yf = (float)gy;
+  float c0[3], c1[3], c2[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float v = sBeta[d];
+    v = fmaf(sBeta[3 + d], xf, v);
+    v = fmaf(sBeta[6 + d], yf, v);
+    v = fmaf(sBeta[12 + d], xf * xf, v);
+    v = fmaf(sBeta[15 + d], yf * yf, v);
+    v = fmaf(sBeta[21 + d], xf * yf, v);
+    c0[d] = v;
+    c1[d] = fmaf(sBeta[27 + d], yf, fmaf(sBeta[24 + d], xf, sBeta[9 + d]));
+    c2[d] = sBeta[18 + d];
+    S0[h][d] = 0.f;
+    S1[h][d] = 0.f;
+  }
+  unsigned yaddr = smem_u32(sY + lx * RS + ly * zs);  // walks the lane's column of the Y tile, 4 B per z step
   float zf = (float)z0;
   for (int zz = 0; zz < nz; ++zz, zf += 1.f, yaddr += 4u) {
     const float q0 = fmaf(zf, fmaf(zf, c2[0], c1[0]), c0[0]);
@@ -672,33 +681,44 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
     sse = fmaf(r, r, sse);
     const float h0 = r * g0, h1 = r * g1, h2 = r * g2;
     const float zf2 = zf * zf;
-    S0[0] += h0;
-    S0[1] += h1;
-    S0[2] += h2;
-    S1[0] = fmaf(zf, h0, S1[0]);
-    S1[1] = fmaf(zf, h1, S1[1]);
-    S1[2] = fmaf(zf, h2, S1[2]);
+    S0[h][0] += h0;
+    S0[h][1] += h1;
+    S0[h][2] += h2;
+    S1[h][0] = fmaf(zf, h0, S1[h][0]);
+    S1[h][1] = fmaf(zf, h1, S1[h][1]);
+    S1[h][2] = fmaf(zf, h2, S1[h][2]);
     S2[0] = fmaf(zf2, h0, S2[0]);
     S2[1] = fmaf(zf2, h1, S2[1]);
     S2[2] = fmaf(zf2, h2, S2[2]);
   }
+  }  // sub-tiles
 
   // ---- expand z-moments with this lane's (x,y) monomials, transposing warp reduction ----
   {
     float v[32];
-    const float xx = xf * xf, yy = yf * yf, xy = xf * yf;
+    const float xx = xf * xf;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      v[0 * 3 + d] = S0[d];
-      v[1 * 3 + d] = xf * S0[d];
-      v[2 * 3 + d] = yf * S0[d];
-      v[3 * 3 + d] = S1[d];
-      v[4 * 3 + d] = xx * S0[d];
-      v[5 * 3 + d] = yy * S0[d];
+      float t0 = 0.f, t1 = 0.f, y0s = 0.f, yy0s = 0.f, y1s = 0.f;  // sums over the sub-tiles' y rows
+#pragma unroll
+      for (int h = 0; h < SUB; ++h) {
+        const float yh_ = (float)(y0 + ly0 + h * kWarpY);
+        t0 += S0[h][d];
+        t1 += S1[h][d];
+        y0s = fmaf(yh_, S0[h][d], y0s);
+        yy0s = fmaf(yh_ * yh_, S0[h][d], yy0s);
+        y1s = fmaf(yh_, S1[h][d], y1s);
+      }
+      v[0 * 3 + d] = t0;
+      v[1 * 3 + d] = xf * t0;
+      v[2 * 3 + d] = y0s;
+      v[3 * 3 + d] = t1;
+      v[4 * 3 + d] = xx * t0;
+      v[5 * 3 + d] = yy0s;
       v[6 * 3 + d] = S2[d];
-      v[7 * 3 + d] = xy * S0[d];
-      v[8 * 3 + d] = xf * S1[d];
-      v[9 * 3 + d] = yf * S1[d];
+      v[7 * 3 + d] = xf * y0s;
+      v[8 * 3 + d] = xf * t1;
+      v[9 * 3 + d] = y1s;
     }
     v[30] = sse;
     v[31] = 0.f;
@@ -869,6 +889,7 @@ struct dnmf_ctx {
   float cutoff = 0.f;
   // tiling
   int nwx = 1, nwy = 1, tz = 0, cap = 0, user_cap = 0;
+  int sub = 1;  // y-adjacent sub-tiles per warp (fit kernel only)
   bool auto_tiling = true;  // until dnmf_set_tiling is called: pick the warp layout from the list lengths
   int tx = 8, ty = 4, ntx = 0, nty = 0, ntz = 0;
   int wmax[3] = {0, 0, 0};
@@ -1026,8 +1047,11 @@ extern "C" void dnmf_destroy(dnmf_ctx* c) {
 // ---- tiling -----------------------------------------------------------------------------------
 static int configure_tiling(dnmf_ctx* c, cudaStream_t st);
 
-extern "C" int dnmf_set_tiling(dnmf_ctx* c, int warps_x, int warps_y, int tz, int slot_capacity) {
+extern "C" int dnmf_set_tiling(dnmf_ctx* c, int warps_x, int warps_y, int tz, int slot_capacity, int subtiles_y) {
   if (!c) return fail("dnmf_set_tiling: ctx is NULL");
+  if (subtiles_y < 1) subtiles_y = 1;
+  if (subtiles_y > 2 || (subtiles_y == 2 && (warps_x != 1 || warps_y != 1)))
+    return fail("dnmf_set_tiling: subtiles_y = 2 is supported for the one-warp layout only");
   const bool ok = (warps_x == 1 && warps_y == 1) || (warps_x == 2 && warps_y == 1) ||
                   (warps_x == 2 && warps_y == 2) || (warps_x == 2 && warps_y == 4);
   if (!ok) return fail("dnmf_set_tiling: supported warp layouts are 1x1, 2x1, 2x2, 2x4");
@@ -1036,6 +1060,7 @@ extern "C" int dnmf_set_tiling(dnmf_ctx* c, int warps_x, int warps_y, int tz, in
   c->nwy = warps_y;
   c->tz = tz;
   c->user_cap = slot_capacity;
+  c->sub = subtiles_y;
   c->auto_tiling = false;
   CU(cudaSetDevice(c->device));
   if (c->have_footprints) return configure_tiling(c, 0);
@@ -1044,7 +1069,7 @@ extern "C" int dnmf_set_tiling(dnmf_ctx* c, int warps_x, int warps_y, int tz, in
 
 extern "C" int dnmf_get_tiling(dnmf_ctx* c, int32_t* out) {
   if (!c || !out) return fail("dnmf_get_tiling: NULL argument");
-  int32_t v[9] = {c->tx, c->ty, c->tz, c->ntx, c->nty, c->ntz, c->nwx, c->nwy, c->cap};
+  int32_t v[10] = {c->tx, c->ty, c->tz, c->ntx, c->nty, c->ntz, c->nwx, c->nwy, c->cap, c->sub};
   memcpy(out, v, sizeof(v));
   return 0;
 }
@@ -1068,31 +1093,33 @@ static int configure_tiling_fixed(dnmf_ctx* c, cudaStream_t st);
 // of the table slices, or shared memory caps occupancy at a few warps per SM.
 static int configure_tiling(dnmf_ctx* c, cudaStream_t st) {
   if (!c->auto_tiling) return configure_tiling_fixed(c, st);
-  static const int layouts[4][2] = {{1, 1}, {2, 1}, {2, 2}, {2, 4}};
+  static const int layouts[5][3] = {{1, 1, 2}, {1, 1, 1}, {2, 1, 1}, {2, 2, 1}, {2, 4, 1}};
   int best = 0;
   double best_per_warp = 1e30;
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 5; ++i) {
     c->nwx = layouts[i][0];
     c->nwy = layouts[i][1];
+    c->sub = layouts[i][2];
     if (configure_tiling_fixed(c, st)) return 1;
     const double per_warp = (double)c->fit_smem / (c->nwx * c->nwy);
     if (per_warp < best_per_warp) {
       best_per_warp = per_warp;
       best = i;
     }
-    if (per_warp <= 11.0 * 1024) {
+    if (per_warp <= 12.0 * 1024) {
       best = i;
       break;
     }
   }
   c->nwx = layouts[best][0];
   c->nwy = layouts[best][1];
+  c->sub = layouts[best][2];
   return configure_tiling_fixed(c, st);
 }
 
 static int configure_tiling_fixed(dnmf_ctx* c, cudaStream_t st) {
   c->tx = kWarpX * c->nwx;
-  c->ty = kWarpY * c->nwy;
+  c->ty = kWarpY * c->nwy * c->sub;
   if (c->tz <= 0 || c->tz > c->Z) c->tz = std::min(c->Z, 32);
   c->ntx = (c->X + c->tx - 1) / c->tx;
   c->nty = (c->Y + c->ty - 1) / c->ty;
@@ -1254,9 +1281,9 @@ extern "C" int dnmf_bin_tiles(dnmf_ctx* c, const float* beta_dev, const int32_t*
 }
 
 // ---- fused step -----------------------------------------------------------------------------------
-template <int NWX, int NWY, bool WY_, bool FD_>
+template <int NWX, int NWY, int SUB, bool WY_, bool FD_>
 static int launch_fit(const FitParams& p0, int B, size_t smem, cudaStream_t st) {
-  auto kern = fit_tile_kernel<NWX, NWY, WY_, FD_>;
+  auto kern = fit_tile_kernel<NWX, NWY, SUB, WY_, FD_>;
   static size_t configured = 0;
   if (smem > configured) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1285,13 +1312,14 @@ static int dispatch_fit(dnmf_ctx* c, const FitParams& p, int B, cudaStream_t st)
   const size_t smem = c->fit_smem;
   if (c->nty > 65535) return fail("dispatch_fit: more than 65535 tiles along y");
   const bool fd = c->fast_div != 0;
-#define DNMF_DISPATCH(a, b)                                                  \
-  if (c->nwx == a && c->nwy == b)                                            \
-    return fd ? launch_fit<a, b, WY_, true>(p, B, smem, st) : launch_fit<a, b, WY_, false>(p, B, smem, st);
-  DNMF_DISPATCH(1, 1)
-  DNMF_DISPATCH(2, 1)
-  DNMF_DISPATCH(2, 2)
-  DNMF_DISPATCH(2, 4)
+#define DNMF_DISPATCH(a, b, sb)                                                       \
+  if (c->nwx == a && c->nwy == b && c->sub == sb)                                      \
+    return fd ? launch_fit<a, b, sb, WY_, true>(p, B, smem, st) : launch_fit<a, b, sb, WY_, false>(p, B, smem, st);
+  DNMF_DISPATCH(1, 1, 1)
+  DNMF_DISPATCH(1, 1, 2)
+  DNMF_DISPATCH(2, 1, 1)
+  DNMF_DISPATCH(2, 2, 1)
+  DNMF_DISPATCH(2, 4, 1)
 #undef DNMF_DISPATCH
   return fail("dispatch_fit: unsupported warp layout");
 }

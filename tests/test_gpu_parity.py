@@ -37,7 +37,7 @@ def test_tables_and_ranges(golden_random, cutoff):
         np.testing.assert_allclose(e.table(d), tabs[d], rtol=3e-6, atol=1e-12)
 
 
-@pytest.mark.parametrize("tiling", [(1, 1, 0, 0), (2, 1, 0, 0), (2, 2, 4, 0), (2, 4, 0, 0)])
+@pytest.mark.parametrize("tiling", [(1, 1, 0, 0), (2, 1, 0, 0), (2, 2, 4, 0), (2, 4, 0, 0), (1, 1, 0, 0, 2)])
 def test_binning_bit_exact(golden_random, tiling):
     g = golden_random
     sz = g["sz"].tolist()
@@ -53,7 +53,7 @@ def test_binning_bit_exact(golden_random, tiling):
     assert np.array_equal(ids, ri)
 
 
-@pytest.mark.parametrize("tiling", [(1, 1, 0, 0), (2, 1, 3, 0), (2, 2, 0, 1), (2, 4, 0, 0)])
+@pytest.mark.parametrize("tiling", [(1, 1, 0, 0), (2, 1, 3, 0), (2, 2, 0, 1), (2, 4, 0, 0), (1, 1, 0, 0, 2), (1, 1, 4, 2, 2)])
 def test_loss_grad_vs_reference_autograd(golden_random, tiling):
     """random quadratic beta incl. 42 % out-of-bounds samples and one identity frame (F2)."""
     g = golden_random
