@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--tiling", default="", help="warps_x,warps_y,tz,cap override")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-mu", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames per reference step (default 4; 1 for --impl reference)")
     return ap.parse_args()
 
@@ -358,6 +359,31 @@ def run_b200(args, cfg):
                         "bytes_per_frame_iter": bytes_per_frame,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}}
 
+    # ---- secondary metric: trace update (update_footprints hot loop #2), frame-MU-iterations/s ----
+    mu = None
+    if not args.no_mu:
+        try:
+            iters = 50                                    # demo.py:46 uses iter_c=50
+            torch.cuda.synchronize()
+            ev0.record()
+            for i in range(0, T, 250):
+                eng.mu_stats(ids_all[i:i + 250], beta)
+            ev1.record()
+            torch.cuda.synchronize()
+            stats_ms = ev0.elapsed_time(ev1)
+            Cmu = dn.C.clone()
+            ev0.record()
+            eng.mu_sweeps(Cmu, 0.0, iters)
+            ev1.record()
+            torch.cuda.synchronize()
+            sweeps_ms = ev0.elapsed_time(ev1)
+            mu = {"metric": "frame-MU-iterations/s", "value": T * iters / ((stats_ms + sweeps_ms) * 1e-3),
+                  "frames": T, "iter_c": iters, "stats_ms": stats_ms, "sweeps_ms": sweeps_ms,
+                  "what": "dnmf_mu_stats over all frames + %d multiplicative sweeps (update_footprints without "
+                          "the dense returns); reference: 1 035 frame-MU-iters/s on the 8-core CPU at cfg1" % iters}
+        except Exception as exc:                          # keep the headline line even if this leg fails
+            mu = {"error": str(exc)}
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         Bc = args.cpu_frames or 4
@@ -375,7 +401,7 @@ def run_b200(args, cfg):
                        "cutoff_sigma": CUTOFF, "lr": LR, "tiling": tl,
                        "l2": "inputs (%.2f GB per step) larger than L2" % (B * N * 4 / 1e9)},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "final_loss": final_loss}
+            "cpu_baseline": cpu_baseline, "final_loss": final_loss, "trace_update": mu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
