@@ -22,6 +22,12 @@
 #include "../../include/dnmf_b200.h"
 #include "dnmf_device.cuh"
 
+#ifndef DNMF_ZUNROLL
+#define DNMF_ZUNROLL 1  // z steps interleaved per lane in the fused kernel's main loop
+#endif
+namespace dnmf {
+constexpr int kZUnroll = DNMF_ZUNROLL;
+}
 #ifndef DNMF_MINB
 #define DNMF_MINB 22  // resident single-warp CTAs per SM the fused kernel is compiled for (register budget)
 #endif
@@ -593,6 +599,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
   }
   unsigned yaddr = smem_u32(sY + lx * RS + ly * zs);  // walks the lane's column of the Y tile, 4 B per z step
   float zf = (float)z0;
+#pragma unroll kZUnroll
   for (int zz = 0; zz < nz; ++zz, zf += 1.f, yaddr += 4u) {
     const float q0 = fmaf(zf, fmaf(zf, c2[0], c1[0]), c0[0]);
     const float q1 = fmaf(zf, fmaf(zf, c2[1], c1[1]), c0[1]);
