@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "dnmf_kernels.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "dnmf_device.cuh"), os.path.join(HERE, "csrc", "dnmf_mu.inc.cu"),
+DEPS = [SRC, os.path.join(HERE, "csrc", "dnmf_device.cuh"), os.path.join(HERE, "csrc", "dnmf_mu.inc.cu"), os.path.join(HERE, "csrc", "dnmf_ext.inc.cu"),
         os.path.join(os.path.dirname(HERE), "include", "dnmf_b200.h")]
 OUT_DIR = os.path.join(HERE, "_C")
 OUT = os.path.join(OUT_DIR, "libdnmf_b200.so")

@@ -1,0 +1,246 @@
+// North-star EXTENSION (no counterpart in the reference, default OFF): gradients of the loss with
+// respect to the SHARED parameters -- neuron positions pos[K][3], widths sigma[K] and a scalar background
+// b -- so that they can be learned next to the per-frame deformation.  Frames are sharded over GPUs, so
+// these are the only gradients that need a collective (one small all-reduce per iteration).
+//
+//   Yhat_t(p) = sum_k C[k,t] A_t(p,k; pos, sigma) + b,     A = discretised Gaussian resampled trilinearly
+//   dL/dpos_kd  = (2/BN) sum_t sum_p r_t(p) C[k,t] a'_kd prod_{e!=d} a_ke,  a' = lerp of dG/dpos
+//   dL/dsigma_k = (2/BN) sum_t sum_p r_t(p) C[k,t] sum_d a^s_kd prod_{e!=d} a_ke,  a^s = lerp of dG/dsigma
+//   dL/db       = (2/BN) sum_t sum_p r_t(p)
+//
+// fit_tile_kernel<MODE=2> writes the residual r; param_grad_kernel (one warp per 8x8xtz tile) walks the
+// tile's neuron list four slots at a time, accumulates the 4 values per slot in registers over the whole
+// tile, reduces across the warp and adds them with fp64 atomics.  Oracle: torch autograd over an extended
+// restatement (oracle.ExtendedPort); every test of this file is labelled "extension, not reference parity".
+namespace dnmf {
+
+constexpr int kExtTX = 8, kExtTY = 8;
+
+struct ExtParams {
+  const float* resid;  // [B][X][Y][Z]
+  const int* frame_ids;
+  const float* beta;
+  const float* C;
+  const float2* tab[3];
+  const float2* tabp[3];
+  const float2* tabs[3];
+  const int* rng;
+  double* gpos;  // [K][3]
+  double* gsig;  // [K]
+  double scale;  // 2 / (B_global * N)
+  int X, Y, Z, K, T;
+  int tz, ntx, nty, ntz;
+};
+
+__global__ void __launch_bounds__(32) param_grad_kernel(const __grid_constant__ ExtParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sBeta = reinterpret_cast<float*>(smem_raw);             // 32 floats
+  int* sInt = reinterpret_cast<int*>(sBeta + 32);                // 8 ints
+  unsigned short* sList = reinterpret_cast<unsigned short*>(sInt + 8);
+
+  const int lane = threadIdx.x;
+  const int bx = blockIdx.x, by = blockIdx.y;
+  const int b = (int)blockIdx.z / p.ntz, bz = (int)blockIdx.z - b * p.ntz;
+  const int t = p.frame_ids[b];
+  const int x0 = bx * kExtTX, y0 = by * kExtTY, z0 = bz * p.tz;
+  const int nx = min(kExtTX, p.X - x0), ny = min(kExtTY, p.Y - y0), nz = min(p.tz, p.Z - z0);
+  const size_t N = (size_t)p.X * p.Y * p.Z;
+  const float* __restrict__ resid = p.resid + (size_t)b * N;
+
+  if (lane < 30) sBeta[lane] = p.beta[(size_t)lane * p.T + t];
+  __syncwarp();
+  if (lane < 3) {
+    const int s = lane == 0 ? p.X : (lane == 1 ? p.Y : p.Z);
+    int wlo, whi;
+    tile_window_axis(sBeta + lane, 3, (float)x0, (float)y0, (float)z0, (float)(x0 + nx - 1), (float)(y0 + ny - 1),
+                     (float)(z0 + nz - 1), s, wlo, whi);
+    sInt[lane] = wlo;
+    sInt[3 + lane] = whi;
+  }
+  __syncwarp();
+  int wlo[3], whi[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    wlo[d] = sInt[d];
+    whi[d] = sInt[3 + d];
+  }
+  int L = 0;
+  for (int k0 = 0; k0 < p.K; k0 += 32) {
+    const int k = k0 + lane;
+    const bool ok = (k < p.K) && neuron_in_window(p.rng + (size_t)k * 6, wlo, whi);
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (ok) sList[L + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
+    L += __popc(m);
+  }
+  __syncwarp();
+  if (L == 0) return;
+
+  const int lx = lane & 7, lyb = lane >> 3;
+  const int gx = x0 + lx;
+  const float xf = (float)gx;
+  const float sm1x = (float)(p.X - 1), sm1y = (float)(p.Y - 1), sm1z = (float)(p.Z - 1);
+  const int sX3 = p.X + 3, sY3 = p.Y + 3, sZ3 = p.Z + 3;
+
+  for (int j0 = 0; j0 < L; j0 += 4) {
+    float acc[4][4];
+    int kk[4];
+    float ck[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      kk[s] = sList[min(j0 + s, L - 1)];
+      ck[s] = (j0 + s < L) ? __ldg(p.C + (size_t)kk[s] * p.T + t) : 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[s][q] = 0.f;
+    }
+    for (int h = 0; h < kExtTY / kWarpY; ++h) {
+      const int gy = y0 + h * kWarpY + lyb;
+      const bool valid = (gx < p.X) && (gy < p.Y);
+      const float yf = (float)gy;
+      float c0[3], c1[3], c2[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        float v = sBeta[d];
+        v = fmaf(sBeta[3 + d], xf, v);
+        v = fmaf(sBeta[6 + d], yf, v);
+        v = fmaf(sBeta[12 + d], xf * xf, v);
+        v = fmaf(sBeta[15 + d], yf * yf, v);
+        v = fmaf(sBeta[21 + d], xf * yf, v);
+        c0[d] = v;
+        c1[d] = fmaf(sBeta[27 + d], yf, fmaf(sBeta[24 + d], xf, sBeta[9 + d]));
+        c2[d] = sBeta[18 + d];
+      }
+      const float* rcol = resid + ((size_t)min(gx, p.X - 1) * p.Y + min(gy, p.Y - 1)) * p.Z + z0;
+      for (int zz = 0; zz < nz; ++zz) {
+        const float zf = (float)(z0 + zz);
+        int i0, i1, i2;
+        float f0, f1, f2;
+        split_coord(sample_coord(fmaf(zf, fmaf(zf, c2[0], c1[0]), c0[0]), sm1x), p.X, i0, f0);
+        split_coord(sample_coord(fmaf(zf, fmaf(zf, c2[1], c1[1]), c0[1]), sm1y), p.Y, i1, f1);
+        split_coord(sample_coord(fmaf(zf, fmaf(zf, c2[2], c1[2]), c0[2]), sm1z), p.Z, i2, f2);
+        const float r = valid ? __ldg(rcol + zz) : 0.f;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const size_t k = (size_t)kk[s];
+          const float2 e0 = __ldg(p.tab[0] + k * sX3 + (i0 + 2)), e1 = __ldg(p.tab[1] + k * sY3 + (i1 + 2)),
+                       e2 = __ldg(p.tab[2] + k * sZ3 + (i2 + 2));
+          const float2 q0 = __ldg(p.tabp[0] + k * sX3 + (i0 + 2)), q1 = __ldg(p.tabp[1] + k * sY3 + (i1 + 2)),
+                       q2 = __ldg(p.tabp[2] + k * sZ3 + (i2 + 2));
+          const float2 s0 = __ldg(p.tabs[0] + k * sX3 + (i0 + 2)), s1 = __ldg(p.tabs[1] + k * sY3 + (i1 + 2)),
+                       s2 = __ldg(p.tabs[2] + k * sZ3 + (i2 + 2));
+          const float a0 = fmaf(f0, e0.y, e0.x), a1 = fmaf(f1, e1.y, e1.x), a2 = fmaf(f2, e2.y, e2.x);
+          const float p0 = fmaf(f0, q0.y, q0.x), p1 = fmaf(f1, q1.y, q1.x), p2 = fmaf(f2, q2.y, q2.x);
+          const float g0 = fmaf(f0, s0.y, s0.x), g1 = fmaf(f1, s1.y, s1.x), g2 = fmaf(f2, s2.y, s2.x);
+          const float w = r * ck[s];
+          const float a12 = a1 * a2, a02 = a0 * a2, a01 = a0 * a1;
+          acc[s][0] = fmaf(w, p0 * a12, acc[s][0]);
+          acc[s][1] = fmaf(w, p1 * a02, acc[s][1]);
+          acc[s][2] = fmaf(w, p2 * a01, acc[s][2]);
+          acc[s][3] = fmaf(w, fmaf(g0, a12, fmaf(g1, a02, g2 * a01)), acc[s][3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[s][q] = warp_sum(acc[s][q]);
+      if (lane == 0 && j0 + s < L) {
+        const int k = kk[s];
+        atomicAdd(p.gpos + (size_t)k * 3 + 0, (double)acc[s][0] * p.scale);
+        atomicAdd(p.gpos + (size_t)k * 3 + 1, (double)acc[s][1] * p.scale);
+        atomicAdd(p.gpos + (size_t)k * 3 + 2, (double)acc[s][2] * p.scale);
+        atomicAdd(p.gsig + k, (double)acc[s][3] * p.scale);
+      }
+    }
+  }
+}
+
+__global__ void ext_finish_kernel(const double* __restrict__ sumr, int B, double scale, double* __restrict__ gbg) {
+  if (threadIdx.x < 32) {
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < B; j += 32) acc += sumr[j];
+    acc = warp_sum_d(acc);
+    if (threadIdx.x == 0) *gbg = acc * scale;
+  }
+}
+
+}  // namespace dnmf
+
+using namespace dnmf;
+
+extern "C" int dnmf_ext_enable(dnmf_ctx* c) {
+  if (!c) return fail("dnmf_ext_enable: ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  const int s[3] = {c->X, c->Y, c->Z};
+  for (int d = 0; d < 3; ++d) {
+    if (!c->d_tab_dpos[d]) CU(cudaMalloc((void**)&c->d_tab_dpos[d], (size_t)c->K * (s[d] + 3) * sizeof(float2)));
+    if (!c->d_tab_dsig[d]) CU(cudaMalloc((void**)&c->d_tab_dsig[d], (size_t)c->K * (s[d] + 3) * sizeof(float2)));
+  }
+  c->have_footprints = false;  // tables must be rebuilt so that the derivative tables exist
+  return 0;
+}
+
+extern "C" int dnmf_ext_loss_grad(dnmf_ctx* c, const float* frames_dev, const int32_t* frame_ids_dev, int B,
+                                  int B_global, const float* beta_dev, const float* C_dev, float background,
+                                  float* grad_beta_dev, double* sse_dev, double* gpos_dev, double* gsig_dev,
+                                  double* gbg_dev, void* stream) {
+  if (!c || !frame_ids_dev || !beta_dev || !C_dev || !grad_beta_dev || !sse_dev || !gpos_dev || !gsig_dev || !gbg_dev)
+    return fail("dnmf_ext_loss_grad: NULL argument");
+  if (!c->d_tab_dpos[0]) return fail("dnmf_ext_loss_grad: call dnmf_ext_enable (then dnmf_set_footprints) first");
+  if (B < 1 || B_global < B) return fail("dnmf_ext_loss_grad: need 1 <= B <= B_global");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaSetDevice(c->device));
+  FitParams p;
+  if (fill_fit_params(c, p, frames_dev, frame_ids_dev, B, beta_dev, C_dev)) return 1;
+  if (ensure(&c->d_resid, &c->resid_cap, (size_t)B * c->N)) return 1;
+  if (ensure(&c->d_sumr, &c->sumr_cap, (size_t)B)) return 1;
+  p.yhat = c->d_resid;
+  p.bg = background;
+  if (dispatch_fit<2>(c, p, B, st)) return 1;
+  const int nt = c->ntx * c->nty * c->ntz;
+  const double scale = 2.0 / ((double)B_global * (double)c->N);
+  reduce_partials_kernel<<<B, 256, 0, st>>>(c->d_partials, frame_ids_dev, nt, c->T, scale, grad_beta_dev, sse_dev,
+                                            c->d_sumr);
+  CU(cudaGetLastError());
+  ext_finish_kernel<<<1, 32, 0, st>>>(c->d_sumr, B, scale, gbg_dev);
+  CU(cudaGetLastError());
+  CU(cudaMemsetAsync(gpos_dev, 0, (size_t)c->K * 3 * sizeof(double), st));
+  CU(cudaMemsetAsync(gsig_dev, 0, (size_t)c->K * sizeof(double), st));
+  ExtParams e;
+  e.resid = c->d_resid;
+  e.frame_ids = frame_ids_dev;
+  e.beta = beta_dev;
+  e.C = C_dev;
+  for (int d = 0; d < 3; ++d) {
+    e.tab[d] = c->d_tab[d];
+    e.tabp[d] = c->d_tab_dpos[d];
+    e.tabs[d] = c->d_tab_dsig[d];
+  }
+  e.rng = c->d_rng;
+  e.gpos = gpos_dev;
+  e.gsig = gsig_dev;
+  e.scale = scale;
+  e.X = c->X;
+  e.Y = c->Y;
+  e.Z = c->Z;
+  e.K = c->K;
+  e.T = c->T;
+  e.tz = c->tz;
+  e.ntx = (c->X + kExtTX - 1) / kExtTX;
+  e.nty = (c->Y + kExtTY - 1) / kExtTY;
+  e.ntz = c->ntz;
+  if (e.nty > 65535) return fail("dnmf_ext_loss_grad: more than 65535 tiles along y");
+  const size_t smem = 32 * 4 + 8 * 4 + (size_t)((c->K + 7) & ~7) * 2;
+  const int maxB = std::max(1, 65535 / e.ntz);
+  for (int b0 = 0; b0 < B; b0 += maxB) {
+    const int nb = std::min(maxB, B - b0);
+    ExtParams q = e;
+    q.frame_ids = frame_ids_dev + b0;
+    q.resid = c->d_resid + (size_t)b0 * c->N;
+    dim3 grid((unsigned)e.ntx, (unsigned)e.nty, (unsigned)(nb * e.ntz));
+    param_grad_kernel<<<grid, 32, smem, st>>>(q);
+    CU(cudaGetLastError());
+  }
+  c->counters[0] += 1;
+  c->counters[1] += 1;
+  return 0;
+}

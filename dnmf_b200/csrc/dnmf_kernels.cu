@@ -84,9 +84,23 @@ __global__ void build_ranges_kernel(const float* __restrict__ pos, const float* 
   }
 }
 
+// d/dpos and d/dsigma of a node value (extension: learnable positions / widths); same truncation window
+__device__ __forceinline__ void gauss_node_derivs(int i, float pos, float sigma, int lo, int hi, float& dpos,
+                                                  float& dsig) {
+  dpos = 0.f;
+  dsig = 0.f;
+  if (i < lo || i > hi) return;
+  const float d = __fsub_rn((float)i, pos);
+  const float s2 = __fmul_rn(sigma, sigma);
+  const float g = expf(-__fdiv_rn(__fmul_rn(d, d), s2));
+  dpos = g * 2.f * d / s2;
+  dsig = g * 2.f * d * d / (s2 * sigma);
+}
+
 __global__ void build_tables_kernel(const float* __restrict__ pos, const float* __restrict__ sigma,
                                     const int* __restrict__ rng, int K, int s, int axis,
-                                    float2* __restrict__ tab) {
+                                    float2* __restrict__ tab, float2* __restrict__ tab_dpos,
+                                    float2* __restrict__ tab_dsig) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;  // entry within a neuron's row, i = e - 2
   int k = blockIdx.y;
   if (e >= s + 3) return;
@@ -96,6 +110,13 @@ __global__ void build_tables_kernel(const float* __restrict__ pos, const float* 
   float g0 = gauss_node(i, p, sg, lo, hi);
   float g1 = gauss_node(i + 1, p, sg, lo, hi);
   tab[(size_t)k * (s + 3) + e] = make_float2(g0, __fsub_rn(g1, g0));
+  if (tab_dpos != nullptr) {
+    float p0, s0, p1, s1;
+    gauss_node_derivs(i, p, sg, lo, hi, p0, s0);
+    gauss_node_derivs(i + 1, p, sg, lo, hi, p1, s1);
+    tab_dpos[(size_t)k * (s + 3) + e] = make_float2(p0, p1 - p0);
+    tab_dsig[(size_t)k * (s + 3) + e] = make_float2(s0, s1 - s0);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -230,7 +251,8 @@ struct FitParams {
   const float2* tab2;
   const int* rng;
   float* partials;
-  float* yhat;
+  float* yhat;   // MODE 1: Yhat output; MODE 2: residual output
+  float bg;      // MODE 2: scalar background added to Yhat
   int frames_are_batch;
   int X, Y, Z, K, T;
   int tz, ntx, nty, ntz;
@@ -355,8 +377,12 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 
 // SUB = y-adjacent 8x4 sub-tiles processed one after the other by each warp: they share the tile
 // prologue (window, list, staging, TMA) and the reduction epilogue.
-template <int NWX, int NWY, int SUB, bool WRITE_YHAT, bool FAST_DIV>
+// MODE 0: fit (loss + gradient).  MODE 1: forward only, writes Yhat.  MODE 2: fit with a scalar background
+// added to Yhat, and the residual written out for the shared-parameter gradient kernel (extension).
+template <int NWX, int NWY, int SUB, int MODE, bool FAST_DIV>
 __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB : 1) fit_tile_kernel(const __grid_constant__ FitParams p) {
+  constexpr bool WRITE_YHAT = MODE == 1;
+  constexpr bool WRITE_RES = MODE == 2;
   constexpr int NW = NWX * NWY;
   constexpr int TX = kWarpX * NWX, TY = kWarpY * NWY * SUB;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -553,7 +579,8 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
   const float sm1x = pin((float)(p.X - 1)), sm1y = pin((float)(p.Y - 1)), sm1z = pin((float)(p.Z - 1));
   const float rcpx = pin(p.rcp0), rcpy = pin(p.rcp1), rcpz = pin(p.rcp2);
   float S0[SUB][3], S1[SUB][3], S2[3] = {0.f, 0.f, 0.f};
-  float sse = 0.f;
+  float sse = 0.f, sum_r = 0.f;
+  const float bg = WRITE_RES ? p.bg : 0.f;
   // shared-memory byte addresses of the three slice regions; one table entry = CAP slots of 8 B
   const unsigned strideB = pin((unsigned)CAP * 8u);
   const unsigned baseX = pin(smem_u32(sTab));
@@ -684,7 +711,11 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
     float yv;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(yv) : "r"(yaddr));
     if (WRITE_YHAT) asm volatile("st.shared.f32 [%0], %1;" ::"r"(yaddr), "f"(yh) : "memory");
-    const float r = valid ? (yh - yv) : 0.f;
+    const float r = valid ? (WRITE_RES ? ((yh + bg) - yv) : (yh - yv)) : 0.f;
+    if (WRITE_RES) {
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(yaddr), "f"(r) : "memory");
+      sum_r += r;
+    }
     sse = fmaf(r, r, sse);
     const float h0 = r * g0, h1 = r * g1, h2 = r * g2;
     const float zf2 = zf * zf;
@@ -728,7 +759,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
       v[9 * 3 + d] = y1s;
     }
     v[30] = sse;
-    v[31] = 0.f;
+    v[31] = sum_r;  // sum of residuals (gradient of the scalar background), MODE 2 only
     const float tot = warp_transpose_sum(v, lane);
     if (NW == 1) {
       p.partials[(size_t)cta_linear * kNumPartials + lane] = tot;
@@ -745,7 +776,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
       p.partials[(size_t)cta_linear * kNumPartials + tid] = v;
     }
   }
-  if (WRITE_YHAT) {
+  if (WRITE_YHAT || WRITE_RES) {
     __syncthreads();
     float* out = p.yhat + (size_t)b * ((size_t)p.X * p.Y * p.Z);
     if (p.full_depth) {
@@ -770,7 +801,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
 // write the frame's gradient column and its sum of squared residuals.  grid = B, block = 256.
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, const int* __restrict__ frame_ids,
                                        int nt, int T, double grad_scale, float* __restrict__ grad,
-                                       double* __restrict__ sse_out) {
+                                       double* __restrict__ sse_out, double* __restrict__ sumr_out) {
   __shared__ double s[8][kNumPartials];
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* src = partials + (size_t)b * nt * kNumPartials;
@@ -785,6 +816,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, const
     const int t = frame_ids[b];
     if (lane < 30) grad[(size_t)lane * T + t] = (float)(v * grad_scale);
     if (lane == 30) sse_out[b] = v;
+    if (lane == 31 && sumr_out != nullptr) sumr_out[b] = v;
   }
 }
 
@@ -892,6 +924,12 @@ struct dnmf_ctx {
   float *d_pos = nullptr, *d_sigma = nullptr;
   int* d_rng = nullptr;
   float2* d_tab[3] = {nullptr, nullptr, nullptr};
+  float2* d_tab_dpos[3] = {nullptr, nullptr, nullptr};  // extension: d/dpos, d/dsigma tables (dnmf_ext_enable)
+  float2* d_tab_dsig[3] = {nullptr, nullptr, nullptr};
+  float* d_resid = nullptr;
+  size_t resid_cap = 0;
+  double* d_sumr = nullptr;
+  size_t sumr_cap = 0;
   bool have_footprints = false;
   float cutoff = 0.f;
   // tiling
@@ -1045,7 +1083,9 @@ extern "C" void dnmf_destroy(dnmf_ctx* c) {
                   c->d_tab[2],  c->d_video, c->d_partials,   c->d_grad,        c->d_sse,
                   c->d_batch,   c->d_ids,   c->d_loss,       c->d_tmp_counts,  c->d_tmp_offsets,
                   c->d_tmp_max, c->d_G,     c->d_b,          c->d_identity_beta,
-                  c->d_Cd[0],   c->d_Cd[1], c->d_keys,       c->d_cand_off,    c->d_cand_ids};
+                  c->d_Cd[0],   c->d_Cd[1], c->d_keys,       c->d_cand_off,    c->d_cand_ids,
+                  c->d_tab_dpos[0], c->d_tab_dpos[1], c->d_tab_dpos[2], c->d_tab_dsig[0], c->d_tab_dsig[1],
+                  c->d_tab_dsig[2], c->d_resid, c->d_sumr};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete c;
@@ -1205,7 +1245,8 @@ extern "C" int dnmf_set_footprints(dnmf_ctx* c, const float* pos_host, const flo
   const int s[3] = {c->X, c->Y, c->Z};
   for (int d = 0; d < 3; ++d) {
     dim3 grid((s[d] + 3 + 127) / 128, c->K);
-    build_tables_kernel<<<grid, 128, 0, st>>>(c->d_pos, c->d_sigma, c->d_rng, c->K, s[d], d, c->d_tab[d]);
+    build_tables_kernel<<<grid, 128, 0, st>>>(c->d_pos, c->d_sigma, c->d_rng, c->K, s[d], d, c->d_tab[d],
+                                              c->d_tab_dpos[d], c->d_tab_dsig[d]);
     CU(cudaGetLastError());
   }
   c->have_footprints = true;
@@ -1288,9 +1329,9 @@ extern "C" int dnmf_bin_tiles(dnmf_ctx* c, const float* beta_dev, const int32_t*
 }
 
 // ---- fused step -----------------------------------------------------------------------------------
-template <int NWX, int NWY, int SUB, bool WY_, bool FD_>
+template <int NWX, int NWY, int SUB, int MD_, bool FD_>
 static int launch_fit(const FitParams& p0, int B, size_t smem, cudaStream_t st) {
-  auto kern = fit_tile_kernel<NWX, NWY, SUB, WY_, FD_>;
+  auto kern = fit_tile_kernel<NWX, NWY, SUB, MD_, FD_>;
   static size_t configured = 0;
   if (smem > configured) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1314,14 +1355,14 @@ static int launch_fit(const FitParams& p0, int B, size_t smem, cudaStream_t st) 
   return 0;
 }
 
-template <bool WY_>
+template <int MD_>
 static int dispatch_fit(dnmf_ctx* c, const FitParams& p, int B, cudaStream_t st) {
   const size_t smem = c->fit_smem;
   if (c->nty > 65535) return fail("dispatch_fit: more than 65535 tiles along y");
   const bool fd = c->fast_div != 0;
 #define DNMF_DISPATCH(a, b, sb)                                                       \
   if (c->nwx == a && c->nwy == b && c->sub == sb)                                      \
-    return fd ? launch_fit<a, b, sb, WY_, true>(p, B, smem, st) : launch_fit<a, b, sb, WY_, false>(p, B, smem, st);
+    return fd ? launch_fit<a, b, sb, MD_, true>(p, B, smem, st) : launch_fit<a, b, sb, MD_, false>(p, B, smem, st);
   DNMF_DISPATCH(1, 1, 1)
   DNMF_DISPATCH(1, 1, 2)
   DNMF_DISPATCH(2, 1, 1)
@@ -1369,6 +1410,7 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
   p.cand_ids = c->d_cand_ids;
   p.cand_expand = c->cand_expand;
   p.yhat = nullptr;
+  p.bg = 0.f;
   const size_t need = (size_t)B * c->ntx * c->nty * c->ntz * kNumPartials;
   if (ensure(&c->d_partials, &c->partials_cap, need)) return 1;
   p.partials = c->d_partials;
@@ -1386,9 +1428,9 @@ extern "C" int dnmf_loss_grad(dnmf_ctx* c, const float* frames_dev, const int32_
   FitParams p;
   if (fill_fit_params(c, p, frames_dev, frame_ids_dev, B, beta_dev, C_dev)) return 1;
   const int nt = c->ntx * c->nty * c->ntz;
-  if (dispatch_fit<false>(c, p, B, st)) return 1;
+  if (dispatch_fit<0>(c, p, B, st)) return 1;
   const double scale = 2.0 / ((double)B_global * (double)c->N);
-  reduce_partials_kernel<<<B, 256, 0, st>>>(c->d_partials, frame_ids_dev, nt, c->T, scale, grad_dev, sse_dev);
+  reduce_partials_kernel<<<B, 256, 0, st>>>(c->d_partials, frame_ids_dev, nt, c->T, scale, grad_dev, sse_dev, nullptr);
   CU(cudaGetLastError());
   c->counters[0] += 1;  // fused launches
   c->counters[1] += 1;  // reduce launches
@@ -1464,7 +1506,7 @@ extern "C" int dnmf_forward(dnmf_ctx* c, const int32_t* frame_ids_dev, int B, co
     FitParams p;
     if (fill_fit_params(c, p, AtC_dev, frame_ids_dev, B, beta_dev, C_dev)) return 1;
     p.yhat = AtC_dev;
-    if (dispatch_fit<true>(c, p, B, st)) return 1;
+    if (dispatch_fit<1>(c, p, B, st)) return 1;
     c->counters[0] += 1;
   }
   if (At_dev || grid_dev) {
@@ -1486,3 +1528,4 @@ extern "C" int dnmf_get_counters(dnmf_ctx* c, int64_t* out) {
 
 // ---- trace update + registered video --------------------------------------------------------------
 #include "dnmf_mu.inc.cu"
+#include "dnmf_ext.inc.cu"

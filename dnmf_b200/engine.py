@@ -239,6 +239,30 @@ class Engine:
                    "dnmf_iwarp")
         return out
 
+    # -- extension: shared-parameter gradients (no reference counterpart) -----------------------------
+    def ext_enable(self):
+        _lib.check(self.lib.dnmf_ext_enable(self._h), "dnmf_ext_enable")
+
+    def ext_loss_grad(self, frame_ids: torch.Tensor, beta, C, background: float = 0.0,
+                      frames: Optional[torch.Tensor] = None, B_global: Optional[int] = None, grad_beta=None):
+        """Returns (grad_beta[10,3,T], sse[B], gpos[K,3], gsig[K], gbg[1]) -- the last three in float64."""
+        _check_dev(beta, torch.float32, "beta")
+        _check_dev(C, torch.float32, "C")
+        ids32 = frame_ids.to(self.device, torch.int32).contiguous()
+        B = int(ids32.numel())
+        if frames is not None:
+            _check_dev(frames, torch.float32, "frames")
+        if grad_beta is None:
+            grad_beta = torch.zeros(10, 3, self.T, dtype=torch.float32, device=self.device)
+        sse = torch.zeros(B, dtype=torch.float64, device=self.device)
+        gpos = torch.zeros(self.K, 3, dtype=torch.float64, device=self.device)
+        gsig = torch.zeros(self.K, dtype=torch.float64, device=self.device)
+        gbg = torch.zeros(1, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.dnmf_ext_loss_grad(self._h, _ptr(frames), _ptr(ids32), B, int(B_global or B), _ptr(beta),
+                                               _ptr(C), float(background), _ptr(grad_beta), _ptr(sse), _ptr(gpos),
+                                               _ptr(gsig), _ptr(gbg), self.stream), "dnmf_ext_loss_grad")
+        return grad_beta, sse, gpos, gsig, gbg
+
     def counters(self) -> dict:
         out = np.zeros(8, np.int64)
         _lib.check(self.lib.dnmf_get_counters(self._h, out.ctypes.data_as(ctypes.c_void_p)), "dnmf_get_counters")

@@ -193,6 +193,8 @@ class DeformableNMF:
         self.loss_history = []                       # python floats / CUDA scalars, one per Adam step
         self._loss_buf = None
         self._video_resident = False
+        self._shared = None                          # extension state (enable_shared_learning)
+        self.background = torch.zeros((), device=dev)
 
     # distance penalty of Demix/dNMF.py:133-135, only used by the (disabled) update_spatial: lazy
     @property
@@ -222,6 +224,54 @@ class DeformableNMF:
             raise DnmfError("video has %d frames, model has T=%d" % (frames.shape[0], self.fp.T))
         self.fp.engine.upload_frames(frames.float().contiguous(), 0, clamp_negative=True)
         self._video_resident = True
+
+    # -- EXTENSION (no reference counterpart, off by default) ---------------------------------------
+    def enable_shared_learning(self, lr_pos=0.0, lr_sigma=0.0, lr_background=0.0, process_group=None):
+        """Also learn the SHARED parameters -- neuron positions, widths and a scalar background added to the
+        model -- with Adam next to the per-frame deformation.  Their gradients come from
+        dnmf_ext_loss_grad; with frames sharded over GPUs they are the only gradients that are all-reduced
+        (one small NCCL all-reduce per iteration).  The reference keeps pos/sigma fixed and has no background
+        (Demix/dNMF.py:29-33), so this has no reference oracle: it is tested against torch autograd."""
+        eng = self.fp.engine
+        eng.ext_enable()
+        self.fp.pos = self.fp.pos.detach().clone().requires_grad_(True)
+        self.fp.sigma = self.fp.sigma.detach().clone().requires_grad_(True)
+        self.background = self.background.detach().clone().requires_grad_(True)
+        groups = [{"params": [self.fp.pos], "lr": lr_pos}, {"params": [self.fp.sigma], "lr": lr_sigma},
+                  {"params": [self.background], "lr": lr_background}]
+        self._shared = {"opt": torch.optim.Adam(groups), "group": process_group}
+        eng.set_footprints(self.fp.pos, self.fp.sigma, self.fp.cutoff)
+
+    def _shared_step(self, ids, frames_dev, optimizer_group, st, step, B_global):
+        """One iteration with shared-parameter learning: fused kernel (residual written) + parameter
+        gradient kernel, all-reduce of the shared gradients, device Adam on beta, Adam on pos/sigma/b,
+        table rebuild."""
+        import torch.distributed as dist
+        eng = self.fp.engine
+        beta = self.fp.beta.detach()
+        grad = getattr(self, "_ext_grad", None)
+        if grad is None:
+            grad = self._ext_grad = torch.zeros_like(beta)
+        _, sse, gpos, gsig, gbg = eng.ext_loss_grad(ids, beta, self.C, float(self.background.detach()), frames=frames_dev,
+                                                    B_global=B_global, grad_beta=grad)
+        loss = sse.sum() / (B_global * eng.N)
+        group = self._shared["group"]
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            flat = torch.cat((gpos.reshape(-1), gsig, gbg, loss.reshape(1)))
+            dist.all_reduce(flat, group=group)       # the one collective of the extension
+            K = eng.K
+            gpos, gsig, gbg, loss = flat[:3 * K].reshape(K, 3), flat[3 * K:4 * K], flat[4 * K:4 * K + 1], flat[4 * K + 1]
+        eng.adam_step(beta, grad, st["exp_avg"], st["exp_avg_sq"], optimizer_group["lr"], optimizer_group["betas"],
+                      optimizer_group["eps"], step, self.affine)
+        self.fp.pos.grad = gpos.float()
+        self.fp.sigma.grad = gsig.float()
+        self.background.grad = gbg.float().reshape(())
+        self._shared["opt"].step()
+        with torch.no_grad():
+            self.fp.sigma.clamp_(min=0.5)
+        eng.set_footprints(self.fp.pos, self.fp.sigma, self.fp.cutoff)
+        self.fp._A = None
+        return loss
 
     # -- Adam state shared with the caller's optimiser ---------------------------------------------
     def _adam_state(self, optimizer):
@@ -257,7 +307,11 @@ class DeformableNMF:
                 ids = torch.as_tensor(data[1]).to(torch.int32)
                 step = int(st["step"]) + 1
                 lr, betas, eps = group["lr"], group["betas"], group["eps"]
-                if self._video_resident:
+                if self._shared is not None:
+                    fd = None if self._video_resident else data[0].float().to(eng.device).contiguous()
+                    loss = self._shared_step(ids.to(eng.device), fd, group, st, step,
+                                             ids.numel() * self.global_batch_scale)
+                elif self._video_resident:
                     if self._loss_buf is None:
                         self._loss_buf = torch.zeros(1024, dtype=torch.float64, device=eng.device)
                     slot = self._loss_buf[(step - 1) % 1024:(step - 1) % 1024 + 1]

@@ -123,6 +123,19 @@ int dnmf_mu_sweeps(dnmf_ctx* ctx, float* C_dev, double gamma, int use_gamma, int
 int dnmf_iwarp(dnmf_ctx* ctx, const float* frames_dev, const int32_t* frame_ids_dev, int B,
                const float* beta_dev, float* out_dev, void* stream);
 
+/* EXTENSION (no counterpart in the reference, off unless called): gradients of the same loss with respect
+ * to the shared parameters -- positions pos[K][3], widths sigma[K] and a scalar background b added to the
+ * model -- for callers that learn them next to the deformation.  dnmf_ext_enable allocates the derivative
+ * tables (call dnmf_set_footprints afterwards).  dnmf_ext_loss_grad does what dnmf_loss_grad does (with b
+ * added to Yhat) and also writes gpos_dev[K][3], gsig_dev[K], gbg_dev[1] (fp64, scaled by 2/(B_global*N),
+ * summed over the B frames); with frames sharded over GPUs these three arrays are the only gradients that
+ * need an all-reduce. */
+int dnmf_ext_enable(dnmf_ctx* ctx);
+int dnmf_ext_loss_grad(dnmf_ctx* ctx, const float* frames_dev, const int32_t* frame_ids_dev, int B,
+                       int B_global, const float* beta_dev, const float* C_dev, float background,
+                       float* grad_beta_dev, double* sse_dev, double* gpos_dev, double* gsig_dev,
+                       double* gbg_dev, void* stream);
+
 /* FFMA microbenchmark: best-of-`repeats` dense FP32 throughput of the device in TFLOP/s (FMA = 2);
  * the roofline denominator for the FP32-bound fused kernel (MEASURED_PEAKS.json has no FP32 entry). */
 int dnmf_measure_fp32_peak(int device, int repeats, double* tflops_out);

@@ -401,3 +401,43 @@ def bin_tiles(beta: np.ndarray, times: Sequence[int], rng: np.ndarray, sz, tile)
     np.cumsum(counts, out=offsets[1:])
     ids = np.concatenate(ids) if ids else np.zeros(0, np.int32)
     return counts, offsets, ids, np.asarray(wins, np.int32).reshape(len(times) * nt, 3, 2)
+
+
+# ------------------------------------------------------------------------------------------------
+# 4. EXTENSION oracle (no reference counterpart): learnable positions, widths and scalar background
+# ------------------------------------------------------------------------------------------------
+
+
+class ExtendedPort:
+    """torch-autograd restatement of the extended model Yhat = sum_k C_k A_t(pos, sigma) + b, where the
+    discretised Gaussian volume of Demix/dNMF.py:39-40 is rebuilt from LEAF pos / sigma on every forward
+    (the reference keeps them fixed).  Used only to test the shared-parameter gradient kernel; every test
+    built on it is labelled "extension, not reference parity"."""
+
+    def __init__(self, sz, positions, sigma, C, beta, background=0.0):
+        self.sz = torch.as_tensor(sz).long()
+        self.grid_id, self.phi = voxel_basis(self.sz.tolist())
+        self.pos = torch.as_tensor(positions).float().clone().requires_grad_(True)
+        self.sigma = torch.as_tensor(sigma).float().clone().requires_grad_(True)
+        self.bg = torch.tensor(float(background), requires_grad=True)
+        self.beta = torch.as_tensor(beta).float().clone().requires_grad_(True)
+        self.C = torch.as_tensor(C).float()
+
+    def loss(self, frames: torch.Tensor, times: Sequence[int]) -> torch.Tensor:
+        times = list(times)
+        A = gaussian_volume(self.grid_id, self.pos, self.sigma)
+        q = torch.einsum("mnza,abt->mnzbt", self.phi, self.beta[:, :, times])
+        u = 2 * q / (self.sz[None, None, None, :, None] - 1) - 1
+        vol = A.permute(3, 2, 1, 0)[None].expand(len(times), -1, -1, -1, -1)
+        A_t = F.grid_sample(vol, u.permute(4, 2, 1, 0, 3), mode="bilinear", padding_mode="zeros",
+                            align_corners=True).permute(0, 1, 4, 3, 2)
+        yhat = torch.einsum("tkmnz,kt->tmnz", A_t, self.C[:, times]) + self.bg
+        return F.mse_loss(yhat, frames)
+
+    def grads(self, frames, times):
+        for t in (self.pos, self.sigma, self.bg, self.beta):
+            t.grad = None
+        loss = self.loss(frames, times)
+        loss.backward()
+        return (float(loss.detach()), self.beta.grad.numpy(), self.pos.grad.numpy(), self.sigma.grad.numpy(),
+                float(self.bg.grad))
