@@ -963,6 +963,7 @@ struct dnmf_ctx {
   long long* d_tmp_offsets = nullptr;
   int* d_tmp_max = nullptr;
   float* d_identity_beta = nullptr;
+  int* d_ids_zero = nullptr;
   // mu statistics
   double* d_G = nullptr;  // [T][K][K]
   double* d_b = nullptr;  // [T][K]
@@ -1040,6 +1041,8 @@ extern "C" int dnmf_create(dnmf_ctx** out, int X, int Y, int Z, int K, int T, in
   memset(idb, 0, sizeof(idb));
   idb[1 * 3 + 0] = idb[2 * 3 + 1] = idb[3 * 3 + 2] = 1.f;
   CU(cudaMemcpy(c->d_identity_beta, idb, sizeof(idb), cudaMemcpyHostToDevice));
+  CU(cudaMalloc((void**)&c->d_ids_zero, sizeof(int)));
+  CU(cudaMemset(c->d_ids_zero, 0, sizeof(int)));
   // enable the 3-instruction exact division only after an exhaustive device-side proof per axis size
   {
     static std::mutex mu;
@@ -1085,7 +1088,7 @@ extern "C" void dnmf_destroy(dnmf_ctx* c) {
                   c->d_tmp_max, c->d_G,     c->d_b,          c->d_identity_beta,
                   c->d_Cd[0],   c->d_Cd[1], c->d_keys,       c->d_cand_off,    c->d_cand_ids,
                   c->d_tab_dpos[0], c->d_tab_dpos[1], c->d_tab_dpos[2], c->d_tab_dsig[0], c->d_tab_dsig[1],
-                  c->d_tab_dsig[2], c->d_resid, c->d_sumr};
+                  c->d_tab_dsig[2], c->d_resid, c->d_sumr, c->d_ids_zero};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete c;
@@ -1213,7 +1216,25 @@ static int configure_tiling_fixed(dnmf_ctx* c, cudaStream_t st) {
     CU(cudaStreamSynchronize(st));
   }
   cudaFree(d_zero);
-  int cap = c->user_cap > 0 ? c->user_cap : c->lmax_identity + c->lmax_identity / 4 + 2;
+  // Staged-slot capacity: the smallest capacity that keeps all but ~2 % of the (tile, neuron) pairs of the
+  // identity-deformation lists in shared memory (+1 slot of slack).  The few longest lists send their tail
+  // through the L2-resident tables instead of forcing every CTA to reserve shared memory for the maximum.
+  int cap = c->user_cap;
+  if (cap <= 0) {
+    std::vector<int> h_counts((size_t)nt);
+    if (run_bin_count(c, c->d_identity_beta, 1, c->d_ids_zero, 1, c->d_tmp_counts, nullptr, st)) return 1;
+    CU(cudaMemcpyAsync(h_counts.data(), c->d_tmp_counts, (size_t)nt * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    long long total = 0;
+    for (int v : h_counts) total += v;
+    cap = 2;
+    for (;; cap += 1) {
+      long long over = 0;
+      for (int v : h_counts) over += std::max(0, v - cap);
+      if (over * 50 <= total || cap >= c->lmax_identity) break;
+    }
+    cap += 1;
+  }
   cap = std::max(2, std::min(cap, c->K + 1));
   cap = (cap + 1) & ~1;               // slots are consumed in pairs (LDS.128)
   if ((cap & 3) == 0) cap += 2;       // slot-row stride = 2 (mod 4) float2: spreads entries over banks
