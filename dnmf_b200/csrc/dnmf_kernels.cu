@@ -939,6 +939,7 @@ struct dnmf_ctx {
   int tx = 8, ty = 4, ntx = 0, nty = 0, ntz = 0;
   int wmax[3] = {0, 0, 0};
   int lmax_identity = 0;
+  double mean_list_identity = 0.0;
   size_t fit_smem = 0;
   int fast_div = 0;
   float rcp[3] = {0.f, 0.f, 0.f};
@@ -1143,22 +1144,26 @@ static int configure_tiling_fixed(dnmf_ctx* c, cudaStream_t st);
 // of the table slices, or shared memory caps occupancy at a few warps per SM.
 static int configure_tiling(dnmf_ctx* c, cudaStream_t st) {
   if (!c->auto_tiling) return configure_tiling_fixed(c, st);
+  // Instruction-count model of the fused kernel per 32-voxel row (from the ncu source pages, profiles/):
+  // ~85 fixed + ~9.5 per listed neuron + the tile prologue/epilogue amortised over the rows of the tile,
+  // inflated when shared memory leaves fewer than ~12 warps per SM to hide latency.
   static const int layouts[5][3] = {{1, 1, 2}, {1, 1, 1}, {2, 1, 1}, {2, 2, 1}, {2, 4, 1}};
   int best = 0;
-  double best_per_warp = 1e30;
+  double best_cost = 1e300;
   for (int i = 0; i < 5; ++i) {
     c->nwx = layouts[i][0];
     c->nwy = layouts[i][1];
     c->sub = layouts[i][2];
     if (configure_tiling_fixed(c, st)) return 1;
-    const double per_warp = (double)c->fit_smem / (c->nwx * c->nwy);
-    if (per_warp < best_per_warp) {
-      best_per_warp = per_warp;
+    const int nw = c->nwx * c->nwy;
+    const int ctas = std::min(32, (int)((size_t)227 * 1024 / (c->fit_smem + 1024)));
+    const double warps = std::min(64, ctas * nw);
+    const double rows = (double)c->sub * c->tz;
+    double cost = (85.0 + 9.5 * c->mean_list_identity + (300.0 + 600.0 / nw) / rows) * std::max(1.0, 12.0 / warps);
+    if (nw > 1 && c->mean_list_identity < 16.0) cost *= 1.25;  // sharing the staged slices only pays for long lists
+    if (cost < best_cost) {
+      best_cost = cost;
       best = i;
-    }
-    if (per_warp <= 12.0 * 1024) {
-      best = i;
-      break;
     }
   }
   c->nwx = layouts[best][0];
@@ -1220,13 +1225,14 @@ static int configure_tiling_fixed(dnmf_ctx* c, cudaStream_t st) {
   // identity-deformation lists in shared memory (+1 slot of slack).  The few longest lists send their tail
   // through the L2-resident tables instead of forcing every CTA to reserve shared memory for the maximum.
   int cap = c->user_cap;
+  std::vector<int> h_counts((size_t)nt);
+  if (run_bin_count(c, c->d_identity_beta, 1, c->d_ids_zero, 1, c->d_tmp_counts, nullptr, st)) return 1;
+  CU(cudaMemcpyAsync(h_counts.data(), c->d_tmp_counts, (size_t)nt * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  long long total = 0;
+  for (int v : h_counts) total += v;
+  c->mean_list_identity = nt > 0 ? (double)total / nt : 0.0;
   if (cap <= 0) {
-    std::vector<int> h_counts((size_t)nt);
-    if (run_bin_count(c, c->d_identity_beta, 1, c->d_ids_zero, 1, c->d_tmp_counts, nullptr, st)) return 1;
-    CU(cudaMemcpyAsync(h_counts.data(), c->d_tmp_counts, (size_t)nt * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    long long total = 0;
-    for (int v : h_counts) total += v;
     cap = 2;
     for (;; cap += 1) {
       long long over = 0;
