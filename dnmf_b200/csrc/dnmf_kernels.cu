@@ -284,14 +284,16 @@ static FitSmem fit_smem_layout(int nw, int tx, int ty, int tz, int cap, int wsum
   return s;
 }
 
-// un-normalised sample coordinate, fast exact-division form (see verify_coord_kernel)
-__device__ __forceinline__ float sample_coord_fast(float q, float sm1, float rcp) {
-  const float x = __fadd_rn(q, q);
-  const float q0 = __fmul_rn(x, rcp);
-  const float r = __fmaf_rn(-q0, sm1, x);
+// un-normalised sample coordinate, fast form (see verify_coord_kernel).  Input is x2 = 2q (the main loop
+// gets it for free by doubling the Horner coefficients: scaling by 2 is exact).  The division by s-1 is the
+// exact 3-instruction sequence, and the final fl(fl(w*0.5)*(s-1)) is folded into one multiply by
+// (s-1)/2, which is exact because w*0.5 is exact and (s-1)/2 is representable.
+__device__ __forceinline__ float sample_coord_fast(float x2, float sm1, float rcp, float half_sm1) {
+  const float q0 = __fmul_rn(x2, rcp);
+  const float r = __fmaf_rn(-q0, sm1, x2);
   const float v = __fmaf_rn(r, rcp, q0);
   const float u = __fsub_rn(v, 1.f);
-  return __fmul_rn(__fmul_rn(__fadd_rn(u, 1.f), 0.5f), sm1);
+  return __fmul_rn(__fadd_rn(u, 1.f), half_sm1);
 }
 
 // Exhaustive check over all 2^32 float bit patterns that the fast form equals the reference op
@@ -304,7 +306,7 @@ __global__ void verify_coord_kernel(float sm1, float rcp, unsigned long long* __
     if (((bits >> 23) & 0xffu) >= 253u) continue;  // |q| >= 2^126, inf, NaN: 2q overflows, reference is UB there
     const float q = __uint_as_float(bits);
     const float a = sample_coord(q, sm1);
-    const float b = sample_coord_fast(q, sm1, rcp);
+    const float b = sample_coord_fast(__fadd_rn(q, q), sm1, rcp, __fmul_rn(0.5f, sm1));
     const bool same = (__float_as_uint(a) == __float_as_uint(b)) || (isnan(a) && isnan(b));
     bad += same ? 0u : 1u;
   }
@@ -578,6 +580,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
   const float xf = (float)gx;
   const float sm1x = pin((float)(p.X - 1)), sm1y = pin((float)(p.Y - 1)), sm1z = pin((float)(p.Z - 1));
   const float rcpx = pin(p.rcp0), rcpy = pin(p.rcp1), rcpz = pin(p.rcp2);
+  const float hsm1x = pin(0.5f * sm1x), hsm1y = pin(0.5f * sm1y), hsm1z = pin(0.5f * sm1z);
   float S0[SUB][3], S1[SUB][3], S2[3] = {0.f, 0.f, 0.f};
   float sse = 0.f, sum_r = 0.f;
   const float bg = WRITE_RES ? p.bg : 0.f;
@@ -621,6 +624,11 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
     c0[d] = v;
     c1[d] = fmaf(sBeta[27 + d], yf, fmaf(sBeta[24 + d], xf, sBeta[9 + d]));
     c2[d] = sBeta[18 + d];
+    if (FAST_DIV) {  // exact doubling: the main loop then evaluates 2q directly
+      c0[d] += c0[d];
+      c1[d] += c1[d];
+      c2[d] += c2[d];
+    }
     S0[h][d] = 0.f;
     S1[h][d] = 0.f;
   }
@@ -628,14 +636,15 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
   float zf = (float)z0;
 #pragma unroll kZUnroll
   for (int zz = 0; zz < nz; ++zz, zf += 1.f, yaddr += 4u) {
+    // with FAST_DIV the Horner coefficients are pre-doubled, so q* below is 2q exactly
     const float q0 = fmaf(zf, fmaf(zf, c2[0], c1[0]), c0[0]);
     const float q1 = fmaf(zf, fmaf(zf, c2[1], c1[1]), c0[1]);
     const float q2 = fmaf(zf, fmaf(zf, c2[2], c1[2]), c0[2]);
     float ix0, ix1, ix2;
     if (FAST_DIV) {
-      ix0 = sample_coord_fast(q0, sm1x, rcpx);
-      ix1 = sample_coord_fast(q1, sm1y, rcpy);
-      ix2 = sample_coord_fast(q2, sm1z, rcpz);
+      ix0 = sample_coord_fast(q0, sm1x, rcpx, hsm1x);
+      ix1 = sample_coord_fast(q1, sm1y, rcpy, hsm1y);
+      ix2 = sample_coord_fast(q2, sm1z, rcpz, hsm1z);
     } else {
       ix0 = sample_coord(q0, sm1x);
       ix1 = sample_coord(q1, sm1y);
@@ -1120,7 +1129,7 @@ extern "C" int dnmf_set_tiling(dnmf_ctx* c, int warps_x, int warps_y, int tz, in
 
 extern "C" int dnmf_get_tiling(dnmf_ctx* c, int32_t* out) {
   if (!c || !out) return fail("dnmf_get_tiling: NULL argument");
-  int32_t v[10] = {c->tx, c->ty, c->tz, c->ntx, c->nty, c->ntz, c->nwx, c->nwy, c->cap, c->sub};
+  int32_t v[11] = {c->tx, c->ty, c->tz, c->ntx, c->nty, c->ntz, c->nwx, c->nwy, c->cap, c->sub, c->fast_div};
   memcpy(out, v, sizeof(v));
   return 0;
 }

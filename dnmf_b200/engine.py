@@ -89,9 +89,9 @@ class Engine:
                    "dnmf_set_tiling")
 
     def tiling(self) -> dict:
-        out = np.zeros(10, np.int32)
+        out = np.zeros(11, np.int32)
         _lib.check(self.lib.dnmf_get_tiling(self._h, out.ctypes.data_as(ctypes.c_void_p)), "dnmf_get_tiling")
-        keys = ("tx", "ty", "tz", "ntx", "nty", "ntz", "warps_x", "warps_y", "cap", "subtiles_y")
+        keys = ("tx", "ty", "tz", "ntx", "nty", "ntz", "warps_x", "warps_y", "cap", "subtiles_y", "fast_div")
         return dict(zip(keys, (int(v) for v in out)))
 
     # -- video ------------------------------------------------------------------------------------

@@ -48,7 +48,8 @@ int dnmf_get_table(dnmf_ctx* ctx, int axis, float* table_host /* [K][s_axis+3][2
  * tile depth tz (0 = whole Z), staged-slot capacity (0 = automatic), y-adjacent sub-tiles processed in
  * sequence by each warp (1 or 2).  Without this call the library picks a layout from the list lengths. */
 int dnmf_set_tiling(dnmf_ctx* ctx, int warps_x, int warps_y, int tz, int slot_capacity, int subtiles_y);
-int dnmf_get_tiling(dnmf_ctx* ctx, int32_t* out /* tx,ty,tz,ntx,nty,ntz,warps_x,warps_y,cap,subtiles_y */);
+int dnmf_get_tiling(dnmf_ctx* ctx, int32_t* out /* tx,ty,tz,ntx,nty,ntz,warps_x,warps_y,cap,subtiles_y,
+                                                     exact_fast_division_verified */);
 
 /* Resident video slab [T][X][Y][Z] on the device (ingest of SimulatedVideoDataset.video,
  * Demix/dNMF.py:203,214-215; negative values are clamped to 0 like __getitem__ does). */

@@ -282,3 +282,13 @@ def test_binning_large_k_bit_exact():
 def test_dense_neurons_loss_grad(tiling):
     """many overlapping wide footprints (long lists, staged + overflow slots) against the closed form."""
     _check([40, 24, 6], 120, 2, seed=13, cutoff=3.5, tiling=tiling, sigma=5.0, tol=5e-5)
+
+
+@pytest.mark.parametrize("sz", [[256, 128, 21], [512, 256, 32], [50, 50, 2], [33, 17, 9]])
+def test_exact_fast_division_is_proven_for_config_sizes(sz):
+    """the 3-instruction division + folded multiply is enabled only after the device proved, over all 2^32
+    inputs per axis, that it reproduces the reference op sequence bit for bit."""
+    from dnmf_b200.engine import Engine
+    e = Engine(sz, 2, 1)
+    e.set_footprints(np.array([[1., 1., 1.], [2., 2., 1.]], np.float32), np.ones(2, np.float32), 3.5)
+    assert e.tiling()["fast_div"] == 1
