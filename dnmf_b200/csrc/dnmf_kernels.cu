@@ -974,6 +974,8 @@ struct dnmf_ctx {
   int* d_tmp_max = nullptr;
   float* d_identity_beta = nullptr;
   int* d_ids_zero = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   // mu statistics
   double* d_G = nullptr;  // [T][K][K]
   double* d_b = nullptr;  // [T][K]
@@ -1101,6 +1103,13 @@ extern "C" void dnmf_destroy(dnmf_ctx* c) {
                   c->d_tab_dsig[2], c->d_resid, c->d_sumr, c->d_ids_zero};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (c->copy_stream) {
+    cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(c->ev_copied[i]);
+      cudaEventDestroy(c->ev_done[i]);
+    }
+  }
   delete c;
 }
 
@@ -1516,14 +1525,41 @@ extern "C" int dnmf_motion_step_host(dnmf_ctx* c, const float* frames_host, cons
                                      const float* C_dev, double lr, double beta1, double beta2, double eps,
                                      int64_t step, int affine, double* loss_host, void* stream) {
   if (!c || !frames_host || !frame_ids_host) return fail("dnmf_motion_step_host: NULL argument");
+  if (B < 1) return fail("dnmf_motion_step_host: B must be >= 1");
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(c->device));
-  if (ensure(&c->d_batch, &c->batch_cap, (size_t)B * c->N)) return 1;
+  // Frames cross PCIe in chunks on a copy stream, double-buffered, while the fused kernel works on the
+  // previous chunk; the device only ever holds two chunks of the batch.
+  const int chunk = std::min(B, std::max(1, (int)(((size_t)96 << 20) / (c->N * sizeof(float)))));
+  if (!c->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
+  }
+  if (ensure(&c->d_batch, &c->batch_cap, (size_t)2 * chunk * c->N)) return 1;
   if (ensure(&c->d_ids, &c->ids_cap, (size_t)B)) return 1;
-  CU(cudaMemcpyAsync(c->d_batch, frames_host, (size_t)B * c->N * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (ensure(&c->d_sse, &c->sse_cap, (size_t)B)) return 1;
   CU(cudaMemcpyAsync(c->d_ids, frame_ids_host, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, st));
-  if (dnmf_motion_step(c, c->d_batch, c->d_ids, B, B_global, beta_dev, m_dev, v_dev, C_dev, lr, beta1, beta2,
-                       eps, step, affine, c->d_loss, stream))
+  CU(cudaEventRecord(c->ev_done[0], st));  // the copy stream must not overtake earlier work on `st`
+  CU(cudaEventRecord(c->ev_done[1], st));
+  int i = 0;
+  for (int b0 = 0; b0 < B; b0 += chunk, ++i) {
+    const int nb = std::min(chunk, B - b0);
+    const int slot = i & 1;
+    float* buf = c->d_batch + (size_t)slot * chunk * c->N;
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_done[slot], 0));
+    CU(cudaMemcpyAsync(buf, frames_host + (size_t)b0 * c->N, (size_t)nb * c->N * sizeof(float),
+                       cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaEventRecord(c->ev_copied[slot], c->copy_stream));
+    CU(cudaStreamWaitEvent(st, c->ev_copied[slot], 0));
+    if (dnmf_loss_grad(c, buf, c->d_ids + b0, nb, B_global, beta_dev, C_dev, c->d_grad, c->d_sse + b0, stream))
+      return 1;
+    CU(cudaEventRecord(c->ev_done[slot], st));
+  }
+  if (dnmf_adam_step(c, beta_dev, c->d_grad, m_dev, v_dev, lr, beta1, beta2, eps, step, affine, c->d_sse, B,
+                     B_global, c->d_loss, stream))
     return 1;
   if (loss_host) {
     CU(cudaMemcpyAsync(loss_host, c->d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
