@@ -581,7 +581,9 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
   const float sm1x = pin((float)(p.X - 1)), sm1y = pin((float)(p.Y - 1)), sm1z = pin((float)(p.Z - 1));
   const float rcpx = pin(p.rcp0), rcpy = pin(p.rcp1), rcpz = pin(p.rcp2);
   const float hsm1x = pin(0.5f * sm1x), hsm1y = pin(0.5f * sm1y), hsm1z = pin(0.5f * sm1z);
+  const float2 sm1xy = make_float2(sm1x, sm1y), rcpxy = make_float2(rcpx, rcpy), hsm1xy = make_float2(hsm1x, hsm1y);
   float S0[SUB][3], S1[SUB][3], S2[3] = {0.f, 0.f, 0.f};
+  float2 S0xy[SUB], S1xy[SUB], S2xy = make_float2(0.f, 0.f);
   float sse = 0.f, sum_r = 0.f;
   const float bg = WRITE_RES ? p.bg : 0.f;
   // shared-memory byte addresses of the three slice regions; one table entry = CAP slots of 8 B
@@ -632,20 +634,32 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
     S0[h][d] = 0.f;
     S1[h][d] = 0.f;
   }
+  S0xy[h] = make_float2(0.f, 0.f);
+  S1xy[h] = make_float2(0.f, 0.f);
+  const float2 c0xy = make_float2(c0[0], c0[1]), c1xy = make_float2(c1[0], c1[1]), c2xy = make_float2(c2[0], c2[1]);
   unsigned yaddr = smem_u32(sY + lx * RS + ly * zs);  // walks the lane's column of the Y tile, 4 B per z step
   float zf = (float)z0;
 #pragma unroll kZUnroll
   for (int zz = 0; zz < nz; ++zz, zf += 1.f, yaddr += 4u) {
-    // with FAST_DIV the Horner coefficients are pre-doubled, so q* below is 2q exactly
-    const float q0 = fmaf(zf, fmaf(zf, c2[0], c1[0]), c0[0]);
-    const float q1 = fmaf(zf, fmaf(zf, c2[1], c1[1]), c0[1]);
-    const float q2 = fmaf(zf, fmaf(zf, c2[2], c1[2]), c0[2]);
+    // with FAST_DIV the Horner coefficients are pre-doubled, so q* below is 2q exactly; the x and y axes
+    // go through the chain as one packed FP32x2 stream (same IEEE roundings per half), z stays scalar
     float ix0, ix1, ix2;
     if (FAST_DIV) {
-      ix0 = sample_coord_fast(q0, sm1x, rcpx, hsm1x);
-      ix1 = sample_coord_fast(q1, sm1y, rcpy, hsm1y);
+      const float2 zz2 = make_float2(zf, zf);
+      const float2 qxy = __ffma2_rn(zz2, __ffma2_rn(zz2, c2xy, c1xy), c0xy);
+      const float q2 = fmaf(zf, fmaf(zf, c2[2], c1[2]), c0[2]);
+      const float2 t0 = __fmul2_rn(qxy, rcpxy);
+      const float2 r = __ffma2_rn(make_float2(-t0.x, -t0.y), sm1xy, qxy);
+      const float2 v = __ffma2_rn(r, rcpxy, t0);
+      const float2 u = __fadd2_rn(v, make_float2(-1.f, -1.f));
+      const float2 ixy = __fmul2_rn(__fadd2_rn(u, make_float2(1.f, 1.f)), hsm1xy);
+      ix0 = ixy.x;
+      ix1 = ixy.y;
       ix2 = sample_coord_fast(q2, sm1z, rcpz, hsm1z);
     } else {
+      const float q0 = fmaf(zf, fmaf(zf, c2[0], c1[0]), c0[0]);
+      const float q1 = fmaf(zf, fmaf(zf, c2[1], c1[1]), c0[1]);
+      const float q2 = fmaf(zf, fmaf(zf, c2[2], c1[2]), c0[2]);
       ix0 = sample_coord(q0, sm1x);
       ix1 = sample_coord(q1, sm1y);
       ix2 = sample_coord(q2, sm1z);
@@ -726,19 +740,24 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
       sum_r += r;
     }
     sse = fmaf(r, r, sse);
-    const float h0 = r * g0, h1 = r * g1, h2 = r * g2;
+    // gradient moments: axes (x, y) as one packed FP32x2 stream, z scalar
     const float zf2 = zf * zf;
-    S0[h][0] += h0;
-    S0[h][1] += h1;
+    const float2 h01 = __fmul2_rn(make_float2(r, r), make_float2(g0, g1));
+    const float h2 = r * g2;
+    S0xy[h] = __fadd2_rn(S0xy[h], h01);
+    S1xy[h] = __ffma2_rn(make_float2(zf, zf), h01, S1xy[h]);
+    S2xy = __ffma2_rn(make_float2(zf2, zf2), h01, S2xy);
     S0[h][2] += h2;
-    S1[h][0] = fmaf(zf, h0, S1[h][0]);
-    S1[h][1] = fmaf(zf, h1, S1[h][1]);
     S1[h][2] = fmaf(zf, h2, S1[h][2]);
-    S2[0] = fmaf(zf2, h0, S2[0]);
-    S2[1] = fmaf(zf2, h1, S2[1]);
     S2[2] = fmaf(zf2, h2, S2[2]);
   }
+  S0[h][0] = S0xy[h].x;
+  S0[h][1] = S0xy[h].y;
+  S1[h][0] = S1xy[h].x;
+  S1[h][1] = S1xy[h].y;
   }  // sub-tiles
+  S2[0] = S2xy.x;
+  S2[1] = S2xy.y;
 
   // ---- expand z-moments with this lane's (x,y) monomials, transposing warp reduction ----
   {
