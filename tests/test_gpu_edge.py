@@ -292,3 +292,26 @@ def test_exact_fast_division_is_proven_for_config_sizes(sz):
     e = Engine(sz, 2, 1)
     e.set_footprints(np.array([[1., 1., 1.], [2., 2., 1.]], np.float32), np.ones(2, np.float32), 3.5)
     assert e.tiling()["fast_div"] == 1
+
+
+def test_launch_chunking_over_grid_z_limit():
+    """B * ntz > 65535 forces the fused kernel out in several launches; per-frame results must equal the
+    ones computed in small batches (fixed-order reductions make them bit-identical)."""
+    from dnmf_b200.engine import Engine
+    sz, K, T = [16, 8, 32], 3, 2100
+    pos, sig, _, _, _ = _case(sz, K, 1, 71)
+    g = torch.Generator().manual_seed(71)
+    frames = torch.rand(T, *sz, generator=g)
+    s = torch.tensor([.3, .01, .01, .01, 1e-4, 1e-4, 1e-4, 1e-4, 1e-4, 1e-4])[:, None, None]
+    beta = (O.identity_beta(T) + s * torch.randn(10, 3, T, generator=g)).cuda()
+    C = torch.rand(K, T, generator=g).cuda()
+    e = Engine(sz, K, T)
+    e.set_tiling(1, 1, 1, 0, 1)                       # tz = 1 -> ntz = 32 -> 67200 grid-z slices
+    e.set_footprints(pos, sig, 3.5)
+    e.upload_frames(frames, clamp_negative=False)
+    g_all, s_all = e.loss_grad(torch.arange(T), beta, C)
+    for lo in (0, 1000, 2000):
+        ids = torch.arange(lo, lo + 100)
+        g_part, s_part = e.loss_grad(ids, beta, C, B_global=T)
+        assert torch.equal(s_part, s_all[lo:lo + 100])
+        assert torch.equal(g_part[:, :, lo:lo + 100], g_all[:, :, lo:lo + 100])
