@@ -1396,10 +1396,12 @@ extern "C" int dnmf_bin_tiles(dnmf_ctx* c, const float* beta_dev, const int32_t*
 template <int NWX, int NWY, int SUB, int MD_, bool FD_>
 static int launch_fit(const FitParams& p0, int B, size_t smem, cudaStream_t st) {
   auto kern = fit_tile_kernel<NWX, NWY, SUB, MD_, FD_>;
-  static size_t configured = 0;
-  if (smem > configured) {
+  static size_t configured[64] = {0};  // per device: the attribute is a per-device property of the function
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || smem > configured[dev]) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    if (dev >= 0 && dev < 64) configured[dev] = smem;
   }
   // grid = (ntx, nty, frames*ntz); gridDim.z <= 65535, so very large batches go out in chunks
   const int maxB = std::max(1, 65535 / p0.ntz);
