@@ -4,7 +4,7 @@ The CUDA library (dnmf_b200/_C/libdnmf_b200.so, C ABI in include/dnmf_b200.h) do
 arithmetic; this package mirrors the reference's Python class surface on top of it.
 """
 from ._lib import DnmfError, LIB_PATH, declared_symbols, load  # noqa: F401
-from .simulate import FrameDataset, SimulatedVideoDataset, generate_video  # noqa: F401
+from .simulate import FrameDataset, NeuroPALVideoDataset, SimulatedVideoDataset, generate_video  # noqa: F401
 
 
 def __getattr__(name):

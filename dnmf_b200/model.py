@@ -139,6 +139,27 @@ class ExponentialFP(nn.Module):
         return torch.log(abs(a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g)))
 
     @staticmethod
+    def log_det_jac_consistent(B, P):
+        """log|det J_tau(P)| with cross-term indices that match quadratic_basis (xy -> row 7, xz -> row 8,
+        yz -> row 9); differentiable in B.  Opt-in fix of the reference's inconsistency."""
+        x, y, z = P[0], P[1], P[2]
+        r = [(B[1, c] + 2 * B[4, c] * x + B[7, c] * y + B[8, c] * z,
+              B[2, c] + 2 * B[5, c] * y + B[7, c] * x + B[9, c] * z,
+              B[3, c] + 2 * B[6, c] * z + B[8, c] * x + B[9, c] * y) for c in range(3)]
+        (a, b, c), (d, e, f), (g, h, i) = r
+        return torch.log(abs(a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g)))
+
+    def jacobian_regularizer_grad(self, ids, gamma):
+        """d/d beta of gamma * mean_t [log|det J_t(sz-1)|^2 + log|det J_t(0)|^2] for the batch frames:
+        [10,3,B] on the device (30 numbers per frame; torch autograd, nothing voxel-sized)."""
+        b = self.beta.detach()[:, :, ids].clone().requires_grad_(True)
+        hi = (self.sz - 1).float()
+        lo = torch.zeros(3, device=b.device)
+        reg = ExponentialFP.log_det_jac_consistent(b, hi) ** 2 + ExponentialFP.log_det_jac_consistent(b, lo) ** 2
+        (gamma * reg.mean()).backward()
+        return b.grad
+
+    @staticmethod
     def spatial_pushforward(dl, batch_size, sz, device, model):
         """Dense outputs of Demix/dNMF.py:69-93: (A_t[X,Y,Z,K,T'] f64, Y_i[X,Y,Z,T'] f64, Y[X,Y,Z,T'] f64)
         as numpy arrays, computed on the GPU batch by batch."""
@@ -173,7 +194,7 @@ class DeformableNMF:
 
     def __init__(self, sz, K, T, positions=None, *, cutoff: float = DEFAULT_CUTOFF, deformation: str = "quadratic",
                  shape_std=3, device=None, tiling=None, verbose: bool = True, frame_offset: int = 0,
-                 global_batch_scale: int = 1):
+                 global_batch_scale: int = 1, jacobian_regularizer: bool = False):
         if deformation not in ("quadratic", "affine"):
             raise ValueError("deformation must be 'quadratic' or 'affine'")
         self.SpatialModel = ExponentialFP
@@ -187,6 +208,9 @@ class DeformableNMF:
         self._size = size
         self._D = None
         self.affine = deformation == "affine"
+        # opt-in: make `gamma` of update_motion act (differentiable, index-consistent log-det-Jacobian
+        # penalty).  OFF reproduces the reference, where the regulariser is a detached constant (F3).
+        self.jacobian_regularizer = bool(jacobian_regularizer)
         self.verbose = verbose
         self.frame_offset = int(frame_offset)        # first global frame id of this rank's slab
         self.global_batch_scale = int(global_batch_scale)   # world size when every rank steps a local batch
@@ -307,7 +331,16 @@ class DeformableNMF:
                 ids = torch.as_tensor(data[1]).to(torch.int32)
                 step = int(st["step"]) + 1
                 lr, betas, eps = group["lr"], group["betas"], group["eps"]
-                if self._shared is not None:
+                if self.jacobian_regularizer and gamma and self._shared is None:
+                    fd = None if self._video_resident else data[0].float().to(eng.device).contiguous()
+                    Bg = ids.numel() * self.global_batch_scale
+                    idd = ids.to(eng.device)
+                    grad, sse = eng.loss_grad(idd, beta, self.C, frames=fd, B_global=Bg)
+                    grad[:, :, idd.long()] += self.fp.jacobian_regularizer_grad(idd.long(), float(gamma)) \
+                        * (ids.numel() / Bg)
+                    eng.adam_step(beta, grad, st["exp_avg"], st["exp_avg_sq"], lr, betas, eps, step, self.affine)
+                    loss = sse.sum() / (Bg * eng.N)
+                elif self._shared is not None:
                     fd = None if self._video_resident else data[0].float().to(eng.device).contiguous()
                     loss = self._shared_step(ids.to(eng.device), fd, group, st, step,
                                              ids.numel() * self.global_batch_scale)

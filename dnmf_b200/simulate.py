@@ -160,3 +160,37 @@ class FrameDataset(Dataset):
         if torch.is_tensor(idx):
             idx = idx.tolist()
         return self.frames[idx], idx
+
+
+class NeuroPALVideoDataset(Dataset):
+    """Real-data loader with the semantics of Demix/dNMF.py:220-248 and portable paths: `file` is a directory
+    holding data.mat (variable `data` [X,Y,Z,T]) and traces_n.mat (`positions` [K,3,T] 1-based,
+    `neuron_names`).  The reference subsamples [::2, ::2, ::10, :100] and rescales the positions to match;
+    the strides and frame count are arguments here with the same defaults."""
+
+    def __init__(self, file, stride=(2, 2, 10), frames=100):
+        import os
+        from scipy.io import loadmat
+        vid = loadmat(os.path.join(file, "data.mat"))["data"]
+        sx, sy, sz_ = stride
+        video = np.ascontiguousarray(vid[::sx, ::sy, ::sz_, :frames]).astype(np.float32)
+        self.frames = torch.from_numpy(np.ascontiguousarray(np.moveaxis(video, 3, 0))).clamp_(min=0)
+        pos_mat = loadmat(os.path.join(file, "traces_n.mat"))
+        positions = torch.tensor(np.asarray(pos_mat["positions"], dtype=np.float32)) - 1
+        positions[:, 0, :] /= sx
+        positions[:, 1, :] /= sy
+        positions[:, 2, :] /= sz_
+        self.positions = positions
+        self.names = pos_mat["neuron_names"][0] if "neuron_names" in pos_mat else None
+
+    @property
+    def video(self) -> torch.Tensor:
+        return self.frames.permute(1, 2, 3, 0)
+
+    def __len__(self):
+        return self.frames.shape[0]
+
+    def __getitem__(self, idx):
+        if torch.is_tensor(idx):
+            idx = idx.tolist()
+        return self.frames[idx], idx

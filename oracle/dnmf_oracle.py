@@ -91,11 +91,19 @@ class TorchPort:
 
     # -- Demix/dNMF.py:185-191 --------------------------------------------------------------------
     def motion_step(self, frames: torch.Tensor, times: Sequence[int], optimizer,
-                    affine: bool = False) -> float:
+                    affine: bool = False, reg_gamma: Optional[float] = None) -> float:
+        """reg_gamma=None is the reference (detached regulariser, F3).  A number adds the OPT-IN
+        differentiable, index-consistent penalty gamma * mean_t [logdetJ_t(sz-1)^2 + logdetJ_t(0)^2]."""
         optimizer.zero_grad()
         A_tC, _, _ = self.forward(times)
         recon = F.mse_loss(A_tC, frames)
-        recon.backward()
+        loss = recon
+        if reg_gamma is not None:
+            b = self.beta[:, :, list(times)]
+            hi = (self.sz - 1).float()
+            reg = log_det_jac_consistent(b, hi) ** 2 + log_det_jac_consistent(b, torch.zeros(3)) ** 2
+            loss = recon + reg_gamma * reg.mean()
+        loss.backward()
         if affine:  # "affine" = quadratic rows frozen (SURVEY section 0 table)
             self.beta.grad[4:] = 0
         optimizer.step()
@@ -147,6 +155,18 @@ def mu_sweep(Gm: np.ndarray, bv: np.ndarray, C: np.ndarray, gamma) -> np.ndarray
         C1 = C1 + gamma * nbr
         C2 = C2 + 2 * gamma * C
     return C * C1 / (C2 + 1e-32)
+
+
+def log_det_jac_consistent(Bm: torch.Tensor, P) -> torch.Tensor:
+    """log|det J| with cross-term rows matching the basis order (xy=7, xz=8, yz=9); opt-in fix of F3."""
+    x, y, z = P[0], P[1], P[2]
+    rows = []
+    for c in range(3):
+        rows.append((Bm[1, c] + 2 * Bm[4, c] * x + Bm[7, c] * y + Bm[8, c] * z,
+                     Bm[2, c] + 2 * Bm[5, c] * y + Bm[7, c] * x + Bm[9, c] * z,
+                     Bm[3, c] + 2 * Bm[6, c] * z + Bm[8, c] * x + Bm[9, c] * y))
+    (a, b, c), (d, e, f), (g, h, i) = rows
+    return torch.log(abs(a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g)))
 
 
 def log_det_jac(Bm: torch.Tensor, P) -> torch.Tensor:

@@ -9,6 +9,8 @@ CUDA path to outputs of the reference's own code.  Seeds: np.random.seed(0), tor
                   first 250 Adam steps, beta after them, then C after
                   update_footprints(gamma_c=0, iter_c=50) and after a further
                   update_footprints(gamma_c=1e-2, iter_c=10); a few frames of A_t / Y_i.
+  demo_shuffle.npz same data (seeds identical, so frames/pos0/C0 equal demo_cfg1.npz), DataLoader(shuffle=True)
+                  with torch.manual_seed(1000+epoch) before each of 2 epochs: batch order, losses, beta.
   random_beta.npz small 3-D case with random quadratic beta (44 % out-of-bounds samples):
                   forward A_tC, A_t, loss and d loss / d beta from the reference's autograd.
 """
@@ -73,6 +75,35 @@ def demo_cfg1(ref):
     print("demo_cfg1: loss %.6g -> %.6g" % (losses[0], losses[-1]))
 
 
+def demo_shuffle(ref):
+    """demo.py:34 uses shuffle=True: two epochs with the batch order drawn from torch's global RNG,
+    re-seeded right before each epoch so that the order can be replayed without the reference."""
+    np.random.seed(0)
+    torch.manual_seed(0)
+    K, T, B = 10, 100, 4
+    sz = torch.tensor([50, 50, 2])
+    ds = ref.SimulatedVideoDataset(K=K, T=T, sz=sz, shape_std=3, density=.2, bg_snr=-120, motion="gp",
+                                   traces="exp", motion_par={"sigma": [5, 5, .01], "ls": [10, 10, 10]})
+    loader = DataLoader(ds, batch_size=B, shuffle=True, num_workers=0)
+    dn = ref.DeformableNMF(sz, K, T, positions=ds.positions[:, :, 0])
+    opt = torch.optim.Adam([dn.fp.beta], lr=1e-5)
+    losses, order = [], []
+    for ep in range(2):
+        torch.manual_seed(1000 + ep)
+        for frames, idx in loader:
+            opt.zero_grad()
+            with quiet():
+                A_tC, _, _, _ = dn.fp(idx.tolist(), dn.C)
+            rec = F.mse_loss(A_tC, frames)
+            rec.backward()
+            opt.step()
+            losses.append(float(rec))
+            order.append(idx.numpy().copy())
+    np.savez_compressed(os.path.join(OUT, "demo_shuffle.npz"), losses=np.asarray(losses), order=np.asarray(order),
+                        beta=dn.fp.beta.detach().numpy(), C0=dn.C.numpy())
+    print("demo_shuffle: loss %.6g -> %.6g" % (losses[0], losses[-1]))
+
+
 def random_beta(ref):
     np.random.seed(1)
     torch.manual_seed(1)
@@ -105,6 +136,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     ref, _ = load_reference()
     demo_cfg1(ref)
+    demo_shuffle(ref)
     random_beta(ref)
 
 

@@ -203,3 +203,70 @@ def test_update_footprints_dense_outputs(golden_demo):
     assert A_t.shape == (50, 50, 2, 10, 8) and Y.shape == (50, 50, 2, 8) and Y_i.shape == Y.shape
     np.testing.assert_allclose(A_t[..., :4], g["A_t_first4"], atol=3e-6)
     np.testing.assert_allclose(Y[..., :4], g["Y_first4"], atol=0)
+
+
+def test_shuffled_loader_matches_reference(golden_demo):
+    """demo.py:34 (shuffle=True): replay the reference's recorded batch order -- and check that a torch
+    DataLoader seeded the same way produces that order -- for two epochs of random minibatches."""
+    import os
+    from torch.utils.data import DataLoader
+    from dnmf_b200 import FrameDataset
+    g = golden_demo
+    gs = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "demo_shuffle.npz")))
+    dn = _demo_model(g, 3.5, False)
+    ds = FrameDataset(torch.tensor(g["frames"]))
+    loader = DataLoader(ds, batch_size=4, shuffle=True, num_workers=0)
+    opt = torch.optim.Adam([dn.fp.beta], lr=1e-5)
+    order = []
+
+    class Recorder:                                   # same loader, re-seeded per epoch like the golden run
+        def __init__(self, ep):
+            self.ep = ep
+
+        def __iter__(self):
+            torch.manual_seed(1000 + self.ep)
+            for frames, idx in loader:
+                order.append(idx.numpy().copy())
+                yield frames, idx
+
+        def __len__(self):
+            return len(loader)
+
+    for ep in range(2):
+        dn.update_motion(Recorder(ep), opt, gamma=1, epochs=1)
+    assert np.array_equal(np.asarray(order), gs["order"])
+    losses = dn.losses()
+    assert np.max(np.abs(losses - gs["losses"]) / gs["losses"]) < 1e-4
+    assert float((dn.fp.beta.detach().cpu() - torch.tensor(gs["beta"])).abs().max()) < 1e-6
+
+
+def test_opt_in_jacobian_regularizer_vs_autograd(golden_demo):
+    """OPT-IN (off by default, not reference behaviour): differentiable index-consistent log-det-Jacobian
+    penalty.  With the flag ON and gamma > 0 the updates follow the oracle's autograd version; with the flag
+    OFF gamma is inert like in the reference."""
+    from torch.utils.data import DataLoader
+    from dnmf_b200 import DeformableNMF, FrameDataset
+    g = golden_demo
+    sz = g["sz"].tolist()
+    K, T = g["C0"].shape
+    frames = torch.tensor(g["frames"][:16])
+    gamma = 1e-3
+    port = O.TorchPort(sz, K, 16, positions=g["pos0"], C0=g["C0"][:, :16])
+    popt = torch.optim.Adam([port.beta], lr=1e-4)
+    ref_losses = [port.motion_step(frames[i:i + 4], list(range(i, i + 4)), popt, reg_gamma=gamma)
+                  for _ in range(3) for i in range(0, 16, 4)]
+    dn = DeformableNMF(sz, K, 16, positions=torch.tensor(g["pos0"]), cutoff=0.0, verbose=False,
+                       jacobian_regularizer=True)
+    dn.C = torch.tensor(g["C0"][:, :16]).contiguous().cuda()
+    opt = torch.optim.Adam([dn.fp.beta], lr=1e-4)
+    dn.update_motion(DataLoader(FrameDataset(frames), batch_size=4, shuffle=False), opt, gamma=gamma, epochs=3)
+    assert np.max(np.abs(dn.losses() - np.asarray(ref_losses)) / np.asarray(ref_losses)) < 1e-4
+    assert float((dn.fp.beta.detach().cpu() - port.beta.detach()).abs().max()) < 2e-6
+    # flag OFF: gamma changes nothing
+    a = DeformableNMF(sz, K, 16, positions=torch.tensor(g["pos0"]), cutoff=0.0, verbose=False)
+    b = DeformableNMF(sz, K, 16, positions=torch.tensor(g["pos0"]), cutoff=0.0, verbose=False)
+    for m, gm in ((a, 0), (b, 5.0)):
+        m.C = torch.tensor(g["C0"][:, :16]).contiguous().cuda()
+        m.update_motion(DataLoader(FrameDataset(frames), batch_size=4, shuffle=False),
+                        torch.optim.Adam([m.fp.beta], lr=1e-4), gamma=gm, epochs=1)
+    assert torch.equal(a.fp.beta, b.fp.beta)

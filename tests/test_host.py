@@ -144,3 +144,20 @@ def test_bench_reference_arm_runs_small():
               "config", "cpu_baseline", "e2e"):
         assert k in line
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+def test_neuropal_dataset_from_mat(tmp_path):
+    """Demix/dNMF.py:220-248 semantics on a synthetic data.mat / traces_n.mat pair."""
+    from scipy.io import savemat
+    from dnmf_b200 import NeuroPALVideoDataset
+    rng = np.random.default_rng(0)
+    data = rng.normal(size=(12, 10, 20, 7)).astype(np.float32)
+    positions = 1 + rng.random((3, 3, 7)) * np.array([12, 10, 20])[None, :, None]
+    savemat(tmp_path / "data.mat", {"data": data})
+    savemat(tmp_path / "traces_n.mat", {"positions": positions, "neuron_names": np.array(["AVA", "AVB", "RIM"], dtype=object)})
+    ds = NeuroPALVideoDataset(str(tmp_path), frames=5)
+    assert len(ds) == 5 and ds.video.shape == (6, 5, 2, 5)
+    frame, idx = ds[3]
+    np.testing.assert_array_equal(frame.numpy(), np.clip(data[::2, ::2, ::10, 3], 0, None))
+    np.testing.assert_allclose(ds.positions[:, 0, :].numpy(), (positions[:, 0, :] - 1) / 2, rtol=1e-6)
+    np.testing.assert_allclose(ds.positions[:, 2, :].numpy(), (positions[:, 2, :] - 1) / 10, rtol=1e-6)
