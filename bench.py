@@ -34,13 +34,14 @@ CONFIGS = {
                  desc="demo.py: 50x50x2, K=10, T=100, quadratic"),
     "cfg2": dict(sz=(256, 128, 21), K=150, T=1000, sigma=3.0, shape_std=3.0, deformation="affine",
                  desc="single-GPU synthetic volume 256x128x21, K=150, T=1000, affine"),
-    "cfg3": dict(sz=(512, 256, 32), K=300, T=625, sigma=3.0, shape_std=3.0, deformation="quadratic",
+    "cfg3": dict(sz=(512, 256, 32), K=300, T=625, sigma=3.0, shape_std=3.0, deformation="quadratic", lr=1e-7,
                  desc="whole-brain 512x256x32, K=300, T=5000 over 8 GPUs (625 per GPU), quadratic"),
-    "cfg4": dict(sz=(256, 128, 21), K=1000, T=250, sigma=6.0, shape_std=18.0, deformation="quadratic",
+    "cfg4": dict(sz=(256, 128, 21), K=1000, T=250, sigma=6.0, shape_std=18.0, deformation="quadratic", lr=1e-7,
                  desc="dense stress 256x128x21, K=1000, sigma=6, T=2000 over 8 GPUs (250 per GPU)"),
 }
 CUTOFF = 3.5
-LR = 1e-5
+LR = 1e-5   # demo.py:42; the raw-pixel quadratic basis needs a smaller step on large volumes (one step of 1e-5
+            # moves a voxel at x=511 by 2.6 px through the x^2 term) -> per-config "lr"
 
 
 def parse():
@@ -411,8 +412,10 @@ def run_b200(args, cfg):
 
 
 def main():
+    global LR
     args = parse()
     cfg = CONFIGS[args.config]
+    LR = cfg.get("lr", LR)
     if args.impl == "reference":
         run_reference(args, cfg)
     else:
