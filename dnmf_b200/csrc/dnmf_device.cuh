@@ -33,14 +33,17 @@ __device__ __forceinline__ void split_coord(float ix, int s, int& i, float& f) {
 // Conservative window of table-entry indices touched by the inclusive voxel box, one axis.
 // Bit-exact twin of oracle.dnmf_oracle.tile_window (fp32 interval arithmetic, fixed order).
 // `b` points at beta[a*3 + d] entries of this frame with stride `bs` between rows a.
+// `clipped` reports whether the clamp to the table domain [-2, s] cut the window: when it did not, every
+// sample of the box is known to fall inside [wlo, whi] (the +-1 margin dominates the rounding of the
+// interval sums and of the coordinate chain), so the consumer may index the staged slices unclamped.
 __device__ __forceinline__ void tile_window_axis(const float* b, int bs, float x0, float y0, float z0,
                                                  float x1, float y1, float z1, int s, int& wlo,
-                                                 int& whi) {
+                                                 int& whi, bool& clipped) {
   const float mlo[kBasis] = {1.f, x0, y0, z0, __fmul_rn(x0, x0), __fmul_rn(y0, y0), __fmul_rn(z0, z0),
                              __fmul_rn(x0, y0), __fmul_rn(x0, z0), __fmul_rn(y0, z0)};
   const float mhi[kBasis] = {1.f, x1, y1, z1, __fmul_rn(x1, x1), __fmul_rn(y1, y1), __fmul_rn(z1, z1),
                              __fmul_rn(x1, y1), __fmul_rn(x1, z1), __fmul_rn(y1, z1)};
-  float lo = b[0], hi = b[0];
+  float lo = b[0], hi = b[0], mag = fabsf(b[0]);
 #pragma unroll
   for (int a = 1; a < kBasis; ++a) {
     float c = b[a * bs];
@@ -48,6 +51,7 @@ __device__ __forceinline__ void tile_window_axis(const float* b, int bs, float x
     float p2 = __fmul_rn(c, mhi[a]);
     lo = __fadd_rn(lo, fminf(p1, p2));
     hi = __fadd_rn(hi, fmaxf(p1, p2));
+    mag = fmaxf(mag, fmaxf(fabsf(p1), fabsf(p2)));
   }
   lo = fminf(fmaxf(lo, -4.f), (float)(s + 4));
   hi = fminf(fmaxf(hi, -4.f), (float)(s + 4));
@@ -55,6 +59,15 @@ __device__ __forceinline__ void tile_window_axis(const float* b, int bs, float x
   int h = (int)floorf(hi) + 1;
   wlo = min(max(l, -2), s);
   whi = min(max(h, -2), s);
+  // terms beyond 2^14 could carry a summed rounding error that is not small against the +-1 margin
+  clipped = (l < -2) || (h > s) || !(lo <= hi) || !(mag <= 16384.f);
+}
+
+__device__ __forceinline__ void tile_window_axis(const float* b, int bs, float x0, float y0, float z0,
+                                                 float x1, float y1, float z1, int s, int& wlo,
+                                                 int& whi) {
+  bool clipped;
+  tile_window_axis(b, bs, x0, y0, z0, x1, y1, z1, s, wlo, whi, clipped);
 }
 
 // Neuron k (ranges r[0..5] = lo0,hi0,lo1,hi1,lo2,hi2) touches the window?

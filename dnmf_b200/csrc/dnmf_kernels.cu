@@ -29,7 +29,7 @@ namespace dnmf {
 constexpr int kZUnroll = DNMF_ZUNROLL;
 }
 #ifndef DNMF_MINB
-#define DNMF_MINB 22  // resident single-warp CTAs per SM the fused kernel is compiled for (register budget)
+#define DNMF_MINB 16  // resident single-warp CTAs per SM the fused kernel is compiled for (128 registers: no spills in the unrolled march)
 #endif
 
 namespace dnmf {
@@ -377,6 +377,202 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
   return v[0];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Specialised main loop of the fused kernel for the common case (two y-adjacent sub-tiles per warp, the
+// whole list staged): each lane carries voxel A = (x, y, z) and voxel B = (x, y+4, z) through the z march
+// TOGETHER, so all per-voxel arithmetic that is not neuron-pair math (Horner q, the F2 coordinate chain,
+// fraction, residual, loss, the nine gradient z-moments) runs as packed FP32x2 over (A, B), while the
+// neuron-pair math stays packed over (slot j, slot j+1).  The number of staged slot pairs NP is a template
+// parameter: the pair loop is fully unrolled with immediate LDS offsets (no loop counter, no address
+// increments, no zeroed accumulators), selected per tile by a uniform switch.  SAFE = false additionally
+// drops the window clamp and the out-of-volume lane mask; it is chosen only for full tiles whose
+// conservative window was not clipped by the table domain (tile_window_axis), where every sample is known to
+// index inside the staged slices.  Same IEEE operations per value as the generic loop below.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxNP = 8;  // unrolled variants up to 16 staged neurons; longer lists take the generic loop
+
+struct MarchArgs {
+  float2 c0[3], c1[3];      // Horner coefficients of 2q for (A, B), per axis
+  float c2[3];              // z^2 coefficient (shared by A and B)
+  float sm1[3], rcp[3], hsm1[3];
+  int wl[3], wm1[3];
+  unsigned base[3];         // shared-memory byte address of each axis' slice region
+  unsigned strideB;         // bytes per table entry (CAP slots of 8 B)
+  unsigned yaddrA, yoffB;   // byte address of A's Y column; B's column is yoffB bytes further
+  float zf0;
+  int nz;
+  bool validA, validB;
+  float bg;                 // MODE 2: scalar background
+};
+
+struct MarchOut {
+  float2 S0[3], S1[3], S2[3];  // z-moments of r * dYhat/dix_d for (A, B)
+  float2 sse, sum_r;
+};
+
+template <int OFF>
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr), "n"(OFF));
+  return v;
+}
+
+// One slot pair (two neurons) for one voxel.  FIRST: the accumulators are produced, not updated.
+template <int OFF, bool FIRST>
+__device__ __forceinline__ void slot_pair(unsigned ax, unsigned ay, unsigned az, float2 f0, float2 f1, float2 f2,
+                                          float2& yh, float2& g0, float2& g1, float2& g2) {
+  const float4 ex = lds128<OFF>(ax), ey = lds128<OFF>(ay), ez = lds128<OFF>(az);
+  const float2 exG = make_float2(ex.x, ex.y), exD = make_float2(ex.z, ex.w);
+  const float2 eyG = make_float2(ey.x, ey.y), eyD = make_float2(ey.z, ey.w);
+  const float2 ezG = make_float2(ez.x, ez.y), ezD = make_float2(ez.z, ez.w);
+  const float2 ca0 = __ffma2_rn(f0, exD, exG);
+  const float2 a1 = __ffma2_rn(f1, eyD, eyG);
+  const float2 a2 = __ffma2_rn(f2, ezD, ezG);
+  const float2 t12 = __fmul2_rn(a1, a2);
+  if (FIRST) {
+    yh = __fmul2_rn(ca0, t12);
+    g0 = __fmul2_rn(exD, t12);
+    g1 = __fmul2_rn(__fmul2_rn(ca0, a2), eyD);
+    g2 = __fmul2_rn(__fmul2_rn(ca0, a1), ezD);
+  } else {
+    yh = __ffma2_rn(ca0, t12, yh);
+    g0 = __ffma2_rn(exD, t12, g0);
+    g1 = __ffma2_rn(__fmul2_rn(ca0, a2), eyD, g1);
+    g2 = __ffma2_rn(__fmul2_rn(ca0, a1), ezD, g2);
+  }
+}
+
+// All NP slot pairs of one voxel -> (Yhat, dYhat/dix_0..2).
+template <int NP>
+__device__ __forceinline__ void voxel_pairs(unsigned ax, unsigned ay, unsigned az, float f0s, float f1s, float f2s,
+                                            float& yh, float& g0, float& g1, float& g2) {
+  static_assert(NP >= 1 && NP <= 8, "unrolled slot pairs");
+  const float2 f0 = make_float2(f0s, f0s), f1 = make_float2(f1s, f1s), f2 = make_float2(f2s, f2s);
+  float2 y2, a2, b2, c2;
+  slot_pair<0, true>(ax, ay, az, f0, f1, f2, y2, a2, b2, c2);
+  if (NP > 1) slot_pair<16, false>(ax, ay, az, f0, f1, f2, y2, a2, b2, c2);
+  if (NP > 2) slot_pair<32, false>(ax, ay, az, f0, f1, f2, y2, a2, b2, c2);
+  if (NP > 3) slot_pair<48, false>(ax, ay, az, f0, f1, f2, y2, a2, b2, c2);
+  if (NP > 4) slot_pair<64, false>(ax, ay, az, f0, f1, f2, y2, a2, b2, c2);
+  if (NP > 5) slot_pair<80, false>(ax, ay, az, f0, f1, f2, y2, a2, b2, c2);
+  if (NP > 6) slot_pair<96, false>(ax, ay, az, f0, f1, f2, y2, a2, b2, c2);
+  if (NP > 7) slot_pair<112, false>(ax, ay, az, f0, f1, f2, y2, a2, b2, c2);
+  yh = y2.x + y2.y;
+  g0 = a2.x + a2.y;
+  g1 = b2.x + b2.y;
+  g2 = c2.x + c2.y;
+}
+
+__device__ __forceinline__ float lds32(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(unsigned addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// MODE as in fit_tile_kernel: 0 fit, 1 forward only (Yhat replaces the Y tile in shared memory), 2 fit with
+// scalar background, residual written back to the Y tile.
+template <int NP, bool SAFE, int MODE>
+__device__ __forceinline__ void march_pairs(const MarchArgs& a, MarchOut& o) {
+  const float2 zero2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) o.S0[d] = o.S1[d] = o.S2[d] = zero2;
+  float2 sse = zero2, sum_r = zero2;
+  unsigned yaddr = a.yaddrA;
+  if constexpr (NP == 0) {  // empty list: Yhat = 0, no gradient; only the loss term
+#pragma unroll 1
+    for (int zz = 0; zz < a.nz; ++zz, yaddr += 4u) {
+      if (MODE == 1) {
+        sts32(yaddr, 0.f);
+        sts32(yaddr + a.yoffB, 0.f);
+        continue;
+      }
+      float2 r = make_float2(-lds32(yaddr), -lds32(yaddr + a.yoffB));
+      if (MODE == 2) r = __fadd2_rn(r, make_float2(a.bg, a.bg));
+      if (SAFE) {
+        r.x = a.validA ? r.x : 0.f;
+        r.y = a.validB ? r.y : 0.f;
+      }
+      if (MODE == 2) {
+        sts32(yaddr, r.x);
+        sts32(yaddr + a.yoffB, r.y);
+        sum_r = __fadd2_rn(sum_r, r);
+      }
+      sse = __ffma2_rn(r, r, sse);
+    }
+  } else {
+    // address of entry i of axis d: (i - wl) * strideB + base  ==  i * strideB + bias   (mod 2^32)
+    unsigned bias[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) bias[d] = a.base[d] - (unsigned)a.wl[d] * a.strideB;
+    float zf = a.zf0;
+#pragma unroll 1
+    for (int zz = 0; zz < a.nz; ++zz, zf += 1.f, yaddr += 4u) {
+      const float2 z2 = make_float2(zf, zf);
+      float2 ix[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float2 rcp2 = make_float2(a.rcp[d], a.rcp[d]);
+        const float2 q = __ffma2_rn(z2, __ffma2_rn(z2, make_float2(a.c2[d], a.c2[d]), a.c1[d]), a.c0[d]);  // = 2q
+        const float2 t0 = __fmul2_rn(q, rcp2);
+        const float2 r = __ffma2_rn(make_float2(-t0.x, -t0.y), make_float2(a.sm1[d], a.sm1[d]), q);
+        const float2 v = __ffma2_rn(r, rcp2, t0);  // = fl(2q / (s-1)), verified exact (verify_coord_kernel)
+        const float2 u = __fadd2_rn(v, make_float2(-1.f, -1.f));
+        ix[d] = __fmul2_rn(__fadd2_rn(u, make_float2(1.f, 1.f)), make_float2(a.hsm1[d], a.hsm1[d]));
+      }
+      unsigned adA[3], adB[3];
+      float2 f[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int iA = __float2int_rd(ix[d].x), iB = __float2int_rd(ix[d].y);
+        f[d] = __fadd2_rn(ix[d], make_float2(-(float)iA, -(float)iB));
+        if (SAFE) {
+          adA[d] = (unsigned)min(max(iA - a.wl[d], 0), a.wm1[d]) * a.strideB + a.base[d];
+          adB[d] = (unsigned)min(max(iB - a.wl[d], 0), a.wm1[d]) * a.strideB + a.base[d];
+        } else {
+          adA[d] = (unsigned)iA * a.strideB + bias[d];
+          adB[d] = (unsigned)iB * a.strideB + bias[d];
+        }
+      }
+      float2 yh, g[3];
+      voxel_pairs<NP>(adA[0], adA[1], adA[2], f[0].x, f[1].x, f[2].x, yh.x, g[0].x, g[1].x, g[2].x);
+      voxel_pairs<NP>(adB[0], adB[1], adB[2], f[0].y, f[1].y, f[2].y, yh.y, g[0].y, g[1].y, g[2].y);
+      if (MODE == 1) {
+        sts32(yaddr, yh.x);
+        sts32(yaddr + a.yoffB, yh.y);
+        continue;
+      }
+      if (MODE == 2) yh = __fadd2_rn(yh, make_float2(a.bg, a.bg));
+      float2 r = __fadd2_rn(yh, make_float2(-lds32(yaddr), -lds32(yaddr + a.yoffB)));
+      if (SAFE) {
+        r.x = a.validA ? r.x : 0.f;
+        r.y = a.validB ? r.y : 0.f;
+      }
+      if (MODE == 2) {
+        sts32(yaddr, r.x);
+        sts32(yaddr + a.yoffB, r.y);
+        sum_r = __fadd2_rn(sum_r, r);
+      }
+      sse = __ffma2_rn(r, r, sse);
+      const float zq = zf * zf;
+      const float2 zq2 = make_float2(zq, zq);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float2 h = __fmul2_rn(r, g[d]);
+        o.S0[d] = __fadd2_rn(o.S0[d], h);
+        o.S1[d] = __ffma2_rn(z2, h, o.S1[d]);
+        o.S2[d] = __ffma2_rn(zq2, h, o.S2[d]);
+      }
+    }
+  }
+  o.sse = sse;
+  o.sum_r = sum_r;
+}
+
 // SUB = y-adjacent 8x4 sub-tiles processed one after the other by each warp: they share the tile
 // prologue (window, list, staging, TMA) and the reduction epilogue.
 // MODE 0: fit (loss + gradient).  MODE 1: forward only, writes Yhat.  MODE 2: fit with a scalar background
@@ -456,10 +652,12 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
   if (tid < 3) {
     const int s = tid == 0 ? p.X : (tid == 1 ? p.Y : p.Z);
     int wlo, whi;
+    bool clipped;
     tile_window_axis(sBeta + tid, 3, (float)x0, (float)y0, (float)z0, (float)(x0 + nx - 1),
-                     (float)(y0 + ny - 1), (float)(z0 + nz - 1), s, wlo, whi);
+                     (float)(y0 + ny - 1), (float)(z0 + nz - 1), s, wlo, whi, clipped);
     sInt[tid] = wlo;
     sInt[3 + tid] = whi;
+    sInt[24 + tid] = clipped ? 1 : 0;
   }
   __syncthreads();
   int wlo[3], whi[3];
@@ -468,6 +666,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
     wlo[d] = sInt[d];
     whi[d] = sInt[3 + d];
   }
+  const bool window_clipped = (sInt[24] | sInt[25] | sInt[26]) != 0;
 
   // ---- neuron list: ascending k, ballot compaction (single pass for one warp, two passes else).
   // Candidates come from the static per-tile lists when the window stays inside the expanded identity
@@ -535,9 +734,13 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
   const int nst = fits ? min(L, CAP) : 0;
   const int sX3 = p.X + 3, sY3 = p.Y + 3, sZ3 = p.Z + 3;
   {
+    // One thread owns table entry e of every slot.  Slot pairs (2p, 2p+1) share one float4
+    // (G_2p, G_2p+1, D_2p, D_2p+1) = the packed operands of FFMA2; an odd list is completed with a zero
+    // footprint.  Loads are issued four pairs at a time ahead of the stores, so the gather costs a couple of
+    // L2 round trips per tile instead of one per slot.
     const int Wt = W0 + W1 + W2;
+    const int npair = (nst + 1) >> 1;
     for (int e = tid; e < Wt; e += 32 * NW) {
-      // this thread owns table entry e of every slot: resolve its axis once
       const float2* src;
       int row, dst_e;
       bool isx = false;
@@ -555,19 +758,33 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
         row = sZ3;
         dst_e = p.wmax0 + p.wmax1 + (e - W0 - W1);
       }
-      // slots j, j+1 share one float4 = (G_j, G_j+1, D_j, D_j+1): packed operands for FFMA2
-      float* dst = reinterpret_cast<float*>(sTab + (size_t)dst_e * CAP);
-      for (int j = 0; j < nst; ++j) {
-        const int k = sList[j];
-        float2 v = __ldg(src + (size_t)k * row);
-        if (isx) {
-          const float ck = __ldg(p.C + (size_t)k * p.T + t);
-          v.x *= ck;
-          v.y *= ck;
+      float4* dst = reinterpret_cast<float4*>(sTab + (size_t)dst_e * CAP);
+      constexpr int kBatch = 4;
+      for (int p0 = 0; p0 < npair; p0 += kBatch) {
+        float2 va[kBatch], vb[kBatch];
+        float ca[kBatch], cb[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int j = 2 * (p0 + u);
+          va[u] = vb[u] = make_float2(0.f, 0.f);
+          ca[u] = cb[u] = 1.f;
+          if (j < nst) {
+            const int k = sList[j];
+            va[u] = __ldg(src + (size_t)k * row);
+            if (isx) ca[u] = __ldg(p.C + (size_t)k * p.T + t);
+          }
+          if (j + 1 < nst) {
+            const int k = sList[j + 1];
+            vb[u] = __ldg(src + (size_t)k * row);
+            if (isx) cb[u] = __ldg(p.C + (size_t)k * p.T + t);
+          }
         }
-        float* d4 = dst + (j >> 1) * 4 + (j & 1);
-        d4[0] = v.x;
-        d4[2] = v.y;
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          if (p0 + u < npair)
+            dst[p0 + u] = isx ? make_float4(va[u].x * ca[u], vb[u].x * cb[u], va[u].y * ca[u], vb[u].y * cb[u])
+                              : make_float4(va[u].x, vb[u].x, va[u].y, vb[u].y);
+        }
       }
     }
   }
@@ -608,6 +825,84 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
     }
   }
 
+  bool marched = false;
+  if constexpr (SUB == 2 && FAST_DIV) {
+    const int np = (nst + 1) >> 1;
+    if (!has_overflow && np <= kMaxNP) {
+      MarchArgs a;
+      const float yfA = (float)(y0 + ly0), yfB = (float)(y0 + ly0 + kWarpY);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float b0 = sBeta[d], bx_ = sBeta[3 + d], by_ = sBeta[6 + d], bz_ = sBeta[9 + d];
+        const float bxx = sBeta[12 + d], byy = sBeta[15 + d], bxy = sBeta[21 + d], bxz = sBeta[24 + d],
+                    byz = sBeta[27 + d];
+        float vA = fmaf(bx_, xf, b0), vB = vA;
+        vA = fmaf(by_, yfA, vA);
+        vB = fmaf(by_, yfB, vB);
+        vA = fmaf(bxx, xf * xf, vA);
+        vB = fmaf(bxx, xf * xf, vB);
+        vA = fmaf(byy, yfA * yfA, vA);
+        vB = fmaf(byy, yfB * yfB, vB);
+        vA = fmaf(bxy, xf * yfA, vA);
+        vB = fmaf(bxy, xf * yfB, vB);
+        const float wA = fmaf(byz, yfA, fmaf(bxz, xf, bz_)), wB = fmaf(byz, yfB, fmaf(bxz, xf, bz_));
+        a.c0[d] = make_float2(vA + vA, vB + vB);  // exact doubling: the march evaluates 2q directly
+        a.c1[d] = make_float2(wA + wA, wB + wB);
+        a.c2[d] = sBeta[18 + d] + sBeta[18 + d];
+      }
+      a.sm1[0] = sm1x, a.sm1[1] = sm1y, a.sm1[2] = sm1z;
+      a.rcp[0] = rcpx, a.rcp[1] = rcpy, a.rcp[2] = rcpz;
+      a.hsm1[0] = hsm1x, a.hsm1[1] = hsm1y, a.hsm1[2] = hsm1z;
+      a.wl[0] = wlo[0], a.wl[1] = wlo[1], a.wl[2] = wlo[2];
+      a.wm1[0] = W0 - 1, a.wm1[1] = W1 - 1, a.wm1[2] = W2 - 1;
+      a.base[0] = baseX, a.base[1] = baseY, a.base[2] = baseZ;
+      a.strideB = strideB;
+      a.yaddrA = smem_u32(sY + lx * RS + ly0 * zs);
+      a.yoffB = (unsigned)(kWarpY * zs) * 4u;
+      a.zf0 = (float)z0;
+      a.nz = nz;
+      a.validA = (gx < p.X) && (y0 + ly0 < p.Y);
+      a.validB = (gx < p.X) && (y0 + ly0 + kWarpY < p.Y);
+      a.bg = bg;
+      MarchOut o;
+      const bool safe = window_clipped || nx < TX || ny < TY;
+      const int sel = np * 2 + (safe ? 1 : 0);
+      switch (sel) {
+#define DNMF_MARCH(n)                   \
+  case 2 * n:                           \
+    march_pairs<n, false, MODE>(a, o);  \
+    break;                              \
+  case 2 * n + 1:                       \
+    march_pairs<n, true, MODE>(a, o);   \
+    break;
+        DNMF_MARCH(0)
+        DNMF_MARCH(1)
+        DNMF_MARCH(2)
+        DNMF_MARCH(3)
+        DNMF_MARCH(4)
+        DNMF_MARCH(5)
+        DNMF_MARCH(6)
+        DNMF_MARCH(7)
+        DNMF_MARCH(8)
+#undef DNMF_MARCH
+        default:
+          break;
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        S0[0][d] = o.S0[d].x;
+        S0[1][d] = o.S0[d].y;
+        S1[0][d] = o.S1[d].x;
+        S1[1][d] = o.S1[d].y;
+        S2[d] = o.S2[d].x + o.S2[d].y;
+      }
+      sse = o.sse.x + o.sse.y;
+      sum_r = o.sum_r.x + o.sum_r.y;
+      marched = true;
+    }
+  }
+
+  if (!marched) {
 #pragma unroll
   for (int h = 0; h < SUB; ++h) {
   const int ly = ly0 + h * kWarpY;
@@ -758,6 +1053,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
   }  // sub-tiles
   S2[0] = S2xy.x;
   S2[1] = S2xy.y;
+  }  // generic loop
 
   // ---- expand z-moments with this lane's (x,y) monomials, transposing warp reduction ----
   {
