@@ -288,7 +288,7 @@ static FitSmem fit_smem_layout(int nw, int tx, int ty, int tz, int cap, int wsum
   s.y_f = tx * ty * tz + 4;
   s.list_u16 = (K + 7) & ~7;
   s.bytes = (size_t)s.tab_f2 * 8 + (size_t)s.y_f * 4 + (size_t)nw * kNumPartials * 4 + 80 * 4 + 16 +
-            (size_t)((cap + 5) & ~3) * 4 + (size_t)cand_cap * 28 + (size_t)((cand_cap + 7) & ~7) * 2 +
+            (size_t)((cap + 5) & ~3) * 4 + (size_t)cand_cap * 28 + (size_t)((cand_cap + 7) & ~7) * 2 + (size_t)((cap + 7) & ~7) * 2 +
             (size_t)s.list_u16 * 2;
   return s;
 }
@@ -597,7 +597,41 @@ __device__ __forceinline__ void march_pairs(const MarchArgs& a, MarchOut& o) {
 // unrolled variants, but ONE loop body for every list length: the kernel's hot code then fits the 32 KB
 // L1.5 instruction cache (the unrolled family did not, and the SMs starved on instruction fetch).
 
-template <bool SAFE, int MODE>
+// Last slot of an odd list, for voxels A and B at once: the slot's (G, D) entries of A and of B are loaded as
+// scalars into adjacent registers, so the ten operations run packed over (A, B) and land directly on the
+// (A, B)-packed Yhat / gradient values.  Half the FP32-pipe cycles of a zero-padded slot pair.
+// FIRST: Yhat is produced as fma(ca0, t12, oz) with the opaque zero `oz`, not as a product: ptxas 12.9 fuses
+// mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even with --fmad=false), which would round Yhat - Y differently from
+// the forward-only instantiation that stores Yhat, and break "fit of the model's own output has zero residual".
+template <bool FIRST>
+__device__ __forceinline__ void tail_slot(const unsigned (&adA)[3], const unsigned (&adB)[3], unsigned off,
+                                          const float2 (&f)[3], float oz, float2& yh, float2 (&g)[3]) {
+  const float2 exG = make_float2(lds32(adA[0] + off), lds32(adB[0] + off));
+  const float2 exD = make_float2(lds32(adA[0] + off + 8u), lds32(adB[0] + off + 8u));
+  const float2 eyG = make_float2(lds32(adA[1] + off), lds32(adB[1] + off));
+  const float2 eyD = make_float2(lds32(adA[1] + off + 8u), lds32(adB[1] + off + 8u));
+  const float2 ezG = make_float2(lds32(adA[2] + off), lds32(adB[2] + off));
+  const float2 ezD = make_float2(lds32(adA[2] + off + 8u), lds32(adB[2] + off + 8u));
+  const float2 ca0 = __ffma2_rn(f[0], exD, exG);
+  const float2 a1 = __ffma2_rn(f[1], eyD, eyG);
+  const float2 a2 = __ffma2_rn(f[2], ezD, ezG);
+  const float2 t12 = __fmul2_rn(a1, a2);
+  if (FIRST) {
+    yh = __ffma2_rn(ca0, t12, make_float2(oz, oz));
+    g[0] = __fmul2_rn(exD, t12);
+    g[1] = __fmul2_rn(__fmul2_rn(ca0, a2), eyD);
+    g[2] = __fmul2_rn(__fmul2_rn(ca0, a1), ezD);
+  } else {
+    yh = __ffma2_rn(ca0, t12, yh);
+    g[0] = __ffma2_rn(exD, t12, g[0]);
+    g[1] = __ffma2_rn(__fmul2_rn(ca0, a2), eyD, g[1]);
+    g[2] = __ffma2_rn(__fmul2_rn(ca0, a1), ezD, g[2]);
+  }
+}
+
+// TAIL 0: even list, np >= 1 full slot pairs.  TAIL 1: np >= 1 full pairs and one last slot.  TAIL 2: a single
+// slot (np == 0).
+template <bool SAFE, int MODE, int TAIL>
 __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOut& o) {
   const float oz = a.oz;
   const float2 zero2 = make_float2(oz, oz);
@@ -640,30 +674,35 @@ __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOu
     }
     const float2 fA0 = make_float2(f[0].x, f[0].x), fA1 = make_float2(f[1].x, f[1].x), fA2 = make_float2(f[2].x, f[2].x);
     const float2 fB0 = make_float2(f[0].y, f[0].y), fB1 = make_float2(f[1].y, f[1].y), fB2 = make_float2(f[2].y, f[2].y);
-    // first slot pair (np >= 1 here) produces the accumulators, the rest of the list updates them
-    float2 yA, gA0, gA1, gA2, yB, gB0, gB1, gB2;
-    slot_pair<0, true>(adA[0], adA[1], adA[2], fA0, fA1, fA2, yA, gA0, gA1, gA2);
-    slot_pair<0, true>(adB[0], adB[1], adB[2], fB0, fB1, fB2, yB, gB0, gB1, gB2);
+    float2 yh, g[3];
+    if (TAIL != 2) {
+      // first slot pair produces the accumulators, the rest of the list updates them
+      float2 yA, gA0, gA1, gA2, yB, gB0, gB1, gB2;
+      slot_pair<0, true>(adA[0], adA[1], adA[2], fA0, fA1, fA2, yA, gA0, gA1, gA2);
+      slot_pair<0, true>(adB[0], adB[1], adB[2], fB0, fB1, fB2, yB, gB0, gB1, gB2);
 #pragma unroll 1
-    for (unsigned off = 16u; off < pair_bytes; off += 16u) {
-      {
-        const float4 ex = lds128r(adA[0] + off), ey = lds128r(adA[1] + off), ez = lds128r(adA[2] + off);
-        pair2_accumulate(make_float2(ex.x, ex.y), make_float2(ex.z, ex.w), make_float2(ey.x, ey.y),
-                         make_float2(ey.z, ey.w), make_float2(ez.x, ez.y), make_float2(ez.z, ez.w), fA0, fA1, fA2,
-                         yA, gA0, gA1, gA2);
+      for (unsigned off = 16u; off < pair_bytes; off += 16u) {
+        {
+          const float4 ex = lds128r(adA[0] + off), ey = lds128r(adA[1] + off), ez = lds128r(adA[2] + off);
+          pair2_accumulate(make_float2(ex.x, ex.y), make_float2(ex.z, ex.w), make_float2(ey.x, ey.y),
+                           make_float2(ey.z, ey.w), make_float2(ez.x, ez.y), make_float2(ez.z, ez.w), fA0, fA1, fA2,
+                           yA, gA0, gA1, gA2);
+        }
+        {
+          const float4 ex = lds128r(adB[0] + off), ey = lds128r(adB[1] + off), ez = lds128r(adB[2] + off);
+          pair2_accumulate(make_float2(ex.x, ex.y), make_float2(ex.z, ex.w), make_float2(ey.x, ey.y),
+                           make_float2(ey.z, ey.w), make_float2(ez.x, ez.y), make_float2(ez.z, ez.w), fB0, fB1, fB2,
+                           yB, gB0, gB1, gB2);
+        }
       }
-      {
-        const float4 ex = lds128r(adB[0] + off), ey = lds128r(adB[1] + off), ez = lds128r(adB[2] + off);
-        pair2_accumulate(make_float2(ex.x, ex.y), make_float2(ex.z, ex.w), make_float2(ey.x, ey.y),
-                         make_float2(ey.z, ey.w), make_float2(ez.x, ez.y), make_float2(ez.z, ez.w), fB0, fB1, fB2,
-                         yB, gB0, gB1, gB2);
-      }
+      yh = make_float2(yA.x + yA.y, yB.x + yB.y);
+      g[0] = make_float2(gA0.x + gA0.y, gB0.x + gB0.y);
+      g[1] = make_float2(gA1.x + gA1.y, gB1.x + gB1.y);
+      g[2] = make_float2(gA2.x + gA2.y, gB2.x + gB2.y);
+      if (TAIL == 1) tail_slot<false>(adA, adB, pair_bytes, f, oz, yh, g);
+    } else {
+      tail_slot<true>(adA, adB, 0u, f, oz, yh, g);
     }
-    float2 yh = make_float2(yA.x + yA.y, yB.x + yB.y);
-    float2 g[3];
-    g[0] = make_float2(gA0.x + gA0.y, gB0.x + gB0.y);
-    g[1] = make_float2(gA1.x + gA1.y, gB1.x + gB1.y);
-    g[2] = make_float2(gA2.x + gA2.y, gB2.x + gB2.y);
     if (MODE == 1) {
       sts32(yaddr, yh.x);
       sts32(yaddr + a.yoffB, yh.y);
@@ -907,7 +946,8 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
   int* sCandRng = reinterpret_cast<int*>(sCk + ((CAP + 5) & ~3));       // [cand_cap][6]
   float* sCandC = reinterpret_cast<float*>(sCandRng + (size_t)p.cand_cap * 6);  // [cand_cap]
   unsigned short* sCand = reinterpret_cast<unsigned short*>(sCandC + p.cand_cap);  // [cand_cap (even)]
-  unsigned short* sList = sCand + ((p.cand_cap + 7) & ~7);
+  unsigned short* sSlotCand = sCand + ((p.cand_cap + 7) & ~7);  // [CAP]: candidate index of each staged slot
+  unsigned short* sList = sSlotCand + ((CAP + 7) & ~7);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   auto cta_sync = [&]() {
@@ -974,19 +1014,18 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
     const int t = __shfl_sync(0xffffffffu, my_frame, fi);
     const float* __restrict__ frame = p.frames + (size_t)(p.frames_are_batch ? b : t) * Nvox;
     if (bulk) {
-      if (tid == 0) {
+      if (tid == 0) {  // one thread arms the barrier and issues every row copy (uniform-datapath instructions)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nx * run * 4)
                      : "memory");
-      }
-      cta_sync();
-      if (tid < nx) {
-        const float* src = frame + ((size_t)(x0 + tid) * p.Y + y0) * p.Z;
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                smem_u32(sY + tid * RS)),
-            "l"(src), "r"(run * 4), "r"(bar)
-            : "memory");
+        const float* src = frame + ((size_t)x0 * p.Y + y0) * p.Z;
+        unsigned dst = smem_u32(sY);
+        const size_t src_step = (size_t)p.Y * p.Z;
+        for (int r = 0; r < nx; ++r, src += src_step, dst += (unsigned)RS * 4u)
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+              "l"(src), "r"(run * 4), "r"(bar)
+              : "memory");
       }
     } else if (p.full_depth) {
       for (int lx = warp; lx < nx; lx += NW) {
@@ -1034,6 +1073,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
 
   // state carried from frame to frame: what the staged slices were built for
   int pw_lo[3] = {0x7fffffff, 0, 0}, pw_hi[3] = {0, 0, 0}, prev_L = -1;
+  bool prev_fast = false;  // previous list came from the cached candidates with prefetched traces
 
   for (int fi = 0; fi < nb; ++fi) {
     const int b = b_first + fi;
@@ -1075,7 +1115,15 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
     // expanded identity window the list was built for, else from a scan over all K neurons.
     int L = 0;
     bool changed = false;
-    {
+    bool same_window = prev_fast;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) same_window = same_window && (wlo[d] == pw_lo[d]) && (whi[d] == pw_hi[d]);
+    if (same_window) {
+      // the list is a function of the window and the static candidates: unchanged.  Only the traces of the
+      // staged slots are new.
+      L = prev_L;
+      for (int pos = tid; pos < min(L, CAP); pos += NT) sCk[pos] = sCandC[sSlotCand[pos]];
+    } else {
       bool inside = false;
       if (p.cand_off != nullptr) {
         const int e = p.cand_expand;
@@ -1102,10 +1150,13 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
         ck = __ldg(p.C + (size_t)k * p.T + t);
         return true;
       };
-      auto put = [&](int pos, int k, float ck) {
+      auto put = [&](int pos, int k, float ck, int idx) {
         changed |= (pos >= prev_L) || (sList[pos] != (unsigned short)k);
         sList[pos] = (unsigned short)k;
-        if (pos < CAP) sCk[pos] = ck;
+        if (pos < CAP) {
+          sCk[pos] = ck;
+          sSlotCand[pos] = (unsigned short)idx;
+        }
       };
       if (NW == 1) {
         for (int c0i = 0; c0i < r1; c0i += 32) {
@@ -1113,7 +1164,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
           float ck;
           const bool ok = probe(c0i + lane, k, ck);
           const unsigned m = __ballot_sync(0xffffffffu, ok);
-          if (ok) put(L + __popc(m & ((1u << lane) - 1u)), k, ck);
+          if (ok) put(L + __popc(m & ((1u << lane) - 1u)), k, ck, c0i + lane);
           L += __popc(m);
         }
         changed = __any_sync(0xffffffffu, changed);
@@ -1140,7 +1191,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
           float ck;
           const bool ok = probe(c0i + lane, k, ck);
           const unsigned m = __ballot_sync(0xffffffffu, ok);
-          if (ok) put(off + __popc(m & ((1u << lane) - 1u)), k, ck);
+          if (ok) put(off + __popc(m & ((1u << lane) - 1u)), k, ck, c0i + lane);
           off += __popc(m);
         }
         changed = __syncthreads_or(changed ? 1 : 0) != 0;
@@ -1148,6 +1199,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
       changed = changed || (L != prev_L);
 #pragma unroll
       for (int d = 0; d < 3; ++d) changed = changed || (wlo[d] != pw_lo[d]) || (whi[d] != pw_hi[d]);
+      prev_fast = from_smem && prefetch_c;
     }
     cta_sync();
 
@@ -1303,10 +1355,17 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
             march_pairs<0, true, MODE>(a, o);
           else
             march_pairs<0, false, MODE>(a, o);
-        } else if (safe) {
-          march_rolled<true, MODE>(a, npair, o);
         } else {
-          march_rolled<false, MODE>(a, npair, o);
+          const int npf = nst >> 1;  // full slot pairs; an odd list ends with a single slot
+          const int tail = (nst & 1) ? (npf == 0 ? 2 : 1) : 0;
+          switch (tail * 2 + (safe ? 1 : 0)) {
+            case 0: march_rolled<false, MODE, 0>(a, npf, o); break;
+            case 1: march_rolled<true, MODE, 0>(a, npf, o); break;
+            case 2: march_rolled<false, MODE, 1>(a, npf, o); break;
+            case 3: march_rolled<true, MODE, 1>(a, npf, o); break;
+            case 4: march_rolled<false, MODE, 2>(a, npf, o); break;
+            default: march_rolled<true, MODE, 2>(a, npf, o); break;
+          }
         }
 #endif
 #pragma unroll
