@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -1784,8 +1785,8 @@ static int configure_tiling(dnmf_ctx* c, cudaStream_t st);
 extern "C" int dnmf_set_tiling(dnmf_ctx* c, int warps_x, int warps_y, int tz, int slot_capacity, int subtiles_y) {
   if (!c) return fail("dnmf_set_tiling: ctx is NULL");
   if (subtiles_y < 1) subtiles_y = 1;
-  if (subtiles_y > 2 || (subtiles_y == 2 && (warps_x != 1 || warps_y != 1)))
-    return fail("dnmf_set_tiling: subtiles_y = 2 is supported for the one-warp layout only");
+  if (subtiles_y > 2 || (subtiles_y == 2 && warps_y > 2))
+    return fail("dnmf_set_tiling: subtiles_y = 2 is supported for the 1x1, 2x1 and 2x2 warp layouts");
   const bool ok = (warps_x == 1 && warps_y == 1) || (warps_x == 2 && warps_y == 1) ||
                   (warps_x == 2 && warps_y == 2) || (warps_x == 2 && warps_y == 4);
   if (!ok) return fail("dnmf_set_tiling: supported warp layouts are 1x1, 2x1, 2x2, 2x4");
@@ -1828,12 +1829,12 @@ static int configure_tiling_fixed(dnmf_ctx* c, cudaStream_t st);
 static int configure_tiling(dnmf_ctx* c, cudaStream_t st) {
   if (!c->auto_tiling) return configure_tiling_fixed(c, st);
   // Instruction-count model of the fused kernel per 32-voxel row (from the ncu source pages, profiles/):
-  // ~85 fixed + ~9.5 per listed neuron + the tile prologue/epilogue amortised over the rows of the tile,
-  // inflated when shared memory leaves fewer than ~12 warps per SM to hide latency.
-  static const int layouts[5][3] = {{1, 1, 2}, {1, 1, 1}, {2, 1, 1}, {2, 2, 1}, {2, 4, 1}};
+  // ~85 fixed + ~9.5 per listed neuron (one sub-tile per warp; the packed two-sub-tile march: 42 + 7.3) + the tile
+  // prologue/epilogue amortised over the rows of the tile, inflated when shared memory leaves too few warps per SM.
+  static const int layouts[7][3] = {{1, 1, 2}, {1, 1, 1}, {2, 1, 2}, {2, 2, 2}, {2, 1, 1}, {2, 2, 1}, {2, 4, 1}};
   int best = 0;
   double best_cost = 1e300;
-  for (int i = 0; i < 5; ++i) {
+  for (int i = 0; i < 7; ++i) {
     c->nwx = layouts[i][0];
     c->nwy = layouts[i][1];
     c->sub = layouts[i][2];
@@ -1842,7 +1843,12 @@ static int configure_tiling(dnmf_ctx* c, cudaStream_t st) {
     const int ctas = std::min(32, (int)((size_t)227 * 1024 / (c->fit_smem + 1024)));
     const double warps = std::min(64, ctas * nw);
     const double rows = (double)c->sub * c->tz;
-    double cost = (85.0 + 9.5 * c->mean_list_identity + (300.0 + 600.0 / nw) / rows) * std::max(1.0, 12.0 / warps);
+    // two sub-tiles per warp run the packed (A, B) march: ~42 fixed + ~7.3 per listed neuron per row
+    const double fixed = c->sub == 2 ? 42.0 : 85.0, per = c->sub == 2 ? 7.3 : 9.5;
+    // fewer than ~8 resident warps per SM cannot keep the FP32 pipe fed (cfg4, measured: 16 warps 1.0, 8 warps
+    // 1.04, 6 warps 1.6, 4 warps 2.0 relative cost)
+    double cost = (fixed + per * c->mean_list_identity + (300.0 + 600.0 / nw) / rows) *
+                  std::pow(std::max(1.0, 8.0 / warps), 1.5);
     if (nw > 1 && c->mean_list_identity < 16.0) cost *= 1.25;  // sharing the staged slices only pays for long lists
     if (cost < best_cost) {
       best_cost = cost;
@@ -2091,7 +2097,9 @@ static int dispatch_fit(dnmf_ctx* c, const FitParams& p, int B, cudaStream_t st)
   DNMF_DISPATCH(1, 1, 1)
   DNMF_DISPATCH(1, 1, 2)
   DNMF_DISPATCH(2, 1, 1)
+  DNMF_DISPATCH(2, 1, 2)
   DNMF_DISPATCH(2, 2, 1)
+  DNMF_DISPATCH(2, 2, 2)
   DNMF_DISPATCH(2, 4, 1)
 #undef DNMF_DISPATCH
   return fail("dispatch_fit: unsupported warp layout");
