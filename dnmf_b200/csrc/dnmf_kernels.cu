@@ -9,6 +9,7 @@
 //   kernel 3b  mu_* kernels             trace statistics + multiplicative non-negative sweeps
 //
 // Reference lines (Demix/dNMF.py, demo.py) are cited next to each piece; math in SURVEY.md App. A.
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -274,6 +275,9 @@ struct FitParams {
   int B;         // frames in this launch
   int fpc;       // consecutive frames walked by one CTA (<= 32)
   float zero;    // 0.0f, opaque to the compiler (see march_pairs)
+  int tmap_ok;   // the frame tile can be fetched with ONE tensor TMA copy (3-D map over [frame][x][y*Z])
+  int b_base;    // index of this launch's first frame in the buffer the tensor map describes
+  alignas(64) CUtensorMap tmap;
 };
 
 struct FitSmem {
@@ -288,7 +292,8 @@ static FitSmem fit_smem_layout(int nw, int tx, int ty, int tz, int cap, int wsum
   s.tab_f2 = cap * (wsum + wmax0);  // live slices + the x slice without traces
   s.y_f = tx * ty * tz + 4;
   s.list_u16 = (K + 7) & ~7;
-  s.bytes = (size_t)s.tab_f2 * 8 + (size_t)s.y_f * 4 + (size_t)nw * kNumPartials * 4 + 80 * 4 + 16 +
+  s.bytes = (((size_t)s.tab_f2 * 8 + 127) & ~(size_t)127) + (size_t)s.y_f * 4 + (size_t)nw * kNumPartials * 4 +
+            80 * 4 + 16 +
             (size_t)((cap + 5) & ~3) * 4 + (size_t)cand_cap * 28 + (size_t)((cand_cap + 7) & ~7) * 2 + (size_t)((cap + 7) & ~7) * 2 +
             (size_t)s.list_u16 * 2;
   return s;
@@ -930,12 +935,12 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
   constexpr int NW = NWX * NWY;
   constexpr int NT = 32 * NW;
   constexpr int TX = kWarpX * NWX, TY = kWarpY * NWY * SUB;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int wsum = p.wmax0 + p.wmax1 + p.wmax2;
   const int CAP = p.cap;
   float2* sTab = reinterpret_cast<float2*>(smem_raw);            // [entry][slot], slot stride 8 B
   float2* sXraw = sTab + (size_t)CAP * wsum;                     // x slice before the traces are folded in
-  float* sY = reinterpret_cast<float*>(sXraw + (size_t)CAP * p.wmax0);
+  float* sY = reinterpret_cast<float*>(smem_raw + ((((size_t)CAP * (wsum + p.wmax0)) * 8 + 127) & ~(size_t)127));  // 128 B: TMA
   const int zs = p.full_depth ? p.Z : p.tz;  // smem z-stride between y rows
   const int RS = TY * zs;                    // smem stride between x rows
   float* sRed = sY + (TX * TY * p.tz + 4);
@@ -1014,7 +1019,18 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
     const int b = b_first + fi;
     const int t = __shfl_sync(0xffffffffu, my_frame, fi);
     const float* __restrict__ frame = p.frames + (size_t)(p.frames_are_batch ? b : t) * Nvox;
-    if (bulk) {
+    if (bulk && p.tmap_ok) {
+      if (tid == 0) {  // the whole 8 x (ty*Z) tile in one tensor copy; rows/columns past the volume are zero-filled
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TX * RS * 4)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+                "r"(smem_u32(sY)), "l"(reinterpret_cast<unsigned long long>(&p.tmap)), "r"(y0 * p.Z), "r"(x0),
+            "r"(p.frames_are_batch ? p.b_base + b : t), "r"(bar)
+            : "memory");
+      }
+    } else if (bulk) {
       if (tid == 0) {  // one thread arms the barrier and issues every row copy (uniform-datapath instructions)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nx * run * 4)
@@ -1620,6 +1636,13 @@ struct dnmf_ctx {
   int cand_expand = 6;
   int cand_cap = 0;
   int fpc_override = 0;  // DNMF_FPC environment override of the frames-per-CTA heuristic (tuning)
+  // tensor map of the frame buffer the fused kernel last ran on (resident slab or caller's batch)
+  alignas(64) CUtensorMap tmap;
+  const float* tmap_ptr = nullptr;
+  long long tmap_frames = -1;
+  int tmap_tx = 0, tmap_ty = 0;
+  bool tmap_valid = false;
+  void* encode_tiled = nullptr;
   // video
   float* d_video = nullptr;
   // scratch
@@ -2074,6 +2097,7 @@ static int launch_fit(const FitParams& p0, int B, size_t smem, cudaStream_t st) 
     FitParams p = p0;
     p.fpc = fpc;
     p.B = nb;
+    p.b_base = b0;
     p.frame_ids = p0.frame_ids + b0;
     p.partials = p0.partials + (size_t)b0 * nt * kNumPartials;
     if (p0.frames_are_batch) p.frames = p0.frames + (size_t)b0 * N;
@@ -2135,6 +2159,47 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
   p.full_depth = (c->tz == c->Z) ? 1 : 0;
   p.bulk_ok = (((uintptr_t)p.frames & 15) == 0) && (((size_t)c->Y * c->Z) % 4 == 0) &&
               (((size_t)c->ty * c->Z) % 4 == 0);
+  p.b_base = 0;
+  p.tmap_ok = 0;
+  memset(&p.tmap, 0, sizeof(p.tmap));
+  if (p.bulk_ok && p.full_depth && (size_t)c->ty * c->Z <= 256 && c->tx <= 256) {
+    // 3-D tensor map over the frame buffer: [frames][X][Y*Z] floats, box = one tile (tx rows of ty*Z floats)
+    const long long nframes = frames_dev ? (long long)B : (long long)c->T;
+    if (c->tmap_ptr != p.frames || c->tmap_frames != nframes || c->tmap_tx != c->tx || c->tmap_ty != c->ty) {
+      c->tmap_valid = false;
+      if (!c->encode_tiled) {
+        cudaDriverEntryPointQueryResult qres;
+        void* fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+          c->encode_tiled = fn;
+        else
+          (void)cudaGetLastError();
+      }
+      if (c->encode_tiled) {
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        const cuuint64_t gdim[3] = {(cuuint64_t)c->Y * c->Z, (cuuint64_t)c->X, (cuuint64_t)nframes};
+        const cuuint64_t gstride[2] = {(cuuint64_t)c->Y * c->Z * 4, (cuuint64_t)c->N * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)(c->ty * c->Z), (cuuint32_t)c->tx, 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        const CUresult r = ((EncodeFn)c->encode_tiled)(
+            &c->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.frames), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        c->tmap_valid = (r == CUDA_SUCCESS);
+      }
+      c->tmap_ptr = p.frames;
+      c->tmap_frames = nframes;
+      c->tmap_tx = c->tx;
+      c->tmap_ty = c->ty;
+    }
+    if (c->tmap_valid) {
+      p.tmap = c->tmap;
+      p.tmap_ok = 1;
+    }
+  }
   p.fast_div = c->fast_div;
   p.rcp0 = c->rcp[0];
   p.rcp1 = c->rcp[1];
