@@ -315,3 +315,27 @@ def test_launch_chunking_over_grid_z_limit():
         g_part, s_part = e.loss_grad(ids, beta, C, B_global=T)
         assert torch.equal(s_part, s_all[lo:lo + 100])
         assert torch.equal(g_part[:, :, lo:lo + 100], g_all[:, :, lo:lo + 100])
+
+
+def test_node_image_main_loop_matches_oracle(monkeypatch):
+    """Opt-in node-image form of the main loop (DNMF_FIELD=1): same loss and gradient."""
+    monkeypatch.setenv("DNMF_FIELD", "1")
+    _check([33, 18, 7], 6, 3, seed=11, cutoff=3.5, tiling=(1, 1, 0, 0, 2))
+    _check([40, 40, 5], 12, 2, seed=12, cutoff=3.5, tiling=(2, 2, 0, 0, 2), beta_scale=0.5)
+
+
+def test_frames_per_cta_do_not_change_results(monkeypatch):
+    """One CTA walking 1, 3 or 8 consecutive frames of its tile (slices cached across frames, traces and tile
+    requested a frame ahead) gives bit-identical gradients."""
+    from dnmf_b200.engine import Engine
+    sz, K, T = [48, 24, 6], 9, 16
+    pos, sig, beta, C, frames = _case(sz, K, T, 77, beta_scale=0.3)
+    out = []
+    for fpc in ("1", "3", "8"):
+        monkeypatch.setenv("DNMF_FPC", fpc)
+        e = Engine(sz, K, T)
+        e.set_tiling(1, 1, 0, 0, 2)
+        e.set_footprints(pos, sig, 3.5)
+        out.append(e.loss_grad(torch.arange(T), beta.cuda(), C.cuda(), frames=frames.cuda()))
+    for g, s_ in out[1:]:
+        assert torch.equal(g, out[0][0]) and torch.equal(s_, out[0][1])
