@@ -275,8 +275,6 @@ struct FitParams {
   int B;         // frames in this launch
   int fpc;       // consecutive frames walked by one CTA (<= 32)
   float zero;    // 0.0f, opaque to the compiler (see march_pairs)
-  int field;     // node-image main loop (build_field + march_field); fPX / fPY = pitches of F in floats
-  int fPX, fPY;
   int tmap_ok;   // the frame tile can be fetched with ONE tensor TMA copy (3-D map over [frame][x][y*Z])
   int b_base;    // index of this launch's first frame in the buffer the tensor map describes
   alignas(64) CUtensorMap tmap;
@@ -289,8 +287,7 @@ struct FitSmem {
   size_t bytes;
 };
 
-static FitSmem fit_smem_layout(int nw, int tx, int ty, int tz, int cap, int wsum, int K, int wmax0, int cand_cap,
-                               int field_floats = 0) {
+static FitSmem fit_smem_layout(int nw, int tx, int ty, int tz, int cap, int wsum, int K, int wmax0, int cand_cap) {
   FitSmem s;
   s.tab_f2 = cap * (wsum + wmax0);  // live slices + the x slice without traces
   s.y_f = tx * ty * tz + 4;
@@ -299,7 +296,6 @@ static FitSmem fit_smem_layout(int nw, int tx, int ty, int tz, int cap, int wsum
             80 * 4 + 16 +
             (size_t)((cap + 5) & ~3) * 4 + (size_t)cand_cap * 28 + (size_t)((cand_cap + 7) & ~7) * 2 + (size_t)((cap + 7) & ~7) * 2 +
             (size_t)s.list_u16 * 2;
-  if (field_floats > 0) s.bytes = ((s.bytes + 15) & ~(size_t)15) + (size_t)field_floats * 4;
   return s;
 }
 
@@ -423,7 +419,6 @@ struct MarchArgs {
   bool validA, validB;
   float bg;                 // MODE 2: scalar background
   float oz;                 // 0.0f the compiler cannot see (FitParams::zero)
-  unsigned fbase, fPX4, fPY4;  // node image: shared-memory byte address, byte pitches along x and y
 };
 
 struct MarchOut {
@@ -731,174 +726,6 @@ __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOu
       sum_r = __fadd2_rn(sum_r, r);
     }
     sse = __ffma2_rn(r, r, sse);
-    // z-moments of r * dYhat/dix_d: the residual is folded into the z weights once for the three axes
-    const float2 zr = __fmul2_rn(z2, r);
-    const float2 zzr = __fmul2_rn(z2, zr);
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      o.S0[d] = __ffma2_rn(r, g[d], o.S0[d]);
-      o.S1[d] = __ffma2_rn(zr, g[d], o.S1[d]);
-      o.S2[d] = __ffma2_rn(zzr, g[d], o.S2[d]);
-    }
-  }
-  o.sse = sse;
-  o.sum_r = sum_r;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Node-image form of the main loop.  Trilinear resampling is linear in the node values, so
-//   Yhat_t(p) = sum_k C[k,t] interp(A_k)(ix(p)) = interp(F_t)(ix(p)),   F_t[n] = sum_k C[k,t] Gx_k[n0] Gy_k[n1] Gz_k[n2],
-// and dYhat/dix is the gradient of the same trilinear interpolant.  build_field evaluates F_t on the tile's
-// window (+1 node per axis) from the staged slices: one FFMA2 per node and slot PAIR; march_field then costs
-// 22 packed operations per voxel pair whatever the list length (the slot-pair loop costs 20 per pair).
-// F is stored [nx][ny][nz] with an odd y pitch and an x pitch = 4 (mod 8): the 8 x 4 lanes of a sub-tile
-// hit 32 different banks at an identity-like deformation.
-// ------------------------------------------------------------------------------------------------
-// node values of slots (2p, 2p+1) at node n of an axis whose staged entries are 0..W-1 (entry e holds G[e] and
-// G[e+1]-G[e]); node W is rebuilt from the last entry
-__device__ __forceinline__ float2 node_pair(unsigned axis_base, unsigned strideB, int n, int W, unsigned pair_off) {
-  const float4 e = lds128r(axis_base + (unsigned)min(n, W - 1) * strideB + pair_off);
-  return n < W ? make_float2(e.x, e.y) : make_float2(e.x + e.z, e.y + e.w);
-}
-
-// One pass over a column of F for NPC slot pairs starting at byte offset poff0 within an entry's slots.
-template <int NPC>
-__device__ __forceinline__ void field_column_pass(const MarchArgs& a, unsigned faddr, int nx, int ny, int W0, int W1,
-                                                  int W2, unsigned poff0, bool accumulate) {
-  float2 pxy[NPC];
-#pragma unroll
-  for (int i = 0; i < NPC; ++i) {
-    const unsigned poff = poff0 + 16u * i;
-    pxy[i] = __fmul2_rn(node_pair(a.base[0], a.strideB, nx, W0, poff), node_pair(a.base[1], a.strideB, ny, W1, poff));
-  }
-  unsigned zaddr = a.base[2] + poff0;
-#pragma unroll 1
-  for (int nz = 0; nz < W2; ++nz, zaddr += a.strideB, faddr += 4u) {
-    float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < NPC; ++i) {
-      const float4 e = lds128r(zaddr + 16u * i);
-      acc = __ffma2_rn(pxy[i], make_float2(e.x, e.y), acc);
-    }
-    float v = acc.x + acc.y;
-    if (accumulate) v += lds32(faddr);
-    sts32(faddr, v);
-  }
-  {  // node W2 = G + D of the last entry
-    zaddr -= a.strideB;
-    float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < NPC; ++i) {
-      const float4 e = lds128r(zaddr + 16u * i);
-      acc = __ffma2_rn(pxy[i], make_float2(e.x + e.z, e.y + e.w), acc);
-    }
-    float v = acc.x + acc.y;
-    if (accumulate) v += lds32(faddr);
-    sts32(faddr, v);
-  }
-}
-
-template <int NT>
-__device__ __forceinline__ void build_field(const MarchArgs& a, int npair, int tid) {
-  const int W0 = a.wm1[0] + 1, W1 = a.wm1[1] + 1, W2 = a.wm1[2] + 1;
-  const int ncol = (W0 + 1) * (W1 + 1);
-  for (int col = tid; col < ncol; col += NT) {
-    const int nx = col / (W1 + 1), ny = col - nx * (W1 + 1);
-    const unsigned faddr = a.fbase + (unsigned)nx * a.fPX4 + (unsigned)ny * a.fPY4;
-    for (int p0 = 0; p0 < npair; p0 += 4) {
-      const unsigned poff0 = (unsigned)p0 * 16u;
-      switch (min(npair - p0, 4)) {
-        case 1: field_column_pass<1>(a, faddr, nx, ny, W0, W1, W2, poff0, p0 > 0); break;
-        case 2: field_column_pass<2>(a, faddr, nx, ny, W0, W1, W2, poff0, p0 > 0); break;
-        case 3: field_column_pass<3>(a, faddr, nx, ny, W0, W1, W2, poff0, p0 > 0); break;
-        default: field_column_pass<4>(a, faddr, nx, ny, W0, W1, W2, poff0, p0 > 0); break;
-      }
-    }
-  }
-}
-
-template <bool SAFE, int MODE>
-__device__ __forceinline__ void march_field(const MarchArgs& a, MarchOut& o) {
-  const float oz = a.oz;
-  const float2 zero2 = make_float2(oz, oz);
-#pragma unroll
-  for (int d = 0; d < 3; ++d) o.S0[d] = o.S1[d] = o.S2[d] = zero2;
-  float2 sse = zero2, sum_r = zero2;
-  unsigned yaddr = a.yaddrA;
-  // byte address of node (i0, i1, i2): fbase + (i0-wl0)*fPX4 + (i1-wl1)*fPY4 + (i2-wl2)*4
-  const unsigned fbias = a.fbase - (unsigned)a.wl[0] * a.fPX4 - (unsigned)a.wl[1] * a.fPY4 - (unsigned)a.wl[2] * 4u;
-  float zf = a.zf0;
-#pragma unroll 1
-  for (int zz = 0; zz < a.nz; ++zz, zf += 1.f, yaddr += 4u) {
-    const float2 z2 = make_float2(zf, zf);
-    float2 ix[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const float2 rcp2 = make_float2(a.rcp[d], a.rcp[d]);
-      const float2 q = __ffma2_rn(z2, __ffma2_rn(z2, make_float2(a.c2[d], a.c2[d]), a.c1[d]), a.c0[d]);  // = 2q
-      const float2 t0 = __fmul2_rn(q, rcp2);
-      const float2 r = __ffma2_rn(make_float2(-t0.x, -t0.y), make_float2(a.sm1[d], a.sm1[d]), q);
-      const float2 v = __ffma2_rn(r, rcp2, t0);  // = fl(2q / (s-1)), verified exact (verify_coord_kernel)
-      const float2 u = __fadd2_rn(v, make_float2(-1.f, -1.f));
-      ix[d] = __fmul2_rn(__fadd2_rn(u, make_float2(1.f, 1.f)), make_float2(a.hsm1[d], a.hsm1[d]));
-    }
-    int iA[3], iB[3];
-    float2 f[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      iA[d] = __float2int_rd(ix[d].x);
-      iB[d] = __float2int_rd(ix[d].y);
-      f[d] = __fadd2_rn(ix[d], make_float2(-(float)iA[d], -(float)iB[d]));
-    }
-    unsigned aA, aB;
-    if (SAFE) {
-      aA = a.fbase + (unsigned)min(max(iA[0] - a.wl[0], 0), a.wm1[0]) * a.fPX4 +
-           (unsigned)min(max(iA[1] - a.wl[1], 0), a.wm1[1]) * a.fPY4 +
-           (unsigned)min(max(iA[2] - a.wl[2], 0), a.wm1[2]) * 4u;
-      aB = a.fbase + (unsigned)min(max(iB[0] - a.wl[0], 0), a.wm1[0]) * a.fPX4 +
-           (unsigned)min(max(iB[1] - a.wl[1], 0), a.wm1[1]) * a.fPY4 +
-           (unsigned)min(max(iB[2] - a.wl[2], 0), a.wm1[2]) * 4u;
-    } else {
-      aA = fbias + (unsigned)iA[0] * a.fPX4 + (unsigned)iA[1] * a.fPY4 + (unsigned)iA[2] * 4u;
-      aB = fbias + (unsigned)iB[0] * a.fPX4 + (unsigned)iB[1] * a.fPY4 + (unsigned)iB[2] * 4u;
-    }
-    const unsigned aA1 = aA + a.fPY4, aB1 = aB + a.fPY4;
-    const unsigned aA2 = aA + a.fPX4, aB2 = aB + a.fPX4;
-    const unsigned aA3 = aA2 + a.fPY4, aB3 = aB2 + a.fPY4;
-    // the 8 cell corners F[x][y][z], (A, B) packed
-    const float2 F000 = make_float2(lds32(aA), lds32(aB)), F001 = make_float2(lds32(aA + 4u), lds32(aB + 4u));
-    const float2 F010 = make_float2(lds32(aA1), lds32(aB1)), F011 = make_float2(lds32(aA1 + 4u), lds32(aB1 + 4u));
-    const float2 F100 = make_float2(lds32(aA2), lds32(aB2)), F101 = make_float2(lds32(aA2 + 4u), lds32(aB2 + 4u));
-    const float2 F110 = make_float2(lds32(aA3), lds32(aB3)), F111 = make_float2(lds32(aA3 + 4u), lds32(aB3 + 4u));
-    auto sub2 = [](float2 x, float2 y) { return __fadd2_rn(x, make_float2(-y.x, -y.y)); };
-    const float2 dz00 = sub2(F001, F000), dz01 = sub2(F011, F010), dz10 = sub2(F101, F100), dz11 = sub2(F111, F110);
-    const float2 v00 = __ffma2_rn(f[2], dz00, F000), v01 = __ffma2_rn(f[2], dz01, F010);
-    const float2 v10 = __ffma2_rn(f[2], dz10, F100), v11 = __ffma2_rn(f[2], dz11, F110);
-    const float2 dy0 = sub2(v01, v00), dy1 = sub2(v11, v10);
-    const float2 v0 = __ffma2_rn(f[1], dy0, v00), v1 = __ffma2_rn(f[1], dy1, v10);
-    float2 g[3];
-    g[0] = sub2(v1, v0);
-    float2 yh = __ffma2_rn(f[0], g[0], v0);
-    g[1] = __ffma2_rn(f[0], sub2(dy1, dy0), dy0);
-    const float2 e0 = __ffma2_rn(f[1], sub2(dz01, dz00), dz00), e1 = __ffma2_rn(f[1], sub2(dz11, dz10), dz10);
-    g[2] = __ffma2_rn(f[0], sub2(e1, e0), e0);
-    if (MODE == 1) {
-      sts32(yaddr, yh.x);
-      sts32(yaddr + a.yoffB, yh.y);
-      continue;
-    }
-    if (MODE == 2) yh = __fadd2_rn(yh, make_float2(a.bg, a.bg));
-    float2 r = __fadd2_rn(yh, make_float2(-lds32(yaddr), -lds32(yaddr + a.yoffB)));
-    if (SAFE) {
-      r.x = a.validA ? r.x : 0.f;
-      r.y = a.validB ? r.y : 0.f;
-    }
-    if (MODE == 2) {
-      sts32(yaddr, r.x);
-      sts32(yaddr + a.yoffB, r.y);
-      sum_r = __fadd2_rn(sum_r, r);
-    }
-    sse = __ffma2_rn(r, r, sse);
     const float zq = zf * zf;
     const float2 zq2 = make_float2(zq, zq);
 #pragma unroll
@@ -1102,7 +929,7 @@ __device__ __forceinline__ void march_generic(const GenericArgs& a, float (&S0)[
 // the frame's window or neuron list differs from the previous frame's; otherwise only the x slice is rescaled
 // by the frame's traces.  In the steady state no global-memory latency sits between two main loops.
 template <int NWX, int NWY, int SUB, int MODE, bool FAST_DIV>
-__global__ void __launch_bounds__(32 * NWX * NWY, (DNMF_MINB / (NWX * NWY)) > 0 ? (DNMF_MINB / (NWX * NWY)) : 1) fit_tile_kernel(const __grid_constant__ FitParams p) {
+__global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB : 1) fit_tile_kernel(const __grid_constant__ FitParams p) {
   constexpr bool WRITE_YHAT = MODE == 1;
   constexpr bool WRITE_RES = MODE == 2;
   constexpr int NW = NWX * NWY;
@@ -1127,8 +954,6 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (DNMF_MINB / (NWX * NWY)) > 0 
   unsigned short* sCand = reinterpret_cast<unsigned short*>(sCandC + p.cand_cap);  // [cand_cap (even)]
   unsigned short* sSlotCand = sCand + ((p.cand_cap + 7) & ~7);  // [CAP]: candidate index of each staged slot
   unsigned short* sList = sSlotCand + ((CAP + 7) & ~7);
-  float* sF = reinterpret_cast<float*>(
-      smem_raw + (((size_t)(reinterpret_cast<unsigned char*>(sList + ((p.K + 7) & ~7)) - smem_raw) + 15) & ~(size_t)15));
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   auto cta_sync = [&]() {
@@ -1547,16 +1372,6 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (DNMF_MINB / (NWX * NWY)) > 0 
             march_pairs<0, true, MODE>(a, o);
           else
             march_pairs<0, false, MODE>(a, o);
-        } else if (p.field) {
-          a.fbase = smem_u32(sF);
-          a.fPX4 = (unsigned)p.fPX * 4u;
-          a.fPY4 = (unsigned)p.fPY * 4u;
-          build_field<NT>(a, npair, tid);
-          cta_sync();
-          if (safe)
-            march_field<true, MODE>(a, o);
-          else
-            march_field<false, MODE>(a, o);
         } else {
           const int npf = nst >> 1;  // full slot pairs; an odd list ends with a single slot
           const int tail = (nst & 1) ? (npf == 0 ? 2 : 1) : 0;
@@ -1821,8 +1636,6 @@ struct dnmf_ctx {
   int cand_expand = 6;
   int cand_cap = 0;
   int fpc_override = 0;  // DNMF_FPC environment override of the frames-per-CTA heuristic (tuning)
-  int field = 0;         // node-image main loop (opt-in, DNMF_FIELD=1): measured slower than the slot-pair march, DESIGN.md 3.3
-  int fPX = 0, fPY = 0, field_floats = 0;
   // tensor map of the frame buffer the fused kernel last ran on (resident slab or caller's batch)
   alignas(64) CUtensorMap tmap;
   const float* tmap_ptr = nullptr;
@@ -1915,7 +1728,6 @@ extern "C" int dnmf_create(dnmf_ctx** out, int X, int Y, int Z, int K, int T, in
   c->num_sms = prop.multiProcessorCount;
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (const char* ev = getenv("DNMF_FPC")) c->fpc_override = atoi(ev);
-  if (const char* ev = getenv("DNMF_FIELD")) c->field = atoi(ev);
   CU(cudaMalloc((void**)&c->d_pos, (size_t)K * 3 * sizeof(float)));
   CU(cudaMalloc((void**)&c->d_sigma, (size_t)K * sizeof(float)));
   CU(cudaMalloc((void**)&c->d_rng, (size_t)K * 6 * sizeof(int)));
@@ -2079,18 +1891,10 @@ static int configure_tiling_fixed(dnmf_ctx* c, cudaStream_t st) {
   c->ntx = (c->X + c->tx - 1) / c->tx;
   c->nty = (c->Y + c->ty - 1) / c->ty;
   c->ntz = (c->Z + c->tz - 1) / c->tz;
-  const bool use_field = c->field && c->sub == 2;
-  const int margin = use_field ? 1 : 2;  // the node image costs shared memory per window node
+  const int margin = 2;
   c->wmax[0] = std::min(c->tx + 2 + margin, c->X + 3);
   c->wmax[1] = std::min(c->ty + 2 + margin, c->Y + 3);
   c->wmax[2] = std::min(c->tz + 2 + margin, c->Z + 3);
-  c->fPY = c->fPX = c->field_floats = 0;
-  if (use_field) {  // F[nx][ny][nz]: odd y pitch, x pitch = 4 (mod 8) -> conflict-free corner loads
-    c->fPY = (c->wmax[2] + 1) | 1;
-    c->fPX = (c->wmax[1] + 1) * c->fPY;
-    while ((c->fPX & 7) != 4) ++c->fPX;
-    c->field_floats = (c->wmax[0] + 1) * c->fPX;
-  }
   // longest list at identity deformation -> staged-slot capacity
   const int nt = c->ntx * c->nty * c->ntz;
   if (ensure(&c->d_tmp_counts, &c->tmp_counts_cap, (size_t)nt)) return 1;
@@ -2163,13 +1967,11 @@ static int configure_tiling_fixed(dnmf_ctx* c, cudaStream_t st) {
   const int nw = c->nwx * c->nwy;
   // keep at least ~2 CTAs per SM worth of shared memory when possible
   const size_t budget = std::min<size_t>((size_t)c->max_smem_optin, (size_t)113 * 1024);
-  while (cap > 2 && fit_smem_layout(nw, c->tx, c->ty, c->tz, cap, wsum, c->K, c->wmax[0], c->cand_cap,
-                                    c->field_floats).bytes > budget)
+  while (cap > 2 && fit_smem_layout(nw, c->tx, c->ty, c->tz, cap, wsum, c->K, c->wmax[0], c->cand_cap).bytes > budget)
     cap -= 4;
   if (cap < 2) cap = 2;
   c->cap = cap;
-  c->fit_smem = fit_smem_layout(nw, c->tx, c->ty, c->tz, cap, wsum, c->K, c->wmax[0], c->cand_cap,
-                                c->field_floats).bytes;
+  c->fit_smem = fit_smem_layout(nw, c->tx, c->ty, c->tz, cap, wsum, c->K, c->wmax[0], c->cand_cap).bytes;
   if (c->fit_smem > (size_t)c->max_smem_optin)
     return fail("configure_tiling: tile does not fit in shared memory; use a smaller tz");
   return 0;
@@ -2357,9 +2159,6 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
   p.full_depth = (c->tz == c->Z) ? 1 : 0;
   p.bulk_ok = (((uintptr_t)p.frames & 15) == 0) && (((size_t)c->Y * c->Z) % 4 == 0) &&
               (((size_t)c->ty * c->Z) % 4 == 0);
-  p.field = c->field_floats > 0 ? 1 : 0;
-  p.fPX = c->fPX;
-  p.fPY = c->fPY;
   p.b_base = 0;
   p.tmap_ok = 0;
   memset(&p.tmap, 0, sizeof(p.tmap));

@@ -317,13 +317,6 @@ def test_launch_chunking_over_grid_z_limit():
         assert torch.equal(g_part[:, :, lo:lo + 100], g_all[:, :, lo:lo + 100])
 
 
-def test_node_image_main_loop_matches_oracle(monkeypatch):
-    """Opt-in node-image form of the main loop (DNMF_FIELD=1): same loss and gradient."""
-    monkeypatch.setenv("DNMF_FIELD", "1")
-    _check([33, 18, 7], 6, 3, seed=11, cutoff=3.5, tiling=(1, 1, 0, 0, 2))
-    _check([40, 40, 5], 12, 2, seed=12, cutoff=3.5, tiling=(2, 2, 0, 0, 2), beta_scale=0.5)
-
-
 def test_frames_per_cta_do_not_change_results(monkeypatch):
     """One CTA walking 1, 3 or 8 consecutive frames of its tile (slices cached across frames, traces and tile
     requested a frame ahead) gives bit-identical gradients."""
