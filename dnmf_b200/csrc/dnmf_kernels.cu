@@ -275,6 +275,8 @@ struct FitParams {
   int B;         // frames in this launch
   int fpc;       // consecutive frames walked by one CTA (<= 32)
   float zero;    // 0.0f, opaque to the compiler (see march_pairs)
+  int y_pitch;   // floats between x rows of the Y tile in shared memory (>= ty * tile depth)
+  int z_skew;    // != 0: lane (lx, ly) starts its z march at ((ly * z_skew) & 3), see march_rolled<SKEW>
   int tmap_ok;   // the frame tile can be fetched with ONE tensor TMA copy (3-D map over [frame][x][y*Z])
   int b_base;    // index of this launch's first frame in the buffer the tensor map describes
   alignas(64) CUtensorMap tmap;
@@ -287,10 +289,11 @@ struct FitSmem {
   size_t bytes;
 };
 
-static FitSmem fit_smem_layout(int nw, int tx, int ty, int tz, int cap, int wsum, int K, int wmax0, int cand_cap) {
+static FitSmem fit_smem_layout(int nw, int tx, int ty, int tz, int cap, int wsum, int K, int wmax0, int cand_cap,
+                               int y_pitch) {
   FitSmem s;
   s.tab_f2 = cap * (wsum + wmax0);  // live slices + the x slice without traces
-  s.y_f = tx * ty * tz + 4;
+  s.y_f = tx * std::max(y_pitch, ty * tz) + 4;
   s.list_u16 = (K + 7) & ~7;
   s.bytes = (((size_t)s.tab_f2 * 8 + 127) & ~(size_t)127) + (size_t)s.y_f * 4 + (size_t)nw * kNumPartials * 4 +
             80 * 4 + 16 +
@@ -419,6 +422,7 @@ struct MarchArgs {
   bool validA, validB;
   float bg;                 // MODE 2: scalar background
   float oz;                 // 0.0f the compiler cannot see (FitParams::zero)
+  int zskew;                // SKEW variants: this lane starts its z march at z0 + zskew and wraps around
 };
 
 struct MarchOut {
@@ -637,21 +641,35 @@ __device__ __forceinline__ void tail_slot(const unsigned (&adA)[3], const unsign
 
 // TAIL 0: even list, np >= 1 full slot pairs.  TAIL 1: np >= 1 full pairs and one last slot.  TAIL 2: a single
 // slot (np == 0).
-template <bool SAFE, int MODE, int TAIL>
+// SKEW: the lanes of a warp walk z in rotated order (lane-dependent start, wrap-around), which spreads their
+// reads of the Y tile over the banks when the tile's y/x pitches are multiples of 32 floats (Z = 32).
+template <bool SAFE, int MODE, int TAIL, bool SKEW>
 __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOut& o) {
   const float oz = a.oz;
   const float2 zero2 = make_float2(oz, oz);
 #pragma unroll
   for (int d = 0; d < 3; ++d) o.S0[d] = o.S1[d] = o.S2[d] = zero2;
   float2 sse = zero2, sum_r = zero2;
-  unsigned yaddr = a.yaddrA;
   unsigned bias[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) bias[d] = a.base[d] - (unsigned)a.wl[d] * a.strideB;
   const unsigned pair_bytes = (unsigned)np * 16u;
-  float zf = a.zf0;
+  int zi = SKEW ? a.zskew : 0;
+  float zf = a.zf0 + (float)zi;
+  unsigned yaddr = a.yaddrA + 4u * (unsigned)zi;
+  auto advance = [&]() {
+    zf += 1.f;
+    yaddr += 4u;
+    if (SKEW) {
+      if (++zi == a.nz) {
+        zi = 0;
+        zf = a.zf0;
+        yaddr = a.yaddrA;
+      }
+    }
+  };
 #pragma unroll 1
-  for (int zz = 0; zz < a.nz; ++zz, zf += 1.f, yaddr += 4u) {
+  for (int zz = 0; zz < a.nz; ++zz, advance()) {
     const float2 z2 = make_float2(zf, zf);
     float2 ix[3];
 #pragma unroll
@@ -942,8 +960,9 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
   float2* sXraw = sTab + (size_t)CAP * wsum;                     // x slice before the traces are folded in
   float* sY = reinterpret_cast<float*>(smem_raw + ((((size_t)CAP * (wsum + p.wmax0)) * 8 + 127) & ~(size_t)127));  // 128 B: TMA
   const int zs = p.full_depth ? p.Z : p.tz;  // smem z-stride between y rows
-  const int RS = TY * zs;                    // smem stride between x rows
-  float* sRed = sY + (TX * TY * p.tz + 4);
+  const int RS = p.y_pitch;                  // smem stride between x rows: TY*zs, padded when that pitch would
+                                             // put the lanes of a warp on the same bank (configure_tiling_fixed)
+  float* sRed = sY + (TX * RS + 4);
   float* sBeta = sRed + NW * kNumPartials;          // 32 floats
   int* sInt = reinterpret_cast<int*>(sBeta + 32);   // 32 ints: win[6], cnt[NW], flags
   float* sK = reinterpret_cast<float*>(sInt + 32);  // 16 floats: main-loop constants (see below)
@@ -1375,13 +1394,21 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
         } else {
           const int npf = nst >> 1;  // full slot pairs; an odd list ends with a single slot
           const int tail = (nst & 1) ? (npf == 0 ? 2 : 1) : 0;
-          switch (tail * 2 + (safe ? 1 : 0)) {
-            case 0: march_rolled<false, MODE, 0>(a, npf, o); break;
-            case 1: march_rolled<true, MODE, 0>(a, npf, o); break;
-            case 2: march_rolled<false, MODE, 1>(a, npf, o); break;
-            case 3: march_rolled<true, MODE, 1>(a, npf, o); break;
-            case 4: march_rolled<false, MODE, 2>(a, npf, o); break;
-            default: march_rolled<true, MODE, 2>(a, npf, o); break;
+          a.zskew = 0;
+          if (p.z_skew != 0 && nz >= 4) a.zskew = ((lane >> 3) * p.z_skew) & 3;
+          switch ((p.z_skew != 0 ? 6 : 0) + tail * 2 + (safe ? 1 : 0)) {
+            case 0: march_rolled<false, MODE, 0, false>(a, npf, o); break;
+            case 1: march_rolled<true, MODE, 0, false>(a, npf, o); break;
+            case 2: march_rolled<false, MODE, 1, false>(a, npf, o); break;
+            case 3: march_rolled<true, MODE, 1, false>(a, npf, o); break;
+            case 4: march_rolled<false, MODE, 2, false>(a, npf, o); break;
+            case 5: march_rolled<true, MODE, 2, false>(a, npf, o); break;
+            case 6: march_rolled<false, MODE, 0, true>(a, npf, o); break;
+            case 7: march_rolled<true, MODE, 0, true>(a, npf, o); break;
+            case 8: march_rolled<false, MODE, 1, true>(a, npf, o); break;
+            case 9: march_rolled<true, MODE, 1, true>(a, npf, o); break;
+            case 10: march_rolled<false, MODE, 2, true>(a, npf, o); break;
+            default: march_rolled<true, MODE, 2, true>(a, npf, o); break;
           }
         }
 #endif
@@ -1636,6 +1663,7 @@ struct dnmf_ctx {
   int cand_expand = 6;
   int cand_cap = 0;
   int fpc_override = 0;  // DNMF_FPC environment override of the frames-per-CTA heuristic (tuning)
+  int y_pitch = 0, z_skew = 0;  // shared-memory layout of the Y tile (bank conflicts, configure_tiling_fixed)
   // tensor map of the frame buffer the fused kernel last ran on (resident slab or caller's batch)
   alignas(64) CUtensorMap tmap;
   const float* tmap_ptr = nullptr;
@@ -1895,6 +1923,24 @@ static int configure_tiling_fixed(dnmf_ctx* c, cudaStream_t st) {
   c->wmax[0] = std::min(c->tx + 2 + margin, c->X + 3);
   c->wmax[1] = std::min(c->ty + 2 + margin, c->Y + 3);
   c->wmax[2] = std::min(c->tz + 2 + margin, c->Z + 3);
+  {
+    // Y tile in shared memory: lane (lx, ly) of a warp reads float lx*pitch + ly*zs + z.  With the dense pitch
+    // ty*zs the 32 lanes can fall on very few banks (Z = 32: all on one).  When the dense layout is worse than
+    // 2-way, pad the x pitch to 4 (mod 32) and rotate the z order of the lanes by ly*(1-zs) (mod 4): bank =
+    // 4*lx + (ly mod 4) + const.  The dense layout is kept otherwise (it allows the single tensor-TMA copy).
+    const int zs = c->tz;
+    const int dense = c->ty * zs;
+    int worst = 0, hist[32] = {0};
+    for (int l = 0; l < 32; ++l) worst = std::max(worst, ++hist[((l & 7) * dense + (l >> 3) * zs) & 31]);
+    c->y_pitch = dense;
+    c->z_skew = 0;
+    if (worst > 2) {
+      int pitch = (dense + 3) & ~3;
+      while ((pitch & 31) != 4) pitch += 4;
+      c->y_pitch = pitch;
+      c->z_skew = ((1 - zs) % 4 + 4) % 4;
+    }
+  }
   // longest list at identity deformation -> staged-slot capacity
   const int nt = c->ntx * c->nty * c->ntz;
   if (ensure(&c->d_tmp_counts, &c->tmp_counts_cap, (size_t)nt)) return 1;
@@ -1967,11 +2013,11 @@ static int configure_tiling_fixed(dnmf_ctx* c, cudaStream_t st) {
   const int nw = c->nwx * c->nwy;
   // keep at least ~2 CTAs per SM worth of shared memory when possible
   const size_t budget = std::min<size_t>((size_t)c->max_smem_optin, (size_t)113 * 1024);
-  while (cap > 2 && fit_smem_layout(nw, c->tx, c->ty, c->tz, cap, wsum, c->K, c->wmax[0], c->cand_cap).bytes > budget)
+  while (cap > 2 && fit_smem_layout(nw, c->tx, c->ty, c->tz, cap, wsum, c->K, c->wmax[0], c->cand_cap, c->y_pitch).bytes > budget)
     cap -= 4;
   if (cap < 2) cap = 2;
   c->cap = cap;
-  c->fit_smem = fit_smem_layout(nw, c->tx, c->ty, c->tz, cap, wsum, c->K, c->wmax[0], c->cand_cap).bytes;
+  c->fit_smem = fit_smem_layout(nw, c->tx, c->ty, c->tz, cap, wsum, c->K, c->wmax[0], c->cand_cap, c->y_pitch).bytes;
   if (c->fit_smem > (size_t)c->max_smem_optin)
     return fail("configure_tiling: tile does not fit in shared memory; use a smaller tz");
   return 0;
@@ -2159,10 +2205,12 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
   p.full_depth = (c->tz == c->Z) ? 1 : 0;
   p.bulk_ok = (((uintptr_t)p.frames & 15) == 0) && (((size_t)c->Y * c->Z) % 4 == 0) &&
               (((size_t)c->ty * c->Z) % 4 == 0);
+  p.y_pitch = c->y_pitch;
+  p.z_skew = c->z_skew;
   p.b_base = 0;
   p.tmap_ok = 0;
   memset(&p.tmap, 0, sizeof(p.tmap));
-  if (p.bulk_ok && p.full_depth && (size_t)c->ty * c->Z <= 256 && c->tx <= 256) {
+  if (p.bulk_ok && p.full_depth && (size_t)c->ty * c->Z <= 256 && c->tx <= 256 && c->y_pitch == c->ty * c->Z) {
     // 3-D tensor map over the frame buffer: [frames][X][Y*Z] floats, box = one tile (tx rows of ty*Z floats)
     const long long nframes = frames_dev ? (long long)B : (long long)c->T;
     if (c->tmap_ptr != p.frames || c->tmap_frames != nframes || c->tmap_tx != c->tx || c->tmap_ty != c->ty) {

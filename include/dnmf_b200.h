@@ -45,8 +45,10 @@ int dnmf_get_ranges(dnmf_ctx* ctx, int32_t* ranges_host /* [K][3][2] */);
 int dnmf_get_table(dnmf_ctx* ctx, int axis, float* table_host /* [K][s_axis+3][2] */);
 
 /* Launch geometry of the fused kernel: warps per CTA along x and y (warp footprint is 8x4 voxels),
- * tile depth tz (0 = whole Z), staged-slot capacity (0 = automatic), y-adjacent sub-tiles processed in
- * sequence by each warp (1 or 2).  Without this call the library picks a layout from the list lengths. */
+ * tile depth tz (0 = whole Z), staged-slot capacity (0 = automatic), y-adjacent sub-tiles carried by each
+ * warp (1, or 2 for the 1x1, 2x1 and 2x2 warp layouts: the two sub-tiles then run as one packed FP32x2 stream).
+ * Without this call the library picks a layout from the list lengths.  One CTA walks up to 8 consecutive
+ * frames of the batch through its tile (environment override for tuning: DNMF_FPC=<1..32>). */
 int dnmf_set_tiling(dnmf_ctx* ctx, int warps_x, int warps_y, int tz, int slot_capacity, int subtiles_y);
 int dnmf_get_tiling(dnmf_ctx* ctx, int32_t* out /* tx,ty,tz,ntx,nty,ntz,warps_x,warps_y,cap,subtiles_y,
                                                      exact_fast_division_verified */);

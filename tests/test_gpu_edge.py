@@ -332,3 +332,11 @@ def test_frames_per_cta_do_not_change_results(monkeypatch):
         out.append(e.loss_grad(torch.arange(T), beta.cuda(), C.cuda(), frames=frames.cuda()))
     for g, s_ in out[1:]:
         assert torch.equal(g, out[0][0]) and torch.equal(s_, out[0][1])
+
+
+@pytest.mark.parametrize("tiling", [(1, 1, 0, 0), (1, 1, 0, 0, 2), (2, 2, 0, 0, 2)])
+def test_depth_32_padded_tile_and_rotated_z_order(tiling):
+    """Z = 32 makes the dense shared-memory pitches multiples of 32 floats: the tile is stored with a padded x
+    pitch and the lanes walk z in rotated order (no tensor-map copy); Z = 64 adds depth-chunked tiles."""
+    _check([24, 16, 32], 6, 3, seed=32, cutoff=3.5, tiling=tiling, beta_scale=0.5)
+    _check([16, 8, 64], 5, 2, seed=64, cutoff=3.0, tiling=tiling)
