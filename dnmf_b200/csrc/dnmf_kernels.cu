@@ -657,14 +657,16 @@ __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOu
   int zi = SKEW ? a.zskew : 0;
   float zf = a.zf0 + (float)zi;
   unsigned yaddr = a.yaddrA + 4u * (unsigned)zi;
+  const float nzf = (float)a.nz;
+  const unsigned nz4 = 4u * (unsigned)a.nz;
   auto advance = [&]() {
     zf += 1.f;
     yaddr += 4u;
     if (SKEW) {
-      if (++zi == a.nz) {
+      if (++zi == a.nz) {  // wrap with uniform decrements: per-lane start values would be rematerialised in the loop
         zi = 0;
-        zf = a.zf0;
-        yaddr = a.yaddrA;
+        zf -= nzf;
+        yaddr -= nz4;
       }
     }
   };
@@ -1898,8 +1900,10 @@ static int configure_tiling(dnmf_ctx* c, cudaStream_t st) {
     const double fixed = c->sub == 2 ? 42.0 : 85.0, per = c->sub == 2 ? 7.3 : 9.5;
     // fewer than ~8 resident warps per SM cannot keep the FP32 pipe fed (cfg4, measured: 16 warps 1.0, 8 warps
     // 1.04, 6 warps 1.6, 4 warps 2.0 relative cost)
+    // lanes past the volume edge still cost: padded volume / volume
+    const double edge = ((double)c->ntx * c->tx / c->X) * ((double)c->nty * c->ty / c->Y);
     double cost = (fixed + per * c->mean_list_identity + (300.0 + 600.0 / nw) / rows) *
-                  std::pow(std::max(1.0, 8.0 / warps), 1.5);
+                  std::pow(std::max(1.0, 8.0 / warps), 1.5) * edge;
     if (nw > 1 && c->mean_list_identity < 16.0) cost *= 1.25;  // sharing the staged slices only pays for long lists
     if (cost < best_cost) {
       best_cost = cost;
