@@ -274,7 +274,6 @@ struct FitParams {
   int cand_cap;  // shared-memory capacity for one tile's candidates (>= the longest static list when possible)
   int B;         // frames in this launch
   int fpc;       // consecutive frames walked by one CTA (<= 32)
-  float zero;    // 0.0f, opaque to the compiler (see march_pairs)
   int y_pitch;   // floats between x rows of the Y tile in shared memory (>= ty * tile depth)
   int z_skew;    // != 0: lane (lx, ly) starts its z march at ((ly * z_skew) & 3), see march_rolled<SKEW>
   int tmap_ok;   // the frame tile can be fetched with ONE tensor TMA copy (3-D map over [frame][x][y*Z])
@@ -421,7 +420,7 @@ struct MarchArgs {
   int nz;
   bool validA, validB;
   float bg;                 // MODE 2: scalar background
-  float oz;                 // 0.0f the compiler cannot see (FitParams::zero)
+  float oz;                 // 0.0f the compiler cannot see (loaded from shared memory, sK[11])
   int zskew;                // SKEW variants: this lane starts its z march at z0 + zskew and wraps around
 };
 
@@ -504,7 +503,7 @@ __device__ __forceinline__ void sts32(unsigned addr, float v) {
 // scalar background, residual written back to the Y tile.
 template <int NP, bool SAFE, int MODE>
 __device__ __forceinline__ void march_pairs(const MarchArgs& a, MarchOut& o) {
-  // accumulators start from an opaque zero (a kernel parameter): with a literal 0 ptxas peels the first z step
+  // accumulators start from an opaque zero (read back from shared memory): with a literal 0 ptxas peels the first z step
   // into a straight-line copy of the whole loop body (fold of 0 + x), which costs instruction-cache footprint
   const float oz = a.oz;
   const float2 zero2 = make_float2(oz, oz);
@@ -2260,7 +2259,6 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
   p.cand_ids = c->d_cand_ids;
   p.cand_expand = c->cand_expand;
   p.cand_cap = c->cand_cap;
-  p.zero = 0.f;
   p.B = B;
   {  // frames per CTA: as many as keep ~8 waves of CTAs in flight, at most 8 (measured: 8 = 341k, 16 = 338k, 1 = 320k frame-iters/s at cfg2)
     const long long tiles = (long long)c->ntx * c->nty * c->ntz;
