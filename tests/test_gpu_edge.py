@@ -340,3 +340,35 @@ def test_depth_32_padded_tile_and_rotated_z_order(tiling):
     pitch and the lanes walk z in rotated order (no tensor-map copy); Z = 64 adds depth-chunked tiles."""
     _check([24, 16, 32], 6, 3, seed=32, cutoff=3.5, tiling=tiling, beta_scale=0.5)
     _check([16, 8, 64], 5, 2, seed=64, cutoff=3.0, tiling=tiling)
+
+
+@pytest.mark.parametrize("tiling", [(1, 1, 0, 0, 2), (2, 2, 0, 0, 2), (1, 1, 0, 3, 2)])
+def test_cached_slices_across_frames_match_oracle(monkeypatch, tiling):
+    """Runs of frames with the same deformation but different traces: the CTA keeps the staged slices and the
+    list and only refreshes the traces (the hot path of a near-converged fit).  Mixed with frames whose window or
+    list changes, and with a slot capacity of 3 that sends part of the lists through the overflow path.
+    Checked against the oracle and against one-frame-per-CTA launches."""
+    from dnmf_b200.engine import Engine
+    sz, K, T = [40, 24, 9], 10, 12
+    pos, sig, beta, C, frames = _case(sz, K, T, 91, sigma=2.5, beta_scale=0.6)
+    beta[:, :, 1] = beta[:, :, 0]          # identity run: frames 0, 1
+    beta[:, :, 4] = beta[:, :, 3]          # a deformed run: frames 3, 4, 5
+    beta[:, :, 5] = beta[:, :, 3]
+    beta[:, :, 9] = beta[:, :, 8]
+    beta[0, 0, 9] += 1e-3                  # almost the same: same window, different samples
+    tabs, _ = O.axis_tables(pos, sig, sz, 3.5)
+    loss, gref = O.closed_form_step(frames.numpy(), list(range(T)), beta.numpy(), C.numpy(), tabs, sz)
+    out = []
+    for fpc in ("1", "4", "12"):
+        monkeypatch.setenv("DNMF_FPC", fpc)
+        e = Engine(sz, K, T)
+        e.set_tiling(*tiling)
+        e.set_footprints(pos, sig, 3.5)
+        grad, sse = e.loss_grad(torch.arange(T), beta.cuda(), C.cuda(), frames=frames.cuda())
+        N = int(np.prod(sz))
+        assert abs(float(sse.sum()) / (T * N) - loss) <= 1e-5 * loss
+        err = np.abs(grad.cpu().numpy() - gref).max() / np.abs(gref).max()
+        assert err < 3e-5, err
+        out.append((grad, sse))
+    for g, s_ in out[1:]:
+        assert torch.equal(g, out[0][0]) and torch.equal(s_, out[0][1])
