@@ -52,6 +52,8 @@ def load(build_if_missing: bool = True):
                                    c_int, c_int, P, P]),
         "dnmf_motion_step": (c_int, [P, P, P, c_int, c_int, P, P, P, P, c_double, c_double, c_double, c_double,
                                      c_int64, c_int, P, P]),
+        "dnmf_motion_epoch": (c_int, [P, P, P, c_int, c_int, P, P, P, P, c_double, c_double, c_double, c_double,
+                                      c_int64, c_int, P, P]),
         "dnmf_motion_step_host": (c_int, [P, P, P, c_int, c_int, P, P, P, P, c_double, c_double, c_double,
                                           c_double, c_int64, c_int, POINTER(c_double), P]),
         "dnmf_forward": (c_int, [P, P, c_int, P, P, P, P, P, P]),

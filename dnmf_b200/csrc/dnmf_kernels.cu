@@ -2332,6 +2332,23 @@ extern "C" int dnmf_motion_step(dnmf_ctx* c, const float* frames_dev, const int3
                         B_global, loss_dev, stream);
 }
 
+extern "C" int dnmf_motion_epoch(dnmf_ctx* c, const int32_t* frame_ids_dev, const int32_t* batch_offsets_host,
+                                 int nbatches, int global_batch_scale, float* beta_dev, float* m_dev, float* v_dev,
+                                 const float* C_dev, double lr, double beta1, double beta2, double eps,
+                                 int64_t first_step, int affine, double* loss_dev, void* stream) {
+  if (!c || !frame_ids_dev || !batch_offsets_host) return fail("dnmf_motion_epoch: NULL argument");
+  if (nbatches < 0 || global_batch_scale < 1) return fail("dnmf_motion_epoch: need nbatches >= 0, global_batch_scale >= 1");
+  if (!c->d_video) return fail("dnmf_motion_epoch: no resident video (dnmf_upload_frames)");
+  for (int i = 0; i < nbatches; ++i) {
+    const int b0 = batch_offsets_host[i], B = batch_offsets_host[i + 1] - b0;
+    if (B < 1) return fail("dnmf_motion_epoch: empty batch");
+    if (dnmf_motion_step(c, nullptr, frame_ids_dev + b0, B, B * global_batch_scale, beta_dev, m_dev, v_dev, C_dev, lr,
+                         beta1, beta2, eps, first_step + i, affine, loss_dev ? loss_dev + i : nullptr, stream))
+      return 1;
+  }
+  return 0;
+}
+
 extern "C" int dnmf_motion_step_host(dnmf_ctx* c, const float* frames_host, const int32_t* frame_ids_host,
                                      int B, int B_global, float* beta_dev, float* m_dev, float* v_dev,
                                      const float* C_dev, double lr, double beta1, double beta2, double eps,

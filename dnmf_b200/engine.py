@@ -173,6 +173,18 @@ class Engine:
                                              float(betas[1]), float(eps), int(step), int(affine), _ptr(loss_out),
                                              self.stream), "dnmf_motion_step")
 
+    def motion_epoch(self, ids_dev: torch.Tensor, offsets, beta, m, v, C, lr, betas, eps, first_step, affine=False,
+                     global_batch_scale: int = 1, loss_out: Optional[torch.Tensor] = None):
+        """All minibatches of an epoch over the resident video in one library call.  ids_dev: int32 CUDA tensor with
+        the batches concatenated; offsets: nbatches+1 host ints; loss_out: float64 CUDA tensor [nbatches]."""
+        off = np.ascontiguousarray(np.asarray(offsets, dtype=np.int32))
+        nb = int(off.size) - 1
+        _lib.check(self.lib.dnmf_motion_epoch(self._h, _ptr(ids_dev), ctypes.c_void_p(off.ctypes.data), nb,
+                                              int(global_batch_scale), _ptr(beta), _ptr(m), _ptr(v), _ptr(C),
+                                              float(lr), float(betas[0]), float(betas[1]), float(eps),
+                                              int(first_step), int(affine), _ptr(loss_out), self.stream),
+                   "dnmf_motion_epoch")
+
     def motion_step_host(self, frames_host: torch.Tensor, ids_host: torch.Tensor, beta, m, v, C, lr, betas, eps,
                          step, affine=False, B_global: Optional[int] = None) -> float:
         """End-to-end step from HOST buffers (H2D copy + kernels + loss read-back)."""

@@ -323,10 +323,30 @@ class DeformableNMF:
         eng = self.fp.engine
         group, st = self._adam_state(optimizer)
         beta = self.fp.beta.detach()
+        # Resident video, reference-parity path: the frames the loader yields are not needed (attach_video), so the
+        # whole epoch goes to the library in one call (dnmf_motion_epoch).  At the reference's batch size of 4
+        # frames a step is ~12 us of device work; per-step Python and launch overhead would dominate.
+        epoch_call = (self._video_resident and self._shared is None and not self.verbose and
+                      not (self.jacobian_regularizer and gamma))   # verbose prints mid-epoch diagnostics per step
         for epoch in range(1, epochs + 1):
             if self.verbose:
                 print("Epoch " + str(epoch))
             self.fp.train()
+            if epoch_call:
+                batches = [torch.as_tensor(data[1]).to(torch.int32).reshape(-1).cpu() for data in dataloader]
+                if not batches:
+                    continue
+                offsets = np.zeros(len(batches) + 1, dtype=np.int32)
+                offsets[1:] = np.cumsum([int(b.numel()) for b in batches])
+                ids_dev = torch.cat(batches).to(eng.device)
+                losses = torch.zeros(len(batches), dtype=torch.float64, device=eng.device)
+                first = int(st["step"]) + 1
+                eng.motion_epoch(ids_dev, offsets, beta, st["exp_avg"], st["exp_avg_sq"], self.C, group["lr"],
+                                 group["betas"], group["eps"], first, self.affine,
+                                 global_batch_scale=self.global_batch_scale, loss_out=losses)
+                st["step"] += len(batches)
+                self.loss_history.extend(losses[i] for i in range(len(batches)))
+                continue
             for batch_idx, data in enumerate(dataloader):
                 ids = torch.as_tensor(data[1]).to(torch.int32)
                 step = int(st["step"]) + 1

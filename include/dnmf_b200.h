@@ -26,7 +26,7 @@ extern "C" {
 
 typedef struct dnmf_ctx dnmf_ctx;
 
-#define DNMF_ABI_VERSION 2
+#define DNMF_ABI_VERSION 3
 
 int dnmf_abi_version(void);
 const char* dnmf_last_error(void);
@@ -89,6 +89,17 @@ int dnmf_motion_step(dnmf_ctx* ctx, const float* frames_dev, const int32_t* fram
                      int B_global, float* beta_dev, float* m_dev, float* v_dev, const float* C_dev,
                      double lr, double beta1, double beta2, double eps, int64_t step, int affine,
                      double* loss_dev, void* stream);
+
+/* All minibatches of one epoch of update_motion over the RESIDENT video (Demix/dNMF.py:185-191 with the
+ * loop over the DataLoader inside the library): batch i = frame_ids_dev[batch_offsets_host[i] ..
+ * batch_offsets_host[i+1]), its global batch size = its length * global_batch_scale (ranks of a sharded fit),
+ * Adam step number first_step + i, loss written to loss_dev[i] (may be NULL).  Identical results to nbatches
+ * calls of dnmf_motion_step; it exists because at the reference's batch size (4 frames) a step is ~12 us of
+ * device work and per-step host overhead dominates. */
+int dnmf_motion_epoch(dnmf_ctx* ctx, const int32_t* frame_ids_dev, const int32_t* batch_offsets_host,
+                      int nbatches, int global_batch_scale, float* beta_dev, float* m_dev, float* v_dev,
+                      const float* C_dev, double lr, double beta1, double beta2, double eps,
+                      int64_t first_step, int affine, double* loss_dev, void* stream);
 
 /* Same, with HOST buffers: copies frames_host[B][X][Y][Z] and the ids to the device, runs the
  * step and copies the loss back (synchronises the stream).  This is the end-to-end call. */

@@ -372,3 +372,33 @@ def test_cached_slices_across_frames_match_oracle(monkeypatch, tiling):
         out.append((grad, sse))
     for g, s_ in out[1:]:
         assert torch.equal(g, out[0][0]) and torch.equal(s_, out[0][1])
+
+
+def test_epoch_call_equals_per_step_calls():
+    """dnmf_motion_epoch (all minibatches of an epoch in one library call, resident video) leaves beta, the Adam
+    moments and the per-step losses bit-identical to one dnmf_motion_step per minibatch."""
+    from dnmf_b200.engine import Engine
+    sz, K, T, B = [32, 16, 5], 6, 12, 4
+    pos, sig, beta0, C, frames = _case(sz, K, T, 5, beta_scale=0.2)
+    ids = torch.randperm(T, generator=torch.Generator().manual_seed(1)).to(torch.int32)
+    res = []
+    for mode in ("steps", "epoch"):
+        e = Engine(sz, K, T)
+        e.set_footprints(pos, sig, 3.5)
+        e.upload_frames(frames, clamp_negative=False)
+        beta = beta0.clone().cuda()
+        m, v = torch.zeros_like(beta), torch.zeros_like(beta)
+        c = C.cuda()
+        losses = torch.zeros(T // B, dtype=torch.float64, device="cuda")
+        idd = ids.cuda()
+        if mode == "steps":
+            for i in range(T // B):
+                e.motion_step(idd[i * B:(i + 1) * B], beta, m, v, c, 1e-3, (0.9, 0.999), 1e-8, i + 1,
+                              loss_out=losses[i:i + 1])
+        else:
+            e.motion_epoch(idd, list(range(0, T + 1, B)), beta, m, v, c, 1e-3, (0.9, 0.999), 1e-8, 1,
+                           loss_out=losses)
+        res.append((beta, m, v, losses))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+    assert float(res[0][3].min()) > 0
