@@ -54,11 +54,13 @@ def load(build_if_missing: bool = True):
                                      c_int64, c_int, P, P]),
         "dnmf_motion_epoch": (c_int, [P, P, P, c_int, c_int, P, P, P, P, c_double, c_double, c_double, c_double,
                                       c_int64, c_int, P, P]),
+        "dnmf_epoch_mode": (c_int, [P, c_int, POINTER(c_int)]),
         "dnmf_motion_step_host": (c_int, [P, P, P, c_int, c_int, P, P, P, P, c_double, c_double, c_double,
                                           c_double, c_int64, c_int, POINTER(c_double), P]),
         "dnmf_forward": (c_int, [P, P, c_int, P, P, P, P, P, P]),
         "dnmf_mu_stats": (c_int, [P, P, P, c_int, P, P]),
         "dnmf_get_mu_stats": (c_int, [P, c_int, P, P]),
+        "dnmf_mu_path": (c_int, [P, c_int, POINTER(c_int)]),
         "dnmf_mu_begin": (c_int, [P, P, P]),
         "dnmf_mu_sweep": (c_int, [P, c_double, c_int, P, P, P]),
         "dnmf_mu_boundary": (c_int, [P, P, P, P]),

@@ -34,6 +34,10 @@ constexpr int kZUnroll = DNMF_ZUNROLL;
 #ifndef DNMF_UNROLLED_MARCH
 #define DNMF_UNROLLED_MARCH 0  // 1: one fully unrolled main loop per slot-pair count (more code than the I-cache holds)
 #endif
+#ifndef DNMF_MU_MINB
+#define DNMF_MU_MINB 12  // the same for the trace-statistics variant (MODE 3) of the single-warp layout: 168 registers
+                         // (measured at cfg2: 16 -> 5.08 ms, 12 -> 4.66 ms per 1000 frames)
+#endif
 #ifndef DNMF_MINB
 #define DNMF_MINB 16  // resident single-warp CTAs per SM the fused kernel is compiled for (128 registers: no spills in the unrolled march)
 #endif
@@ -274,6 +278,9 @@ struct FitParams {
   int cand_cap;  // shared-memory capacity for one tile's candidates (>= the longest static list when possible)
   int B;         // frames in this launch
   int fpc;       // consecutive frames walked by one CTA (<= 32)
+  double* muG;   // MODE 3 (trace statistics): G_t[K][K], b_t[K] of every frame, accumulated with fp64 atomics
+  double* mub;
+  int* mu_overflow;  // MODE 3: set when a tile's list is not fully staged (the caller reruns the generic kernel)
   int y_pitch;   // floats between x rows of the Y tile in shared memory (>= ty * tile depth)
   int z_skew;    // != 0: lane (lx, ly) starts its z march at ((ly * z_skew) & 3), see march_rolled<SKEW>
   int tmap_ok;   // the frame tile can be fetched with ONE tensor TMA copy (3-D map over [frame][x][y*Z])
@@ -759,6 +766,154 @@ __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOu
   o.sum_r = sum_r;
 }
 
+// ------------------------------------------------------------------------------------------------
+// MODE 3: trace statistics G_t = A_t^T A_t, b_t = A_t^T Y_t (Demix/dNMF.py:141-142) on the fused kernel's
+// machinery (same tiles, lists, staged slices WITHOUT the traces, packed (A, B) coordinate chain).  Per voxel the
+// footprint values of NP "row" slot pairs are formed packed over (slot 2p, slot 2p+1); every column slot value
+// is broadcast against them: acc[p][c] += (a_2p, a_2p+1) * a_c is one FFMA2 per voxel.  Accumulators stay in
+// registers over the tile-frame: a block of 3 row pairs x 6 column slots at a time (longer lists make several
+// passes over the tile, one per block pair on or above the diagonal).  Flushed per tile-frame with the
+// transposing warp reduction and fp64 atomics.
+// ------------------------------------------------------------------------------------------------
+// footprint values of slots (2p, 2p+1) at one voxel from the three staged slices
+__device__ __forceinline__ float2 slot_values(unsigned ax, unsigned ay, unsigned az, unsigned off, float f0, float f1,
+                                              float f2) {
+  const float4 ex = lds128r(ax + off), ey = lds128r(ay + off), ez = lds128r(az + off);
+  const float2 a0 = __ffma2_rn(make_float2(f0, f0), make_float2(ex.z, ex.w), make_float2(ex.x, ex.y));
+  const float2 a1 = __ffma2_rn(make_float2(f1, f1), make_float2(ey.z, ey.w), make_float2(ey.x, ey.y));
+  const float2 a2 = __ffma2_rn(make_float2(f2, f2), make_float2(ez.z, ez.w), make_float2(ez.x, ez.y));
+  return __fmul2_rn(__fmul2_rn(a0, a1), a2);
+}
+
+// NP row pairs starting at byte offset rowoff (rowp of them real), and -- TWO -- three column pairs at coloff
+// (colp real); without TWO the columns are the rows.  G[p][c]: (row slots 2p, 2p+1) x column slot c.
+template <int NP, bool TWO>
+__device__ __forceinline__ void march_stats(const MarchArgs& a, unsigned rowoff, unsigned coloff, int rowp, int colp,
+                                            float2 (&G)[3][6], float2 (&bv)[3]) {
+  constexpr int NC = TWO ? 3 : NP;  // column pairs
+  int zi = a.zskew;
+  float zf = a.zf0 + (float)zi;
+  unsigned yaddr = a.yaddrA + 4u * (unsigned)zi;
+  const float nzf = (float)a.nz;
+  const unsigned nz4 = 4u * (unsigned)a.nz;
+  unsigned roff[NP], coff[NC];
+  float rw[NP], cw[NC];  // 0 for padding pairs (they re-read a real pair)
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    roff[i] = rowoff + 16u * (unsigned)min(i, rowp - 1);
+    rw[i] = i < rowp ? 1.f : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    coff[i] = coloff + 16u * (unsigned)min(i, colp - 1);
+    cw[i] = i < colp ? 1.f : 0.f;
+  }
+#pragma unroll 1
+  for (int zz = 0; zz < a.nz; ++zz) {
+    const float2 z2 = make_float2(zf, zf);
+    float2 ix[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float2 rcp2 = make_float2(a.rcp[d], a.rcp[d]);
+      const float2 q = __ffma2_rn(z2, __ffma2_rn(z2, make_float2(a.c2[d], a.c2[d]), a.c1[d]), a.c0[d]);  // = 2q
+      const float2 t0 = __fmul2_rn(q, rcp2);
+      const float2 r = __ffma2_rn(make_float2(-t0.x, -t0.y), make_float2(a.sm1[d], a.sm1[d]), q);
+      const float2 v = __ffma2_rn(r, rcp2, t0);
+      const float2 u = __fadd2_rn(v, make_float2(-1.f, -1.f));
+      ix[d] = __fmul2_rn(__fadd2_rn(u, make_float2(1.f, 1.f)), make_float2(a.hsm1[d], a.hsm1[d]));
+    }
+    unsigned adA[3], adB[3];
+    float2 f[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const int iA = __float2int_rd(ix[d].x), iB = __float2int_rd(ix[d].y);
+      f[d] = __fadd2_rn(ix[d], make_float2(-(float)iA, -(float)iB));
+      adA[d] = (unsigned)min(max(iA - a.wl[d], 0), a.wm1[d]) * a.strideB + a.base[d];
+      adB[d] = (unsigned)min(max(iB - a.wl[d], 0), a.wm1[d]) * a.strideB + a.base[d];
+    }
+    const float yA = a.validA ? lds32(yaddr) : 0.f, yB = a.validB ? lds32(yaddr + a.yoffB) : 0.f;
+    const float mA = a.validA ? 1.f : 0.f, mB = a.validB ? 1.f : 0.f;
+    float2 rA[NP], rB[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const float2 vA = slot_values(adA[0], adA[1], adA[2], roff[i], f[0].x, f[1].x, f[2].x);
+      const float2 vB = slot_values(adB[0], adB[1], adB[2], roff[i], f[0].y, f[1].y, f[2].y);
+      rA[i] = __fmul2_rn(vA, make_float2(rw[i] * mA, rw[i] * mA));
+      rB[i] = __fmul2_rn(vB, make_float2(rw[i] * mB, rw[i] * mB));
+      bv[i] = __ffma2_rn(rA[i], make_float2(yA, yA), bv[i]);
+      bv[i] = __ffma2_rn(rB[i], make_float2(yB, yB), bv[i]);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      float2 cA, cB;
+      if (TWO) {
+        cA = slot_values(adA[0], adA[1], adA[2], coff[c], f[0].x, f[1].x, f[2].x);
+        cB = slot_values(adB[0], adB[1], adB[2], coff[c], f[0].y, f[1].y, f[2].y);
+        cA = __fmul2_rn(cA, make_float2(cw[c], cw[c]));
+        cB = __fmul2_rn(cB, make_float2(cw[c], cw[c]));
+      } else {
+        cA = rA[c];
+        cB = rB[c];
+      }
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        G[i][2 * c] = __ffma2_rn(rA[i], make_float2(cA.x, cA.x), G[i][2 * c]);
+        G[i][2 * c] = __ffma2_rn(rB[i], make_float2(cB.x, cB.x), G[i][2 * c]);
+        G[i][2 * c + 1] = __ffma2_rn(rA[i], make_float2(cA.y, cA.y), G[i][2 * c + 1]);
+        G[i][2 * c + 1] = __ffma2_rn(rB[i], make_float2(cB.y, cB.y), G[i][2 * c + 1]);
+      }
+    }
+    zf += 1.f;
+    yaddr += 4u;
+    if (++zi == a.nz) {
+      zi = 0;
+      zf -= nzf;
+      yaddr -= nz4;
+    }
+  }
+}
+
+// Warp-reduce the accumulators of one block pair and add them to G_t / b_t.  Row slots start at slot 6*pb,
+// column slots at 6*lb; off-diagonal blocks are mirrored, b_t is accumulated on diagonal blocks only.
+template <int NP, bool TWO>
+__device__ __forceinline__ void flush_stats(const float2 (&G)[3][6], const float2 (&bv)[3], int pb, int lb, int nst,
+                                            const unsigned short* sList, double* Gt, double* bt, int K, int lane) {
+  constexpr int NCS = TWO ? 6 : 2 * NP;        // column slots
+  constexpr int NG = 2 * NP * NCS;              // G outputs, index = (p*NCS + c)*2 + half
+  constexpr int NOUT = NG + (TWO ? 0 : 2 * NP);  // + b outputs
+#pragma unroll
+  for (int r0 = 0; r0 < NOUT; r0 += 32) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int idx = r0 + i;
+      float x = 0.f;
+      if (idx < NG) {
+        const int pc = idx >> 1, pp = pc / NCS, cc = pc % NCS;
+        x = (idx & 1) ? G[pp][cc].y : G[pp][cc].x;
+      } else if (idx < NOUT) {
+        const int q = idx - NG;
+        x = (q & 1) ? bv[q >> 1].y : bv[q >> 1].x;
+      }
+      v[i] = x;
+    }
+    const float tot = warp_transpose_sum(v, lane);
+    const int idx = r0 + lane;
+    if (idx < NG) {
+      const int pc = idx >> 1, pp = pc / NCS, cc = pc % NCS;
+      const int j = 6 * pb + 2 * pp + (idx & 1), l = 6 * lb + cc;
+      if (j < nst && l < nst) {
+        const int kj = sList[j], kl = sList[l];
+        atomicAdd(Gt + (size_t)kj * K + kl, (double)tot);
+        if (TWO) atomicAdd(Gt + (size_t)kl * K + kj, (double)tot);
+      }
+    } else if (idx < NOUT) {
+      const int q = idx - NG, j = 6 * pb + q;
+      if (j < nst) atomicAdd(bt + sList[j], (double)tot);
+    }
+  }
+}
+
 // Generic main loop (any list length, overflow slots from the L2-resident tables, SUB = 1 or 2, true
 // division when the fast form is not verified): one sub-tile after the other, slot pairs in a rolled loop.
 struct GenericArgs {
@@ -948,7 +1103,7 @@ __device__ __forceinline__ void march_generic(const GenericArgs& a, float (&S0)[
 // the frame's window or neuron list differs from the previous frame's; otherwise only the x slice is rescaled
 // by the frame's traces.  In the steady state no global-memory latency sits between two main loops.
 template <int NWX, int NWY, int SUB, int MODE, bool FAST_DIV>
-__global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB : 1) fit_tile_kernel(const __grid_constant__ FitParams p) {
+__global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 ? DNMF_MU_MINB : DNMF_MINB) : 1) fit_tile_kernel(const __grid_constant__ FitParams p) {
   constexpr bool WRITE_YHAT = MODE == 1;
   constexpr bool WRITE_RES = MODE == 2;
   constexpr int NW = NWX * NWY;
@@ -1007,7 +1162,8 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
       for (int q = 0; q < 6; ++q) sCandRng[i * 6 + q] = p.rng[(size_t)k * 6 + q];
     }
   }
-  const bool prefetch_c = have_cand && ncand <= 2 * NT;
+  const bool track_c = have_cand && ncand <= 2 * NT;  // candidate traces carried in shared memory
+  const bool prefetch_c = track_c && MODE != 3;       // the trace statistics do not read C
   // Loop constants of the march go through shared memory: values the compiler can trace back to kernel
   // parameters are rematerialised inside the z loop (constant-bank loads, int->float conversions, address
   // arithmetic: ~25 instructions per z step), values loaded from shared memory stay in registers.
@@ -1159,7 +1315,8 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
       // the list is a function of the window and the static candidates: unchanged.  Only the traces of the
       // staged slots are new.
       L = prev_L;
-      for (int pos = tid; pos < min(L, CAP); pos += NT) sCk[pos] = sCandC[sSlotCand[pos]];
+      if constexpr (MODE != 3)
+        for (int pos = tid; pos < min(L, CAP); pos += NT) sCk[pos] = sCandC[sSlotCand[pos]];
     } else {
       bool inside = false;
       if (p.cand_off != nullptr) {
@@ -1179,12 +1336,12 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
         if (from_smem) {
           k = sCand[idx];
           if (!neuron_in_window(sCandRng + idx * 6, wlo, whi)) return false;
-          ck = prefetch_c ? sCandC[idx] : __ldg(p.C + (size_t)k * p.T + t);
+          if constexpr (MODE != 3) ck = prefetch_c ? sCandC[idx] : __ldg(p.C + (size_t)k * p.T + t);
           return true;
         }
         k = cand ? cand[idx] : idx;
         if (!neuron_in_window(p.rng + (size_t)k * 6, wlo, whi)) return false;
-        ck = __ldg(p.C + (size_t)k * p.T + t);
+        if constexpr (MODE != 3) ck = __ldg(p.C + (size_t)k * p.T + t);
         return true;
       };
       auto put = [&](int pos, int k, float ck, int idx) {
@@ -1236,7 +1393,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
       changed = changed || (L != prev_L);
 #pragma unroll
       for (int d = 0; d < 3; ++d) changed = changed || (wlo[d] != pw_lo[d]) || (whi[d] != pw_hi[d]);
-      prev_fast = from_smem && prefetch_c;
+      prev_fast = from_smem && track_c;
     }
     cta_sync();
 
@@ -1292,7 +1449,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
       float4* dst = reinterpret_cast<float4*>(sTab + (size_t)e * CAP);
       for (int pp = 0; pp < npair; ++pp) {
         const float4 v = src[pp];
-        const float2 c = *reinterpret_cast<const float2*>(sCk + 2 * pp);
+        const float2 c = MODE == 3 ? make_float2(1.f, 1.f) : *reinterpret_cast<const float2*>(sCk + 2 * pp);
         dst[pp] = make_float4(v.x * c.x, v.y * c.y, v.z * c.x, v.w * c.y);
       }
     }
@@ -1315,6 +1472,94 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
       }
     }
 
+    auto fill_march_args = [&](MarchArgs& a) {
+      const float yfA = (float)(y0 + ly0), yfB = (float)(y0 + ly0 + kWarpY);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float b0 = sBeta[d], bx_ = sBeta[3 + d], by_ = sBeta[6 + d], bz_ = sBeta[9 + d];
+        const float bxx = sBeta[12 + d], byy = sBeta[15 + d], bxy = sBeta[21 + d], bxz = sBeta[24 + d],
+                    byz = sBeta[27 + d];
+        float vA = fmaf(bx_, xf, b0), vB = vA;
+        vA = fmaf(by_, yfA, vA);
+        vB = fmaf(by_, yfB, vB);
+        vA = fmaf(bxx, xf * xf, vA);
+        vB = fmaf(bxx, xf * xf, vB);
+        vA = fmaf(byy, yfA * yfA, vA);
+        vB = fmaf(byy, yfB * yfB, vB);
+        vA = fmaf(bxy, xf * yfA, vA);
+        vB = fmaf(bxy, xf * yfB, vB);
+        const float wA = fmaf(byz, yfA, fmaf(bxz, xf, bz_)), wB = fmaf(byz, yfB, fmaf(bxz, xf, bz_));
+        a.c0[d] = make_float2(vA + vA, vB + vB);  // exact doubling: the march evaluates 2q directly
+        a.c1[d] = make_float2(wA + wA, wB + wB);
+        a.c2[d] = sBeta[18 + d] + sBeta[18 + d];
+      }
+      {
+        const unsigned ka = smem_u32(sK);
+        const float4 k0 = lds128r(ka), k1 = lds128r(ka + 16u), k2 = lds128r(ka + 32u), k3 = lds128r(ka + 48u);
+        a.base[0] = __float_as_uint(k3.x), a.base[1] = __float_as_uint(k3.y), a.base[2] = __float_as_uint(k3.z);
+        a.rcp[0] = k0.x, a.rcp[1] = k0.y, a.rcp[2] = k0.z;
+        a.sm1[0] = k0.w, a.sm1[1] = k1.x, a.sm1[2] = k1.y;
+        a.hsm1[0] = k1.z, a.hsm1[1] = k1.w, a.hsm1[2] = k2.x;
+        a.strideB = __float_as_uint(k2.y);
+        a.yoffB = __float_as_uint(k2.z);
+        a.oz = k2.w;
+      }
+      a.wl[0] = wlo[0], a.wl[1] = wlo[1], a.wl[2] = wlo[2];
+      a.wm1[0] = W0 - 1, a.wm1[1] = W1 - 1, a.wm1[2] = W2 - 1;
+      a.yaddrA = smem_u32(sY + lx * RS + ly0 * zs);
+      a.zf0 = (float)z0;
+      a.nz = nz;
+      a.validA = (gx < p.X) && (y0 + ly0 < p.Y);
+      a.validB = (gx < p.X) && (y0 + ly0 + kWarpY < p.Y);
+      a.bg = bg;
+      a.zskew = 0;
+      if (p.z_skew != 0 && nz >= 4) a.zskew = ((lane >> 3) * p.z_skew) & 3;
+    };
+
+    if constexpr (MODE == 3) {
+      // ---- trace statistics of this tile-frame ----
+      if constexpr (SUB == 2 && FAST_DIV) {
+        if (L > nst) {
+          if (tid == 0) atomicMax(p.mu_overflow, L);  // not fully staged: the caller reruns the generic kernel
+        } else if (npair > 0) {
+          MarchArgs a;
+          fill_march_args(a);
+          double* Gt = p.muG + (size_t)t * p.K * p.K;
+          double* bt = p.mub + (size_t)t * p.K;
+          const int nblk = (npair + 2) / 3;
+          for (int pb = 0; pb < nblk; ++pb) {
+            for (int lb = pb; lb < nblk; ++lb) {
+              float2 G[3][6], bv[3];
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                bv[i] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < 6; ++c) G[i][c] = make_float2(0.f, 0.f);
+              }
+              const int rowp = min(3, npair - 3 * pb), colp = min(3, npair - 3 * lb);
+              const unsigned rowoff = 48u * (unsigned)pb, coloff = 48u * (unsigned)lb;
+              if (pb != lb) {
+                march_stats<3, true>(a, rowoff, coloff, rowp, colp, G, bv);
+                flush_stats<3, true>(G, bv, pb, lb, nst, sList, Gt, bt, p.K, lane);
+              } else if (rowp == 1) {
+                march_stats<1, false>(a, rowoff, rowoff, 1, 1, G, bv);
+                flush_stats<1, false>(G, bv, pb, lb, nst, sList, Gt, bt, p.K, lane);
+              } else if (rowp == 2) {
+                march_stats<2, false>(a, rowoff, rowoff, 2, 2, G, bv);
+                flush_stats<2, false>(G, bv, pb, lb, nst, sList, Gt, bt, p.K, lane);
+              } else {
+                march_stats<3, false>(a, rowoff, rowoff, 3, 3, G, bv);
+                flush_stats<3, false>(G, bv, pb, lb, nst, sList, Gt, bt, p.K, lane);
+              }
+            }
+          }
+        }
+      }
+      cta_sync();
+      if (bulk && fi + 1 < nb) load_tile(fi + 1);
+      continue;
+    }
+
     // ---- main loop: one (x,y) column per lane (per sub-tile), march along z ----
     float S0[SUB][3], S1[SUB][3], S2[3] = {0.f, 0.f, 0.f};
     float sse = 0.f, sum_r = 0.f;
@@ -1323,45 +1568,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
     if constexpr (SUB == 2 && FAST_DIV) {
       if (!has_overflow && (npair <= kMaxNP || !DNMF_UNROLLED_MARCH)) {
         MarchArgs a;
-        const float yfA = (float)(y0 + ly0), yfB = (float)(y0 + ly0 + kWarpY);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const float b0 = sBeta[d], bx_ = sBeta[3 + d], by_ = sBeta[6 + d], bz_ = sBeta[9 + d];
-          const float bxx = sBeta[12 + d], byy = sBeta[15 + d], bxy = sBeta[21 + d], bxz = sBeta[24 + d],
-                      byz = sBeta[27 + d];
-          float vA = fmaf(bx_, xf, b0), vB = vA;
-          vA = fmaf(by_, yfA, vA);
-          vB = fmaf(by_, yfB, vB);
-          vA = fmaf(bxx, xf * xf, vA);
-          vB = fmaf(bxx, xf * xf, vB);
-          vA = fmaf(byy, yfA * yfA, vA);
-          vB = fmaf(byy, yfB * yfB, vB);
-          vA = fmaf(bxy, xf * yfA, vA);
-          vB = fmaf(bxy, xf * yfB, vB);
-          const float wA = fmaf(byz, yfA, fmaf(bxz, xf, bz_)), wB = fmaf(byz, yfB, fmaf(bxz, xf, bz_));
-          a.c0[d] = make_float2(vA + vA, vB + vB);  // exact doubling: the march evaluates 2q directly
-          a.c1[d] = make_float2(wA + wA, wB + wB);
-          a.c2[d] = sBeta[18 + d] + sBeta[18 + d];
-        }
-        {
-          const unsigned ka = smem_u32(sK);
-          const float4 k0 = lds128r(ka), k1 = lds128r(ka + 16u), k2 = lds128r(ka + 32u), k3 = lds128r(ka + 48u);
-          a.base[0] = __float_as_uint(k3.x), a.base[1] = __float_as_uint(k3.y), a.base[2] = __float_as_uint(k3.z);
-          a.rcp[0] = k0.x, a.rcp[1] = k0.y, a.rcp[2] = k0.z;
-          a.sm1[0] = k0.w, a.sm1[1] = k1.x, a.sm1[2] = k1.y;
-          a.hsm1[0] = k1.z, a.hsm1[1] = k1.w, a.hsm1[2] = k2.x;
-          a.strideB = __float_as_uint(k2.y);
-          a.yoffB = __float_as_uint(k2.z);
-          a.oz = k2.w;
-        }
-        a.wl[0] = wlo[0], a.wl[1] = wlo[1], a.wl[2] = wlo[2];
-        a.wm1[0] = W0 - 1, a.wm1[1] = W1 - 1, a.wm1[2] = W2 - 1;
-        a.yaddrA = smem_u32(sY + lx * RS + ly0 * zs);
-        a.zf0 = (float)z0;
-        a.nz = nz;
-        a.validA = (gx < p.X) && (y0 + ly0 < p.Y);
-        a.validB = (gx < p.X) && (y0 + ly0 + kWarpY < p.Y);
-        a.bg = bg;
+        fill_march_args(a);
         MarchOut o;
         const bool safe = window_clipped || nx < TX || ny < TY;
 #if DNMF_UNROLLED_MARCH
@@ -1395,8 +1602,6 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
         } else {
           const int npf = nst >> 1;  // full slot pairs; an odd list ends with a single slot
           const int tail = (nst & 1) ? (npf == 0 ? 2 : 1) : 0;
-          a.zskew = 0;
-          if (p.z_skew != 0 && nz >= 4) a.zskew = ((lane >> 3) * p.z_skew) & 3;
           switch ((p.z_skew != 0 ? 6 : 0) + tail * 2 + (safe ? 1 : 0)) {
             case 0: march_rolled<false, MODE, 0, false>(a, npf, o); break;
             case 1: march_rolled<true, MODE, 0, false>(a, npf, o); break;
@@ -1517,7 +1722,8 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? DNMF_MINB :
 // write the frame's gradient column and its sum of squared residuals.  grid = B, block = 256.
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, const int* __restrict__ frame_ids,
                                        int nt, int T, double grad_scale, float* __restrict__ grad,
-                                       double* __restrict__ sse_out, double* __restrict__ sumr_out) {
+                                       double* __restrict__ sse_out, double* __restrict__ sumr_out,
+                                       const double* __restrict__ scale_per_frame = nullptr) {
   __shared__ double s[8][kNumPartials];
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* src = partials + (size_t)b * nt * kNumPartials;
@@ -1530,6 +1736,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, const
 #pragma unroll
     for (int w = 0; w < 8; ++w) v += s[w][lane];
     const int t = frame_ids[b];
+    if (scale_per_frame != nullptr) grad_scale = scale_per_frame[b];
     if (lane < 30) grad[(size_t)lane * T + t] = (float)(v * grad_scale);
     if (lane == 30) sse_out[b] = v;
     if (lane == 31 && sumr_out != nullptr) sumr_out[b] = v;
@@ -1550,6 +1757,94 @@ struct AdamParams {
   float eps;
 };
 
+__device__ __forceinline__ void adam_update(float& pi, float& mi, float& vi, float gi, float w1, float b2, float w2,
+                                            float step_size, float bc2_sqrt, float eps) {
+  mi = fmaf(w1, __fsub_rn(gi, mi), mi);
+  vi = __fadd_rn(__fmul_rn(vi, b2), __fmul_rn(__fmul_rn(w2, gi), gi));
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), bc2_sqrt), eps);
+  pi = __fsub_rn(pi, __fmul_rn(step_size, __fdiv_rn(mi, denom)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Frame-parallel epoch (dnmf_motion_epoch).  The reference's model has no parameter shared between frames
+// (Demix/dNMF.py:29-33: only beta[:, :, t] is learnable), and Adam is elementwise, so the minibatches of an
+// epoch in which every frame occurs once touch disjoint columns: the column of frame t sees the steps of the
+// other minibatches as Adam updates with a zero gradient (momentum keeps moving it) and one step
+// with its own gradient.  The epoch therefore runs as
+//   phase 0: each column replays the zero-gradient steps that precede its minibatch,
+//   ONE fused launch over all frames of the epoch (each minibatch with its own 2/(B N) scale),
+//   phase 1: each column takes its gradient step and replays the zero-gradient steps that follow,
+// with the same fp32 operations in the same order per column as the step-by-step schedule: bit-identical
+// (tests/test_gpu_edge.py::test_epoch_call_equals_per_step_calls).
+// ------------------------------------------------------------------------------------------------
+// batch_of[t] = minibatch index of frame t (-1: not in this epoch); scale[b] = 2/(B_i * global scale * N);
+// status: bit 0 = a frame occurs twice, bit 1 = frame id out of range.
+__global__ void epoch_index_kernel(const int* __restrict__ frame_ids, const int* __restrict__ offsets, int nbatches,
+                                   int T, double n_vox, int global_batch_scale, int* __restrict__ batch_of,
+                                   double* __restrict__ scale, int* __restrict__ status) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= offsets[nbatches]) return;
+  int lo = 0, hi = nbatches - 1;  // last i with offsets[i] <= b
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (offsets[mid] <= b) lo = mid; else hi = mid - 1;
+  }
+  const int Bi = offsets[lo + 1] - offsets[lo];
+  scale[b] = 2.0 / ((double)Bi * (double)global_batch_scale * n_vox);
+  const int t = frame_ids[b];
+  if (t < 0 || t >= T) {
+    atomicOr(status, 2);
+    return;
+  }
+  if (atomicExch(batch_of + t, lo) != -1) atomicOr(status, 1);
+}
+
+// step_scalars[s] = (lr / (1 - beta1^step), sqrt(1 - beta2^step)) of step first_step + s, computed in double on
+// the host like torch does.
+__global__ void epoch_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                  float* __restrict__ v, int n, int T, int affine, float w1, float b2, float w2,
+                                  float eps, const float2* __restrict__ step_scalars, int nsteps,
+                                  const int* __restrict__ batch_of, int phase) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int it = batch_of[i % T];
+  int lo, hi;
+  float gi = 0.f;
+  if (phase == 0) {
+    lo = 0;
+    hi = it < 0 ? nsteps : it;
+  } else {
+    if (it < 0) return;
+    lo = it;
+    hi = nsteps;
+    gi = g[i];
+    g[i] = 0.f;
+    if (affine && (i / (3 * T)) >= 4) gi = 0.f;
+  }
+  if (lo >= hi) return;
+  float pi = p[i], mi = m[i], vi = v[i];
+  for (int s_ = lo; s_ < hi; ++s_) {
+    const float2 a = __ldg(step_scalars + s_);
+    adam_update(pi, mi, vi, gi, w1, b2, w2, a.x, a.y, eps);
+    gi = 0.f;
+  }
+  p[i] = pi;
+  m[i] = mi;
+  v[i] = vi;
+}
+
+// loss of minibatch i = sum of its frames' SSE / (B_i * global scale * N), summed as adam_kernel's block 0 does
+__global__ void epoch_loss_kernel(const double* __restrict__ sse, const int* __restrict__ offsets, int nbatches,
+                                  double n_vox, int global_batch_scale, double* __restrict__ loss_out) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= nbatches) return;
+  const int b0 = offsets[i], B = offsets[i + 1] - b0;
+  double acc = 0.0;
+  for (int j = lane; j < B; j += 32) acc += sse[b0 + j];
+  acc = warp_sum_d(acc);
+  if (lane == 0) loss_out[i] = acc * (1.0 / ((double)B * (double)global_batch_scale * n_vox));
+}
+
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int n, int row_len, int affine, AdamParams a,
                             const double* __restrict__ sse, int B, double loss_scale,
@@ -1559,11 +1854,9 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
     float gi = g[i];
     g[i] = 0.f;
     if (affine && (i / row_len) >= 4) gi = 0.f;
-    float mi = m[i], vi = v[i];
-    mi = fmaf(a.w1, __fsub_rn(gi, mi), mi);
-    vi = __fadd_rn(__fmul_rn(vi, a.b2), __fmul_rn(__fmul_rn(a.w2, gi), gi));
-    float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), a.bc2_sqrt), a.eps);
-    p[i] = __fsub_rn(p[i], __fmul_rn(a.step_size, __fdiv_rn(mi, denom)));
+    float pi = p[i], mi = m[i], vi = v[i];
+    adam_update(pi, mi, vi, gi, a.w1, a.b2, a.w2, a.step_size, a.bc2_sqrt, a.eps);
+    p[i] = pi;
     m[i] = mi;
     v[i] = vi;
   }
@@ -1699,6 +1992,21 @@ struct dnmf_ctx {
   double* d_Cd[2] = {nullptr, nullptr};  // traces in fp64 during the sweeps, [T][K]
   int cd_cur = 0;
   int mu_capM = 0;
+  // frame-parallel epoch (dnmf_motion_epoch)
+  int* d_epoch_batch_of = nullptr;
+  size_t epoch_batch_of_cap = 0;
+  int* d_epoch_offsets = nullptr;
+  size_t epoch_offsets_cap = 0;
+  float2* d_epoch_scalars = nullptr;
+  size_t epoch_scalars_cap = 0;
+  double* d_epoch_scale = nullptr;
+  size_t epoch_scale_cap = 0;
+  int epoch_sequential = 0;     // DNMF_EPOCH_SEQUENTIAL / dnmf_epoch_mode: one launch sequence per minibatch
+  int epoch_last_parallel = 0;  // what the last dnmf_motion_epoch did
+  int mu_force_panel = 0;  // dnmf_mu_path / DNMF_MU_PANEL: skip the fused-tile statistics kernel
+  int mu_last_path = 0;    // 1 = fused tiles, 0 = panel kernel
+  int mu_fused_need = 0;   // longest list seen by an overflowing fused-tile statistics launch (capacity hint)
+  int mu_fused_off = 0;    // that capacity does not fit in shared memory: go straight to the panel kernel
   unsigned long long* d_keys = nullptr;
   size_t keys_cap = 0;
   int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -1757,6 +2065,8 @@ extern "C" int dnmf_create(dnmf_ctx** out, int X, int Y, int Z, int K, int T, in
   c->num_sms = prop.multiProcessorCount;
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (const char* ev = getenv("DNMF_FPC")) c->fpc_override = atoi(ev);
+  if (const char* ev = getenv("DNMF_MU_PANEL")) c->mu_force_panel = atoi(ev) != 0;
+  if (const char* ev = getenv("DNMF_EPOCH_SEQUENTIAL")) c->epoch_sequential = atoi(ev) != 0;
   CU(cudaMalloc((void**)&c->d_pos, (size_t)K * 3 * sizeof(float)));
   CU(cudaMalloc((void**)&c->d_sigma, (size_t)K * sizeof(float)));
   CU(cudaMalloc((void**)&c->d_rng, (size_t)K * 6 * sizeof(int)));
@@ -1818,7 +2128,8 @@ extern "C" void dnmf_destroy(dnmf_ctx* c) {
                   c->d_tmp_max, c->d_G,     c->d_b,          c->d_identity_beta,
                   c->d_Cd[0],   c->d_Cd[1], c->d_keys,       c->d_cand_off,    c->d_cand_ids,
                   c->d_tab_dpos[0], c->d_tab_dpos[1], c->d_tab_dpos[2], c->d_tab_dsig[0], c->d_tab_dsig[1],
-                  c->d_tab_dsig[2], c->d_resid, c->d_sumr, c->d_ids_zero};
+                  c->d_tab_dsig[2], c->d_resid, c->d_sumr, c->d_ids_zero,
+                  c->d_epoch_batch_of, c->d_epoch_offsets, c->d_epoch_scalars, c->d_epoch_scale};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->copy_stream) {
@@ -2047,6 +2358,8 @@ extern "C" int dnmf_set_footprints(dnmf_ctx* c, const float* pos_host, const flo
   }
   c->have_footprints = true;
   c->mu_capM = 0;
+  c->mu_fused_need = 0;
+  c->mu_fused_off = 0;
   c->counters[3]++;
   return configure_tiling(c, st);
 }
@@ -2178,6 +2491,18 @@ static int dispatch_fit(dnmf_ctx* c, const FitParams& p, int B, cudaStream_t st)
   return fail("dispatch_fit: unsupported warp layout");
 }
 
+// MODE 3 (trace statistics) exists for the two-sub-tile layouts with the verified fast division only
+static bool fused_stats_available(const dnmf_ctx* c) {
+  return c->sub == 2 && c->fast_div != 0 && ((c->nwx == 1 && c->nwy == 1) || (c->nwx == 2 && c->nwy <= 2));
+}
+static int dispatch_stats(dnmf_ctx* c, const FitParams& p, int B, size_t smem, cudaStream_t st) {
+  if (c->nty > 65535) return fail("dispatch_stats: more than 65535 tiles along y");
+  if (!fused_stats_available(c)) return fail("dispatch_stats: layout without a fused statistics kernel");
+  if (c->nwx == 1) return launch_fit<1, 1, 2, 3, true>(p, B, smem, st);
+  if (c->nwy == 1) return launch_fit<2, 1, 2, 3, true>(p, B, smem, st);
+  return launch_fit<2, 2, 2, 3, true>(p, B, smem, st);
+}
+
 static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, const int32_t* ids, int B,
                            const float* beta, const float* C) {
   if (!c->have_footprints) return fail("fit: call dnmf_set_footprints first");
@@ -2208,6 +2533,9 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
   p.full_depth = (c->tz == c->Z) ? 1 : 0;
   p.bulk_ok = (((uintptr_t)p.frames & 15) == 0) && (((size_t)c->Y * c->Z) % 4 == 0) &&
               (((size_t)c->ty * c->Z) % 4 == 0);
+  p.muG = nullptr;
+  p.mub = nullptr;
+  p.mu_overflow = nullptr;
   p.y_pitch = c->y_pitch;
   p.z_skew = c->z_skew;
   p.b_base = 0;
@@ -2339,13 +2667,88 @@ extern "C" int dnmf_motion_epoch(dnmf_ctx* c, const int32_t* frame_ids_dev, cons
   if (!c || !frame_ids_dev || !batch_offsets_host) return fail("dnmf_motion_epoch: NULL argument");
   if (nbatches < 0 || global_batch_scale < 1) return fail("dnmf_motion_epoch: need nbatches >= 0, global_batch_scale >= 1");
   if (!c->d_video) return fail("dnmf_motion_epoch: no resident video (dnmf_upload_frames)");
+  if (!beta_dev || !m_dev || !v_dev || !C_dev) return fail("dnmf_motion_epoch: NULL argument");
+  if (first_step < 1) return fail("dnmf_motion_epoch: step is 1-based");
+  if (nbatches == 0) return 0;
+  for (int i = 0; i < nbatches; ++i)
+    if (batch_offsets_host[i + 1] - batch_offsets_host[i] < 1) return fail("dnmf_motion_epoch: empty batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaSetDevice(c->device));
+  const int b_first = batch_offsets_host[0];
+  const long long Btot = (long long)batch_offsets_host[nbatches] - b_first;
+  // ---- frame-parallel epoch (see epoch_adam_kernel): every frame at most once, one fused launch ----
+  bool parallel = nbatches > 1 && c->epoch_sequential == 0 && Btot <= c->T &&
+                  Btot * c->ntx * c->nty * c->ntz <= 2147483647LL;
+  if (parallel) {
+    if (ensure(&c->d_epoch_batch_of, &c->epoch_batch_of_cap, (size_t)c->T + 1)) return 1;  // [T] + status
+    if (ensure(&c->d_epoch_offsets, &c->epoch_offsets_cap, (size_t)nbatches + 1)) return 1;
+    if (ensure(&c->d_epoch_scalars, &c->epoch_scalars_cap, (size_t)nbatches)) return 1;
+    if (ensure(&c->d_epoch_scale, &c->epoch_scale_cap, (size_t)Btot)) return 1;
+    if (ensure(&c->d_sse, &c->sse_cap, (size_t)Btot)) return 1;
+    std::vector<int> off((size_t)nbatches + 1);
+    for (int i = 0; i <= nbatches; ++i) off[(size_t)i] = batch_offsets_host[i] - b_first;
+    std::vector<float2> sc((size_t)nbatches);
+    for (int i = 0; i < nbatches; ++i) {
+      const double step = (double)(first_step + i);
+      sc[(size_t)i] = make_float2((float)(lr / (1.0 - pow(beta1, step))), (float)sqrt(1.0 - pow(beta2, step)));
+    }
+    int* status = c->d_epoch_batch_of + c->T;
+    CU(cudaMemsetAsync(c->d_epoch_batch_of, 0xff, (size_t)c->T * sizeof(int), st));
+    CU(cudaMemsetAsync(status, 0, sizeof(int), st));
+    CU(cudaMemcpyAsync(c->d_epoch_offsets, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->d_epoch_scalars, sc.data(), sc.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
+    const int32_t* ids = frame_ids_dev + b_first;
+    epoch_index_kernel<<<(unsigned)((Btot + 255) / 256), 256, 0, st>>>(ids, c->d_epoch_offsets, nbatches, c->T,
+                                                                      (double)c->N, global_batch_scale,
+                                                                      c->d_epoch_batch_of, c->d_epoch_scale, status);
+    CU(cudaGetLastError());
+    int h_status = 0;
+    CU(cudaMemcpyAsync(&h_status, status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));  // also: off / sc may go out of scope
+    if (h_status & 2) return fail("dnmf_motion_epoch: frame id out of range");
+    parallel = h_status == 0;  // a frame drawn twice in the epoch: its steps depend on each other
+  }
+  if (parallel) {
+    const int n = 30 * c->T;
+    const float w1 = (float)(1.0 - beta1), b2 = (float)beta2, w2 = (float)(1.0 - beta2), epsf = (float)eps;
+    epoch_adam_kernel<<<(n + 127) / 128, 128, 0, st>>>(beta_dev, c->d_grad, m_dev, v_dev, n, c->T, affine, w1, b2, w2,
+                                                       epsf, c->d_epoch_scalars, nbatches, c->d_epoch_batch_of, 0);
+    CU(cudaGetLastError());
+    FitParams p;
+    if (fill_fit_params(c, p, nullptr, frame_ids_dev + b_first, (int)Btot, beta_dev, C_dev)) return 1;
+    const int nt = c->ntx * c->nty * c->ntz;
+    if (dispatch_fit<0>(c, p, (int)Btot, st)) return 1;
+    reduce_partials_kernel<<<(unsigned)Btot, 256, 0, st>>>(c->d_partials, frame_ids_dev + b_first, nt, c->T, 0.0,
+                                                          c->d_grad, c->d_sse, nullptr, c->d_epoch_scale);
+    CU(cudaGetLastError());
+    epoch_adam_kernel<<<(n + 127) / 128, 128, 0, st>>>(beta_dev, c->d_grad, m_dev, v_dev, n, c->T, affine, w1, b2, w2,
+                                                       epsf, c->d_epoch_scalars, nbatches, c->d_epoch_batch_of, 1);
+    CU(cudaGetLastError());
+    if (loss_dev) {
+      epoch_loss_kernel<<<(nbatches + 3) / 4, 128, 0, st>>>(c->d_sse, c->d_epoch_offsets, nbatches, (double)c->N,
+                                                            global_batch_scale, loss_dev);
+      CU(cudaGetLastError());
+    }
+    c->counters[0] += 1;
+    c->counters[1] += 1;
+    c->counters[4] += 2;
+    c->epoch_last_parallel = 1;
+    return 0;
+  }
+  c->epoch_last_parallel = 0;
   for (int i = 0; i < nbatches; ++i) {
     const int b0 = batch_offsets_host[i], B = batch_offsets_host[i + 1] - b0;
-    if (B < 1) return fail("dnmf_motion_epoch: empty batch");
     if (dnmf_motion_step(c, nullptr, frame_ids_dev + b0, B, B * global_batch_scale, beta_dev, m_dev, v_dev, C_dev, lr,
                          beta1, beta2, eps, first_step + i, affine, loss_dev ? loss_dev + i : nullptr, stream))
       return 1;
   }
+  return 0;
+}
+
+extern "C" int dnmf_epoch_mode(dnmf_ctx* c, int sequential, int* last_parallel_out) {
+  if (!c) return fail("dnmf_epoch_mode: NULL context");
+  if (sequential >= 0) c->epoch_sequential = sequential != 0;
+  if (last_parallel_out) *last_parallel_out = c->epoch_last_parallel;
   return 0;
 }
 

@@ -428,6 +428,53 @@ extern "C" int dnmf_mu_stats(dnmf_ctx* c, const float* frames_dev, const int32_t
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(c->device));
   if (mu_alloc(c)) return 1;
+  // Fast path: the fused kernel's tiles, lists and staged slices (fit_tile_kernel<MODE=3>).  A tile whose list
+  // is longer than the staged capacity under the current deformation sets the overflow flag and everything is
+  // redone by the panel kernel below.
+  while (fused_stats_available(c) && c->mu_force_panel == 0 && c->mu_fused_off == 0) {  // at most one pass
+    FitParams p;
+    if (fill_fit_params(c, p, frames_dev, frame_ids_dev, B, beta_dev, nullptr)) return 1;
+    p.muG = c->d_G;
+    p.mub = c->d_b;
+    p.mu_overflow = c->d_tmp_max;
+    // Every slot must be staged here (there is no global-table tail as in the fit): capacity for the longest
+    // identity-deformation list + 2 when that fits the shared-memory budget of ~2 CTAs per SM.
+    size_t smem = c->fit_smem;
+    {
+      int cap = (std::min(c->K + 1, std::max(c->lmax_identity, c->mu_fused_need) + 2) + 1) & ~1;
+      if ((cap & 3) == 0) cap += 2;
+      if (cap > c->cap) {
+        const int wsum = c->wmax[0] + c->wmax[1] + c->wmax[2];
+        const size_t need = fit_smem_layout(c->nwx * c->nwy, c->tx, c->ty, c->tz, cap, wsum, c->K, c->wmax[0],
+                                            c->cand_cap, c->y_pitch).bytes;
+        if (need <= std::min<size_t>((size_t)c->max_smem_optin, (size_t)113 * 1024)) {
+          p.cap = cap;
+          smem = need;
+        } else if (c->mu_fused_need > 0) {
+          c->mu_fused_off = 1;  // known to overflow and no room to grow
+          break;
+        }
+      }
+    }
+    CU(cudaMemsetAsync(c->d_tmp_max, 0, sizeof(int), st));
+    mu_zero_kernel<<<B, 256, 0, st>>>(c->d_G, c->d_b, frame_ids_dev, c->K);
+    CU(cudaGetLastError());
+    if (dispatch_stats(c, p, B, smem, st)) return 1;
+    int over = 0;
+    CU(cudaMemcpyAsync(&over, c->d_tmp_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    c->counters[6] += 1;
+    if (over == 0) {
+      c->mu_last_path = 1;
+      return 0;
+    }
+    // Remembered until the next dnmf_set_footprints.  A list longer than the capacity: stage that many slots
+    // next time.  Otherwise a window wider than the staged slices raised the flag: not a matter of capacity.
+    if (over > p.cap) c->mu_fused_need = over;
+    else c->mu_fused_off = 1;
+    break;
+  }
+  c->mu_last_path = 0;
   // geometry of the statistics kernel (16 x 8 x tz tiles) and its longest identity-deformation list
   dnmf_ctx g = *c;  // shallow copy used only for geometry helpers
   g.tx = kMuTX;
@@ -501,6 +548,13 @@ extern "C" int dnmf_mu_stats(dnmf_ctx* c, const float* frames_dev, const int32_t
     c->mu_capM = (std::min(c->K + 1, over + over / 4 + 4) + 3) & ~3;
   }
   return fail("dnmf_mu_stats: neuron list longer than the A panel after regrowth");
+}
+
+extern "C" int dnmf_mu_path(dnmf_ctx* c, int force_panel, int* last_path_out) {
+  if (!c) return fail("dnmf_mu_path: NULL context");
+  if (force_panel >= 0) c->mu_force_panel = force_panel != 0;
+  if (last_path_out) *last_path_out = c->mu_last_path;
+  return 0;
 }
 
 extern "C" int dnmf_get_mu_stats(dnmf_ctx* c, int t, double* G_host, double* b_host) {

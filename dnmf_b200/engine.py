@@ -185,6 +185,13 @@ class Engine:
                                               int(first_step), int(affine), _ptr(loss_out), self.stream),
                    "dnmf_motion_epoch")
 
+    def epoch_mode(self, sequential: int = -1) -> int:
+        """Select (1 = batch by batch, 0 = automatic) and/or query how `motion_epoch` runs: returns 1 when the last
+        call ran frame-parallel (one fused launch over all frames of the epoch)."""
+        last = ctypes.c_int(0)
+        _lib.check(self.lib.dnmf_epoch_mode(self._h, int(sequential), ctypes.byref(last)), "dnmf_epoch_mode")
+        return int(last.value)
+
     def motion_step_host(self, frames_host: torch.Tensor, ids_host: torch.Tensor, beta, m, v, C, lr, betas, eps,
                          step, affine=False, B_global: Optional[int] = None) -> float:
         """End-to-end step from HOST buffers (H2D copy + kernels + loss read-back)."""
@@ -214,6 +221,13 @@ class Engine:
             _check_dev(frames, torch.float32, "frames")
         _lib.check(self.lib.dnmf_mu_stats(self._h, _ptr(frames), _ptr(ids32), int(ids32.numel()), _ptr(beta),
                                           self.stream), "dnmf_mu_stats")
+
+    def mu_path(self, force_panel: int = -1) -> int:
+        """Select (1 = panel kernel only, 0 = automatic) and/or query the device path of `mu_stats`:
+        returns 1 when the last call ran on the fused kernel's tiles, 0 for the panel kernel."""
+        last = ctypes.c_int(0)
+        _lib.check(self.lib.dnmf_mu_path(self._h, int(force_panel), ctypes.byref(last)), "dnmf_mu_path")
+        return int(last.value)
 
     def get_mu_stats(self, t: int):
         G = np.zeros((self.K, self.K))

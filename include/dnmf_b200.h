@@ -26,7 +26,7 @@ extern "C" {
 
 typedef struct dnmf_ctx dnmf_ctx;
 
-#define DNMF_ABI_VERSION 3
+#define DNMF_ABI_VERSION 4
 
 int dnmf_abi_version(void);
 const char* dnmf_last_error(void);
@@ -93,13 +93,19 @@ int dnmf_motion_step(dnmf_ctx* ctx, const float* frames_dev, const int32_t* fram
 /* All minibatches of one epoch of update_motion over the RESIDENT video (Demix/dNMF.py:185-191 with the
  * loop over the DataLoader inside the library): batch i = frame_ids_dev[batch_offsets_host[i] ..
  * batch_offsets_host[i+1]), its global batch size = its length * global_batch_scale (ranks of a sharded fit),
- * Adam step number first_step + i, loss written to loss_dev[i] (may be NULL).  Identical results to nbatches
- * calls of dnmf_motion_step; it exists because at the reference's batch size (4 frames) a step is ~12 us of
- * device work and per-step host overhead dominates. */
+ * Adam step number first_step + i, loss written to loss_dev[i] (may be NULL).  Bit-identical results to
+ * nbatches calls of dnmf_motion_step.  When no frame occurs twice in the epoch (a DataLoader pass) the
+ * minibatches touch disjoint columns of beta and of the Adam moments -- the model has no parameter shared
+ * between frames -- so the library runs them as ONE fused launch over all frames of the epoch; each column
+ * replays the zero-gradient Adam steps of the other minibatches before and after its own gradient step, in
+ * the same fp32 operations as the step-by-step schedule.  Epochs with repeated frames run batch by batch. */
 int dnmf_motion_epoch(dnmf_ctx* ctx, const int32_t* frame_ids_dev, const int32_t* batch_offsets_host,
                       int nbatches, int global_batch_scale, float* beta_dev, float* m_dev, float* v_dev,
                       const float* C_dev, double lr, double beta1, double beta2, double eps,
                       int64_t first_step, int affine, double* loss_dev, void* stream);
+/* sequential: 1 = dnmf_motion_epoch always runs batch by batch, 0 = automatic, negative = leave unchanged.
+ * last_parallel_out (may be NULL): 1 when the most recent dnmf_motion_epoch ran frame-parallel. */
+int dnmf_epoch_mode(dnmf_ctx* ctx, int sequential, int* last_parallel_out);
 
 /* Same, with HOST buffers: copies frames_host[B][X][Y][Z] and the ids to the device, runs the
  * step and copies the loss back (synchronises the stream).  This is the end-to-end call. */
@@ -119,6 +125,12 @@ int dnmf_forward(dnmf_ctx* ctx, const int32_t* frame_ids_dev, int B, const float
 int dnmf_mu_stats(dnmf_ctx* ctx, const float* frames_dev, const int32_t* frame_ids_dev, int B,
                   const float* beta_dev, void* stream);
 int dnmf_get_mu_stats(dnmf_ctx* ctx, int t, double* G_host /* [K][K] */, double* b_host /* [K] */);
+/* dnmf_mu_stats has two device paths: the fused kernel's tiles with register-blocked accumulators (short
+ * neuron lists, the default when the tiling allows it) and a shared-memory panel kernel (any list length,
+ * also the automatic redo when a list outgrows the staged capacity).  force_panel: 1 = always the panel
+ * kernel, 0 = automatic, negative = leave unchanged.  last_path_out (may be NULL): path of the most recent
+ * dnmf_mu_stats call, 1 = fused tiles, 0 = panel kernel. */
+int dnmf_mu_path(dnmf_ctx* ctx, int force_panel, int* last_path_out);
 
 /* Multiplicative sweeps C <- C (b + g nbr) / (G C + 2 g C + 1e-32) over all T frames in fp64
  * (Demix/dNMF.py:143-148,172-173); use_gamma == 0 reproduces gamma=None.

@@ -374,31 +374,124 @@ def test_cached_slices_across_frames_match_oracle(monkeypatch, tiling):
         assert torch.equal(g, out[0][0]) and torch.equal(s_, out[0][1])
 
 
-def test_epoch_call_equals_per_step_calls():
+@pytest.mark.parametrize("case", ["full", "ragged_subset", "affine", "repeated_frame", "single_batch"])
+def test_epoch_call_equals_per_step_calls(case):
     """dnmf_motion_epoch (all minibatches of an epoch in one library call, resident video) leaves beta, the Adam
-    moments and the per-step losses bit-identical to one dnmf_motion_step per minibatch."""
+    moments and the per-step losses bit-identical to one dnmf_motion_step per minibatch -- batch by batch and
+    frame-parallel (one fused launch over the epoch, each column replaying the zero-gradient Adam steps of the
+    other minibatches).  Two epochs, so that the second starts from non-zero moments and step numbers; ragged last
+    batch, frames left out of the epoch, frozen quadratic rows, and an epoch that draws a frame twice (must fall
+    back to batch by batch)."""
     from dnmf_b200.engine import Engine
-    sz, K, T, B = [32, 16, 5], 6, 12, 4
+    sz, K, T, B = [32, 16, 5], 6, 14, 4
     pos, sig, beta0, C, frames = _case(sz, K, T, 5, beta_scale=0.2)
-    ids = torch.randperm(T, generator=torch.Generator().manual_seed(1)).to(torch.int32)
+    gen = torch.Generator().manual_seed(1)
+    epochs = []
+    for ep in range(2):
+        ids = torch.randperm(T, generator=gen).to(torch.int32)
+        if case == "full":
+            ids, off = ids[:12], list(range(0, 13, B))
+        elif case == "ragged_subset":
+            ids, off = ids[:11], [0, 4, 8, 11]
+        elif case == "affine":
+            off = [0, 4, 8, 12, 14]
+        elif case == "repeated_frame":
+            ids = torch.cat([ids[:8], ids[2:6]])
+            off = [0, 4, 8, 12]
+        else:
+            ids, off = ids[:4], [0, 4]
+        epochs.append((ids, off))
+    affine = case == "affine"
     res = []
-    for mode in ("steps", "epoch"):
+    for mode in ("steps", "epoch_sequential", "epoch"):
         e = Engine(sz, K, T)
         e.set_footprints(pos, sig, 3.5)
         e.upload_frames(frames, clamp_negative=False)
         beta = beta0.clone().cuda()
         m, v = torch.zeros_like(beta), torch.zeros_like(beta)
         c = C.cuda()
-        losses = torch.zeros(T // B, dtype=torch.float64, device="cuda")
-        idd = ids.cuda()
-        if mode == "steps":
-            for i in range(T // B):
-                e.motion_step(idd[i * B:(i + 1) * B], beta, m, v, c, 1e-3, (0.9, 0.999), 1e-8, i + 1,
-                              loss_out=losses[i:i + 1])
-        else:
-            e.motion_epoch(idd, list(range(0, T + 1, B)), beta, m, v, c, 1e-3, (0.9, 0.999), 1e-8, 1,
-                           loss_out=losses)
-        res.append((beta, m, v, losses))
-    for a, b in zip(*res):
-        assert torch.equal(a, b)
+        all_losses = []
+        step = 1
+        for ids, off in epochs:
+            nb = len(off) - 1
+            losses = torch.zeros(nb, dtype=torch.float64, device="cuda")
+            idd = ids.cuda()
+            if mode == "steps":
+                for i in range(nb):
+                    e.motion_step(idd[off[i]:off[i + 1]], beta, m, v, c, 1e-3, (0.9, 0.999), 1e-8, step + i,
+                                  affine=affine, loss_out=losses[i:i + 1])
+            else:
+                e.epoch_mode(1 if mode == "epoch_sequential" else 0)
+                e.motion_epoch(idd, off, beta, m, v, c, 1e-3, (0.9, 0.999), 1e-8, step, affine=affine,
+                               loss_out=losses)
+                expect_parallel = mode == "epoch" and case not in ("repeated_frame", "single_batch")
+                assert e.epoch_mode() == (1 if expect_parallel else 0)
+            step += nb
+            all_losses.append(losses)
+        res.append((beta, m, v, torch.cat(all_losses)))
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            assert torch.equal(a, b)
     assert float(res[0][3].min()) > 0
+    if affine:
+        assert torch.equal(res[0][0][4:].cpu(), beta0[4:])
+
+
+def _mu_both_paths(sz, K, T, seed, tiling, sigma=2.5, cutoff=3.5, beta_scale=1.0, expect_fused=True, resident=False):
+    """Trace statistics through the fused-tile kernel and through the panel kernel, both against the oracle."""
+    from dnmf_b200.engine import Engine
+    pos, sig, beta, C, frames = _case(sz, K, T, seed, sigma, beta_scale)
+    e = Engine(sz, K, T)
+    e.set_tiling(*tiling)
+    e.set_footprints(pos, sig, cutoff)
+    ids = torch.arange(T)
+    dev_frames = frames.cuda()
+    if resident:
+        e.upload_frames(frames, clamp_negative=False)
+        dev_frames = None
+    tabs, _ = O.axis_tables(pos, sig, sz, cutoff)
+    Gm, bv = O.closed_form_mu_stats(frames.numpy(), list(range(T)), beta.numpy(), tabs, sz)
+    res = []
+    for force_panel in (0, 1):
+        e.mu_path(force_panel)
+        e.mu_stats(ids, beta.cuda(), frames=dev_frames)
+        path = e.mu_path()
+        if force_panel == 0 and e.tiling()["fast_div"]:
+            assert expect_fused is None or path == (1 if expect_fused else 0), (path, e.tiling())
+        if force_panel == 1:
+            assert path == 0
+        G = np.stack([e.get_mu_stats(t)[0] for t in range(T)])
+        b = np.stack([e.get_mu_stats(t)[1] for t in range(T)])
+        np.testing.assert_allclose(G, Gm, rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(b, bv, rtol=2e-5, atol=1e-6)
+        assert np.array_equal(G, np.swapaxes(G, 1, 2)) or np.allclose(G, np.swapaxes(G, 1, 2), rtol=1e-6, atol=1e-9)
+        res.append((G, b))
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=2e-5, atol=1e-6)
+    return e
+
+
+@pytest.mark.parametrize("tiling", [(1, 1, 0, 0, 2), (2, 1, 0, 0, 2), (2, 2, 0, 0, 2)])
+def test_mu_stats_fused_tiles_short_lists(tiling):
+    """fit_tile_kernel<MODE=3>: one diagonal block of 1, 2 or 3 slot pairs (lists of 1..6 neurons), ragged
+    volumes, a batch passed by pointer and the resident video."""
+    _mu_both_paths([33, 18, 5], 4, 3, seed=7, tiling=tiling)
+    _mu_both_paths([50, 50, 2], 10, 4, seed=8, tiling=tiling, sigma=3.0, resident=True,
+                   beta_scale=1.0 if tiling[1] == 1 else 0.2)
+    _mu_both_paths([17, 30, 11], 2, 2, seed=9, tiling=tiling)
+
+
+@pytest.mark.parametrize("tiling", [(1, 1, 0, 16, 2), (2, 2, 0, 16, 2)])
+def test_mu_stats_fused_tiles_long_lists(tiling):
+    """lists of 7..16 neurons: several row blocks and the mirrored off-diagonal blocks."""
+    e = _mu_both_paths([32, 24, 6], 14, 3, seed=21, tiling=tiling, sigma=4.0, cutoff=0.0)
+    assert e.tiling()["cap"] >= 14
+    _mu_both_paths([40, 24, 9], 30, 2, seed=22, tiling=tiling, sigma=3.0, beta_scale=0.5)
+
+
+def test_mu_stats_fused_tiles_capacity_redo_and_depth_32():
+    """The statistics launch stages every listed neuron (its own capacity, larger than the fit's: 40 slots where
+    the fit was given 4).  A window wider than the staged slices raises the overflow flag and the panel kernel
+    redoes the call.  Z = 32 runs the rotated z order of the padded tile."""
+    _mu_both_paths([24, 16, 6], 40, 2, seed=9, tiling=(1, 1, 0, 4, 2), sigma=4.0, cutoff=0.0)
+    _mu_both_paths([24, 16, 32], 6, 3, seed=32, tiling=(1, 1, 0, 0, 2), beta_scale=0.5)
+    _mu_both_paths([24, 16, 6], 8, 3, seed=11, tiling=(1, 1, 0, 0, 2), beta_scale=8.0, expect_fused=False)
