@@ -1991,6 +1991,15 @@ struct dnmf_ctx {
   double* d_b = nullptr;  // [T][K]
   double* d_Cd[2] = {nullptr, nullptr};  // traces in fp64 during the sweeps, [T][K]
   int cd_cur = 0;
+  // sparse sweeps: static neighbour lists (neurons whose truncated supports overlap) and G compacted to them
+  int* d_mu_nbr = nullptr;     // [K][mu_nbrw], ascending, -1 padded
+  int mu_nbrw = 0;             // 0: lists not worth it (cutoff off / dense overlap) -> dense sweeps
+  bool mu_nbr_built = false;
+  double* d_Gc = nullptr;      // [T][K][mu_nbrw]
+  size_t gc_cap = 0;
+  bool gc_valid = false;       // compacted copy matches d_G
+  int mu_dense_sweeps = 0;     // dnmf_mu_path flag bit 1 / DNMF_MU_DENSE_SWEEPS
+  int mu_last_sparse = 0;
   int mu_capM = 0;
   // frame-parallel epoch (dnmf_motion_epoch)
   int* d_epoch_batch_of = nullptr;
@@ -2066,6 +2075,7 @@ extern "C" int dnmf_create(dnmf_ctx** out, int X, int Y, int Z, int K, int T, in
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (const char* ev = getenv("DNMF_FPC")) c->fpc_override = atoi(ev);
   if (const char* ev = getenv("DNMF_MU_PANEL")) c->mu_force_panel = atoi(ev) != 0;
+  if (const char* ev = getenv("DNMF_MU_DENSE_SWEEPS")) c->mu_dense_sweeps = atoi(ev) != 0;
   if (const char* ev = getenv("DNMF_EPOCH_SEQUENTIAL")) c->epoch_sequential = atoi(ev) != 0;
   CU(cudaMalloc((void**)&c->d_pos, (size_t)K * 3 * sizeof(float)));
   CU(cudaMalloc((void**)&c->d_sigma, (size_t)K * sizeof(float)));
@@ -2129,7 +2139,8 @@ extern "C" void dnmf_destroy(dnmf_ctx* c) {
                   c->d_Cd[0],   c->d_Cd[1], c->d_keys,       c->d_cand_off,    c->d_cand_ids,
                   c->d_tab_dpos[0], c->d_tab_dpos[1], c->d_tab_dpos[2], c->d_tab_dsig[0], c->d_tab_dsig[1],
                   c->d_tab_dsig[2], c->d_resid, c->d_sumr, c->d_ids_zero,
-                  c->d_epoch_batch_of, c->d_epoch_offsets, c->d_epoch_scalars, c->d_epoch_scale};
+                  c->d_epoch_batch_of, c->d_epoch_offsets, c->d_epoch_scalars, c->d_epoch_scale,
+                  c->d_mu_nbr, c->d_Gc};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->copy_stream) {
@@ -2358,6 +2369,8 @@ extern "C" int dnmf_set_footprints(dnmf_ctx* c, const float* pos_host, const flo
   }
   c->have_footprints = true;
   c->mu_capM = 0;
+  c->mu_nbr_built = false;
+  c->gc_valid = false;
   c->mu_fused_need = 0;
   c->mu_fused_off = 0;
   c->counters[3]++;

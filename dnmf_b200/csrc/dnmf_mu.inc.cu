@@ -279,10 +279,10 @@ __global__ void mu_sweep_kernel(const double* __restrict__ G, const double* __re
                                 const double* __restrict__ Cin, double* __restrict__ Cout, int T, int K,
                                 double gamma, int use_gamma, const double* __restrict__ halo_prev,
                                 const double* __restrict__ halo_next) {
-  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // grid = (T, ceil(K / warps per block))
   const int lane = threadIdx.x & 31;
-  if (w >= (long long)T * K) return;
-  const int t = (int)(w / K), k = (int)(w - (long long)t * K);
+  const int t = blockIdx.x, k = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= K) return;
   const double* g = G + ((size_t)t * K + k) * K;
   const double* c = Cin + (size_t)t * K;
   double dot = 0.0;
@@ -299,6 +299,96 @@ __global__ void mu_sweep_kernel(const double* __restrict__ G, const double* __re
       c2 += 2.0 * gamma * ck;
     }
     Cout[(size_t)t * K + k] = ck * c1 / (c2 + 1e-32);
+  }
+}
+
+// Sparse sweeps.  G_t[k][l] can only be non-zero when the truncated supports of neurons k and l overlap, which
+// does not depend on the deformation: the static neighbour list nbr[k][0..W) (ascending, -1 padded).  One warp per
+// (t, k) row gathers the row's neighbour entries from the dense statistics into Gc[t][k][0..W) and checks that
+// every other entry of the row is exactly zero (flag otherwise: the caller keeps the dense sweeps).
+__global__ void mu_compact_kernel(const double* __restrict__ G, const int* __restrict__ nbr, int W, int T, int K,
+                                  double* __restrict__ Gc, int* __restrict__ violation) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= (long long)T * K) return;
+  const int k = (int)(row % K);
+  const double* g = G + (size_t)row * K;
+  const int* nb = nbr + (size_t)k * W;
+  bool bad = false;
+  for (int l = lane; l < K; l += 32) {
+    if (g[l] != 0.0) {
+      int lo = 0, hi = W - 1;  // is l in nb[] ? (-1 padding sorts last: treat as +inf)
+      bool found = false;
+      while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const int v = nb[mid];
+        if (v == l) {
+          found = true;
+          break;
+        }
+        if (v < 0 || v > l) hi = mid - 1; else lo = mid + 1;
+      }
+      bad |= !found;
+    }
+  }
+  if (bad) atomicOr(violation, 1);
+  for (int s_ = lane; s_ < W; s_ += 32) {
+    const int l = nb[s_];
+    Gc[(size_t)row * W + s_] = l >= 0 ? g[l] : 0.0;
+  }
+}
+
+// Ws = min(W, 32) lanes per neuron k (W a power of two below 32, else a multiple of 32); one thread walks kMuTB
+// consecutive frames of its (k, list slot): the neighbour id is loaded once and the kMuTB (G, C) pairs are
+// independent loads in flight (one row per warp and frame was latency-bound: nbr -> C gather -> reduce -> store).
+// grid = (ceil(T / kMuTB), ceil(K / rows per block)).
+constexpr int kMuTB = 4;
+__global__ void mu_sweep_sparse_kernel(const double* __restrict__ Gc, const int* __restrict__ nbr, int W, int Ws,
+                                       const double* __restrict__ bvec, const double* __restrict__ Cin,
+                                       double* __restrict__ Cout, int T, int K, double gamma, int use_gamma,
+                                       const double* __restrict__ halo_prev, const double* __restrict__ halo_next) {
+  const int sub = threadIdx.x & (Ws - 1);
+  const int wshift = 31 - __clz(Ws);
+  const int t0 = blockIdx.x * kMuTB;
+  const int k = blockIdx.y * (blockDim.x >> wshift) + (threadIdx.x >> wshift);
+  const bool live = k < K;
+  double dot[kMuTB];
+#pragma unroll
+  for (int u = 0; u < kMuTB; ++u) dot[u] = 0.0;
+  // the epilogue's operands of frame t0 + sub (lanes sub < kMuTB), requested before the dot products
+  const int te = t0 + sub;
+  const bool epi = live && sub < kMuTB && te < T;
+  double ck = 0.0, c1 = 0.0, prev = 0.0, next = 0.0;
+  if (epi) {
+    ck = Cin[(size_t)te * K + k];
+    c1 = bvec[(size_t)te * K + k];
+    if (use_gamma) {
+      prev = te > 0 ? Cin[(size_t)(te - 1) * K + k] : (halo_prev ? halo_prev[k] : ck);
+      next = te < T - 1 ? Cin[(size_t)(te + 1) * K + k] : (halo_next ? halo_next[k] : ck);
+    }
+  }
+  if (live) {
+    for (int s_ = sub; s_ < W; s_ += Ws) {
+      const int l = max(nbr[(size_t)k * W + s_], 0);  // padding slots hold G = 0
+#pragma unroll
+      for (int u = 0; u < kMuTB; ++u) {
+        const int t = min(t0 + u, T - 1);
+        dot[u] = fma(Gc[((size_t)t * K + k) * W + s_], Cin[(size_t)t * K + l], dot[u]);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kMuTB; ++u)
+    for (int o = Ws >> 1; o > 0; o >>= 1) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
+  if (epi) {
+    double c2 = dot[0];
+#pragma unroll
+    for (int u = 1; u < kMuTB; ++u) c2 = sub == u ? dot[u] : c2;
+    if (use_gamma) {
+      c1 += gamma * (prev + next);
+      c2 += 2.0 * gamma * ck;
+    }
+    Cout[(size_t)te * K + k] = ck * c1 / (c2 + 1e-32);
   }
 }
 
@@ -428,6 +518,7 @@ extern "C" int dnmf_mu_stats(dnmf_ctx* c, const float* frames_dev, const int32_t
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(c->device));
   if (mu_alloc(c)) return 1;
+  c->gc_valid = false;
   // Fast path: the fused kernel's tiles, lists and staged slices (fit_tile_kernel<MODE=3>).  A tile whose list
   // is longer than the staged capacity under the current deformation sets the overflow flag and everything is
   // redone by the panel kernel below.
@@ -552,8 +643,11 @@ extern "C" int dnmf_mu_stats(dnmf_ctx* c, const float* frames_dev, const int32_t
 
 extern "C" int dnmf_mu_path(dnmf_ctx* c, int force_panel, int* last_path_out) {
   if (!c) return fail("dnmf_mu_path: NULL context");
-  if (force_panel >= 0) c->mu_force_panel = force_panel != 0;
-  if (last_path_out) *last_path_out = c->mu_last_path;
+  if (force_panel >= 0) {
+    c->mu_force_panel = (force_panel & 1) != 0;
+    c->mu_dense_sweeps = (force_panel & 2) != 0;
+  }
+  if (last_path_out) *last_path_out = c->mu_last_path | (c->mu_last_sparse << 1);
   return 0;
 }
 
@@ -566,10 +660,67 @@ extern "C" int dnmf_get_mu_stats(dnmf_ctx* c, int t, double* G_host, double* b_h
   return 0;
 }
 
+// Static neighbour lists from the integer node ranges of the truncated footprints: A_k(ix) != 0 needs
+// lo_k - 1 < ix_d < hi_k + 1 on every axis, so G[k][l] != 0 needs the open intervals of k and l to meet.
+static int mu_build_neighbours(dnmf_ctx* c) {
+  c->mu_nbr_built = true;
+  c->mu_nbrw = 0;
+  const int K = c->K;
+  std::vector<int> rng((size_t)K * 6);
+  CU(cudaMemcpy(rng.data(), c->d_rng, rng.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<std::vector<int>> lists((size_t)K);
+  size_t longest = 1;
+  for (int k = 0; k < K; ++k) {
+    const int* a = &rng[(size_t)k * 6];
+    for (int l = 0; l < K; ++l) {
+      const int* b = &rng[(size_t)l * 6];
+      bool meet = true;
+      for (int d = 0; d < 3; ++d)
+        meet = meet && a[2 * d] <= a[2 * d + 1] && b[2 * d] <= b[2 * d + 1] &&  // non-empty ranges
+               a[2 * d] - 1 <= b[2 * d + 1] + 1 && b[2 * d] - 1 <= a[2 * d + 1] + 1;
+      if (meet || l == k) lists[(size_t)k].push_back(l);
+    }
+    longest = std::max(longest, lists[(size_t)k].size());
+    if (longest * 2 > (size_t)K) return 0;  // dense overlap: the dense sweep reads less
+  }
+  int W = 8;
+  while (W < 32 && (size_t)W < longest) W *= 2;
+  if ((size_t)W < longest) W = (int)((longest + 31) / 32) * 32;
+  std::vector<int> flat((size_t)K * W, -1);
+  for (int k = 0; k < K; ++k) std::copy(lists[(size_t)k].begin(), lists[(size_t)k].end(), flat.begin() + (size_t)k * W);
+  if (c->d_mu_nbr) cudaFree(c->d_mu_nbr);
+  c->d_mu_nbr = nullptr;
+  CU(cudaMalloc((void**)&c->d_mu_nbr, flat.size() * sizeof(int)));
+  CU(cudaMemcpy(c->d_mu_nbr, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
+  c->mu_nbrw = W;
+  return 0;
+}
+
 extern "C" int dnmf_mu_begin(dnmf_ctx* c, const float* C_dev, void* stream) {
   if (!c || !C_dev) return fail("dnmf_mu_begin: NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(c->device));
+  // compact the statistics to the static neighbour lists (once per set of statistics)
+  c->mu_last_sparse = 0;
+  if (c->d_G && c->have_footprints && c->mu_dense_sweeps == 0) {
+    if (!c->mu_nbr_built && mu_build_neighbours(c)) return 1;
+    if (c->mu_nbrw > 0) {
+      if (!c->gc_valid) {
+        if (ensure(&c->d_Gc, &c->gc_cap, (size_t)c->T * c->K * c->mu_nbrw)) return 1;
+        CU(cudaMemsetAsync(c->d_tmp_max, 0, sizeof(int), st));
+        const long long threads = (long long)c->T * c->K * 32;
+        mu_compact_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(c->d_G, c->d_mu_nbr, c->mu_nbrw, c->T, c->K,
+                                                                           c->d_Gc, c->d_tmp_max);
+        CU(cudaGetLastError());
+        int bad = 0;
+        CU(cudaMemcpyAsync(&bad, c->d_tmp_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (bad) c->mu_nbrw = 0;  // a non-zero outside the lists: never expected; keep the dense sweeps
+        else c->gc_valid = true;
+      }
+      c->mu_last_sparse = c->mu_nbrw > 0 ? 1 : 0;
+    }
+  }
   const size_t n = (size_t)c->K * c->T;
   if (!c->d_Cd[0]) {
     CU(cudaMalloc((void**)&c->d_Cd[0], n * sizeof(double)));
@@ -588,10 +739,19 @@ extern "C" int dnmf_mu_sweep(dnmf_ctx* c, double gamma, int use_gamma, const dou
   if (!c->d_Cd[0]) return fail("dnmf_mu_sweep: call dnmf_mu_begin first");
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(c->device));
-  const long long threads = (long long)c->T * c->K * 32;
-  mu_sweep_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
-      c->d_G, c->d_b, c->d_Cd[c->cd_cur], c->d_Cd[c->cd_cur ^ 1], c->T, c->K, gamma, use_gamma, halo_prev_dev,
-      halo_next_dev);
+  if (c->mu_last_sparse && c->gc_valid && c->mu_nbrw > 0) {
+    const int W = c->mu_nbrw, Ws = std::min(W, 32);
+    const int rows_per_block = 256 / Ws;
+    const dim3 grid((unsigned)((c->T + kMuTB - 1) / kMuTB), (unsigned)((c->K + rows_per_block - 1) / rows_per_block));
+    mu_sweep_sparse_kernel<<<grid, 256, 0, st>>>(
+        c->d_Gc, c->d_mu_nbr, W, Ws, c->d_b, c->d_Cd[c->cd_cur], c->d_Cd[c->cd_cur ^ 1], c->T, c->K, gamma, use_gamma,
+        halo_prev_dev, halo_next_dev);
+  } else {
+    const dim3 grid((unsigned)c->T, (unsigned)((c->K + 7) / 8));
+    mu_sweep_kernel<<<grid, 256, 0, st>>>(
+        c->d_G, c->d_b, c->d_Cd[c->cd_cur], c->d_Cd[c->cd_cur ^ 1], c->T, c->K, gamma, use_gamma, halo_prev_dev,
+        halo_next_dev);
+  }
   CU(cudaGetLastError());
   c->cd_cur ^= 1;
   c->counters[7] += 1;

@@ -222,11 +222,12 @@ class Engine:
         _lib.check(self.lib.dnmf_mu_stats(self._h, _ptr(frames), _ptr(ids32), int(ids32.numel()), _ptr(beta),
                                           self.stream), "dnmf_mu_stats")
 
-    def mu_path(self, force_panel: int = -1) -> int:
-        """Select (1 = panel kernel only, 0 = automatic) and/or query the device path of `mu_stats`:
-        returns 1 when the last call ran on the fused kernel's tiles, 0 for the panel kernel."""
+    def mu_path(self, flags: int = -1) -> int:
+        """Select (bit 0 = panel statistics kernel only, bit 1 = dense sweeps only, 0 = automatic) and/or query the
+        device paths of the trace update: returns bit 0 = the last `mu_stats` ran on the fused kernel's tiles,
+        bit 1 = the last `mu_begin` / `mu_sweeps` used the neighbour-compacted statistics."""
         last = ctypes.c_int(0)
-        _lib.check(self.lib.dnmf_mu_path(self._h, int(force_panel), ctypes.byref(last)), "dnmf_mu_path")
+        _lib.check(self.lib.dnmf_mu_path(self._h, int(flags), ctypes.byref(last)), "dnmf_mu_path")
         return int(last.value)
 
     def get_mu_stats(self, t: int):

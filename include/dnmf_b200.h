@@ -127,10 +127,12 @@ int dnmf_mu_stats(dnmf_ctx* ctx, const float* frames_dev, const int32_t* frame_i
 int dnmf_get_mu_stats(dnmf_ctx* ctx, int t, double* G_host /* [K][K] */, double* b_host /* [K] */);
 /* dnmf_mu_stats has two device paths: the fused kernel's tiles with register-blocked accumulators (short
  * neuron lists, the default when the tiling allows it) and a shared-memory panel kernel (any list length,
- * also the automatic redo when a list outgrows the staged capacity).  force_panel: 1 = always the panel
- * kernel, 0 = automatic, negative = leave unchanged.  last_path_out (may be NULL): path of the most recent
- * dnmf_mu_stats call, 1 = fused tiles, 0 = panel kernel. */
-int dnmf_mu_path(dnmf_ctx* ctx, int force_panel, int* last_path_out);
+ * also the automatic redo when a list outgrows the staged capacity).  The sweeps read G either dense or
+ * compacted to the static neighbour lists (neurons whose truncated supports overlap; the default when the
+ * lists are shorter than K/2).  flags: bit 0 = always the panel kernel, bit 1 = always dense sweeps,
+ * 0 = automatic, negative = leave unchanged.  last_path_out (may be NULL): bit 0 = the most recent
+ * dnmf_mu_stats ran on the fused tiles, bit 1 = the most recent dnmf_mu_begin set up sparse sweeps. */
+int dnmf_mu_path(dnmf_ctx* ctx, int flags, int* last_path_out);
 
 /* Multiplicative sweeps C <- C (b + g nbr) / (G C + 2 g C + 1e-32) over all T frames in fp64
  * (Demix/dNMF.py:143-148,172-173); use_gamma == 0 reproduces gamma=None.

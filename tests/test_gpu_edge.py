@@ -455,7 +455,7 @@ def _mu_both_paths(sz, K, T, seed, tiling, sigma=2.5, cutoff=3.5, beta_scale=1.0
     for force_panel in (0, 1):
         e.mu_path(force_panel)
         e.mu_stats(ids, beta.cuda(), frames=dev_frames)
-        path = e.mu_path()
+        path = e.mu_path() & 1
         if force_panel == 0 and e.tiling()["fast_div"]:
             assert expect_fused is None or path == (1 if expect_fused else 0), (path, e.tiling())
         if force_panel == 1:
@@ -495,3 +495,33 @@ def test_mu_stats_fused_tiles_capacity_redo_and_depth_32():
     _mu_both_paths([24, 16, 6], 40, 2, seed=9, tiling=(1, 1, 0, 4, 2), sigma=4.0, cutoff=0.0)
     _mu_both_paths([24, 16, 32], 6, 3, seed=32, tiling=(1, 1, 0, 0, 2), beta_scale=0.5)
     _mu_both_paths([24, 16, 6], 8, 3, seed=11, tiling=(1, 1, 0, 0, 2), beta_scale=8.0, expect_fused=False)
+
+
+@pytest.mark.parametrize("gamma", [None, 1e-2])
+def test_mu_sweeps_sparse_neighbour_lists_match_dense_and_oracle(gamma):
+    """The sweeps over G compacted to the static neighbour lists (neurons whose truncated supports overlap) equal
+    the dense sweeps and the oracle's multiplicative update (Demix/dNMF.py:143-148), with and without the temporal
+    coupling; without a cutoff every neuron neighbours every other and the dense kernel is kept."""
+    from dnmf_b200.engine import Engine
+    sz, K, T, iters = [48, 32, 6], 40, 5, 7
+    pos, sig, beta, C, frames = _case(sz, K, T, 77, sigma=2.0, beta_scale=0.5)
+    pos[-1] = [-40.0, -40.0, -40.0]                    # a neuron outside the volume: empty range, no neighbours
+    for cutoff, expect_sparse in ((3.0, True), (0.0, False)):
+        e = Engine(sz, K, T)
+        e.set_tiling(1, 1, 0, 0, 2)
+        e.set_footprints(pos, sig, cutoff)
+        e.mu_stats(torch.arange(T), beta.cuda(), frames=frames.cuda())
+        G = np.stack([e.get_mu_stats(t)[0] for t in range(T)])
+        b = np.stack([e.get_mu_stats(t)[1] for t in range(T)])
+        ref = C.numpy().astype(np.float64)
+        for _ in range(iters):
+            ref = O.mu_sweep(np.transpose(G, (1, 2, 0)), b.T, ref, gamma)
+        out = []
+        for flags in (0, 2):
+            e.mu_path(flags)
+            c = C.clone().cuda()
+            e.mu_sweeps(c, gamma, iters)
+            assert (e.mu_path() >> 1) == (1 if (flags == 0 and expect_sparse) else 0)
+            out.append(c.cpu().numpy())
+            np.testing.assert_allclose(out[-1], ref.astype(np.float32), rtol=2e-6, atol=1e-30)
+        np.testing.assert_allclose(out[0], out[1], rtol=1e-6, atol=1e-30)
