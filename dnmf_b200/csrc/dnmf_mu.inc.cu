@@ -30,19 +30,26 @@ struct MuParams {
   int full_depth;
 };
 
-static size_t mu_smem_bytes(int capM, int tz, int K) {
-  const int mb = capM / 4;
-  return (size_t)capM * kMuVS * 4 + (size_t)(kMuTX * kMuTY * tz + 4) * 4 + 64 * 4 +
+// BS = 4: panel [row][voxel] (stride kMuVS), 4x4 register blocks -- short lists.
+// BS = 8: panel [voxel][row] (stride capM + 4 floats, 16-byte aligned rows), 8x8 register blocks fed by four
+// LDS.128 per voxel (64 FMAs per 4 shared-memory instructions instead of 16 per 8 scalar ones, whose row
+// stride put the 4x4 variant's lanes on 8 banks) -- long lists (cfg4: ~100 neurons per tile).
+static size_t mu_smem_bytes(int capM, int tz, int K, int bs) {
+  const int mb = (capM + bs - 1) / bs;
+  const size_t panel = bs == 8 ? (size_t)kMuThreads * (capM + 4) * 4 : (size_t)capM * kMuVS * 4;
+  return panel + (size_t)(kMuTX * kMuTY * tz + 4) * 4 + 64 * 4 +
          (size_t)((K + 7) & ~7) * 2 + (size_t)((mb * (mb + 1) / 2 + 3) & ~3) * 2;
 }
 
-template <int R>
+template <int R, int BS>
 __global__ void __launch_bounds__(kMuThreads) mu_stats_kernel(const __grid_constant__ MuParams p) {
   constexpr int NW = kMuThreads / 32, NWX = 2;
   constexpr int TX = kMuTX, TY = kMuTY;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sA = reinterpret_cast<float*>(smem_raw);
-  float* sY = sA + (size_t)p.capM * kMuVS;
+  const int PS = p.capM + 4;  // BS == 8: floats per voxel row of the panel (capM is a multiple of 8 there)
+  const int panel_floats = BS == 8 ? kMuThreads * PS : p.capM * kMuVS;
+  float* sY = sA + (size_t)panel_floats;
   float* sBeta = sY + (TX * TY * p.tz + 4);
   int* sInt = reinterpret_cast<int*>(sBeta + 32);
   unsigned short* sList = reinterpret_cast<unsigned short*>(sInt + 32);
@@ -75,7 +82,7 @@ __global__ void __launch_bounds__(kMuThreads) mu_stats_kernel(const __grid_const
       }
     }
   }
-  for (int e = tid; e < p.capM * kMuVS; e += kMuThreads) sA[e] = 0.f;
+  for (int e = tid; e < panel_floats; e += kMuThreads) sA[e] = 0.f;
   __syncthreads();
   if (tid < 3) {
     const int s = tid == 0 ? p.X : (tid == 1 ? p.Y : p.Z);
@@ -125,8 +132,8 @@ __global__ void __launch_bounds__(kMuThreads) mu_stats_kernel(const __grid_const
     if (tid == 0) atomicMax(p.overflow, L + 1);
     return;
   }
-  const int M = L + 1;            // neurons + the Y pseudo-neuron
-  const int mb = (M + 3) >> 2;    // 4x4 blocks per side
+  const int M = L + 1;               // neurons + the Y pseudo-neuron
+  const int mb = (M + BS - 1) / BS;  // BS x BS blocks per side
   const int nblk = mb * (mb + 1) / 2;
   for (int e = tid; e < nblk; e += kMuThreads) {  // decode triangular block index -> (bi, bj), bi <= bj
     int bi = 0, rem = e;
@@ -167,11 +174,11 @@ __global__ void __launch_bounds__(kMuThreads) mu_stats_kernel(const __grid_const
   const size_t gbase = (size_t)t * p.K * p.K;
 
   for (int base = 0; base < nblk; base += groups * R) {
-    float acc[R][16];
+    float acc[R][BS * BS];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[r][i] = 0.f;
+      for (int i = 0; i < BS * BS; ++i) acc[r][i] = 0.f;
 
     for (int zz = 0; zz < nz; ++zz) {
       // phase 1: A_j(p) for every listed neuron at this thread's voxel
@@ -187,29 +194,45 @@ __global__ void __launch_bounds__(kMuThreads) mu_stats_kernel(const __grid_const
         float2 ey = __ldg(p.tab1 + (size_t)k * sY3 + (i1 + 2));
         float2 ez = __ldg(p.tab2 + (size_t)k * sZ3 + (i2 + 2));
         float a = (fmaf(f0, ex.y, ex.x) * fmaf(f1, ey.y, ey.x)) * fmaf(f2, ez.y, ez.x);
-        sA[j * kMuVS + tid] = valid ? a : 0.f;
+        sA[BS == 8 ? tid * PS + j : j * kMuVS + tid] = valid ? a : 0.f;
       }
-      sA[L * kMuVS + tid] = valid ? sY[ybase + zz] : 0.f;
+      sA[BS == 8 ? tid * PS + L : L * kMuVS + tid] = valid ? sY[ybase + zz] : 0.f;
       __syncthreads();
-      // phase 2: 4x4 register blocks of [A|Y]^T [A|Y], split-K over the 128 voxels
+      // phase 2: BS x BS register blocks of [A|Y]^T [A|Y], split-K over the 128 voxels
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int blk = base + r * groups + grp;
         if (blk < nblk) {
           const int code = sBlk[blk];
-          const float* ra = sA + (size_t)((code >> 8) * 4) * kMuVS;
-          const float* rb = sA + (size_t)((code & 255) * 4) * kMuVS;
-          for (int v = ksl; v < kMuThreads; v += ks) {
-            float a[4], bb[4];
+          if constexpr (BS == 8) {
+            const float4* ra = reinterpret_cast<const float4*>(sA + (code >> 8) * 8);
+            const float4* rb = reinterpret_cast<const float4*>(sA + (code & 255) * 8);
+            const int ps4 = PS >> 2;
+#pragma unroll 2
+            for (int v = ksl; v < kMuThreads; v += ks) {
+              const float4 a0 = ra[v * ps4], a1 = ra[v * ps4 + 1], b0 = rb[v * ps4], b1 = rb[v * ps4 + 1];
+              const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              a[i] = ra[i * kMuVS + v];
-              bb[i] = rb[i * kMuVS + v];
+              for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[r][i * 8 + c] = fmaf(a[i], bb[c], acc[r][i * 8 + c]);
             }
+          } else {
+            const float* ra = sA + (size_t)((code >> 8) * 4) * kMuVS;
+            const float* rb = sA + (size_t)((code & 255) * 4) * kMuVS;
+            for (int v = ksl; v < kMuThreads; v += ks) {
+              float a[4], bb[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+              for (int i = 0; i < 4; ++i) {
+                a[i] = ra[i * kMuVS + v];
+                bb[i] = rb[i * kMuVS + v];
+              }
 #pragma unroll
-              for (int c = 0; c < 4; ++c) acc[r][i * 4 + c] = fmaf(a[i], bb[c], acc[r][i * 4 + c]);
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][i * 4 + c] = fmaf(a[i], bb[c], acc[r][i * 4 + c]);
+            }
           }
         }
       }
@@ -221,7 +244,7 @@ __global__ void __launch_bounds__(kMuThreads) mu_stats_kernel(const __grid_const
     for (int r = 0; r < R; ++r) {
       const int blk = base + r * groups + grp;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < BS * BS; ++i) {
         float v = acc[r][i];
         for (int o = ks >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         acc[r][i] = v;
@@ -230,14 +253,14 @@ __global__ void __launch_bounds__(kMuThreads) mu_stats_kernel(const __grid_const
         const int code = sBlk[blk];
         const int bi = code >> 8, bj = code & 255;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int jr = bi * 4 + i;
+        for (int i = 0; i < BS; ++i) {
+          const int jr = bi * BS + i;
           if (jr >= L) continue;  // Y pseudo-row or padding
           const int kr = sList[jr];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int jc = bj * 4 + c;
-            const double v = (double)acc[r][i * 4 + c];
+          for (int c = 0; c < BS; ++c) {
+            const int jc = bj * BS + c;
+            const double v = (double)acc[r][i * BS + c];
             if (jc < L) {
               const int kc = sList[jc];
               atomicAdd(p.G + gbase + (size_t)kr * p.K + kc, v);
@@ -501,9 +524,9 @@ static int mu_alloc(dnmf_ctx* c) {
   return 0;
 }
 
-template <int R>
+template <int R, int BS>
 static int launch_mu(const MuParams& p, int grid, size_t smem, cudaStream_t st) {
-  auto kern = mu_stats_kernel<R>;
+  auto kern = mu_stats_kernel<R, BS>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kMuThreads, smem, st>>>(p);
   CU(cudaGetLastError());
@@ -589,11 +612,13 @@ extern "C" int dnmf_mu_stats(dnmf_ctx* c, const float* frames_dev, const int32_t
     CU(cudaMemcpyAsync(&lmax, c->d_tmp_max, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     int capM = std::min(c->K, lmax + lmax / 2 + 8) + 1;
-    c->mu_capM = (capM + 3) & ~3;
+    c->mu_capM = (capM + 7) & ~7;
   }
   for (int attempt = 0; attempt < 2; ++attempt) {
     const int capM = c->mu_capM;
-    const size_t smem = mu_smem_bytes(capM, c->tz, c->K);
+    // 8x8 register blocks from 32 rows up (enough blocks to occupy the CTA), 4x4 below
+    const int bs = (capM >= 32 && c->mu_block4 == 0) ? 8 : 4;
+    const size_t smem = mu_smem_bytes(capM, c->tz, c->K, bs);
     if (smem > (size_t)c->max_smem_optin)
       return fail("dnmf_mu_stats: neuron lists too long for the shared-memory A panel (K_eff too large)");
     MuParams p;
@@ -622,13 +647,16 @@ extern "C" int dnmf_mu_stats(dnmf_ctx* c, const float* frames_dev, const int32_t
     CU(cudaMemsetAsync(c->d_tmp_max, 0, sizeof(int), st));
     mu_zero_kernel<<<B, 256, 0, st>>>(c->d_G, c->d_b, frame_ids_dev, c->K);
     CU(cudaGetLastError());
-    const int mb = capM / 4;
+    const int mb = (capM + bs - 1) / bs;
     const int nblk = mb * (mb + 1) / 2;
     const int need = (nblk + kMuThreads - 1) / kMuThreads;
     int rc;
-    if (need <= 1) rc = launch_mu<1>(p, B * nt, smem, st);
-    else if (need <= 2) rc = launch_mu<2>(p, B * nt, smem, st);
-    else rc = launch_mu<4>(p, B * nt, smem, st);
+    if (bs == 8) {
+      if (need <= 1) rc = launch_mu<1, 8>(p, B * nt, smem, st);
+      else rc = launch_mu<2, 8>(p, B * nt, smem, st);
+    } else if (need <= 1) rc = launch_mu<1, 4>(p, B * nt, smem, st);
+    else if (need <= 2) rc = launch_mu<2, 4>(p, B * nt, smem, st);
+    else rc = launch_mu<4, 4>(p, B * nt, smem, st);
     if (rc) return rc;
     int over = 0;
     CU(cudaMemcpyAsync(&over, c->d_tmp_max, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -636,7 +664,7 @@ extern "C" int dnmf_mu_stats(dnmf_ctx* c, const float* frames_dev, const int32_t
     c->counters[6] += 1;
     if (over == 0) return 0;
     // a tile's list outgrew the panel under the current deformation: grow once and redo
-    c->mu_capM = (std::min(c->K + 1, over + over / 4 + 4) + 3) & ~3;
+    c->mu_capM = (std::min(c->K + 1, over + over / 4 + 4) + 7) & ~7;
   }
   return fail("dnmf_mu_stats: neuron list longer than the A panel after regrowth");
 }

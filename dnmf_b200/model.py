@@ -333,19 +333,21 @@ class DeformableNMF:
                 print("Epoch " + str(epoch))
             self.fp.train()
             if epoch_call:
-                batches = [torch.as_tensor(data[1]).to(torch.int32).reshape(-1).cpu() for data in dataloader]
+                # one pass over the loader on the host: ids as numpy (no per-batch torch dispatch), one H2D copy
+                batches = [np.asarray(data[1].cpu() if torch.is_tensor(data[1]) else data[1]).reshape(-1)
+                           for data in dataloader]
                 if not batches:
                     continue
                 offsets = np.zeros(len(batches) + 1, dtype=np.int32)
-                offsets[1:] = np.cumsum([int(b.numel()) for b in batches])
-                ids_dev = torch.cat(batches).to(eng.device)
+                offsets[1:] = np.cumsum([b.size for b in batches])
+                ids_dev = torch.from_numpy(np.concatenate(batches).astype(np.int32)).to(eng.device)
                 losses = torch.zeros(len(batches), dtype=torch.float64, device=eng.device)
                 first = int(st["step"]) + 1
                 eng.motion_epoch(ids_dev, offsets, beta, st["exp_avg"], st["exp_avg_sq"], self.C, group["lr"],
                                  group["betas"], group["eps"], first, self.affine,
                                  global_batch_scale=self.global_batch_scale, loss_out=losses)
                 st["step"] += len(batches)
-                self.loss_history.extend(losses[i] for i in range(len(batches)))
+                self.loss_history.extend(losses.unbind(0))
                 continue
             for batch_idx, data in enumerate(dataloader):
                 ids = torch.as_tensor(data[1]).to(torch.int32)
@@ -394,7 +396,10 @@ class DeformableNMF:
 
     def losses(self) -> np.ndarray:
         """Per-step reconstruction losses recorded by update_motion (one device sync)."""
-        return np.asarray([float(l) for l in self.loss_history])
+        hist = self.loss_history
+        if hist and all(torch.is_tensor(l) for l in hist):
+            return torch.stack([l.reshape(()) for l in hist]).double().cpu().numpy()   # one D2H copy
+        return np.asarray([float(l) for l in hist])
 
     # -- traces -------------------------------------------------------------------------------------
     @staticmethod

@@ -525,3 +525,30 @@ def test_mu_sweeps_sparse_neighbour_lists_match_dense_and_oracle(gamma):
             out.append(c.cpu().numpy())
             np.testing.assert_allclose(out[-1], ref.astype(np.float32), rtol=2e-6, atol=1e-30)
         np.testing.assert_allclose(out[0], out[1], rtol=1e-6, atol=1e-30)
+
+
+@pytest.mark.parametrize("K", [40, 140])
+def test_mu_stats_panel_kernel_8x8_blocks_long_lists(monkeypatch, K):
+    """Panel kernel with 8x8 register blocks over the [voxel][row] panel (lists of 32 rows and more): split-K
+    over the voxels when there are few blocks (K = 40), two blocks per thread (K = 140); against the oracle and
+    against the 4x4 variant."""
+    from dnmf_b200.engine import Engine
+    sz, T = [24, 16, 6], 2
+    pos, sig, beta, C, frames = _case(sz, K, T, 9, sigma=4.0)
+    tabs, _ = O.axis_tables(pos, sig, sz, 0.0)
+    Gm, bv = O.closed_form_mu_stats(frames.numpy(), list(range(T)), beta.numpy(), tabs, sz)
+    out = []
+    for block4 in ("0", "1"):
+        monkeypatch.setenv("DNMF_MU_BLOCK4", block4)
+        e = Engine(sz, K, T)
+        e.set_tiling(1, 1, 0, 0, 2)
+        e.set_footprints(pos, sig, 0.0)
+        e.mu_path(1)                                    # panel kernel
+        e.mu_stats(torch.arange(T), beta.cuda(), frames=frames.cuda())
+        assert e.mu_path() & 1 == 0
+        G = np.stack([e.get_mu_stats(t)[0] for t in range(T)])
+        b = np.stack([e.get_mu_stats(t)[1] for t in range(T)])
+        np.testing.assert_allclose(G, Gm, rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(b, bv, rtol=2e-5, atol=1e-6)
+        out.append(G)
+    np.testing.assert_allclose(out[0], out[1], rtol=2e-5, atol=1e-6)
