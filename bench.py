@@ -315,6 +315,10 @@ def run_b200(args, cfg):
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         e2e = {"value": Be * steps_e * world / (float(t_e) * 1e-3), "unit": "frame-iterations/s",
                "h2d_bytes_per_step": Be * N * 4 + Be * 4, "d2h_bytes_per_step": 8,
+               "h2d_gbps_per_gpu": (Be * N * 4 + Be * 4) * steps_e / (float(t_e) * 1e-3) * 1e-9,
+               "bound": "host-to-device link: every step ships its %.2f GB of fp32 frames from pinned host memory, "
+                        "double-buffered against the fused kernel (compare h2d_gbps_per_gpu with the link rate)"
+                        % (Be * N * 4 / 1e9),
                "api": "DeformableNMF.update_motion(host loader, torch.optim.Adam) -> dnmf_motion_step_host"}
         dn._video_resident = True
 
