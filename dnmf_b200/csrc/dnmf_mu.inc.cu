@@ -361,7 +361,7 @@ __global__ void mu_compact_kernel(const double* __restrict__ G, const int* __res
   }
 }
 
-// Ws = min(W, 32) lanes per neuron k (W a power of two below 32, else a multiple of 32); one thread walks kMuTB
+// Ws lanes per neuron k (the power of two covering the row length W, at most 32); one thread walks kMuTB
 // consecutive frames of its (k, list slot): the neighbour id is loaded once and the kMuTB (G, C) pairs are
 // independent loads in flight (one row per warp and frame was latency-bound: nbr -> C gather -> reduce -> store).
 // grid = (ceil(T / kMuTB), ceil(K / rows per block)).
@@ -711,9 +711,7 @@ static int mu_build_neighbours(dnmf_ctx* c) {
     longest = std::max(longest, lists[(size_t)k].size());
     if (longest * 2 > (size_t)K) return 0;  // dense overlap: the dense sweep reads less
   }
-  int W = 8;
-  while (W < 32 && (size_t)W < longest) W *= 2;
-  if ((size_t)W < longest) W = (int)((longest + 31) / 32) * 32;
+  const int W = std::max(4, (int)((longest + 3) & ~(size_t)3));  // row length of the compacted statistics
   std::vector<int> flat((size_t)K * W, -1);
   for (int k = 0; k < K; ++k) std::copy(lists[(size_t)k].begin(), lists[(size_t)k].end(), flat.begin() + (size_t)k * W);
   if (c->d_mu_nbr) cudaFree(c->d_mu_nbr);
@@ -768,7 +766,9 @@ extern "C" int dnmf_mu_sweep(dnmf_ctx* c, double gamma, int use_gamma, const dou
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(c->device));
   if (c->mu_last_sparse && c->gc_valid && c->mu_nbrw > 0) {
-    const int W = c->mu_nbrw, Ws = std::min(W, 32);
+    const int W = c->mu_nbrw;
+    int Ws = 8;  // lanes per row: the power of two covering W, 8..32 (lanes past W idle, longer rows loop)
+    while (Ws < 32 && Ws < W) Ws *= 2;
     const int rows_per_block = 256 / Ws;
     const dim3 grid((unsigned)((c->T + kMuTB - 1) / kMuTB), (unsigned)((c->K + rows_per_block - 1) / rows_per_block));
     mu_sweep_sparse_kernel<<<grid, 256, 0, st>>>(

@@ -438,10 +438,17 @@ class DeformableNMF:
         `halo_exchange(first, last) -> (prev, next)` lets a multi-GPU caller swap boundary columns."""
         eng = self.fp.engine
         beta = self.fp.beta.detach()
-        if self._video_resident and testloader is None:
-            ids = torch.arange(self.fp.T, dtype=torch.int32)
-            step = 256
-            for i in range(0, self.fp.T, step):
+        if self._video_resident:
+            # attached video: the loader is walked for its frame ids only (no host frames cross the link again)
+            if testloader is None:
+                ids = torch.arange(self.fp.T, dtype=torch.int32)
+            else:
+                parts = [np.asarray(data[1].cpu() if torch.is_tensor(data[1]) else data[1]).reshape(-1)
+                         for data in testloader]
+                ids = torch.from_numpy(np.concatenate(parts).astype(np.int32)) if parts else torch.zeros(0, dtype=torch.int32)
+            ids = ids.to(eng.device)
+            step = 512
+            for i in range(0, int(ids.numel()), step):
                 eng.mu_stats(ids[i:i + step], beta)
         else:
             for data in testloader:
