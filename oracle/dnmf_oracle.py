@@ -329,6 +329,37 @@ def adam_dense(p, g, m, v, step: int, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
     return p, m, v
 
 
+def epoch_frame_parallel(beta, m, v, batches, grad_fn, first_step=1, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+    """Restatement of the schedule behind dnmf_motion_epoch's one-launch path: an epoch whose minibatches
+    `batches` (lists of frame ids, no frame twice) touch disjoint columns of beta[10,3,T] is run column by
+    column -- the zero-gradient Adam steps of the minibatches before the frame's own (the reference's
+    dense Adam moves every column at every step, Demix/dNMF.py:190-191), its gradient step, the zero-gradient
+    steps after.  `grad_fn(beta_columns[10,3,B], ids) -> grad[10,3,B]` stands for the fused kernel.  Must equal
+    the step-by-step schedule (adam_dense over the whole tensor per minibatch) bit for bit."""
+    beta, m, v = (np.array(a, f32) for a in (beta, m, v))
+    n = len(batches)
+    batch_of = {}
+    for i, ids in enumerate(batches):
+        for t in ids:
+            assert t not in batch_of, "a frame drawn twice couples its steps: run batch by batch"
+            batch_of[int(t)] = i
+    kw = dict(lr=lr, b1=b1, b2=b2, eps=eps)
+    zero = np.zeros((10, 3), f32)
+    for t in range(beta.shape[2]):           # phase 0: replay the steps that precede the frame's minibatch
+        for s_ in range(batch_of.get(t, n)):
+            beta[:, :, t], m[:, :, t], v[:, :, t] = adam_dense(beta[:, :, t], zero, m[:, :, t], v[:, :, t],
+                                                               first_step + s_, **kw)
+    ids_all = [int(t) for ids in batches for t in ids]
+    grads = np.concatenate([np.asarray(grad_fn(beta[:, :, list(ids)], list(ids)), f32) for ids in batches], axis=2)
+    for j, t in enumerate(ids_all):          # phase 1: the gradient step, then the steps that follow
+        g = grads[:, :, j]
+        for s_ in range(batch_of[t], n):
+            beta[:, :, t], m[:, :, t], v[:, :, t] = adam_dense(beta[:, :, t], g, m[:, :, t], v[:, :, t],
+                                                               first_step + s_, **kw)
+            g = zero
+    return beta, m, v
+
+
 def closed_form_mu_stats(frames: np.ndarray, times, beta, tabs, sz):
     """G[T',K,K], b[T',K] in float64 from the closed-form footprints (A_t values rounded to
     fp32 first, accumulated in fp64 like Demix/dNMF.py:141-142)."""
