@@ -35,11 +35,12 @@ constexpr int kZUnroll = DNMF_ZUNROLL;
 #define DNMF_UNROLLED_MARCH 0  // 1: one fully unrolled main loop per slot-pair count (more code than the I-cache holds)
 #endif
 #ifndef DNMF_MU_MINB
-#define DNMF_MU_MINB 12  // the same for the trace-statistics variant (MODE 3) of the single-warp layout: 168 registers
-                         // (measured at cfg2: 16 -> 5.08 ms, 12 -> 4.66 ms per 1000 frames)
+#define DNMF_MU_MINB 10  // the same for the trace-statistics variant (MODE 3) of the single-warp layout: 167 registers
+                         // (measured at cfg2, ms per 1000 frames: 16 -> 5.08, 14 -> 5.12 (128 regs, spills), 12 -> 4.66, 10 -> 4.35)
 #endif
 #ifndef DNMF_MINB
-#define DNMF_MINB 16  // resident single-warp CTAs per SM the fused kernel is compiled for (128 registers: no spills in the unrolled march)
+#define DNMF_MINB 16  // resident single-warp CTAs per SM the fused kernel is compiled for (124 registers used; 18 / 20 CTAs
+                      // per SM compile to 94 registers without spills but measured 2 % slower at cfg2: 3.67e5 vs 3.75e5)
 #endif
 
 namespace dnmf {
