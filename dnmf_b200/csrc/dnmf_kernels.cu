@@ -2001,6 +2001,7 @@ struct dnmf_ctx {
   bool gc_valid = false;       // compacted copy matches d_G
   int mu_dense_sweeps = 0;     // dnmf_mu_path flag bit 1 / DNMF_MU_DENSE_SWEEPS
   int mu_last_sparse = 0;
+  int mu_sweep_per_launch = 0; // DNMF_MU_SWEEP_PER_LAUNCH / dnmf_mu_path bit 2: one launch per sweep even without coupling
   int mu_block4 = 0;           // DNMF_MU_BLOCK4: keep the 4x4 register blocks of the panel kernel for every list length
   int mu_capM = 0;
   // frame-parallel epoch (dnmf_motion_epoch)
@@ -2077,6 +2078,7 @@ extern "C" int dnmf_create(dnmf_ctx** out, int X, int Y, int Z, int K, int T, in
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (const char* ev = getenv("DNMF_FPC")) c->fpc_override = atoi(ev);
   if (const char* ev = getenv("DNMF_MU_PANEL")) c->mu_force_panel = atoi(ev) != 0;
+  if (const char* ev = getenv("DNMF_MU_SWEEP_PER_LAUNCH")) c->mu_sweep_per_launch = atoi(ev) != 0;
   if (const char* ev = getenv("DNMF_MU_BLOCK4")) c->mu_block4 = atoi(ev) != 0;
   if (const char* ev = getenv("DNMF_MU_DENSE_SWEEPS")) c->mu_dense_sweeps = atoi(ev) != 0;
   if (const char* ev = getenv("DNMF_EPOCH_SEQUENTIAL")) c->epoch_sequential = atoi(ev) != 0;

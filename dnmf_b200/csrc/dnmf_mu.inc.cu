@@ -415,6 +415,53 @@ __global__ void mu_sweep_sparse_kernel(const double* __restrict__ Gc, const int*
   }
 }
 
+// All `iters` sweeps of one frame in one CTA, for the update without temporal coupling (gamma = None or 0:
+// demo.py:46 runs update_footprints(gamma_c=0, iter_c=50)): the frames are independent.  The CTA stages its
+// frame's compacted statistics and the neighbour ids in shared memory, transposed to [slot][k] so that one
+// thread per neuron walks its row conflict-free with four independent accumulators (no shuffles, no global
+// memory inside the sweep loop); traces and b_t live in shared memory, one barrier per sweep.
+__global__ void mu_sweeps_local_kernel(const double* __restrict__ Gc, const int* __restrict__ nbr, int W,
+                                       const double* __restrict__ bvec, const double* __restrict__ Cin,
+                                       double* __restrict__ Cout, int K, int iters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sG = reinterpret_cast<double*>(smem_raw);  // [W][K]
+  double* sC0 = sG + (size_t)W * K;
+  double* sC1 = sC0 + K;
+  double* sB = sC1 + K;
+  int* sN = reinterpret_cast<int*>(sB + K);           // [W][K]
+  const int t = blockIdx.x;
+  const double* g = Gc + (size_t)t * K * W;
+  for (int e = threadIdx.x; e < K * W; e += blockDim.x) {
+    const int k = e / W, s_ = e - k * W;
+    sG[s_ * K + k] = g[e];
+    sN[s_ * K + k] = max(nbr[e], 0);  // padding slots hold G = 0
+  }
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    sC0[k] = Cin[(size_t)t * K + k];
+    sB[k] = bvec[(size_t)t * K + k];
+  }
+  __syncthreads();
+  double* cur = sC0;
+  double* nxt = sC1;
+  for (int it = 0; it < iters; ++it) {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+      for (int s_ = 0; s_ < W; s_ += 4) {  // W is a multiple of 4
+        d0 = fma(sG[(s_ + 0) * K + k], cur[sN[(s_ + 0) * K + k]], d0);
+        d1 = fma(sG[(s_ + 1) * K + k], cur[sN[(s_ + 1) * K + k]], d1);
+        d2 = fma(sG[(s_ + 2) * K + k], cur[sN[(s_ + 2) * K + k]], d2);
+        d3 = fma(sG[(s_ + 3) * K + k], cur[sN[(s_ + 3) * K + k]], d3);
+      }
+      nxt[k] = cur[k] * sB[k] / (((d0 + d1) + (d2 + d3)) + 1e-32);
+    }
+    __syncthreads();
+    double* tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+  for (int k = threadIdx.x; k < K; k += blockDim.x) Cout[(size_t)t * K + k] = cur[k];
+}
+
 __global__ void mu_boundary_kernel(const double* __restrict__ Cd, int T, int K, double* first, double* last) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
@@ -674,6 +721,7 @@ extern "C" int dnmf_mu_path(dnmf_ctx* c, int force_panel, int* last_path_out) {
   if (force_panel >= 0) {
     c->mu_force_panel = (force_panel & 1) != 0;
     c->mu_dense_sweeps = (force_panel & 2) != 0;
+    c->mu_sweep_per_launch = (force_panel & 4) != 0;
   }
   if (last_path_out) *last_path_out = c->mu_last_path | (c->mu_last_sparse << 1);
   return 0;
@@ -809,6 +857,21 @@ extern "C" int dnmf_mu_end(dnmf_ctx* c, float* C_dev, void* stream) {
 
 extern "C" int dnmf_mu_sweeps(dnmf_ctx* c, float* C_dev, double gamma, int use_gamma, int iters, void* stream) {
   if (dnmf_mu_begin(c, C_dev, stream)) return 1;
+  // no temporal coupling (gamma None or exactly 0) and compacted statistics: all sweeps of a frame in one CTA
+  const size_t local_smem = (size_t)c->K * c->mu_nbrw * 12 + (size_t)c->K * 24;
+  if ((use_gamma == 0 || gamma == 0.0) && iters > 0 && c->mu_last_sparse && c->gc_valid && c->mu_nbrw > 0 &&
+      c->mu_sweep_per_launch == 0 && local_smem <= (size_t)c->max_smem_optin) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (local_smem > 48 * 1024)
+      CU(cudaFuncSetAttribute(mu_sweeps_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)local_smem));
+    const int threads = std::min(1024, (c->K + 31) & ~31);
+    mu_sweeps_local_kernel<<<c->T, threads, local_smem, st>>>(c->d_Gc, c->d_mu_nbr, c->mu_nbrw, c->d_b,
+                                                             c->d_Cd[c->cd_cur], c->d_Cd[c->cd_cur ^ 1], c->K, iters);
+    CU(cudaGetLastError());
+    c->cd_cur ^= 1;
+    c->counters[7] += 1;
+    return dnmf_mu_end(c, C_dev, stream);
+  }
   for (int i = 0; i < iters; ++i)
     if (dnmf_mu_sweep(c, gamma, use_gamma, nullptr, nullptr, stream)) return 1;
   return dnmf_mu_end(c, C_dev, stream);

@@ -129,8 +129,9 @@ int dnmf_get_mu_stats(dnmf_ctx* ctx, int t, double* G_host /* [K][K] */, double*
  * neuron lists, the default when the tiling allows it) and a shared-memory panel kernel (any list length,
  * also the automatic redo when a list outgrows the staged capacity).  The sweeps read G either dense or
  * compacted to the static neighbour lists (neurons whose truncated supports overlap; the default when the
- * lists are shorter than K/2).  flags: bit 0 = always the panel kernel, bit 1 = always dense sweeps,
- * 0 = automatic, negative = leave unchanged.  last_path_out (may be NULL): bit 0 = the most recent
+ * lists are shorter than K/2); without temporal coupling (gamma None or 0) dnmf_mu_sweeps runs all sweeps of
+ * a frame in one CTA.  flags: bit 0 = always the panel kernel, bit 1 = always dense sweeps, bit 2 = one
+ * launch per sweep, 0 = automatic, negative = leave unchanged.  last_path_out (may be NULL): bit 0 = the most recent
  * dnmf_mu_stats ran on the fused tiles, bit 1 = the most recent dnmf_mu_begin set up sparse sweeps. */
 int dnmf_mu_path(dnmf_ctx* ctx, int flags, int* last_path_out);
 

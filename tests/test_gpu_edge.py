@@ -517,14 +517,22 @@ def test_mu_sweeps_sparse_neighbour_lists_match_dense_and_oracle(gamma):
         for _ in range(iters):
             ref = O.mu_sweep(np.transpose(G, (1, 2, 0)), b.T, ref, gamma)
         out = []
-        for flags in (0, 2):
+        for flags in (0, 4, 2):   # automatic (all sweeps of a frame in one CTA when uncoupled), per-sweep launches, dense
             e.mu_path(flags)
             c = C.clone().cuda()
             e.mu_sweeps(c, gamma, iters)
-            assert (e.mu_path() >> 1) == (1 if (flags == 0 and expect_sparse) else 0)
+            assert ((e.mu_path() >> 1) & 1) == (1 if (flags != 2 and expect_sparse) else 0)
             out.append(c.cpu().numpy())
             np.testing.assert_allclose(out[-1], ref.astype(np.float32), rtol=2e-6, atol=1e-30)
         np.testing.assert_allclose(out[0], out[1], rtol=1e-6, atol=1e-30)
+        np.testing.assert_allclose(out[0], out[2], rtol=1e-6, atol=1e-30)
+        if expect_sparse:                           # gamma = 0.0 is the uncoupled update too (demo.py:46)
+            e.mu_path(0)
+            c0 = C.clone().cuda()
+            e.mu_sweeps(c0, 0.0, iters)
+            cn = C.clone().cuda()
+            e.mu_sweeps(cn, None, iters)
+            assert torch.equal(c0, cn)
 
 
 @pytest.mark.parametrize("K", [40, 140])
