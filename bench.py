@@ -390,6 +390,36 @@ def run_b200(args, cfg):
                         "bytes_per_frame_iter": bytes_per_frame,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}}
 
+    # ---- secondary metric: the same fused pass late in a fit, when every frame has its own deformation ----
+    # (at the start of a fit all beta_t are the identity, so consecutive frames of a CTA share the window, the
+    # neuron list and the staged slices; here each frame gets its own translation / affine / quadratic terms and
+    # the CTA rebuilds list and slices for every frame)
+    deformed = None
+    try:
+        gen = torch.Generator().manual_seed(7)
+        scale = torch.tensor([2.0, 5e-3, 5e-3, 5e-3, 1e-5, 1e-5, 1e-5, 1e-5, 1e-5, 1e-5])[:, None, None]
+        if dn.affine:
+            scale[4:] = 0.0
+        scale = scale * torch.tensor([1.0, 1.0, 0.25])[None, :, None]   # z is shallow: a quarter of the x, y motion
+        beta_keep = beta.clone()
+        beta.add_((scale * torch.randn(10, 3, T, generator=gen)).to(dev))
+        for _ in range(3):
+            fit_only()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(reps):
+            fit_only()
+        ev1.record()
+        torch.cuda.synchronize()
+        d_ms = ev0.elapsed_time(ev1) / reps
+        beta.copy_(beta_keep)
+        deformed = {"value": B / (d_ms * 1e-3), "unit": "frame-iterations/s", "kernel_ms_per_launch": d_ms,
+                    "what": "fit_tile_kernel + reduction with a different deformation per frame (translations "
+                            "sigma = 2 px in x, y and 0.5 px in z, linear terms 0.5 %, no two frames alike): list and "
+                            "slices rebuilt for every frame"}
+    except Exception as ex:  # pragma: no cover
+        deformed = {"error": repr(ex)}
+
     # ---- secondary metric: the reference's own minibatch size (demo.py: 4 frames) through the public API ----
     ref_batch = None
     if T >= 8:
@@ -455,7 +485,7 @@ def run_b200(args, cfg):
                        "l2": "inputs (%.2f GB per step) larger than L2" % (B * N * 4 / 1e9)},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "final_loss": final_loss, "trace_update": mu,
-            "reference_batch": ref_batch}
+            "reference_batch": ref_batch, "deformed_beta": deformed}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
