@@ -34,6 +34,9 @@ constexpr int kZUnroll = DNMF_ZUNROLL;
 #ifndef DNMF_UNROLLED_MARCH
 #define DNMF_UNROLLED_MARCH 0  // 1: one fully unrolled main loop per slot-pair count (more code than the I-cache holds)
 #endif
+#ifndef DNMF_ALWAYS_SAFE
+#define DNMF_ALWAYS_SAFE 0  // 1: every tile takes the clamped main loop (one loop body fewer in the instruction cache)
+#endif
 #ifndef DNMF_MU_MINB
 #define DNMF_MU_MINB 10  // the same for the trace-statistics variant (MODE 3) of the single-warp layout: 167 registers
                          // (measured at cfg2, ms per 1000 frames: 16 -> 5.08, 14 -> 5.12 (128 regs, spills), 12 -> 4.66, 10 -> 4.35)
@@ -282,6 +285,8 @@ struct FitParams {
   double* muG;   // MODE 3 (trace statistics): G_t[K][K], b_t[K] of every frame, accumulated with fp64 atomics
   double* mub;
   int* mu_overflow;  // MODE 3: set when a tile's list is not fully staged (the caller reruns the generic kernel)
+  int dyn_tail;  // != 0: main loop with the run-time tail kind (one loop body per SAFE; see march_rolled TAIL 3)
+  unsigned* restage_count;  // [32] frames whose slices were rebuilt, counted per CTA (MODE 0; may be NULL)
   int y_pitch;   // floats between x rows of the Y tile in shared memory (>= ty * tile depth)
   int z_skew;    // != 0: lane (lx, ly) starts its z march at ((ly * z_skew) & 3), see march_rolled<SKEW>
   int tmap_ok;   // the frame tile can be fetched with ONE tensor TMA copy (3-D map over [frame][x][y*Z])
@@ -647,11 +652,15 @@ __device__ __forceinline__ void tail_slot(const unsigned (&adA)[3], const unsign
 }
 
 // TAIL 0: even list, np >= 1 full slot pairs.  TAIL 1: np >= 1 full pairs and one last slot.  TAIL 2: a single
-// slot (np == 0).
+// slot (np == 0).  TAIL 3: the kind is the run-time value `tail` (warp-uniform branches inside the z loop): one
+// loop body per SAFE instead of three.  The three specialised bodies are 4 % faster while consecutive frames of a
+// CTA share window, list and slices (start of a fit); once every frame has its own deformation the per-frame
+// list / restage code joins the hot set, the 32 KB instruction cache thrashes (stall_no_instruction 1.7 per issue,
+// profiles/README.md) and the single body is 9-16 % faster.  FitParams::dyn_tail picks per launch.
 // SKEW: the lanes of a warp walk z in rotated order (lane-dependent start, wrap-around), which spreads their
 // reads of the Y tile over the banks when the tile's y/x pitches are multiples of 32 floats (Z = 32).
 template <bool SAFE, int MODE, int TAIL, bool SKEW>
-__device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOut& o) {
+__device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOut& o, int tail = 0) {
   const float oz = a.oz;
   const float2 zero2 = make_float2(oz, oz);
 #pragma unroll
@@ -708,7 +717,7 @@ __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOu
     const float2 fA0 = make_float2(f[0].x, f[0].x), fA1 = make_float2(f[1].x, f[1].x), fA2 = make_float2(f[2].x, f[2].x);
     const float2 fB0 = make_float2(f[0].y, f[0].y), fB1 = make_float2(f[1].y, f[1].y), fB2 = make_float2(f[2].y, f[2].y);
     float2 yh, g[3];
-    if (TAIL != 2) {
+    if (TAIL == 3 ? (tail != 2) : (TAIL != 2)) {
       // first slot pair produces the accumulators, the rest of the list updates them
       float2 yA, gA0, gA1, gA2, yB, gB0, gB1, gB2;
       slot_pair<0, true>(adA[0], adA[1], adA[2], fA0, fA1, fA2, yA, gA0, gA1, gA2);
@@ -732,7 +741,7 @@ __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOu
       g[0] = make_float2(gA0.x + gA0.y, gB0.x + gB0.y);
       g[1] = make_float2(gA1.x + gA1.y, gB1.x + gB1.y);
       g[2] = make_float2(gA2.x + gA2.y, gB2.x + gB2.y);
-      if (TAIL == 1) tail_slot<false>(adA, adB, pair_bytes, f, oz, yh, g);
+      if (TAIL == 3 ? (tail == 1) : (TAIL == 1)) tail_slot<false>(adA, adB, pair_bytes, f, oz, yh, g);
     } else {
       tail_slot<true>(adA, adB, 0u, f, oz, yh, g);
     }
@@ -1267,6 +1276,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
 
   // state carried from frame to frame: what the staged slices were built for
   int pw_lo[3] = {0x7fffffff, 0, 0}, pw_hi[3] = {0, 0, 0}, prev_L = -1;
+  int n_restaged = 0;  // frames whose slices had to be (re)built
   bool prev_fast = false;  // previous list came from the cached candidates with prefetched traces
 
   for (int fi = 0; fi < nb; ++fi) {
@@ -1405,6 +1415,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
     const int npair = (nst + 1) >> 1;
     if ((nst & 1) && tid == 0) sCk[nst] = 0.f;  // partner of the last neuron of an odd list: zero footprint
     if (changed) {
+      ++n_restaged;
       // One thread owns table entry e of every slot.  Slot pairs (2p, 2p+1) share one float4
       // (G_2p, G_2p+1, D_2p, D_2p+1) = the packed operands of FFMA2; an odd list is completed with a zero
       // footprint.  Loads are issued four pairs at a time ahead of the stores.  The x slice is kept without
@@ -1571,7 +1582,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
         MarchArgs a;
         fill_march_args(a);
         MarchOut o;
-        const bool safe = window_clipped || nx < TX || ny < TY;
+        const bool safe = DNMF_ALWAYS_SAFE || window_clipped || nx < TX || ny < TY;
 #if DNMF_UNROLLED_MARCH
         switch (npair * 2 + (safe ? 1 : 0)) {
 #define DNMF_MARCH(n)                   \
@@ -1603,6 +1614,14 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
         } else {
           const int npf = nst >> 1;  // full slot pairs; an odd list ends with a single slot
           const int tail = (nst & 1) ? (npf == 0 ? 2 : 1) : 0;
+          if (p.dyn_tail) {
+            switch ((p.z_skew != 0 ? 2 : 0) + (safe ? 1 : 0)) {
+              case 0: march_rolled<false, MODE, 3, false>(a, npf, o, tail); break;
+              case 1: march_rolled<true, MODE, 3, false>(a, npf, o, tail); break;
+              case 2: march_rolled<false, MODE, 3, true>(a, npf, o, tail); break;
+              default: march_rolled<true, MODE, 3, true>(a, npf, o, tail); break;
+            }
+          } else
           switch ((p.z_skew != 0 ? 6 : 0) + tail * 2 + (safe ? 1 : 0)) {
             case 0: march_rolled<false, MODE, 0, false>(a, npf, o); break;
             case 1: march_rolled<true, MODE, 0, false>(a, npf, o); break;
@@ -1717,6 +1736,8 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
     cta_sync();
     if (bulk && fi + 1 < nb) load_tile(fi + 1);
   }
+  if (MODE == 0 && p.restage_count != nullptr && tid == 0 && n_restaged > 0)
+    atomicAdd(p.restage_count + ((blockIdx.x + blockIdx.y) & 31), (unsigned)n_restaged);
 }
 
 // Second stage: per frame, sum the CTA partials in a fixed order (double), scale by 2/(B_global*N),
@@ -2004,6 +2025,13 @@ struct dnmf_ctx {
   int mu_sweep_per_launch = 0; // DNMF_MU_SWEEP_PER_LAUNCH / dnmf_mu_path bit 2: one launch per sweep even without coupling
   int mu_block4 = 0;           // DNMF_MU_BLOCK4: keep the 4x4 register blocks of the panel kernel for every list length
   int mu_capM = 0;
+  // adaptive main-loop variant (FitParams::dyn_tail): restage counts of the previous fused launch
+  unsigned* d_restage = nullptr;   // [32]
+  unsigned* h_restage = nullptr;   // pinned [32], refreshed asynchronously after every fused launch
+  long long restage_den_pending = 0;  // tile-frames of the launch the pending copy of the counters describes
+  cudaEvent_t ev_restage = nullptr;
+  int dyn_tail_mode = -1;          // DNMF_DYN_TAIL: 0 / 1 force, -1 automatic
+  int dyn_tail_cur = 0;
   // frame-parallel epoch (dnmf_motion_epoch)
   int* d_epoch_batch_of = nullptr;
   size_t epoch_batch_of_cap = 0;
@@ -2077,6 +2105,7 @@ extern "C" int dnmf_create(dnmf_ctx** out, int X, int Y, int Z, int K, int T, in
   c->num_sms = prop.multiProcessorCount;
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (const char* ev = getenv("DNMF_FPC")) c->fpc_override = atoi(ev);
+  if (const char* ev = getenv("DNMF_DYN_TAIL")) c->dyn_tail_mode = atoi(ev);
   if (const char* ev = getenv("DNMF_MU_PANEL")) c->mu_force_panel = atoi(ev) != 0;
   if (const char* ev = getenv("DNMF_MU_SWEEP_PER_LAUNCH")) c->mu_sweep_per_launch = atoi(ev) != 0;
   if (const char* ev = getenv("DNMF_MU_BLOCK4")) c->mu_block4 = atoi(ev) != 0;
@@ -2145,7 +2174,7 @@ extern "C" void dnmf_destroy(dnmf_ctx* c) {
                   c->d_tab_dpos[0], c->d_tab_dpos[1], c->d_tab_dpos[2], c->d_tab_dsig[0], c->d_tab_dsig[1],
                   c->d_tab_dsig[2], c->d_resid, c->d_sumr, c->d_ids_zero,
                   c->d_epoch_batch_of, c->d_epoch_offsets, c->d_epoch_scalars, c->d_epoch_scale,
-                  c->d_mu_nbr, c->d_Gc};
+                  c->d_mu_nbr, c->d_Gc, c->d_restage};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->copy_stream) {
@@ -2155,6 +2184,11 @@ extern "C" void dnmf_destroy(dnmf_ctx* c) {
       cudaEventDestroy(c->ev_done[i]);
     }
   }
+  if (c->ev_restage) {
+    cudaEventSynchronize(c->ev_restage);  // a copy into the pinned counters may still be in flight
+    cudaEventDestroy(c->ev_restage);
+  }
+  if (c->h_restage) cudaFreeHost(c->h_restage);
   delete c;
 }
 
@@ -2554,6 +2588,8 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
   p.muG = nullptr;
   p.mub = nullptr;
   p.mu_overflow = nullptr;
+  p.dyn_tail = 0;
+  p.restage_count = nullptr;
   p.y_pitch = c->y_pitch;
   p.z_skew = c->z_skew;
   p.b_base = 0;
@@ -2620,6 +2656,45 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
   return 0;
 }
 
+// Fused fit launch (MODE 0) with the main-loop variant picked from what the previous launches did: the kernel
+// counts the tile-frames whose slices were (re)built, the counters come back through pinned memory without a
+// synchronisation (read one or two launches late), and above half of all tile-frames the single-body main loop
+// is used (march_rolled TAIL 3).  Both variants execute the same arithmetic: results do not depend on the choice.
+static int launch_fused_fit(dnmf_ctx* c, FitParams& p, int B, cudaStream_t st) {
+  if (!c->d_restage) {
+    CU(cudaMalloc((void**)&c->d_restage, 32 * sizeof(unsigned)));
+    CU(cudaMemset(c->d_restage, 0, 32 * sizeof(unsigned)));
+    CU(cudaMallocHost((void**)&c->h_restage, 32 * sizeof(unsigned)));
+    CU(cudaEventCreateWithFlags(&c->ev_restage, cudaEventDisableTiming));
+  }
+  bool can_enqueue = true;
+  if (c->restage_den_pending > 0) {
+    const cudaError_t q = cudaEventQuery(c->ev_restage);
+    if (q == cudaSuccess) {
+      unsigned long long sum = 0;
+      for (int i = 0; i < 32; ++i) sum += c->h_restage[i];
+      const double frac = (double)sum / (double)c->restage_den_pending;
+      if (frac > 0.5) c->dyn_tail_cur = 1;
+      else if (frac < 0.35) c->dyn_tail_cur = 0;
+      c->restage_den_pending = 0;
+    } else if (q == cudaErrorNotReady) {
+      can_enqueue = false;  // the pinned buffer is still owed a copy
+    } else {
+      CU(q);
+    }
+  }
+  p.dyn_tail = c->dyn_tail_mode >= 0 ? (c->dyn_tail_mode != 0) : c->dyn_tail_cur;
+  p.restage_count = c->d_restage;
+  if (dispatch_fit<0>(c, p, B, st)) return 1;
+  if (can_enqueue) {
+    CU(cudaMemcpyAsync(c->h_restage, c->d_restage, 32 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemsetAsync(c->d_restage, 0, 32 * sizeof(unsigned), st));
+    CU(cudaEventRecord(c->ev_restage, st));
+    c->restage_den_pending = (long long)B * c->ntx * c->nty * c->ntz;
+  }
+  return 0;
+}
+
 extern "C" int dnmf_loss_grad(dnmf_ctx* c, const float* frames_dev, const int32_t* frame_ids_dev, int B,
                               int B_global, const float* beta_dev, const float* C_dev, float* grad_dev,
                               double* sse_dev, void* stream) {
@@ -2631,7 +2706,7 @@ extern "C" int dnmf_loss_grad(dnmf_ctx* c, const float* frames_dev, const int32_
   FitParams p;
   if (fill_fit_params(c, p, frames_dev, frame_ids_dev, B, beta_dev, C_dev)) return 1;
   const int nt = c->ntx * c->nty * c->ntz;
-  if (dispatch_fit<0>(c, p, B, st)) return 1;
+  if (launch_fused_fit(c, p, B, st)) return 1;
   const double scale = 2.0 / ((double)B_global * (double)c->N);
   reduce_partials_kernel<<<B, 256, 0, st>>>(c->d_partials, frame_ids_dev, nt, c->T, scale, grad_dev, sse_dev, nullptr);
   CU(cudaGetLastError());
@@ -2735,7 +2810,7 @@ extern "C" int dnmf_motion_epoch(dnmf_ctx* c, const int32_t* frame_ids_dev, cons
     FitParams p;
     if (fill_fit_params(c, p, nullptr, frame_ids_dev + b_first, (int)Btot, beta_dev, C_dev)) return 1;
     const int nt = c->ntx * c->nty * c->ntz;
-    if (dispatch_fit<0>(c, p, (int)Btot, st)) return 1;
+    if (launch_fused_fit(c, p, (int)Btot, st)) return 1;
     reduce_partials_kernel<<<(unsigned)Btot, 256, 0, st>>>(c->d_partials, frame_ids_dev + b_first, nt, c->T, 0.0,
                                                           c->d_grad, c->d_sse, nullptr, c->d_epoch_scale);
     CU(cudaGetLastError());
