@@ -34,6 +34,11 @@ constexpr int kZUnroll = DNMF_ZUNROLL;
 #ifndef DNMF_UNROLLED_MARCH
 #define DNMF_UNROLLED_MARCH 0  // 1: one fully unrolled main loop per slot-pair count (more code than the I-cache holds)
 #endif
+#ifndef DNMF_MERGE_TAIL01
+#define DNMF_MERGE_TAIL01 1  // 1: the specialised main loops keep "single slot" apart and merge even / odd lists
+                             // (4 bodies instead of 6; measured at cfg2: identity beta 2.65 ms either way, a different
+                             // deformation per frame 3.40 -> 2.94 ms per 1000 frames)
+#endif
 #ifndef DNMF_ALWAYS_SAFE
 #define DNMF_ALWAYS_SAFE 0  // 1: every tile takes the clamped main loop (one loop body fewer in the instruction cache)
 #endif
@@ -653,10 +658,12 @@ __device__ __forceinline__ void tail_slot(const unsigned (&adA)[3], const unsign
 
 // TAIL 0: even list, np >= 1 full slot pairs.  TAIL 1: np >= 1 full pairs and one last slot.  TAIL 2: a single
 // slot (np == 0).  TAIL 3: the kind is the run-time value `tail` (warp-uniform branches inside the z loop): one
-// loop body per SAFE instead of three.  The three specialised bodies are 4 % faster while consecutive frames of a
-// CTA share window, list and slices (start of a fit); once every frame has its own deformation the per-frame
+// loop body per SAFE instead of three.  TAIL 4: np >= 1 and a run-time choice between kinds 0 and 1 only.
+// Why: with three specialised bodies per SAFE, once every frame of a CTA has its own deformation the per-frame
 // list / restage code joins the hot set, the 32 KB instruction cache thrashes (stall_no_instruction 1.7 per issue,
-// profiles/README.md) and the single body is 9-16 % faster.  FitParams::dyn_tail picks per launch.
+// profiles/README.md) and the kernel loses 20-25 %.  Measured at cfg2, ms per 1000 frames, identity beta / a
+// different deformation per frame: TAIL {0,1,2} 2.65 / 3.40, TAIL 3 2.77 / 3.05, TAIL {4,2} 2.65 / 2.94 (default,
+// DNMF_MERGE_TAIL01).  FitParams::dyn_tail selects TAIL 3 per launch (DNMF_DYN_TAIL=1, or -1: from the counters).
 // SKEW: the lanes of a warp walk z in rotated order (lane-dependent start, wrap-around), which spreads their
 // reads of the Y tile over the banks when the tile's y/x pitches are multiples of 32 floats (Z = 32).
 template <bool SAFE, int MODE, int TAIL, bool SKEW>
@@ -717,7 +724,7 @@ __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOu
     const float2 fA0 = make_float2(f[0].x, f[0].x), fA1 = make_float2(f[1].x, f[1].x), fA2 = make_float2(f[2].x, f[2].x);
     const float2 fB0 = make_float2(f[0].y, f[0].y), fB1 = make_float2(f[1].y, f[1].y), fB2 = make_float2(f[2].y, f[2].y);
     float2 yh, g[3];
-    if (TAIL == 3 ? (tail != 2) : (TAIL != 2)) {
+    if (TAIL == 3 ? (tail != 2) : (TAIL != 2)) {  // TAIL 4: np >= 1, run-time choice between kinds 0 and 1
       // first slot pair produces the accumulators, the rest of the list updates them
       float2 yA, gA0, gA1, gA2, yB, gB0, gB1, gB2;
       slot_pair<0, true>(adA[0], adA[1], adA[2], fA0, fA1, fA2, yA, gA0, gA1, gA2);
@@ -741,7 +748,7 @@ __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOu
       g[0] = make_float2(gA0.x + gA0.y, gB0.x + gB0.y);
       g[1] = make_float2(gA1.x + gA1.y, gB1.x + gB1.y);
       g[2] = make_float2(gA2.x + gA2.y, gB2.x + gB2.y);
-      if (TAIL == 3 ? (tail == 1) : (TAIL == 1)) tail_slot<false>(adA, adB, pair_bytes, f, oz, yh, g);
+      if ((TAIL == 3 || TAIL == 4) ? (tail == 1) : (TAIL == 1)) tail_slot<false>(adA, adB, pair_bytes, f, oz, yh, g);
     } else {
       tail_slot<true>(adA, adB, 0u, f, oz, yh, g);
     }
@@ -1622,6 +1629,18 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
               default: march_rolled<true, MODE, 3, true>(a, npf, o, tail); break;
             }
           } else
+#if DNMF_MERGE_TAIL01
+          switch ((p.z_skew != 0 ? 4 : 0) + (tail == 2 ? 2 : 0) + (safe ? 1 : 0)) {
+            case 0: march_rolled<false, MODE, 4, false>(a, npf, o, tail); break;
+            case 1: march_rolled<true, MODE, 4, false>(a, npf, o, tail); break;
+            case 2: march_rolled<false, MODE, 2, false>(a, npf, o); break;
+            case 3: march_rolled<true, MODE, 2, false>(a, npf, o); break;
+            case 4: march_rolled<false, MODE, 4, true>(a, npf, o, tail); break;
+            case 5: march_rolled<true, MODE, 4, true>(a, npf, o, tail); break;
+            case 6: march_rolled<false, MODE, 2, true>(a, npf, o); break;
+            default: march_rolled<true, MODE, 2, true>(a, npf, o); break;
+          }
+#else
           switch ((p.z_skew != 0 ? 6 : 0) + tail * 2 + (safe ? 1 : 0)) {
             case 0: march_rolled<false, MODE, 0, false>(a, npf, o); break;
             case 1: march_rolled<true, MODE, 0, false>(a, npf, o); break;
@@ -1636,6 +1655,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
             case 10: march_rolled<false, MODE, 2, true>(a, npf, o); break;
             default: march_rolled<true, MODE, 2, true>(a, npf, o); break;
           }
+#endif
         }
 #endif
 #pragma unroll
@@ -2030,7 +2050,7 @@ struct dnmf_ctx {
   unsigned* h_restage = nullptr;   // pinned [32], refreshed asynchronously after every fused launch
   long long restage_den_pending = 0;  // tile-frames of the launch the pending copy of the counters describes
   cudaEvent_t ev_restage = nullptr;
-  int dyn_tail_mode = -1;          // DNMF_DYN_TAIL: 0 / 1 force, -1 automatic
+  int dyn_tail_mode = 0;           // DNMF_DYN_TAIL: 0 (default) / 1 force a variant, -1 automatic from the counters
   int dyn_tail_cur = 0;
   // frame-parallel epoch (dnmf_motion_epoch)
   int* d_epoch_batch_of = nullptr;
