@@ -211,6 +211,28 @@ def axis_ranges(pos: np.ndarray, sigma: np.ndarray, sz: Sequence[int], cutoff: f
     return out
 
 
+def neighbour_lists(rng: np.ndarray) -> List[List[int]]:
+    """Static neighbour lists behind the sparse trace sweeps (twin of `mu_build_neighbours` in the CUDA library):
+    A_k(ix) != 0 needs lo_k - 1 < ix_d < hi_k + 1 on every axis (table entry i holds (G[i], G[i+1]-G[i]), zero
+    outside [lo, hi]), so G_t[k][l] = sum_p A_k A_l (Demix/dNMF.py:141) can only be non-zero when those open
+    intervals of k and l meet on all three axes -- whatever the deformation.  The test is the conservative
+    lo_k - 1 <= hi_l + 1 and lo_l - 1 <= hi_k + 1; a neuron with an empty range has only itself."""
+    K = rng.shape[0]
+    out = []
+    for k in range(K):
+        row = []
+        for l in range(K):
+            meet = True
+            for d in range(3):
+                a_lo, a_hi = int(rng[k, d, 0]), int(rng[k, d, 1])
+                b_lo, b_hi = int(rng[l, d, 0]), int(rng[l, d, 1])
+                meet = meet and a_lo <= a_hi and b_lo <= b_hi and a_lo - 1 <= b_hi + 1 and b_lo - 1 <= a_hi + 1
+            if meet or l == k:
+                row.append(l)
+        out.append(row)
+    return out
+
+
 def axis_tables(pos, sigma, sz, cutoff) -> Tuple[List[np.ndarray], np.ndarray]:
     """Per axis d: table[K, s_d+3, 2] of (G[i], G[i+1]-G[i]) for i = -2..s_d, with
     G[i] = exp(-(i-pos)^2/sigma^2) inside [lo,hi] and 0 outside (zero padding of grid_sample
