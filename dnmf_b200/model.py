@@ -188,6 +188,42 @@ class ExponentialFP(nn.Module):
         return A_t, Y_i, Y
 
 
+def loader_index_batches(loader):
+    """The frame-id batches a `torch.utils.data.DataLoader` would yield, WITHOUT loading a frame.
+
+    With an attached (HBM-resident) video the hot path needs only the ids of each minibatch, but walking the
+    reference's DataLoader (`demo.py:34-35`) makes the dataset slice and collate every frame on the host: 2.75 GB of
+    memcpy per epoch at cfg2 next to 3 ms of device work.  For datasets whose items are `(frame, own index)`
+    (`Demix/dNMF.py:214-217`; marked `returns_frame_index`, or the reference's class names) the loader's batch sampler
+    yields the same ids in the same order.  The random stream is consumed exactly as DataLoader iteration does
+    (the iterator draws its base seed before the sampler seeds itself), so shuffled runs stay reproducible against
+    the reference under the same `torch.manual_seed`.  Returns None when the shortcut does not apply."""
+    from torch.utils.data import DataLoader
+    if not isinstance(loader, DataLoader) or loader.batch_sampler is None:
+        return None
+    ds = loader.dataset
+    if not (getattr(ds, "returns_frame_index", False) or
+            type(ds).__name__ in ("SimulatedVideoDataset", "NeuroPALVideoDataset")):
+        return None
+    torch.empty((), dtype=torch.int64).random_(generator=loader.generator)      # _BaseDataLoaderIter._base_seed
+    return [np.asarray(b, dtype=np.int64).reshape(-1) for b in loader.batch_sampler]
+
+
+def collect_id_batches(loader):
+    """(ids int32[sum of batch sizes], offsets int32[nbatches + 1]) of one pass over `loader`: through the sampler
+    when `loader_index_batches` applies, else from the second element of every item the loader yields."""
+    batches = loader_index_batches(loader)
+    if batches is None:
+        batches = [np.asarray(data[1].cpu() if torch.is_tensor(data[1]) else data[1]).reshape(-1) for data in loader]
+    offsets = np.zeros(len(batches) + 1, dtype=np.int32)
+    if batches:
+        offsets[1:] = np.cumsum([b.size for b in batches])
+        ids = np.ascontiguousarray(np.concatenate(batches).astype(np.int32))
+    else:
+        ids = np.zeros(0, dtype=np.int32)
+    return ids, offsets
+
+
 class DeformableNMF:
     """dNMF fit: Adam on the per-frame deformation + multiplicative updates of the traces
     (reference: Demix/dNMF.py:124-194)."""
@@ -333,20 +369,19 @@ class DeformableNMF:
                 print("Epoch " + str(epoch))
             self.fp.train()
             if epoch_call:
-                # one pass over the loader on the host: ids as numpy (no per-batch torch dispatch), one H2D copy
-                batches = [np.asarray(data[1].cpu() if torch.is_tensor(data[1]) else data[1]).reshape(-1)
-                           for data in dataloader]
-                if not batches:
+                # one pass over the loader on the host: ids as numpy (no per-batch torch dispatch), one H2D copy;
+                # a DataLoader over an index-returning dataset is walked through its sampler (no frame is loaded)
+                ids_np, offsets = collect_id_batches(dataloader)
+                nbatches = int(offsets.size) - 1
+                if nbatches == 0:
                     continue
-                offsets = np.zeros(len(batches) + 1, dtype=np.int32)
-                offsets[1:] = np.cumsum([b.size for b in batches])
-                ids_dev = torch.from_numpy(np.concatenate(batches).astype(np.int32)).to(eng.device)
-                losses = torch.zeros(len(batches), dtype=torch.float64, device=eng.device)
+                ids_dev = torch.from_numpy(ids_np).to(eng.device)
+                losses = torch.zeros(nbatches, dtype=torch.float64, device=eng.device)
                 first = int(st["step"]) + 1
                 eng.motion_epoch(ids_dev, offsets, beta, st["exp_avg"], st["exp_avg_sq"], self.C, group["lr"],
                                  group["betas"], group["eps"], first, self.affine,
                                  global_batch_scale=self.global_batch_scale, loss_out=losses)
-                st["step"] += len(batches)
+                st["step"] += nbatches
                 self.loss_history.extend(losses.unbind(0))
                 continue
             for batch_idx, data in enumerate(dataloader):
@@ -443,9 +478,7 @@ class DeformableNMF:
             if testloader is None:
                 ids = torch.arange(self.fp.T, dtype=torch.int32)
             else:
-                parts = [np.asarray(data[1].cpu() if torch.is_tensor(data[1]) else data[1]).reshape(-1)
-                         for data in testloader]
-                ids = torch.from_numpy(np.concatenate(parts).astype(np.int32)) if parts else torch.zeros(0, dtype=torch.int32)
+                ids = torch.from_numpy(collect_id_batches(testloader)[0])
             ids = ids.to(eng.device)
             step = 512
             for i in range(0, int(ids.numel()), step):

@@ -125,6 +125,7 @@ def generate_video(K, T, sz=(20, 20, 1), shape_std=3, density=.1, bg_snr=-1, tra
 class SimulatedVideoDataset(Dataset):
     """Drop-in for Demix/dNMF.py:196-217: items are (frame[X,Y,Z] clamped at 0, idx).
     `.video` is [X,Y,Z,T] like the reference; frames are kept frame-major internally."""
+    returns_frame_index = True   # item = (frame, its own index): loaders over an attached video are walked for ids only
 
     def __init__(self, K, T, sz, shape_std, density, bg_snr, traces, motion, motion_par, seed=None, device="cpu"):
         frames, positions, tr = generate_video(K, T, sz, shape_std, density, bg_snr, traces, motion, motion_par,
@@ -148,6 +149,7 @@ class SimulatedVideoDataset(Dataset):
 
 class FrameDataset(Dataset):
     """Wraps existing frames [T,X,Y,Z] (e.g. a golden fixture or a rank's slab) as (frame, idx) items."""
+    returns_frame_index = True
 
     def __init__(self, frames: torch.Tensor, offset: int = 0):
         self.frames = frames
@@ -167,6 +169,7 @@ class NeuroPALVideoDataset(Dataset):
     holding data.mat (variable `data` [X,Y,Z,T]) and traces_n.mat (`positions` [K,3,T] 1-based,
     `neuron_names`).  The reference subsamples [::2, ::2, ::10, :100] and rescales the positions to match;
     the strides and frame count are arguments here with the same defaults."""
+    returns_frame_index = True
 
     def __init__(self, file, stride=(2, 2, 10), frames=100):
         import os

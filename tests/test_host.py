@@ -161,3 +161,71 @@ def test_neuropal_dataset_from_mat(tmp_path):
     np.testing.assert_array_equal(frame.numpy(), np.clip(data[::2, ::2, ::10, 3], 0, None))
     np.testing.assert_allclose(ds.positions[:, 0, :].numpy(), (positions[:, 0, :] - 1) / 2, rtol=1e-6)
     np.testing.assert_allclose(ds.positions[:, 2, :].numpy(), (positions[:, 2, :] - 1) / 10, rtol=1e-6)
+
+
+def test_loader_index_batches_match_dataloader_iteration():
+    """Walking a DataLoader's sampler for the minibatch ids (attached video: no frame is loaded) yields the same
+    ids in the same order as iterating the DataLoader, consumes the global random stream identically (shuffled
+    epochs stay reproducible against the reference under one torch.manual_seed), and never touches the dataset."""
+    import numpy as np
+    import torch
+    from torch.utils.data import DataLoader, Dataset
+    from dnmf_b200.model import loader_index_batches
+    from dnmf_b200.simulate import FrameDataset
+
+    class Untouchable(Dataset):
+        returns_frame_index = True
+
+        def __len__(self):
+            return 23
+
+        def __getitem__(self, idx):
+            raise AssertionError("the dataset must not be read")
+
+    real = FrameDataset(torch.zeros(23, 2, 2, 1))
+    for kw in (dict(batch_size=4, shuffle=True), dict(batch_size=4, shuffle=False),
+               dict(batch_size=5, shuffle=True, drop_last=True)):
+        torch.manual_seed(123)
+        ref = [[np.asarray(d[1]).reshape(-1).tolist() for d in DataLoader(real, **kw)] for _ in range(3)]
+        state_ref = torch.get_rng_state()
+        torch.manual_seed(123)
+        loader = DataLoader(Untouchable(), **kw)
+        got = [[b.tolist() for b in loader_index_batches(loader)] for _ in range(3)]
+        assert got == ref
+        assert torch.equal(torch.get_rng_state(), state_ref)
+    g = torch.Generator().manual_seed(5)
+    ref = [np.asarray(d[1]).tolist() for d in DataLoader(real, batch_size=3, shuffle=True, generator=g)]
+    g2 = torch.Generator().manual_seed(5)
+    got = [b.tolist() for b in loader_index_batches(DataLoader(Untouchable(), batch_size=3, shuffle=True, generator=g2))]
+    assert got == ref and torch.equal(g.get_state(), g2.get_state())
+    # not a DataLoader, or a dataset that does not declare (frame, index) items: no shortcut
+    assert loader_index_batches([(None, torch.arange(4))]) is None
+    assert loader_index_batches(DataLoader(torch.utils.data.TensorDataset(torch.zeros(8, 1)), batch_size=2)) is None
+
+
+def test_collect_id_batches_from_dataloaders_and_plain_iterables():
+    """ids + batch offsets handed to dnmf_motion_epoch / dnmf_mu_stats: the same from a DataLoader (sampler walk),
+    from a DataLoader over an unmarked dataset (items are read) and from a plain list of (frames, ids) items;
+    ragged last batch; empty loader."""
+    import numpy as np
+    import torch
+    from torch.utils.data import DataLoader, Dataset
+    from dnmf_b200.model import collect_id_batches
+    from dnmf_b200.simulate import FrameDataset
+
+    class Unmarked(Dataset):
+        def __len__(self):
+            return 10
+
+        def __getitem__(self, idx):
+            return torch.zeros(1), idx
+
+    for ds in (FrameDataset(torch.zeros(10, 1, 1, 1)), Unmarked()):
+        ids, off = collect_id_batches(DataLoader(ds, batch_size=4, shuffle=False))
+        assert ids.dtype == np.int32 and off.dtype == np.int32 and ids.flags["C_CONTIGUOUS"]
+        assert ids.tolist() == list(range(10)) and off.tolist() == [0, 4, 8, 10]
+    items = [(None, torch.tensor([3, 1])), (None, np.array([7])), (None, [2, 0, 5])]
+    ids, off = collect_id_batches(items)
+    assert ids.tolist() == [3, 1, 7, 2, 0, 5] and off.tolist() == [0, 2, 3, 6]
+    ids, off = collect_id_batches([])
+    assert ids.size == 0 and off.tolist() == [0]
