@@ -229,3 +229,72 @@ def test_collect_id_batches_from_dataloaders_and_plain_iterables():
     assert ids.tolist() == [3, 1, 7, 2, 0, 5] and off.tolist() == [0, 2, 3, 6]
     ids, off = collect_id_batches([])
     assert ids.size == 0 and off.tolist() == [0]
+
+
+def test_update_motion_and_traces_host_plumbing_with_a_recording_engine(monkeypatch):
+    """Host logic of the attached-video path without a GPU: a recording stand-in for the ctypes engine checks
+    what `update_motion` / `update_footprints` hand to dnmf_motion_epoch and dnmf_mu_stats when the loaders are
+    torch DataLoaders (sampler walk: the dataset is never read) -- ids, batch offsets, Adam step numbering over
+    epochs, loss bookkeeping."""
+    import numpy as np
+    import torch
+    from torch.utils.data import DataLoader, Dataset
+    import dnmf_b200.model as M
+
+    calls = []
+
+    class RecordingEngine:
+        def __init__(self, sz, K, T, device=None):
+            self.device = torch.device("cpu")
+            self.X, self.Y, self.Z = sz
+            self.K, self.T, self.N = K, T, int(np.prod(sz))
+
+        def set_tiling(self, *a):
+            pass
+
+        def set_footprints(self, *a):
+            pass
+
+        def upload_frames(self, frames, t0=0, clamp_negative=True):
+            calls.append(("upload", tuple(frames.shape)))
+
+        def motion_epoch(self, ids_dev, offsets, beta, m, v, C, lr, betas, eps, first_step, affine=False,
+                         global_batch_scale=1, loss_out=None):
+            assert ids_dev.dtype == torch.int32 and np.asarray(offsets).dtype == np.int32
+            calls.append(("epoch", ids_dev.tolist(), np.asarray(offsets).tolist(), int(first_step), float(lr)))
+            loss_out.copy_(torch.arange(len(offsets) - 1, dtype=torch.float64) + first_step)
+
+        def mu_stats(self, ids, beta, frames=None):
+            assert frames is None
+            calls.append(("stats", ids.tolist()))
+
+        def mu_sweeps(self, C, gamma, iters):
+            calls.append(("sweeps", gamma, iters))
+
+    class NeverRead(Dataset):
+        returns_frame_index = True
+
+        def __len__(self):
+            return 10
+
+        def __getitem__(self, idx):
+            raise AssertionError("an attached video makes the loader's frames unnecessary")
+
+    monkeypatch.setattr(M, "Engine", RecordingEngine)
+    sz, K, T = [6, 5, 2], 3, 10
+    dn = M.DeformableNMF(sz, K, T, positions=np.ones((K, 3), np.float32), verbose=False)
+    dn.attach_video(torch.zeros(T, *sz), layout="TXYZ")
+    opt = torch.optim.Adam([dn.fp.beta], lr=1e-5)
+    loader = DataLoader(NeverRead(), batch_size=4, shuffle=False)
+    dn.update_motion(loader, opt, gamma=1, epochs=2)
+    epochs = [c for c in calls if c[0] == "epoch"]
+    assert len(epochs) == 2
+    assert epochs[0][1] == list(range(10)) and epochs[0][2] == [0, 4, 8, 10]
+    assert epochs[0][3] == 1 and epochs[1][3] == 4                  # 3 minibatches per epoch: Adam steps 1-3, 4-6
+    assert abs(epochs[0][4] - 1e-5) < 1e-12
+    assert int(opt.state[dn.fp.beta]["step"]) == 6
+    assert dn.losses().tolist() == [1.0, 2.0, 3.0, 4.0, 5.0, 6.0]
+    dn.update_footprints(loader, 4, sz, gamma_c=0, iter_c=50, dense=False)
+    stats = [c for c in calls if c[0] == "stats"]
+    assert sum((c[1] for c in stats), []) == list(range(10))
+    assert calls[-1] == ("sweeps", 0, 50)
