@@ -1,18 +1,26 @@
 """Build the CUDA shared library in-tree with nvcc for sm_100a (no JIT cache, no torch extension).
 
-    python -m dnmf_b200.build            # -> dnmf_b200/_C/libdnmf_b200.so
+    python -m dnmf_b200.build [--force] [-v]      # -> dnmf_b200/_C/libdnmf_b200.so
+
+Every translation unit under csrc/ is compiled to its own object (in parallel; an object is rebuilt only when
+its source or one of the headers is newer) and the objects are linked into one shared library.  The fused
+kernel's template instantiations are spread over fit_mode<N>.cu for that reason.
 """
 import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "csrc", "dnmf_kernels.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "dnmf_device.cuh"), os.path.join(HERE, "csrc", "dnmf_mu.inc.cu"), os.path.join(HERE, "csrc", "dnmf_ext.inc.cu"),
-        os.path.join(os.path.dirname(HERE), "include", "dnmf_b200.h")]
+CSRC = os.path.join(HERE, "csrc")
+UNITS = ["dnmf_kernels.cu", "fit_mode0.cu", "fit_mode1.cu", "fit_mode2.cu", "fit_mode3.cu", "dnmf_gram_tc.cu",
+         "dnmf_aux.cu"]
 OUT_DIR = os.path.join(HERE, "_C")
+OBJ_DIR = os.path.join(OUT_DIR, "obj")
 OUT = os.path.join(OUT_DIR, "libdnmf_b200.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-lineinfo", "-std=c++17", "--fmad=true", "-Xcompiler", "-fPIC,-O2"]
 
 
 def nvcc_path() -> str:
@@ -22,27 +30,60 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found; the CUDA library cannot be built")
 
 
+def _headers():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".inc.cu"))]
+    hs.append(os.path.join(os.path.dirname(HERE), "include", "dnmf_b200.h"))
+    return hs
+
+
+def _units():
+    return [u for u in UNITS if os.path.isfile(os.path.join(CSRC, u))]
+
+
+def _obj(unit: str) -> str:
+    return os.path.join(OBJ_DIR, os.path.splitext(unit)[0] + ".o")
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.isfile(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
 def up_to_date() -> bool:
-    if not os.path.isfile(OUT):
-        return False
-    t = os.path.getmtime(OUT)
-    return all(os.path.getmtime(d) <= t for d in DEPS)
+    hs = _headers()
+    srcs = [os.path.join(CSRC, u) for u in _units()]
+    return not _stale(OUT, srcs + hs)
+
+
+def _compile(unit: str, verbose: bool) -> str:
+    cmd = [nvcc_path()] + ARCH + FLAGS + ["-c", "-o", _obj(unit), os.path.join(CSRC, unit)]
+    if verbose:
+        cmd[1:1] = ["-Xptxas", "-v"]
+    extra = os.environ.get("DNMF_NVCC_FLAGS")
+    if extra:
+        cmd[1:1] = extra.split()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed on %s:\n%s\n%s" % (unit, res.stdout, res.stderr))
+    return res.stderr
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUT
-    os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "--fmad=true", "-Xcompiler", "-fPIC,-O2", "-shared", "-o", OUT, SRC]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hs = _headers()
+    todo = [u for u in _units() if force or _stale(_obj(u), [os.path.join(CSRC, u)] + hs)]
+    with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 1) or 1) as pool:
+        for u, log in zip(todo, pool.map(lambda u: _compile(u, verbose), todo)):
+            if verbose:
+                sys.stderr.write("== %s\n%s" % (u, log))
+    cmd = [nvcc_path()] + ARCH + ["-shared", "-o", OUT] + [_obj(u) for u in _units()]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (res.stdout, res.stderr))
-    if verbose:
-        sys.stderr.write(res.stderr)
+        raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))
     return OUT
 
 

@@ -22,6 +22,18 @@ __device__ __forceinline__ float sample_coord(float q, float sm1) {
   return __fmul_rn(__fmul_rn(__fadd_rn(u, 1.f), 0.5f), sm1);
 }
 
+// un-normalised sample coordinate, fast form (see verify_coord_kernel).  Input is x2 = 2q (the main loop
+// gets it for free by doubling the Horner coefficients: scaling by 2 is exact).  The division by s-1 is the
+// exact 3-instruction sequence, and the final fl(fl(w*0.5)*(s-1)) is folded into one multiply by
+// (s-1)/2, which is exact because w*0.5 is exact and (s-1)/2 is representable.
+__device__ __forceinline__ float sample_coord_fast(float x2, float sm1, float rcp, float half_sm1) {
+  const float q0 = __fmul_rn(x2, rcp);
+  const float r = __fmaf_rn(-q0, sm1, x2);
+  const float v = __fmaf_rn(r, rcp, q0);
+  const float u = __fsub_rn(v, 1.f);
+  return __fmul_rn(__fadd_rn(u, 1.f), half_sm1);
+}
+
 // floor + fraction of a coordinate already clamped to [-2, s]; table index domain is i in [-2, s].
 __device__ __forceinline__ void split_coord(float ix, int s, int& i, float& f) {
   float c = fminf(fmaxf(ix, -2.f), (float)s);
