@@ -68,6 +68,7 @@ def load(build_if_missing: bool = True):
         "dnmf_mu_sweeps": (c_int, [P, P, c_double, c_int, c_int, P]),
         "dnmf_iwarp": (c_int, [P, P, P, c_int, P, P, P]),
         "dnmf_get_counters": (c_int, [P, P]),
+        "dnmf_check_status": (c_int, [P, P]),
         "dnmf_ext_enable": (c_int, [P]),
         "dnmf_ext_loss_grad": (c_int, [P, P, P, c_int, c_int, P, P, c_float, P, P, P, P, P, P]),
         "dnmf_measure_fp32_peak": (c_int, [c_int, c_int, POINTER(c_double)]),

@@ -62,6 +62,19 @@ struct Geom {
   int tx, ty, tz, ntx, nty, ntz;
 };
 
+// Per-(frame, tile) partial blocks of the trace statistics, written by a first-stage kernel (fused tiles, SIMT
+// panel or tensor-core panel) and summed per frame in ascending tile order by stats_reduce_kernel: tile-frame
+// tf = (batch position) * nt + tile holds its list length count[tf], the listed neuron ids[tf][0..L), the
+// values vals[tf][j][l] = sum_p A_j A_l (l < L) and vals[tf][j][capL] = sum_p A_j Y; slot_of[b][k][tile] is the
+// row of neuron k in that tile's list (0xffff: not listed).
+struct StatsPartials {
+  float* vals;
+  unsigned short* ids;
+  int* count;
+  unsigned short* slot_of;
+  int capL, ld;  // rows available per block, floats per row (capL + 4: rows stay 16-byte aligned)
+};
+
 struct FitParams {
   const float* frames;
   const int* frame_ids;
@@ -89,8 +102,7 @@ struct FitParams {
   int cand_cap;  // shared-memory capacity for one tile's candidates (>= the longest static list when possible)
   int B;         // frames in this launch
   int fpc;       // consecutive frames walked by one CTA (<= 32)
-  double* muG;   // MODE 3 (trace statistics): G_t[K][K], b_t[K] of every frame, accumulated with fp64 atomics
-  double* mub;
+  StatsPartials stats;  // MODE 3 (trace statistics): partial blocks of this launch's tile-frames
   int* mu_overflow;  // MODE 3: set when a tile's list is not fully staged (the caller reruns the generic kernel)
   int dyn_tail;  // != 0: main loop with the run-time tail kind (one loop body per SAFE; see march_rolled TAIL 3)
   unsigned* restage_count;  // [32] frames whose slices were rebuilt, counted per CTA (MODE 0; may be NULL)
@@ -114,7 +126,7 @@ inline FitSmem fit_smem_layout(int nw, int tx, int ty, int tz, int cap, int wsum
   s.tab_f2 = cap * (wsum + wmax0);  // live slices + the x slice without traces
   s.y_f = tx * std::max(y_pitch, ty * tz) + 4;
   s.list_u16 = (K + 7) & ~7;
-  s.bytes = (((size_t)s.tab_f2 * 8 + 127) & ~(size_t)127) + (size_t)s.y_f * 4 + (size_t)nw * kNumPartials * 4 +
+  s.bytes = (((size_t)s.tab_f2 * 8 + 127) & ~(size_t)127) + (size_t)s.y_f * 4 + (size_t)nw * kWarpScratch * 4 +
             80 * 4 + 16 +
             (size_t)((cap + 5) & ~3) * 4 + (size_t)cand_cap * 28 + (size_t)((cand_cap + 7) & ~7) * 2 + (size_t)((cap + 7) & ~7) * 2 +
             (size_t)s.list_u16 * 2;
@@ -128,6 +140,26 @@ int launch_fit_mode0(int nwx, int nwy, int sub, bool fast_div, const FitParams& 
 int launch_fit_mode1(int nwx, int nwy, int sub, bool fast_div, const FitParams& p, int B, size_t smem, cudaStream_t st);
 int launch_fit_mode2(int nwx, int nwy, int sub, bool fast_div, const FitParams& p, int B, size_t smem, cudaStream_t st);
 int launch_fit_mode3(int nwx, int nwy, int sub, bool fast_div, const FitParams& p, int B, size_t smem, cudaStream_t st);
+
+// Tensor-core panel Gram (dnmf_gram_tc.cu): one CTA per (frame, 8 x 8 x Z tile), lists of up to 127 neurons.
+constexpr int kGramRows = 128, kGramTX = 8, kGramTY = 8;
+struct GramTcParams {
+  const float* frames;
+  const int* frame_ids;
+  const float* beta;
+  const float2* tab0;
+  const float2* tab1;
+  const float2* tab2;
+  const int* rng;
+  StatsPartials out;
+  int* overflow;
+  int frames_are_batch;
+  int X, Y, Z, K, T;
+  int ntx, nty;
+  int b_base;  // batch position of this launch's first frame in the partial buffers
+};
+int launch_gram_tc(const GramTcParams& p, int B, cudaStream_t st);
+size_t gram_tc_smem_bytes(int X, int Y, int Z);
 
 }  // namespace dnmf
 
@@ -191,6 +223,15 @@ struct dnmf_ctx {
   int* d_tmp_max = nullptr;
   float* d_identity_beta = nullptr;
   int* d_ids_zero = nullptr;
+  // frame-id validation (check_ids_kernel): clamped copy of the caller's ids, per-frame stamps, per-call flags and
+  // the sticky error word in host-mapped memory
+  int* d_ids_safe = nullptr;
+  size_t ids_safe_cap = 0;
+  int* d_id_mark = nullptr;   // [T]
+  int id_stamp = 0;
+  int* d_id_flags = nullptr;  // [4]
+  int* h_sticky = nullptr;    // cudaHostAllocMapped
+  int* d_sticky = nullptr;    // device alias of h_sticky
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   // mu statistics
@@ -232,6 +273,18 @@ struct dnmf_ctx {
   int mu_last_path = 0;    // 1 = fused tiles, 0 = panel kernel
   int mu_fused_need = 0;   // longest list seen by an overflowing fused-tile statistics launch (capacity hint)
   int mu_fused_off = 0;    // that capacity does not fit in shared memory: go straight to the panel kernel
+  // partial blocks of the trace statistics (StatsPartials) for one chunk of frames
+  float* d_pb_vals = nullptr;
+  size_t pb_vals_cap = 0;
+  unsigned short* d_pb_ids = nullptr;
+  size_t pb_ids_cap = 0;
+  int* d_pb_count = nullptr;
+  size_t pb_count_cap = 0;
+  unsigned short* d_pb_slot = nullptr;
+  size_t pb_slot_cap = 0;
+  int mu_fused_cap_used = 0;  // staged-slot capacity of the last fused-tile statistics pass
+  int mu_prefer_tc = 0;    // dnmf_mu_path bit 3: tensor-core panel kernel instead of the fused tiles
+  int mu_last_tc = 0;
   unsigned long long* d_keys = nullptr;
   size_t keys_cap = 0;
   int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -10,6 +10,7 @@ constexpr int kWarpX = 8;   // warp footprint in x (lanes & 7)
 constexpr int kWarpY = 4;   // warp footprint in y (lanes >> 3)
 constexpr int kBasis = 10;  // [1,x,y,z,x2,y2,z2,xy,xz,yz]  (Demix/dNMF.py:47-51)
 constexpr int kNumPartials = 32;  // 30 gradient moments + sse + pad
+constexpr int kWarpScratch = 96;  // floats per warp of the fused kernel's cross-warp reduction area
 
 // Un-normalised sample coordinate with the reference's fp32 op order:
 //   u  = fl(fl(fl(2 q) / (s-1)) - 1)                      Demix/dNMF.py:55

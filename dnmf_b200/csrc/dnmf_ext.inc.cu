@@ -189,6 +189,7 @@ extern "C" int dnmf_ext_loss_grad(dnmf_ctx* c, const float* frames_dev, const in
   if (B < 1 || B_global < B) return fail("dnmf_ext_loss_grad: need 1 <= B <= B_global");
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(c->device));
+  if (check_sticky(c, "dnmf_ext_loss_grad") || sanitize_ids(c, frame_ids_dev, B, st, &frame_ids_dev)) return 1;
   FitParams p;
   if (fill_fit_params(c, p, frames_dev, frame_ids_dev, B, beta_dev, C_dev)) return 1;
   if (ensure(&c->d_resid, &c->resid_cap, (size_t)B * c->N)) return 1;
@@ -198,8 +199,8 @@ extern "C" int dnmf_ext_loss_grad(dnmf_ctx* c, const float* frames_dev, const in
   if (dispatch_fit<2>(c, p, B, st)) return 1;
   const int nt = c->ntx * c->nty * c->ntz;
   const double scale = 2.0 / ((double)B_global * (double)c->N);
-  reduce_partials_kernel<<<B, 256, 0, st>>>(c->d_partials, frame_ids_dev, nt, c->T, scale, grad_beta_dev, sse_dev,
-                                            c->d_sumr);
+  reduce_partials_kernel<<<B, 256, 0, st>>>(c->d_partials, frame_ids_dev, B, nt, c->T, scale, grad_beta_dev, sse_dev,
+                                            c->d_sumr, nullptr, c->d_id_flags);
   CU(cudaGetLastError());
   ext_finish_kernel<<<1, 32, 0, st>>>(c->d_sumr, B, scale, gbg_dev);
   CU(cudaGetLastError());

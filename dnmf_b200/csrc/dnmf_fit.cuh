@@ -564,14 +564,19 @@ __device__ __forceinline__ void march_stats(const MarchArgs& a, unsigned rowoff,
   }
 }
 
-// Warp-reduce the accumulators of one block pair and add them to G_t / b_t.  Row slots start at slot 6*pb,
-// column slots at 6*lb; off-diagonal blocks are mirrored, b_t is accumulated on diagonal blocks only.
-template <int NP, bool TWO>
+// Warp-reduce the accumulators of one block pair and store them in the tile-frame's partial block
+// (StatsPartials: blk[j * ld + l] = sum A_j A_l, blk[j * ld + capL] = sum A_j Y).  Row slots start at slot 6*pb,
+// column slots at 6*lb; off-diagonal blocks are mirrored, b_t comes from the diagonal blocks only.  With several
+// warps per CTA the warps' totals are added in warp order through shared memory (sRed: kWarpScratch floats per
+// warp): every entry of the block is written exactly once, by plain stores -- the per-frame sum over tiles
+// happens in stats_reduce_kernel in a fixed order.
+template <int NP, bool TWO, int NW>
 __device__ __forceinline__ void flush_stats(const float2 (&G)[3][6], const float2 (&bv)[3], int pb, int lb, int nst,
-                                            const unsigned short* sList, double* Gt, double* bt, int K, int lane) {
+                                            float* blk, int ld, int capL, float* sRed, int lane, int warp) {
   constexpr int NCS = TWO ? 6 : 2 * NP;        // column slots
   constexpr int NG = 2 * NP * NCS;              // G outputs, index = (p*NCS + c)*2 + half
   constexpr int NOUT = NG + (TWO ? 0 : 2 * NP);  // + b outputs
+  static_assert(NOUT <= kWarpScratch, "per-warp reduction area too small");
 #pragma unroll
   for (int r0 = 0; r0 < NOUT; r0 += 32) {
     float v[32];
@@ -588,20 +593,31 @@ __device__ __forceinline__ void flush_stats(const float2 (&G)[3][6], const float
       }
       v[i] = x;
     }
-    const float tot = warp_transpose_sum(v, lane);
+    float tot = warp_transpose_sum(v, lane);
     const int idx = r0 + lane;
-    if (idx < NG) {
-      const int pc = idx >> 1, pp = pc / NCS, cc = pc % NCS;
-      const int j = 6 * pb + 2 * pp + (idx & 1), l = 6 * lb + cc;
-      if (j < nst && l < nst) {
-        const int kj = sList[j], kl = sList[l];
-        atomicAdd(Gt + (size_t)kj * K + kl, (double)tot);
-        if (TWO) atomicAdd(Gt + (size_t)kl * K + kj, (double)tot);
+    if (NW > 1) {
+      if (idx < NOUT) sRed[warp * kWarpScratch + idx] = tot;
+      __syncthreads();
+      if (warp == 0 && idx < NOUT) {
+        tot = sRed[idx];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) tot += sRed[w * kWarpScratch + idx];
       }
-    } else if (idx < NOUT) {
-      const int q = idx - NG, j = 6 * pb + q;
-      if (j < nst) atomicAdd(bt + sList[j], (double)tot);
     }
+    if (NW == 1 || warp == 0) {
+      if (idx < NG) {
+        const int pc = idx >> 1, pp = pc / NCS, cc = pc % NCS;
+        const int j = 6 * pb + 2 * pp + (idx & 1), l = 6 * lb + cc;
+        if (j < nst && l < nst) {
+          blk[(size_t)j * ld + l] = tot;
+          if (TWO) blk[(size_t)l * ld + j] = tot;
+        }
+      } else if (idx < NOUT) {
+        const int q = idx - NG, j = 6 * pb + q;
+        if (j < nst) blk[(size_t)j * ld + capL] = tot;
+      }
+    }
+    if (NW > 1) __syncthreads();  // sRed is reused by the next round / block pair
   }
 }
 
@@ -810,7 +826,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
   const int RS = p.y_pitch;                  // smem stride between x rows: TY*zs, padded when that pitch would
                                              // put the lanes of a warp on the same bank (configure_tiling_fixed)
   float* sRed = sY + (TX * RS + 4);
-  float* sBeta = sRed + NW * kNumPartials;          // 32 floats
+  float* sBeta = sRed + NW * kWarpScratch;          // 32 floats
   int* sInt = reinterpret_cast<int*>(sBeta + 32);   // 32 ints: win[6], cnt[NW], flags
   float* sK = reinterpret_cast<float*>(sInt + 32);  // 16 floats: main-loop constants (see below)
   unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sK + 16);  // 16 B
@@ -1212,13 +1228,24 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
     if constexpr (MODE == 3) {
       // ---- trace statistics of this tile-frame ----
       if constexpr (SUB == 2 && FAST_DIV) {
-        if (L > nst) {
-          if (tid == 0) atomicMax(p.mu_overflow, L);  // not fully staged: the caller reruns the generic kernel
-        } else if (npair > 0) {
+        const int tile = (bz * p.nty + by) * p.ntx + bx;
+        const int ntl = p.ntx * p.nty * p.ntz;
+        const size_t tf = (size_t)(p.b_base + b) * ntl + tile;
+        if (L > nst || L > p.stats.capL) {
+          if (tid == 0) atomicMax(p.mu_overflow, L);  // not fully staged: the caller reruns a panel kernel
+        } else {
+          if (tid == 0) p.stats.count[tf] = L;
+          for (int pos = tid; pos < L; pos += NT) {
+            const int k = sList[pos];
+            p.stats.ids[tf * p.stats.capL + pos] = (unsigned short)k;
+            p.stats.slot_of[((size_t)(p.b_base + b) * p.K + k) * ntl + tile] = (unsigned short)pos;
+          }
+        }
+        if (L <= nst && L <= p.stats.capL && npair > 0) {
           MarchArgs a;
           fill_march_args(a);
-          double* Gt = p.muG + (size_t)t * p.K * p.K;
-          double* bt = p.mub + (size_t)t * p.K;
+          float* blk = p.stats.vals + tf * (size_t)p.stats.capL * p.stats.ld;
+          const int ld = p.stats.ld, capL = p.stats.capL;
           const int nblk = (npair + 2) / 3;
           for (int pb = 0; pb < nblk; ++pb) {
             for (int lb = pb; lb < nblk; ++lb) {
@@ -1233,16 +1260,16 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
               const unsigned rowoff = 48u * (unsigned)pb, coloff = 48u * (unsigned)lb;
               if (pb != lb) {
                 march_stats<3, true>(a, rowoff, coloff, rowp, colp, G, bv);
-                flush_stats<3, true>(G, bv, pb, lb, nst, sList, Gt, bt, p.K, lane);
+                flush_stats<3, true, NW>(G, bv, pb, lb, nst, blk, ld, capL, sRed, lane, warp);
               } else if (rowp == 1) {
                 march_stats<1, false>(a, rowoff, rowoff, 1, 1, G, bv);
-                flush_stats<1, false>(G, bv, pb, lb, nst, sList, Gt, bt, p.K, lane);
+                flush_stats<1, false, NW>(G, bv, pb, lb, nst, blk, ld, capL, sRed, lane, warp);
               } else if (rowp == 2) {
                 march_stats<2, false>(a, rowoff, rowoff, 2, 2, G, bv);
-                flush_stats<2, false>(G, bv, pb, lb, nst, sList, Gt, bt, p.K, lane);
+                flush_stats<2, false, NW>(G, bv, pb, lb, nst, blk, ld, capL, sRed, lane, warp);
               } else {
                 march_stats<3, false>(a, rowoff, rowoff, 3, 3, G, bv);
-                flush_stats<3, false>(G, bv, pb, lb, nst, sList, Gt, bt, p.K, lane);
+                flush_stats<3, false, NW>(G, bv, pb, lb, nst, blk, ld, capL, sRed, lane, warp);
               }
             }
           }

@@ -1,0 +1,412 @@
+// Trace statistics of dense neuron lists on the 5th-generation tensor cores (kernel 3b, dense form).
+//
+//   G_t = A_t^T A_t,  b_t = A_t^T Y_t          Demix/dNMF.py:141-142 (numpy fp64 einsum in the reference)
+//
+// With ~100 neurons reaching every tile (BASELINE configuration 4: K = 1000, sigma = 6) the per-tile Gram
+// [A|Y]^T [A|Y] is a real dense contraction: M = N = listed neurons + the Y pseudo-neuron (<= 128), K = the
+// tile's voxels.  One CTA (4 warps) per (frame, 8 x 8 x Z tile):
+//   * prologue: beta_t -> conservative window -> neuron list (same device code as the binning kernel) -> the
+//     listed neurons' table slices staged in shared memory, two slots per float4 (G_j, G_j+1, D_j, D_j+1);
+//   * producers: warp w owns the 8 x 4 (x, y) half `w & 1` of the tile and every second z plane (`w >> 1`).
+//     Per plane it evaluates the closed-form footprint value of every listed neuron at its 32 voxels from the
+//     staged slices (3 LDS.128 + 5 packed FP32x2 operations per slot pair and voxel, no global memory, no
+//     transcendental) and writes them as ONE K-major panel stage [128 rows][32 voxels] in the canonical
+//     SWIZZLE_128B layout -- twice: hi = tf32(a) and lo = tf32(a - hi);
+//   * tensor cores: lane 0 of the warp issues tcgen05.mma.cta_group::1.kind::tf32 (UMMA 128 x N x 8, N = list
+//     length rounded up to 16) on that stage: SYRK has ONE operand, so the same shared-memory panel serves the A
+//     and the B descriptor; fp32-accurate products come from the 3xTF32 split D += hi hi^T + hi lo^T + lo hi^T.
+//     Each warp accumulates into its OWN 128-column TMEM accumulator (4 x 128 = all 512 columns): no ordering is
+//     needed between the issuing threads, and the truncating fp32 accumulation of the tensor pipe (measured with
+//     tools/experiments/syrk_tf32_umma.cu: relative error 3e-6 per 256 accumulated voxels, growing linearly)
+//     stays at a quarter of the chain length.  tcgen05.commit -> mbarrier hands the stage back to its producer;
+//   * epilogue: every thread reads its row of the four accumulators with tcgen05.ld, adds them in a fixed order
+//     and writes the tile-frame's partial block; the row-owner second stage (stats_reduce_kernel) sums the
+//     blocks of a frame in ascending tile order in fp64: deterministic, no atomics.
+#include "dnmf_common.h"
+
+namespace dnmf {
+
+namespace {
+
+constexpr int kTcThreads = 128;
+constexpr int kTcStageBytes = kGramRows * 128;        // 128 rows x 32 voxels of tf32
+constexpr int kTcPairs = kGramRows / 2;               // slot pairs per slice entry
+constexpr int kTcEntryBytes = (kTcPairs + 1) * 16;    // padded: consecutive entries start 16 B apart mod 128
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row atoms
+  d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcSmem {
+  size_t slices, ytile, misc, bytes;
+};
+
+}  // namespace
+
+__host__ __device__ static TcSmem gram_tc_layout(int wsum, int Z) {
+  TcSmem s;
+  s.slices = (size_t)4 * 2 * kTcStageBytes;                        // panel stages come first (1024-byte aligned)
+  s.ytile = s.slices + (size_t)wsum * kTcEntryBytes;
+  s.misc = s.ytile + (((size_t)kGramTX * kGramTY * Z + 3) & ~(size_t)3) * 4;
+  s.bytes = s.misc + kGramRows * 2 + 32 * 4 + 32 * 4 + 4 * 8 + 16 + 1024;  // list, beta, ints, barriers, tmem ptr, slack
+  return s;
+}
+
+size_t gram_tc_smem_bytes(int X, int Y, int Z) {
+  const int w0 = std::min(kGramTX + 4, X + 3), w1 = std::min(kGramTY + 4, Y + 3), w2 = Z + 3;
+  return gram_tc_layout(w0 + w1 + w2, Z).bytes;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_constant__ GramTcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+  const int wmax0 = min(kGramTX + 4, p.X + 3), wmax1 = min(kGramTY + 4, p.Y + 3), wmax2 = p.Z + 3;
+  const TcSmem lay = gram_tc_layout(wmax0 + wmax1 + wmax2, p.Z);
+  unsigned char* sSl = base + lay.slices;
+  float* sY = reinterpret_cast<float*>(base + lay.ytile);
+  unsigned short* sList = reinterpret_cast<unsigned short*>(base + lay.misc);
+  float* sBeta = reinterpret_cast<float*>(sList + kGramRows);
+  int* sInt = reinterpret_cast<int*>(sBeta + 32);
+  unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sInt + 32);
+  uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 4);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x, b = blockIdx.y;
+  const int nt = p.ntx * p.nty;
+  const int bx = tile % p.ntx, by = tile / p.ntx;
+  const int t = p.frame_ids[b];
+  const int x0 = bx * kGramTX, y0 = by * kGramTY;
+  const int nx = min(kGramTX, p.X - x0), ny = min(kGramTY, p.Y - y0), nz = p.Z;
+  const size_t Nvox = (size_t)p.X * p.Y * p.Z;
+  const float* __restrict__ frame = p.frames + (size_t)(p.frames_are_batch ? b : t) * Nvox;
+  const size_t tf = (size_t)(p.b_base + b) * nt + tile;  // tile-frame index in the partial buffers
+
+  // ---- beta, Y tile, window, neuron list ----
+  if (tid < 30) sBeta[tid] = p.beta[(size_t)tid * p.T + t];
+  {
+    const int run = ny * p.Z;
+    for (int lx = warp; lx < nx; lx += 4) {
+      const float* src = frame + ((size_t)(x0 + lx) * p.Y + y0) * p.Z;
+      for (int e = lane; e < run; e += 32) sY[lx * kGramTY * p.Z + e] = __ldg(src + e);
+    }
+  }
+  __syncthreads();
+  if (tid < 3) {
+    const int s = tid == 0 ? p.X : (tid == 1 ? p.Y : p.Z);
+    int wlo, whi;
+    tile_window_axis(sBeta + tid, 3, (float)x0, (float)y0, 0.f, (float)(x0 + nx - 1), (float)(y0 + ny - 1),
+                     (float)(nz - 1), s, wlo, whi);
+    sInt[tid] = wlo;
+    sInt[3 + tid] = whi;
+  }
+  __syncthreads();
+  int wlo[3], whi[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    wlo[d] = sInt[d];
+    whi[d] = sInt[3 + d];
+  }
+  const int per = ((p.K + kTcThreads - 1) / kTcThreads) * 32;
+  const int kb = warp * per;
+  {
+    int cnt = 0;
+    for (int k0 = kb; k0 < kb + per; k0 += 32) {
+      const int k = k0 + lane;
+      const bool ok = (k < p.K) && neuron_in_window(p.rng + (size_t)k * 6, wlo, whi);
+      cnt += __popc(__ballot_sync(0xffffffffu, ok));
+    }
+    if (lane == 0) sInt[8 + warp] = cnt;
+  }
+  __syncthreads();
+  int L = 0, off = 0;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const int c = sInt[8 + w];
+    if (w < warp) off += c;
+    L += c;
+  }
+  const int W0 = whi[0] - wlo[0] + 1, W1 = whi[1] - wlo[1] + 1, W2 = whi[2] - wlo[2] + 1;
+  if (L + 1 > kGramRows || W0 > wmax0 || W1 > wmax1 || W2 > wmax2) {  // loud: the host reruns the SIMT panel kernel
+    if (tid == 0) atomicMax(p.overflow, max(L + 1, kGramRows + 1));
+    return;
+  }
+  if (tid == 0) p.out.count[tf] = L;
+  if (L == 0) return;
+  for (int k0 = kb; k0 < kb + per; k0 += 32) {
+    const int k = k0 + lane;
+    const bool ok = (k < p.K) && neuron_in_window(p.rng + (size_t)k * 6, wlo, whi);
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const int pos = off + __popc(m & ((1u << lane) - 1u));
+      sList[pos] = (unsigned short)k;
+      p.out.ids[tf * p.out.capL + pos] = (unsigned short)k;
+      p.out.slot_of[((size_t)(p.b_base + b) * p.K + k) * nt + tile] = (unsigned short)pos;
+    }
+    off += __popc(m);
+  }
+
+  // ---- TMEM (all 512 columns: one 128-column accumulator per warp), stage barriers ----
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(sTmem)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int w = 0; w < 4; ++w) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sBar[w])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();  // also: sList complete
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = *sTmem;
+
+  // ---- table slices of the listed neurons: [entry][slot pair] float4 (G_2p, G_2p+1, D_2p, D_2p+1) ----
+  const int npair = (L + 2) >> 1;  // rows 0 .. L (the Y pseudo-row L overwrites its half of the last pair)
+  {
+    const int sX3 = p.X + 3, sY3 = p.Y + 3, sZ3 = p.Z + 3;
+    const int Wt = W0 + W1 + W2;
+    for (int item = tid; item < Wt * npair; item += kTcThreads) {
+      const int e = item / npair, pp = item - e * npair;
+      const float2* src;
+      int row, ent;
+      if (e < W0) {
+        src = p.tab0 + (wlo[0] + 2 + e);
+        row = sX3;
+        ent = e;
+      } else if (e < W0 + W1) {
+        src = p.tab1 + (wlo[1] + 2 + (e - W0));
+        row = sY3;
+        ent = wmax0 + (e - W0);
+      } else {
+        src = p.tab2 + (wlo[2] + 2 + (e - W0 - W1));
+        row = sZ3;
+        ent = wmax0 + wmax1 + (e - W0 - W1);
+      }
+      const int j = 2 * pp;
+      float2 va = make_float2(0.f, 0.f), vb = va;
+      if (j < L) va = __ldg(src + (size_t)sList[j] * row);
+      if (j + 1 < L) vb = __ldg(src + (size_t)sList[j + 1] * row);
+      *reinterpret_cast<float4*>(sSl + (size_t)ent * kTcEntryBytes + (size_t)pp * 16) = make_float4(va.x, vb.x, va.y, vb.y);
+    }
+  }
+  __syncthreads();
+
+  // ---- producers + MMA issue ----
+  const int sub = warp & 1, zpar = warp >> 1;
+  const int lx = lane & 7, ly = (lane >> 3) + 4 * sub;
+  const int gx = x0 + lx, gy = y0 + ly;
+  const bool valid = (gx < p.X) && (gy < p.Y);
+  const float vmask = valid ? 1.f : 0.f;
+  const float xf = (float)gx, yf = (float)gy;
+  float c0[3], c1[3], c2[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {  // same operation order as the fused kernel's Horner form in z
+    float v = sBeta[d];
+    v = fmaf(sBeta[3 + d], xf, v);
+    v = fmaf(sBeta[6 + d], yf, v);
+    v = fmaf(sBeta[12 + d], xf * xf, v);
+    v = fmaf(sBeta[15 + d], yf * yf, v);
+    v = fmaf(sBeta[21 + d], xf * yf, v);
+    c0[d] = v;
+    c1[d] = fmaf(sBeta[27 + d], yf, fmaf(sBeta[24 + d], xf, sBeta[9 + d]));
+    c2[d] = sBeta[18 + d];
+  }
+  const float sm1x = (float)(p.X - 1), sm1y = (float)(p.Y - 1), sm1z = (float)(p.Z - 1);
+  const uint32_t hi_base = smem_addr(base) + (uint32_t)warp * 2u * kTcStageBytes;
+  const uint32_t lo_base = hi_base + kTcStageBytes;
+  const uint32_t slx = smem_addr(sSl), sly = slx + (uint32_t)wmax0 * kTcEntryBytes,
+                 slz = sly + (uint32_t)wmax1 * kTcEntryBytes;
+  const uint32_t bar = smem_addr(&sBar[warp]);
+  // byte offset of this lane's column inside row r8 of an 8-row atom (16-byte chunks XOR-swizzled with the row)
+  uint32_t off8[8];
+#pragma unroll
+  for (int r8 = 0; r8 < 8; ++r8) off8[r8] = (uint32_t)(r8 * 128 + (((lane >> 2) ^ r8) << 4) + ((lane & 3) << 2));
+  const int npad = (L + 1 + 15) & ~15;  // MMA N
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(kGramRows >> 4) << 24);
+  const uint32_t acc = tmem + (uint32_t)warp * 128u;
+  const int uses = nz > zpar ? (nz - zpar + 1) >> 1 : 0;
+  const int natom = (npair + 3) >> 2;
+  const int yL_atom = L >> 3, yL_r8 = L & 7;
+  for (int u = 0; u < uses; ++u) {
+    const int z = zpar + 2 * u;
+    if (u > 0) mbar_wait(bar, (uint32_t)((u - 1) & 1));  // the MMAs that read this stage have completed
+    const float zf = (float)z;
+    int i0, i1, i2;
+    float f0, f1, f2;
+    split_coord(sample_coord(fmaf(zf, fmaf(zf, c2[0], c1[0]), c0[0]), sm1x), p.X, i0, f0);
+    split_coord(sample_coord(fmaf(zf, fmaf(zf, c2[1], c1[1]), c0[1]), sm1y), p.Y, i1, f1);
+    split_coord(sample_coord(fmaf(zf, fmaf(zf, c2[2], c1[2]), c0[2]), sm1z), p.Z, i2, f2);
+    const uint32_t ax = slx + (uint32_t)min(max(i0 - wlo[0], 0), W0 - 1) * kTcEntryBytes;
+    const uint32_t ay = sly + (uint32_t)min(max(i1 - wlo[1], 0), W1 - 1) * kTcEntryBytes;
+    const uint32_t az = slz + (uint32_t)min(max(i2 - wlo[2], 0), W2 - 1) * kTcEntryBytes;
+    const float2 ff0 = make_float2(f0, f0), ff1 = make_float2(f1, f1), ff2 = make_float2(f2, f2);
+    const float2 mm = make_float2(vmask, vmask);
+#pragma unroll 1
+    for (int at = 0; at < natom; ++at) {
+      const uint32_t rowh = hi_base + (uint32_t)at * 1024u, rowl = lo_base + (uint32_t)at * 1024u;
+      const uint32_t pofs = (uint32_t)at * 64u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 ex = lds128(ax + pofs + q * 16), ey = lds128(ay + pofs + q * 16), ez = lds128(az + pofs + q * 16);
+        const float2 a0 = __ffma2_rn(ff0, make_float2(ex.z, ex.w), make_float2(ex.x, ex.y));
+        const float2 a1 = __ffma2_rn(ff1, make_float2(ey.z, ey.w), make_float2(ey.x, ey.y));
+        const float2 a2 = __ffma2_rn(ff2, make_float2(ez.z, ez.w), make_float2(ez.x, ez.y));
+        const float2 a = __fmul2_rn(__fmul2_rn(__fmul2_rn(a0, a1), a2), mm);
+        const float2 h = make_float2(to_tf32(a.x), to_tf32(a.y));
+        const float2 l = make_float2(to_tf32(a.x - h.x), to_tf32(a.y - h.y));
+        sts32(rowh + off8[2 * q], h.x);
+        sts32(rowh + off8[2 * q + 1], h.y);
+        sts32(rowl + off8[2 * q], l.x);
+        sts32(rowl + off8[2 * q + 1], l.y);
+      }
+    }
+    {  // the Y pseudo-neuron (row L): b_t = A_t^T Y_t rides in column L of the same product
+      const float y = valid ? sY[(lx * kGramTY + ly) * p.Z + z] : 0.f;
+      const float h = to_tf32(y), l = to_tf32(y - h);
+      const uint32_t o = (uint32_t)yL_atom * 1024u + (uint32_t)(yL_r8 * 128 + (((lane >> 2) ^ yL_r8) << 4) + ((lane & 3) << 2));
+      sts32(hi_base + o, h);
+      sts32(lo_base + o, l);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA's async proxy
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      const uint64_t dh = make_desc(hi_base), dl = make_desc(lo_base);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {  // UMMA_K = 8 tf32 = 32 bytes along the swizzled row: +2 in the address field
+        const uint64_t ah = dh + (uint64_t)(2 * k), al = dl + (uint64_t)(2 * k);
+        umma_tf32(acc, ah, ah, idesc, (u > 0 || k > 0) ? 1u : 0u);
+        umma_tf32(acc, ah, al, idesc, 1u);
+        umma_tf32(acc, al, ah, idesc, 1u);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    }
+    __syncwarp();
+  }
+
+  // ---- epilogue: wait for every warp's last MMAs, add the four accumulators, write the partial block ----
+  int nacc = 0;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const int uw = nz > (w >> 1) ? (nz - (w >> 1) + 1) >> 1 : 0;
+    if (uw > 0) {
+      mbar_wait(smem_addr(&sBar[w]), (uint32_t)((uw - 1) & 1));
+      nacc = w + 1;  // warps with planes are 0..nacc-1 (warps 2, 3 have none when nz == 1)
+    }
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  {
+    const int row = warp * 32 + lane;
+    float* out = p.out.vals + tf * (size_t)p.out.capL * p.out.ld + (size_t)row * p.out.ld;
+    for (int cb = 0; cb < npad; cb += 32) {
+      float sum[32];
+      uint32_t r[32];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb;
+      tmem_ld32(taddr, r);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sum[i] = __uint_as_float(r[i]);
+      for (int w = 1; w < nacc; ++w) {
+        tmem_ld32(taddr + (uint32_t)w * 128u, r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sum[i] += __uint_as_float(r[i]);
+      }
+      if (row < L) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const int col = cb + i;
+          if (col + 3 < L) {
+            *reinterpret_cast<float4*>(out + col) = make_float4(sum[i], sum[i + 1], sum[i + 2], sum[i + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (col + q < L) out[col + q] = sum[i + q];
+              else if (col + q == L) out[p.out.capL] = sum[i + q];
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
+int launch_gram_tc(const GramTcParams& p, int B, cudaStream_t st) {
+  const size_t smem = gram_tc_smem_bytes(p.X, p.Y, p.Z);
+  static size_t configured[64] = {0};
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || smem > configured[dev]) {
+    CU(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev >= 0 && dev < 64) configured[dev] = smem;
+  }
+  for (int b0 = 0; b0 < B; b0 += 65535) {
+    GramTcParams q = p;
+    const int nb = std::min(65535, B - b0);
+    q.b_base = p.b_base + b0;
+    q.frame_ids = p.frame_ids + b0;
+    if (p.frames_are_batch) q.frames = p.frames + (size_t)b0 * p.X * p.Y * p.Z;
+    gram_tc_kernel<<<dim3((unsigned)(p.ntx * p.nty), (unsigned)nb), kTcThreads, smem, st>>>(q);
+    CU(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace dnmf

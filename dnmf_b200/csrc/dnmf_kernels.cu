@@ -206,29 +206,87 @@ __global__ void verify_coord_kernel(float sm1, float rcp, unsigned long long* __
   if (bad) atomicAdd(mismatches, (unsigned long long)bad);
 }
 
+// Frame ids handed to the C ABI are checked on the device before any kernel indexes with them: one block walks
+// the batch, writes a copy clamped to [0, T) (what every kernel of the call then reads: an id out of range can
+// no longer touch memory outside the slab), raises the sticky error bit of the context (host-mapped memory, read
+// without a synchronisation at the next entry point) for an id outside [0, T), and tells the second-stage
+// reduction whether an id occurs twice in the batch (stamp trick: mark[t] holds the number of the last call that
+// listed frame t).  flags[0]: bit 0 = duplicates, bit 1 = out of range; rewritten by every call.
+__global__ void check_ids_kernel(const int* __restrict__ ids, int B, int T, int* __restrict__ mark, int stamp,
+                                 int* __restrict__ ids_safe, int* __restrict__ flags, int* __restrict__ sticky) {
+  __shared__ int s_flags;
+  if (threadIdx.x == 0) s_flags = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int t = ids[b];
+    if (t < 0 || t >= T) {
+      mine |= 2;
+      t = min(max(t, 0), T - 1);
+    } else if (atomicExch(mark + t, stamp) == stamp) {
+      mine |= 1;
+    }
+    ids_safe[b] = t;
+  }
+  if (mine) atomicOr(&s_flags, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    flags[0] = s_flags;
+    if (s_flags & 2) atomicOr(sticky, 2);
+  }
+}
+
 // Second stage: per frame, sum the CTA partials in a fixed order (double), scale by 2/(B_global*N),
 // write the frame's gradient column and its sum of squared residuals.  grid = B, block = 256.
-__global__ void reduce_partials_kernel(const float* __restrict__ partials, const int* __restrict__ frame_ids,
+// A frame id that occurs more than once in the batch (a sampler with replacement) owns ONE gradient column: the
+// reference's autograd adds the contributions of all its occurrences (index_put with accumulate,
+// Demix/dNMF.py:54,190).  Here the block of the first occurrence sums them in ascending batch position and the
+// other blocks leave; every position still reports its own squared residuals (F.mse_loss averages over all B
+// entries, :188).  flags[0] bit 0 (check_ids_kernel) says whether the batch has duplicates at all.
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, const int* __restrict__ frame_ids, int B,
                                        int nt, int T, double grad_scale, float* __restrict__ grad,
                                        double* __restrict__ sse_out, double* __restrict__ sumr_out,
-                                       const double* __restrict__ scale_per_frame = nullptr) {
+                                       const double* __restrict__ scale_per_frame, const int* __restrict__ flags) {
   __shared__ double s[8][kNumPartials];
+  __shared__ int s_rel[2];
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* src = partials + (size_t)b * nt * kNumPartials;
-  double acc = 0.0;
-  for (int i = warp; i < nt; i += 8) acc += (double)src[(size_t)i * kNumPartials + lane];
-  s[warp][lane] = acc;
-  __syncthreads();
-  if (warp == 0) {
-    double v = 0.0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) v += s[w][lane];
-    const int t = frame_ids[b];
-    if (scale_per_frame != nullptr) grad_scale = scale_per_frame[b];
-    if (lane < 30) grad[(size_t)lane * T + t] = (float)(v * grad_scale);
-    if (lane == 30) sse_out[b] = v;
-    if (lane == 31 && sumr_out != nullptr) sumr_out[b] = v;
+  const int t = frame_ids[b];
+  int last = b;  // positions b..last may hold further occurrences of t
+  if (flags != nullptr && (flags[0] & 1)) {
+    if (threadIdx.x < 2) s_rel[threadIdx.x] = 0;
+    __syncthreads();
+    bool earlier = false, later = false;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+      const bool same = frame_ids[i] == t;
+      earlier |= same && i < b;
+      later |= same && i > b;
+    }
+    if (earlier) s_rel[0] = 1;
+    if (later) s_rel[1] = 1;
+    __syncthreads();
+    if (s_rel[0]) return;          // not the first occurrence: the owner block accounts for this position
+    if (s_rel[1]) last = B - 1;
   }
+  double gsum = 0.0;
+  for (int i = b; i <= last; ++i) {
+    if (i != b && frame_ids[i] != t) continue;  // block-uniform
+    const float* src = partials + (size_t)i * nt * kNumPartials;
+    double acc = 0.0;
+    for (int j = warp; j < nt; j += 8) acc += (double)src[(size_t)j * kNumPartials + lane];
+    __syncthreads();  // the previous position's s[][] has been read
+    s[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += s[w][lane];
+      const double sc = scale_per_frame != nullptr ? scale_per_frame[i] : grad_scale;
+      if (lane < 30) gsum = i == b ? v * sc : gsum + v * sc;
+      if (lane == 30) sse_out[i] = v;
+      if (lane == 31 && sumr_out != nullptr) sumr_out[i] = v;
+    }
+  }
+  if (warp == 0 && lane < 30) grad[(size_t)lane * T + t] = (float)gsum;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -415,6 +473,10 @@ using namespace dnmf;
 extern "C" int dnmf_abi_version(void) { return DNMF_ABI_VERSION; }
 extern "C" const char* dnmf_last_error(void) { return g_err.c_str(); }
 
+static int create_impl(dnmf_ctx* c, int X, int Y, int Z, int K, int T, int device);
+
+extern "C" void dnmf_destroy(dnmf_ctx* c);
+
 extern "C" int dnmf_create(dnmf_ctx** out, int X, int Y, int Z, int K, int T, int device) {
   if (!out) return fail("dnmf_create: out is NULL");
   if (X < 1 || Y < 1 || Z < 1 || K < 1 || T < 1) return fail("dnmf_create: sizes must be positive");
@@ -426,6 +488,16 @@ extern "C" int dnmf_create(dnmf_ctx** out, int X, int Y, int Z, int K, int T, in
                 "); this library has no CPU fallback");
   CU(cudaSetDevice(device));
   dnmf_ctx* c = new dnmf_ctx();
+  c->device = device;
+  if (create_impl(c, X, Y, Z, K, T, device)) {  // the error text is already set; do not leak what was allocated
+    dnmf_destroy(c);
+    return 1;
+  }
+  *out = c;
+  return 0;
+}
+
+static int create_impl(dnmf_ctx* c, int X, int Y, int Z, int K, int T, int device) {
   c->X = X;
   c->Y = Y;
   c->Z = Z;
@@ -460,6 +532,13 @@ extern "C" int dnmf_create(dnmf_ctx** out, int X, int Y, int Z, int K, int T, in
   CU(cudaMemcpy(c->d_identity_beta, idb, sizeof(idb), cudaMemcpyHostToDevice));
   CU(cudaMalloc((void**)&c->d_ids_zero, sizeof(int)));
   CU(cudaMemset(c->d_ids_zero, 0, sizeof(int)));
+  CU(cudaMalloc((void**)&c->d_id_mark, (size_t)T * sizeof(int)));
+  CU(cudaMemset(c->d_id_mark, 0, (size_t)T * sizeof(int)));
+  CU(cudaMalloc((void**)&c->d_id_flags, 4 * sizeof(int)));
+  CU(cudaMemset(c->d_id_flags, 0, 4 * sizeof(int)));
+  CU(cudaHostAlloc((void**)&c->h_sticky, sizeof(int), cudaHostAllocMapped));
+  *c->h_sticky = 0;
+  CU(cudaHostGetDevicePointer((void**)&c->d_sticky, c->h_sticky, 0));
   // enable the 3-instruction exact division only after an exhaustive device-side proof per axis size
   {
     static std::mutex mu;
@@ -492,7 +571,6 @@ extern "C" int dnmf_create(dnmf_ctx** out, int X, int Y, int Z, int K, int T, in
     cudaFree(d_bad);
     c->fast_div = all_ok;
   }
-  *out = c;
   return 0;
 }
 
@@ -507,7 +585,8 @@ extern "C" void dnmf_destroy(dnmf_ctx* c) {
                   c->d_tab_dpos[0], c->d_tab_dpos[1], c->d_tab_dpos[2], c->d_tab_dsig[0], c->d_tab_dsig[1],
                   c->d_tab_dsig[2], c->d_resid, c->d_sumr, c->d_ids_zero,
                   c->d_epoch_batch_of, c->d_epoch_offsets, c->d_epoch_scalars, c->d_epoch_scale,
-                  c->d_mu_nbr, c->d_Gc, c->d_restage};
+                  c->d_mu_nbr, c->d_Gc, c->d_restage, c->d_ids_safe, c->d_id_mark, c->d_id_flags,
+                  c->d_pb_vals, c->d_pb_ids, c->d_pb_count, c->d_pb_slot};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->copy_stream) {
@@ -522,6 +601,7 @@ extern "C" void dnmf_destroy(dnmf_ctx* c) {
     cudaEventDestroy(c->ev_restage);
   }
   if (c->h_restage) cudaFreeHost(c->h_restage);
+  if (c->h_sticky) cudaFreeHost(c->h_sticky);
   delete c;
 }
 
@@ -791,6 +871,39 @@ extern "C" int dnmf_video_devptr(dnmf_ctx* c, float** out) {
   return 0;
 }
 
+// ---- frame-id validation ------------------------------------------------------------------------------
+// Errors found on the device by an asynchronous call (a frame id outside [0, T)) are kept in a sticky word in
+// host-mapped memory and reported by the next entry point, or by dnmf_check_status.
+static int check_sticky(dnmf_ctx* c, const char* who) {
+  if (!c->h_sticky) return 0;
+  const int bits = *(volatile int*)c->h_sticky;
+  if (bits == 0) return 0;
+  *(volatile int*)c->h_sticky = 0;
+  std::string what;
+  if (bits & 2) what += " a frame id outside [0, T) was passed (the call ran on ids clamped into the slab; its results are invalid)";
+  if (bits & ~2) what += " device status " + std::to_string(bits);
+  return fail(std::string(who) + ": an earlier asynchronous call failed:" + what);
+}
+
+// ids_dev[B] -> the context's clamped copy (what the kernels of this call read) + the duplicate / range flags
+static int sanitize_ids(dnmf_ctx* c, const int32_t* ids_dev, int B, cudaStream_t st, const int32_t** out) {
+  if (B < 1) return fail("frame id batch is empty");
+  if (ensure(&c->d_ids_safe, &c->ids_safe_cap, (size_t)B)) return 1;
+  c->id_stamp = c->id_stamp == 0x7fffffff ? 1 : c->id_stamp + 1;
+  check_ids_kernel<<<1, 256, 0, st>>>(ids_dev, B, c->T, c->d_id_mark, c->id_stamp, c->d_ids_safe, c->d_id_flags,
+                                      c->d_sticky);
+  CU(cudaGetLastError());
+  *out = c->d_ids_safe;
+  return 0;
+}
+
+extern "C" int dnmf_check_status(dnmf_ctx* c, void* stream) {
+  if (!c) return fail("dnmf_check_status: ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return check_sticky(c, "dnmf_check_status");
+}
+
 // ---- stand-alone binning ---------------------------------------------------------------------------
 extern "C" int dnmf_bin_tiles(dnmf_ctx* c, const float* beta_dev, const int32_t* frame_ids_dev, int B,
                               int32_t* counts_dev, int64_t* offsets_dev, int32_t* windows_dev,
@@ -800,6 +913,7 @@ extern "C" int dnmf_bin_tiles(dnmf_ctx* c, const float* beta_dev, const int32_t*
   if (!c->have_footprints) return fail("dnmf_bin_tiles: call dnmf_set_footprints first");
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(c->device));
+  if (check_sticky(c, "dnmf_bin_tiles") || sanitize_ids(c, frame_ids_dev, B, st, &frame_ids_dev)) return 1;
   const long long items = (long long)B * c->ntx * c->nty * c->ntz;
   if (run_bin_count(c, beta_dev, c->T, frame_ids_dev, B, counts_dev, windows_dev, st)) return 1;
   scan_counts_kernel<<<1, 1024, 0, st>>>(counts_dev, items, (long long*)offsets_dev, nullptr);
@@ -874,8 +988,7 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
   p.full_depth = (c->tz == c->Z) ? 1 : 0;
   p.bulk_ok = (((uintptr_t)p.frames & 15) == 0) && (((size_t)c->Y * c->Z) % 4 == 0) &&
               (((size_t)c->ty * c->Z) % 4 == 0);
-  p.muG = nullptr;
-  p.mub = nullptr;
+  memset(&p.stats, 0, sizeof(p.stats));
   p.mu_overflow = nullptr;
   p.dyn_tail = 0;
   p.restage_count = nullptr;
@@ -992,12 +1105,14 @@ extern "C" int dnmf_loss_grad(dnmf_ctx* c, const float* frames_dev, const int32_
   if (B < 1 || B_global < B) return fail("dnmf_loss_grad: need 1 <= B <= B_global");
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(c->device));
+  if (check_sticky(c, "dnmf_loss_grad") || sanitize_ids(c, frame_ids_dev, B, st, &frame_ids_dev)) return 1;
   FitParams p;
   if (fill_fit_params(c, p, frames_dev, frame_ids_dev, B, beta_dev, C_dev)) return 1;
   const int nt = c->ntx * c->nty * c->ntz;
   if (launch_fused_fit(c, p, B, st)) return 1;
   const double scale = 2.0 / ((double)B_global * (double)c->N);
-  reduce_partials_kernel<<<B, 256, 0, st>>>(c->d_partials, frame_ids_dev, nt, c->T, scale, grad_dev, sse_dev, nullptr);
+  reduce_partials_kernel<<<B, 256, 0, st>>>(c->d_partials, frame_ids_dev, B, nt, c->T, scale, grad_dev, sse_dev, nullptr,
+                                            nullptr, c->d_id_flags);
   CU(cudaGetLastError());
   c->counters[0] += 1;  // fused launches
   c->counters[1] += 1;  // reduce launches
@@ -1011,6 +1126,7 @@ extern "C" int dnmf_adam_step(dnmf_ctx* c, float* beta_dev, float* grad_dev, flo
   if (step < 1) return fail("dnmf_adam_step: step is 1-based");
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(c->device));
+  if (check_sticky(c, "dnmf_adam_step")) return 1;
   AdamParams a;
   const double bc1 = 1.0 - pow(beta1, (double)step);
   const double bc2 = 1.0 - pow(beta2, (double)step);
@@ -1100,8 +1216,8 @@ extern "C" int dnmf_motion_epoch(dnmf_ctx* c, const int32_t* frame_ids_dev, cons
     if (fill_fit_params(c, p, nullptr, frame_ids_dev + b_first, (int)Btot, beta_dev, C_dev)) return 1;
     const int nt = c->ntx * c->nty * c->ntz;
     if (launch_fused_fit(c, p, (int)Btot, st)) return 1;
-    reduce_partials_kernel<<<(unsigned)Btot, 256, 0, st>>>(c->d_partials, frame_ids_dev + b_first, nt, c->T, 0.0,
-                                                          c->d_grad, c->d_sse, nullptr, c->d_epoch_scale);
+    reduce_partials_kernel<<<(unsigned)Btot, 256, 0, st>>>(c->d_partials, frame_ids_dev + b_first, (int)Btot, nt, c->T,
+                                                          0.0, c->d_grad, c->d_sse, nullptr, c->d_epoch_scale, nullptr);
     CU(cudaGetLastError());
     epoch_adam_kernel<<<(n + 127) / 128, 128, 0, st>>>(beta_dev, c->d_grad, m_dev, v_dev, n, c->T, affine, w1, b2, w2,
                                                        epsf, c->d_epoch_scalars, nbatches, c->d_epoch_batch_of, 1);
@@ -1142,6 +1258,20 @@ extern "C" int dnmf_motion_step_host(dnmf_ctx* c, const float* frames_host, cons
   if (B < 1) return fail("dnmf_motion_step_host: B must be >= 1");
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(c->device));
+  if (check_sticky(c, "dnmf_motion_step_host")) return 1;
+  {  // the ids are on the host here: validate them before anything is launched
+    std::vector<char> seen((size_t)c->T, 0);
+    for (int b = 0; b < B; ++b) {
+      const int t = frame_ids_host[b];
+      if (t < 0 || t >= c->T)
+        return fail("dnmf_motion_step_host: frame id " + std::to_string(t) + " outside [0, " + std::to_string(c->T) + ")");
+      if (seen[(size_t)t])
+        return fail("dnmf_motion_step_host: frame id " + std::to_string(t) +
+                    " occurs twice in the batch (the chunked host path keeps one gradient column per frame; use "
+                    "dnmf_motion_step with device frames for batches drawn with replacement)");
+      seen[(size_t)t] = 1;
+    }
+  }
   // Frames cross PCIe in chunks on a copy stream, double-buffered, while the fused kernel works on the
   // previous chunk; the device only ever holds two chunks of the batch.
   const int chunk = std::min(B, std::max(1, (int)(((size_t)96 << 20) / (c->N * sizeof(float)))));
@@ -1187,6 +1317,7 @@ extern "C" int dnmf_forward(dnmf_ctx* c, const int32_t* frame_ids_dev, int B, co
   if (!c || !frame_ids_dev || !beta_dev || !C_dev) return fail("dnmf_forward: NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(c->device));
+  if (check_sticky(c, "dnmf_forward") || sanitize_ids(c, frame_ids_dev, B, st, &frame_ids_dev)) return 1;
   if (AtC_dev) {
     // Yhat does not depend on the video: the WRITE_YHAT instantiation never reads `frames`.
     FitParams p;

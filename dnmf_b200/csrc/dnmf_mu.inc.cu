@@ -4,8 +4,10 @@
 // the closed-form footprint value A_j(p) of each listed neuron at its voxel and parks it in shared
 // memory next to the voxel's Y value (pseudo-neuron).  Phase 2: the CTA computes the small SYRK
 // [A|Y]^T [A|Y] of those 128 voxels with 4x4 register blocks and split-K over the voxel index.
-// Accumulators live in registers for the whole tile and are flushed once with fp64 atomics into
-// the dense per-frame G_t[K][K], b_t[K].   Reference: Demix/dNMF.py:141-142 (fp64 einsum).
+// Accumulators live in registers for the whole tile and are stored once into the tile-frame's partial block
+// (StatsPartials); stats_reduce_kernel sums the blocks of a frame in ascending tile order in fp64 into the
+// dense per-frame G_t[K][K], b_t[K].   Reference: Demix/dNMF.py:141-142 (fp64 einsum).
+// This SIMT form serves lists longer than the 127 rows of the tensor-core panel kernel (dnmf_gram_tc.cu).
 namespace dnmf {
 
 constexpr int kMuThreads = 128;
@@ -20,8 +22,8 @@ struct MuParams {
   const float2* tab1;
   const float2* tab2;
   const int* rng;
-  double* G;
-  double* bvec;
+  StatsPartials out;
+  int b_base;  // batch position of this launch's first frame in the partial buffers
   int* overflow;
   int frames_are_batch;
   int X, Y, Z, K, T;
@@ -128,10 +130,20 @@ __global__ void __launch_bounds__(kMuThreads) mu_stats_kernel(const __grid_const
       off += __popc(m);
     }
   }
-  if (L + 1 > p.capM) {  // loud failure: the host checks this flag after the launch
+  if (L + 1 > p.capM || L > p.out.capL) {  // loud failure: the host checks this flag after the launch
     if (tid == 0) atomicMax(p.overflow, L + 1);
     return;
   }
+  const size_t tf = (size_t)(p.b_base + b) * nt + tile;
+  if (tid == 0) p.out.count[tf] = L;
+  if (L == 0) return;
+  __syncthreads();  // sList complete
+  for (int pos = tid; pos < L; pos += kMuThreads) {
+    const int k = sList[pos];
+    p.out.ids[tf * p.out.capL + pos] = (unsigned short)k;
+    p.out.slot_of[((size_t)(p.b_base + b) * p.K + k) * nt + tile] = (unsigned short)pos;
+  }
+  float* pblock = p.out.vals + tf * (size_t)p.out.capL * p.out.ld;
   const int M = L + 1;               // neurons + the Y pseudo-neuron
   const int mb = (M + BS - 1) / BS;  // BS x BS blocks per side
   const int nblk = mb * (mb + 1) / 2;
@@ -171,7 +183,6 @@ __global__ void __launch_bounds__(kMuThreads) mu_stats_kernel(const __grid_const
   const float sm1x = (float)(p.X - 1), sm1y = (float)(p.Y - 1), sm1z = (float)(p.Z - 1);
   const int sX3 = p.X + 3, sY3 = p.Y + 3, sZ3 = p.Z + 3;
   const int ybase = lx * RS + ly * zs;
-  const size_t gbase = (size_t)t * p.K * p.K;
 
   for (int base = 0; base < nblk; base += groups * R) {
     float acc[R][BS * BS];
@@ -239,34 +250,33 @@ __global__ void __launch_bounds__(kMuThreads) mu_stats_kernel(const __grid_const
       __syncthreads();
     }
 
-    // flush: reduce the split-K lanes, then fp64 atomics into G_t / b_t
+    // flush: reduce the split-K lanes, then plain stores into the tile-frame's partial block (every entry of the
+    // block is produced by exactly one register block; diagonal blocks hold both triangles)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int blk = base + r * groups + grp;
+      const int blk_i = base + r * groups + grp;
 #pragma unroll
       for (int i = 0; i < BS * BS; ++i) {
         float v = acc[r][i];
         for (int o = ks >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         acc[r][i] = v;
       }
-      if (blk < nblk && ksl == 0) {
-        const int code = sBlk[blk];
+      if (blk_i < nblk && ksl == 0) {
+        const int code = sBlk[blk_i];
         const int bi = code >> 8, bj = code & 255;
 #pragma unroll
         for (int i = 0; i < BS; ++i) {
           const int jr = bi * BS + i;
           if (jr >= L) continue;  // Y pseudo-row or padding
-          const int kr = sList[jr];
 #pragma unroll
           for (int c = 0; c < BS; ++c) {
             const int jc = bj * BS + c;
-            const double v = (double)acc[r][i * BS + c];
+            const float v = acc[r][i * BS + c];
             if (jc < L) {
-              const int kc = sList[jc];
-              atomicAdd(p.G + gbase + (size_t)kr * p.K + kc, v);
-              if (bi != bj) atomicAdd(p.G + gbase + (size_t)kc * p.K + kr, v);
+              pblock[(size_t)jr * p.out.ld + jc] = v;
+              if (bi != bj) pblock[(size_t)jc * p.out.ld + jr] = v;
             } else if (jc == L) {
-              atomicAdd(p.bvec + (size_t)t * p.K + kr, v);
+              pblock[(size_t)jr * p.out.ld + p.out.capL] = v;
             }
           }
         }
@@ -275,12 +285,47 @@ __global__ void __launch_bounds__(kMuThreads) mu_stats_kernel(const __grid_const
   }
 }
 
-__global__ void mu_zero_kernel(double* __restrict__ G, double* __restrict__ bvec, const int* __restrict__ frame_ids,
-                               int K) {
-  const int t = frame_ids[blockIdx.x];
-  double* g = G + (size_t)t * K * K;
-  for (size_t i = threadIdx.x; i < (size_t)K * K; i += blockDim.x) g[i] = 0.0;
-  for (int i = threadIdx.x; i < K; i += blockDim.x) bvec[(size_t)t * K + i] = 0.0;
+// Second stage of the trace statistics, one warp per (frame of the chunk, neuron k) = one row of G_t: the warp
+// walks the tiles in ascending order, finds the ones that list k (slot_of), and adds that tile's partial row to
+// its row accumulators in shared memory (fp64), then writes the whole row G_t[k][:] and b_t[k] once.  A row has
+// one owner and tiles are visited in a fixed order: bitwise reproducible, no atomics, and exactly symmetric --
+// G_t[k][l] and G_t[l][k] both read the element (min slot, max slot) of every block (the tensor-core blocks are
+// not bitwise symmetric: the two cross terms of the 3xTF32 split arrive in swapped order).
+__global__ void stats_reduce_kernel(StatsPartials sp, const int* __restrict__ frame_ids, int nt, int K,
+                                    double* __restrict__ G, double* __restrict__ bvec) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int k = blockIdx.x * wpb + warp, b = blockIdx.y;
+  if (k >= K) return;
+  double* row = reinterpret_cast<double*>(smem_raw) + (size_t)warp * K;
+  for (int l = lane; l < K; l += 32) row[l] = 0.0;
+  double bsum = 0.0;
+  __syncwarp();
+  const unsigned short* slots = sp.slot_of + ((size_t)b * K + k) * nt;
+  for (int tile0 = 0; tile0 < nt; tile0 += 32) {
+    const int tl = tile0 + lane;
+    const unsigned s = tl < nt ? slots[tl] : 0xffffu;
+    unsigned mask = __ballot_sync(0xffffffffu, s != 0xffffu);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int j = (int)__shfl_sync(0xffffffffu, s, src);
+      const size_t tf = (size_t)b * nt + tile0 + src;
+      const int L = sp.count[tf];
+      const float* blk = sp.vals + tf * (size_t)sp.capL * sp.ld;
+      const unsigned short* ids = sp.ids + tf * sp.capL;
+      for (int i = lane; i < L; i += 32) {
+        const float v = i >= j ? blk[(size_t)j * sp.ld + i] : blk[(size_t)i * sp.ld + j];
+        row[ids[i]] += (double)v;
+      }
+      if (lane == 0) bsum += (double)blk[(size_t)j * sp.ld + sp.capL];
+      __syncwarp();
+    }
+  }
+  const int t = frame_ids[b];
+  double* g = G + ((size_t)t * K + k) * K;
+  for (int l = lane; l < K; l += 32) g[l] = row[l];
+  if (lane == 0) bvec[(size_t)t * K + k] = bsum;
 }
 
 __global__ void mu_load_kernel(const float* __restrict__ C, double* __restrict__ Cd, int K, int T) {
@@ -471,31 +516,40 @@ __global__ void mu_boundary_kernel(const double* __restrict__ Cd, int T, int K, 
 
 // Nearest-neighbour registration (ExponentialFP.image_iwarp, Demix/dNMF.py:81-83,95-103): the
 // reference scatters frame values at the deformed points f(p) = ((u+1)/2)*s (note: s, not s-1) and
-// reads the nearest scattered point at every integer voxel.  Here every scattered point votes for
-// the integer voxels in its 3x3x3 neighbourhood with a packed (distance, source index) key and an
-// atomicMin; voxels that receive no vote fall back to an exact brute-force search.
-__global__ void iwarp_vote_kernel(Geom g, const int* __restrict__ frame_ids, int B, const float* __restrict__ beta,
-                                  unsigned long long* __restrict__ keys) {
-  const size_t N = (size_t)g.X * g.Y * g.Z;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= N * B) return;
-  const int b = (int)(idx / N);
-  const size_t v = idx - (size_t)b * N;
-  const int z = (int)(v % g.Z), y = (int)((v / g.Z) % g.Y), x = (int)(v / ((size_t)g.Z * g.Y));
-  const int t = frame_ids[b];
+// reads the nearest scattered point at every integer voxel (scipy NearestNDInterpolator: exact nearest
+// neighbour on float64 coordinates).  Here every scattered point votes for the integer voxels within
+// 2 of it on every axis: pass 0 keeps the smallest squared distance (fp64, compared as its bit pattern),
+// pass 1 the lowest source index among the points at exactly that distance.  A point that did not vote for
+// a voxel is at least 2 away from it on some axis, so a winning distance below 4 is the true nearest
+// neighbour; voxels without a vote or with a winner at distance >= 4 take an exact brute-force search
+// (ties: lowest source index, like the votes).
+__device__ __forceinline__ void iwarp_point(const Geom& g, const float* __restrict__ beta, int t, int x, int y, int z,
+                                            float (&f)[3]) {
   const float xf = (float)x, yf = (float)y, zf = (float)z;
   const float phi[kBasis] = {1.f, xf, yf, zf, xf * xf, yf * yf, zf * zf, xf * yf, xf * zf, yf * zf};
   const int sz[3] = {g.X, g.Y, g.Z};
-  float f[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     float q = 0.f;
 #pragma unroll
     for (int a = 0; a < kBasis; ++a) q = __fadd_rn(q, __fmul_rn(phi[a], beta[((size_t)a * 3 + d) * g.T + t]));
     const float sm1 = (float)(sz[d] - 1);
-    float u = sm1 == 0.f ? 0.f : __fsub_rn(__fdiv_rn(__fmul_rn(2.f, q), sm1), 1.f);
+    const float u = sm1 == 0.f ? 0.f : __fsub_rn(__fdiv_rn(__fmul_rn(2.f, q), sm1), 1.f);
     f[d] = __fmul_rn(__fmul_rn(__fadd_rn(u, 1.f), 0.5f), (float)sz[d]);
   }
+}
+
+template <int PASS>
+__global__ void iwarp_vote_kernel(Geom g, const int* __restrict__ frame_ids, int B, const float* __restrict__ beta,
+                                  unsigned long long* __restrict__ best, unsigned* __restrict__ winner) {
+  const size_t N = (size_t)g.X * g.Y * g.Z;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * B) return;
+  const int b = (int)(idx / N);
+  const size_t v = idx - (size_t)b * N;
+  const int z = (int)(v % g.Z), y = (int)((v / g.Z) % g.Y), x = (int)(v / ((size_t)g.Z * g.Y));
+  float f[3];
+  iwarp_point(g, beta, frame_ids[b], x, y, z, f);
   const int cx = (int)floorf(fminf(fmaxf(f[0], -2.f), (float)g.X + 1.f));
   const int cy = (int)floorf(fminf(fmaxf(f[1], -2.f), (float)g.Y + 1.f));
   const int cz = (int)floorf(fminf(fmaxf(f[2], -2.f), (float)g.Z + 1.f));
@@ -505,15 +559,17 @@ __global__ void iwarp_vote_kernel(Geom g, const int* __restrict__ frame_ids, int
         const int px = cx + dx, py = cy + dy, pz = cz + dz;
         if (px < 0 || py < 0 || pz < 0 || px >= g.X || py >= g.Y || pz >= g.Z) continue;
         const double ddx = (double)f[0] - px, ddy = (double)f[1] - py, ddz = (double)f[2] - pz;
-        const float dist = (float)(ddx * ddx + ddy * ddy + ddz * ddz);
-        const unsigned long long key = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)v;
-        atomicMin(keys + (size_t)b * N + ((size_t)px * g.Y + py) * g.Z + pz, key);
+        const unsigned long long key = (unsigned long long)__double_as_longlong(ddx * ddx + ddy * ddy + ddz * ddz);
+        const size_t o = (size_t)b * N + ((size_t)px * g.Y + py) * g.Z + pz;
+        if (PASS == 0) atomicMin(best + o, key);
+        else if (best[o] == key) atomicMin(winner + o, (unsigned)v);
       }
 }
 
 __global__ void iwarp_gather_kernel(Geom g, const float* __restrict__ frames, int frames_are_batch,
                                     const int* __restrict__ frame_ids, int B, const float* __restrict__ beta,
-                                    const unsigned long long* __restrict__ keys, float* __restrict__ out) {
+                                    const unsigned long long* __restrict__ best, const unsigned* __restrict__ winner,
+                                    float* __restrict__ out) {
   const size_t N = (size_t)g.X * g.Y * g.Z;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * B) return;
@@ -521,34 +577,23 @@ __global__ void iwarp_gather_kernel(Geom g, const float* __restrict__ frames, in
   const size_t v = idx - (size_t)b * N;
   const int t = frame_ids[b];
   const float* frame = frames + (size_t)(frames_are_batch ? b : t) * N;
-  unsigned long long key = keys[idx];
-  if (key != ~0ull) {
-    out[idx] = frame[(unsigned)(key & 0xffffffffu)];
+  const unsigned long long key = best[idx];
+  if (key != ~0ull && __longlong_as_double((long long)key) < 4.0) {
+    out[idx] = frame[winner[idx]];
     return;
   }
   // no scattered point within reach: exact nearest by brute force (rare; large deformations only)
   const int z = (int)(v % g.Z), y = (int)((v / g.Z) % g.Y), x = (int)(v / ((size_t)g.Z * g.Y));
-  const int sz[3] = {g.X, g.Y, g.Z};
-  double best = 1e300;
+  double bestd = 1e300;
   size_t besti = 0;
   for (size_t s = 0; s < N; ++s) {
     const int sz_ = (int)(s % g.Z), sy = (int)((s / g.Z) % g.Y), sx = (int)(s / ((size_t)g.Z * g.Y));
-    const float xf = (float)sx, yf = (float)sy, zf = (float)sz_;
-    const float phi[kBasis] = {1.f, xf, yf, zf, xf * xf, yf * yf, zf * zf, xf * yf, xf * zf, yf * zf};
-    double d2 = 0.0;
-    const int pt[3] = {x, y, z};
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      float q = 0.f;
-#pragma unroll
-      for (int a = 0; a < kBasis; ++a) q = __fadd_rn(q, __fmul_rn(phi[a], beta[((size_t)a * 3 + d) * g.T + t]));
-      const float sm1 = (float)(sz[d] - 1);
-      float u = sm1 == 0.f ? 0.f : __fsub_rn(__fdiv_rn(__fmul_rn(2.f, q), sm1), 1.f);
-      const double fd = (double)__fmul_rn(__fmul_rn(__fadd_rn(u, 1.f), 0.5f), (float)sz[d]) - pt[d];
-      d2 += fd * fd;
-    }
-    if (d2 < best) {
-      best = d2;
+    float f[3];
+    iwarp_point(g, beta, t, sx, sy, sz_, f);
+    const double ddx = (double)f[0] - x, ddy = (double)f[1] - y, ddz = (double)f[2] - z;
+    const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+    if (d2 < bestd) {
+      bestd = d2;
       besti = s;
     }
   }
@@ -580,6 +625,202 @@ static int launch_mu(const MuParams& p, int grid, size_t smem, cudaStream_t st) 
   return 0;
 }
 
+// ---- trace statistics: first stage (one of three kernels) + row-owner second stage ------------------------
+// Scratch for the partial blocks of `frames` frames with nt tiles each and blocks of capL rows.
+static size_t stats_bytes_per_frame(int nt, int capL, int K) {
+  const size_t ld = (size_t)capL + 4;
+  return (size_t)nt * ((size_t)capL * ld * 4 + (size_t)capL * 2 + 4) + (size_t)K * nt * 2;
+}
+
+static int stats_scratch(dnmf_ctx* c, int frames, int nt, int capL, StatsPartials& sp, cudaStream_t st) {
+  sp.capL = capL;
+  sp.ld = capL + 4;
+  if (ensure(&c->d_pb_vals, &c->pb_vals_cap, (size_t)frames * nt * capL * sp.ld)) return 1;
+  if (ensure(&c->d_pb_ids, &c->pb_ids_cap, (size_t)frames * nt * capL)) return 1;
+  if (ensure(&c->d_pb_count, &c->pb_count_cap, (size_t)frames * nt)) return 1;
+  if (ensure(&c->d_pb_slot, &c->pb_slot_cap, (size_t)frames * c->K * nt)) return 1;
+  sp.vals = c->d_pb_vals;
+  sp.ids = c->d_pb_ids;
+  sp.count = c->d_pb_count;
+  sp.slot_of = c->d_pb_slot;
+  CU(cudaMemsetAsync(sp.slot_of, 0xff, (size_t)frames * c->K * nt * sizeof(unsigned short), st));
+  return 0;
+}
+
+static int stats_reduce(dnmf_ctx* c, const StatsPartials& sp, const int32_t* ids_dev, int frames, int nt,
+                        cudaStream_t st) {
+  const size_t row_bytes = (size_t)c->K * sizeof(double);
+  int wpb = (int)std::min<size_t>(8, ((size_t)c->max_smem_optin - 1024) / row_bytes);
+  if (wpb < 1) return fail("dnmf_mu_stats: K too large for the row accumulators of the second stage");
+  const size_t smem = (size_t)wpb * row_bytes;
+  static size_t configured[64] = {0};
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  if (smem > 48 * 1024 && (dev < 0 || dev >= 64 || smem > configured[dev])) {
+    CU(cudaFuncSetAttribute(stats_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev >= 0 && dev < 64) configured[dev] = smem;
+  }
+  for (int b0 = 0; b0 < frames; b0 += 65535) {
+    const int nb = std::min(65535, frames - b0);
+    StatsPartials q = sp;
+    q.vals += (size_t)b0 * nt * sp.capL * sp.ld;
+    q.ids += (size_t)b0 * nt * sp.capL;
+    q.count += (size_t)b0 * nt;
+    q.slot_of += (size_t)b0 * c->K * nt;
+    stats_reduce_kernel<<<dim3((unsigned)((c->K + wpb - 1) / wpb), (unsigned)nb), 32 * wpb, smem, st>>>(
+        q, ids_dev + b0, nt, c->K, c->d_G, c->d_b);
+    CU(cudaGetLastError());
+  }
+  return 0;
+}
+
+// One pass over the batch with one first-stage kernel.  which: 0 = fused tiles (fit_tile_kernel<MODE 3>),
+// 1 = tensor-core panel, 2 = SIMT panel.  *over receives the kernel's overflow value (0 = the pass is complete;
+// otherwise nothing of this pass may be used and the caller moves on to the next kernel).
+static int stats_pass(dnmf_ctx* c, int which, const float* frames_dev, const int32_t* ids_dev, int B,
+                      const float* beta_dev, cudaStream_t st, int* over) {
+  *over = 0;
+  const size_t budget = (size_t)3 << 29;  // 1.5 GB of partial blocks in flight
+  int nt, capL;
+  size_t smem = 0;
+  MuParams mp;
+  GramTcParams tp;
+  int mu_bs = 4, mu_need = 1;
+  int fused_cap = c->cap;
+  if (which == 0) {
+    // Every slot must be staged here (there is no global-table tail as in the fit): capacity for the longest
+    // identity-deformation list + 2 when that fits the shared-memory budget of ~2 CTAs per SM.
+    smem = c->fit_smem;
+    int cap = (std::min(c->K + 1, std::max(c->lmax_identity, c->mu_fused_need) + 2) + 1) & ~1;
+    if ((cap & 3) == 0) cap += 2;
+    if (cap > c->cap) {
+      const int wsum = c->wmax[0] + c->wmax[1] + c->wmax[2];
+      const size_t need = fit_smem_layout(c->nwx * c->nwy, c->tx, c->ty, c->tz, cap, wsum, c->K, c->wmax[0],
+                                          c->cand_cap, c->y_pitch).bytes;
+      if (need <= std::min<size_t>((size_t)c->max_smem_optin, (size_t)113 * 1024)) {
+        fused_cap = cap;
+        smem = need;
+      } else if (c->mu_fused_need > 0) {
+        c->mu_fused_off = 1;  // known to overflow and no room to grow
+        *over = c->mu_fused_need;
+        return 0;
+      }
+    }
+    c->mu_fused_cap_used = fused_cap;
+    nt = c->ntx * c->nty * c->ntz;
+    capL = (fused_cap + 3) & ~3;
+  } else if (which == 1) {
+    tp.beta = beta_dev;
+    tp.tab0 = c->d_tab[0];
+    tp.tab1 = c->d_tab[1];
+    tp.tab2 = c->d_tab[2];
+    tp.rng = c->d_rng;
+    tp.overflow = c->d_tmp_max;
+    tp.frames_are_batch = frames_dev ? 1 : 0;
+    tp.X = c->X;
+    tp.Y = c->Y;
+    tp.Z = c->Z;
+    tp.K = c->K;
+    tp.T = c->T;
+    tp.ntx = (c->X + kGramTX - 1) / kGramTX;
+    tp.nty = (c->Y + kGramTY - 1) / kGramTY;
+    if (gram_tc_smem_bytes(c->X, c->Y, c->Z) > (size_t)c->max_smem_optin) {
+      *over = 1 << 30;  // volume too deep for whole-depth tiles in shared memory
+      return 0;
+    }
+    nt = tp.ntx * tp.nty;
+    capL = kGramRows;
+  } else {
+    dnmf_ctx g = *c;  // shallow copy used only for geometry helpers
+    g.tx = kMuTX;
+    g.ty = kMuTY;
+    g.ntx = (c->X + kMuTX - 1) / kMuTX;
+    g.nty = (c->Y + kMuTY - 1) / kMuTY;
+    nt = g.ntx * g.nty * g.ntz;
+    if (c->mu_capM == 0) {
+      if (ensure(&c->d_tmp_counts, &c->tmp_counts_cap, (size_t)nt)) return 1;
+      if (c->d_tmp_offsets) cudaFree(c->d_tmp_offsets);
+      c->d_tmp_offsets = nullptr;
+      CU(cudaMalloc((void**)&c->d_tmp_offsets, ((size_t)nt + 1) * sizeof(long long)));
+      if (run_bin_count(&g, c->d_identity_beta, 1, c->d_ids_zero, 1, c->d_tmp_counts, nullptr, st)) return 1;
+      scan_counts_kernel<<<1, 1024, 0, st>>>(c->d_tmp_counts, nt, c->d_tmp_offsets, c->d_tmp_max);
+      CU(cudaGetLastError());
+      int lmax = 0;
+      CU(cudaMemcpyAsync(&lmax, c->d_tmp_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      const int capM = std::min(c->K, lmax + lmax / 2 + 8) + 1;
+      c->mu_capM = (capM + 7) & ~7;
+    }
+    const int capM = c->mu_capM;
+    mu_bs = (capM >= 32 && c->mu_block4 == 0) ? 8 : 4;  // 8x8 register blocks from 32 rows up, 4x4 below
+    smem = mu_smem_bytes(capM, c->tz, c->K, mu_bs);
+    if (smem > (size_t)c->max_smem_optin)
+      return fail("dnmf_mu_stats: neuron lists too long for the shared-memory A panel (K_eff too large)");
+    mp.beta = beta_dev;
+    mp.tab0 = c->d_tab[0];
+    mp.tab1 = c->d_tab[1];
+    mp.tab2 = c->d_tab[2];
+    mp.rng = c->d_rng;
+    mp.overflow = c->d_tmp_max;
+    mp.frames_are_batch = frames_dev ? 1 : 0;
+    mp.X = c->X;
+    mp.Y = c->Y;
+    mp.Z = c->Z;
+    mp.K = c->K;
+    mp.T = c->T;
+    mp.tz = c->tz;
+    mp.ntx = g.ntx;
+    mp.nty = g.nty;
+    mp.ntz = g.ntz;
+    mp.capM = capM;
+    mp.full_depth = (c->tz == c->Z) ? 1 : 0;
+    const int mb = (capM + mu_bs - 1) / mu_bs;
+    mu_need = (mb * (mb + 1) / 2 + kMuThreads - 1) / kMuThreads;
+    capL = (capM + 3) & ~3;
+  }
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, budget / stats_bytes_per_frame(nt, capL, c->K)));
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = std::min(chunk, B - b0);
+    StatsPartials sp;
+    if (stats_scratch(c, nb, nt, capL, sp, st)) return 1;
+    CU(cudaMemsetAsync(c->d_tmp_max, 0, sizeof(int), st));
+    const float* fr = frames_dev ? frames_dev + (size_t)b0 * c->N : nullptr;
+    if (which == 0) {
+      FitParams q;
+      if (fill_fit_params(c, q, fr, ids_dev + b0, nb, beta_dev, nullptr)) return 1;
+      q.mu_overflow = c->d_tmp_max;
+      q.cap = fused_cap;
+      q.stats = sp;
+      if (dispatch_stats(c, q, nb, smem, st)) return 1;
+    } else if (which == 1) {
+      GramTcParams q = tp;
+      q.frames = frames_dev ? fr : c->d_video;
+      q.frame_ids = ids_dev + b0;
+      q.out = sp;
+      q.b_base = 0;
+      if (launch_gram_tc(q, nb, st)) return 1;
+    } else {
+      MuParams q = mp;
+      q.frames = frames_dev ? fr : c->d_video;
+      q.frame_ids = ids_dev + b0;
+      q.out = sp;
+      q.b_base = 0;
+      int rc;
+      if (mu_bs == 8) rc = mu_need <= 1 ? launch_mu<1, 8>(q, nb * nt, smem, st) : launch_mu<2, 8>(q, nb * nt, smem, st);
+      else if (mu_need <= 1) rc = launch_mu<1, 4>(q, nb * nt, smem, st);
+      else if (mu_need <= 2) rc = launch_mu<2, 4>(q, nb * nt, smem, st);
+      else rc = launch_mu<4, 4>(q, nb * nt, smem, st);
+      if (rc) return rc;
+    }
+    c->counters[6] += 1;
+    CU(cudaMemcpyAsync(over, c->d_tmp_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (*over != 0) return 0;
+    if (stats_reduce(c, sp, ids_dev + b0, nb, nt, st)) return 1;
+  }
+  return 0;
+}
+
 extern "C" int dnmf_mu_stats(dnmf_ctx* c, const float* frames_dev, const int32_t* frame_ids_dev, int B,
                              const float* beta_dev, void* stream) {
   if (!c || !frame_ids_dev || !beta_dev) return fail("dnmf_mu_stats: NULL argument");
@@ -587,130 +828,48 @@ extern "C" int dnmf_mu_stats(dnmf_ctx* c, const float* frames_dev, const int32_t
   if (!frames_dev && !c->d_video) return fail("dnmf_mu_stats: no resident video and frames_dev is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(c->device));
+  if (check_sticky(c, "dnmf_mu_stats") || sanitize_ids(c, frame_ids_dev, B, st, &frame_ids_dev)) return 1;
+  {  // statistics are stored per frame id: an id listed twice has no defined result; out of range is an error
+    int flags = 0;
+    CU(cudaMemcpyAsync(&flags, c->d_id_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (flags & 2) {
+      *(volatile int*)c->h_sticky = 0;
+      return fail("dnmf_mu_stats: frame id outside [0, T)");
+    }
+    if (flags & 1) return fail("dnmf_mu_stats: a frame id occurs twice in the batch");
+  }
   if (mu_alloc(c)) return 1;
   c->gc_valid = false;
-  // Fast path: the fused kernel's tiles, lists and staged slices (fit_tile_kernel<MODE=3>).  A tile whose list
-  // is longer than the staged capacity under the current deformation sets the overflow flag and everything is
-  // redone by the panel kernel below.
-  while (fused_stats_available(c) && c->mu_force_panel == 0 && c->mu_fused_off == 0) {  // at most one pass
-    FitParams p;
-    if (fill_fit_params(c, p, frames_dev, frame_ids_dev, B, beta_dev, nullptr)) return 1;
-    p.muG = c->d_G;
-    p.mub = c->d_b;
-    p.mu_overflow = c->d_tmp_max;
-    // Every slot must be staged here (there is no global-table tail as in the fit): capacity for the longest
-    // identity-deformation list + 2 when that fits the shared-memory budget of ~2 CTAs per SM.
-    size_t smem = c->fit_smem;
-    {
-      int cap = (std::min(c->K + 1, std::max(c->lmax_identity, c->mu_fused_need) + 2) + 1) & ~1;
-      if ((cap & 3) == 0) cap += 2;
-      if (cap > c->cap) {
-        const int wsum = c->wmax[0] + c->wmax[1] + c->wmax[2];
-        const size_t need = fit_smem_layout(c->nwx * c->nwy, c->tx, c->ty, c->tz, cap, wsum, c->K, c->wmax[0],
-                                            c->cand_cap, c->y_pitch).bytes;
-        if (need <= std::min<size_t>((size_t)c->max_smem_optin, (size_t)113 * 1024)) {
-          p.cap = cap;
-          smem = need;
-        } else if (c->mu_fused_need > 0) {
-          c->mu_fused_off = 1;  // known to overflow and no room to grow
-          break;
-        }
-      }
-    }
-    CU(cudaMemsetAsync(c->d_tmp_max, 0, sizeof(int), st));
-    mu_zero_kernel<<<B, 256, 0, st>>>(c->d_G, c->d_b, frame_ids_dev, c->K);
-    CU(cudaGetLastError());
-    if (dispatch_stats(c, p, B, smem, st)) return 1;
-    int over = 0;
-    CU(cudaMemcpyAsync(&over, c->d_tmp_max, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    c->counters[6] += 1;
+  c->mu_last_path = 0;
+  c->mu_last_tc = 0;
+  int over = 0;
+  // 1. the fused kernel's tiles, lists and staged slices (short lists).  A tile whose list is longer than the
+  //    staged capacity under the current deformation raises the overflow flag: remembered until the next
+  //    dnmf_set_footprints (capacity hint, or "does not fit").
+  if (fused_stats_available(c) && c->mu_force_panel == 0 && c->mu_prefer_tc == 0 && c->mu_fused_off == 0) {
+    if (stats_pass(c, 0, frames_dev, frame_ids_dev, B, beta_dev, st, &over)) return 1;
     if (over == 0) {
       c->mu_last_path = 1;
       return 0;
     }
-    // Remembered until the next dnmf_set_footprints.  A list longer than the capacity: stage that many slots
-    // next time.  Otherwise a window wider than the staged slices raised the flag: not a matter of capacity.
-    if (over > p.cap) c->mu_fused_need = over;
+    // A list longer than the capacity: stage that many slots next time.  Otherwise a window wider than the
+    // staged slices raised the flag: not a matter of capacity.
+    if (over > c->mu_fused_cap_used) c->mu_fused_need = over;
     else c->mu_fused_off = 1;
-    break;
   }
-  c->mu_last_path = 0;
-  // geometry of the statistics kernel (16 x 8 x tz tiles) and its longest identity-deformation list
-  dnmf_ctx g = *c;  // shallow copy used only for geometry helpers
-  g.tx = kMuTX;
-  g.ty = kMuTY;
-  g.ntx = (c->X + kMuTX - 1) / kMuTX;
-  g.nty = (c->Y + kMuTY - 1) / kMuTY;
-  const int nt = g.ntx * g.nty * g.ntz;
-  if (c->mu_capM == 0) {
-    if (ensure(&c->d_tmp_counts, &c->tmp_counts_cap, (size_t)nt)) return 1;
-    if (c->d_tmp_offsets) cudaFree(c->d_tmp_offsets);
-    c->d_tmp_offsets = nullptr;
-    CU(cudaMalloc((void**)&c->d_tmp_offsets, ((size_t)nt + 1) * sizeof(long long)));
-    int zero = 0;
-    if (ensure(&c->d_ids, &c->ids_cap, (size_t)1)) return 1;
-    CU(cudaMemcpyAsync(c->d_ids, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
-    g.d_tmp_counts = c->d_tmp_counts;
-    if (run_bin_count(&g, c->d_identity_beta, 1, c->d_ids, 1, c->d_tmp_counts, nullptr, st)) return 1;
-    scan_counts_kernel<<<1, 1024, 0, st>>>(c->d_tmp_counts, nt, c->d_tmp_offsets, c->d_tmp_max);
-    CU(cudaGetLastError());
-    int lmax = 0;
-    CU(cudaMemcpyAsync(&lmax, c->d_tmp_max, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    int capM = std::min(c->K, lmax + lmax / 2 + 8) + 1;
-    c->mu_capM = (capM + 7) & ~7;
+  // 2. tensor-core panel kernel: lists of up to 127 neurons per 8 x 8 x Z tile
+  if (c->mu_force_panel == 0 || c->mu_prefer_tc != 0) {
+    if (stats_pass(c, 1, frames_dev, frame_ids_dev, B, beta_dev, st, &over)) return 1;
+    if (over == 0) {
+      c->mu_last_tc = 1;
+      return 0;
+    }
   }
+  // 3. SIMT panel kernel: any list length the shared-memory panel holds; grows once when a list outgrew it
   for (int attempt = 0; attempt < 2; ++attempt) {
-    const int capM = c->mu_capM;
-    // 8x8 register blocks from 32 rows up (enough blocks to occupy the CTA), 4x4 below
-    const int bs = (capM >= 32 && c->mu_block4 == 0) ? 8 : 4;
-    const size_t smem = mu_smem_bytes(capM, c->tz, c->K, bs);
-    if (smem > (size_t)c->max_smem_optin)
-      return fail("dnmf_mu_stats: neuron lists too long for the shared-memory A panel (K_eff too large)");
-    MuParams p;
-    p.frames = frames_dev ? frames_dev : c->d_video;
-    p.frames_are_batch = frames_dev ? 1 : 0;
-    p.frame_ids = frame_ids_dev;
-    p.beta = beta_dev;
-    p.tab0 = c->d_tab[0];
-    p.tab1 = c->d_tab[1];
-    p.tab2 = c->d_tab[2];
-    p.rng = c->d_rng;
-    p.G = c->d_G;
-    p.bvec = c->d_b;
-    p.overflow = c->d_tmp_max;
-    p.X = c->X;
-    p.Y = c->Y;
-    p.Z = c->Z;
-    p.K = c->K;
-    p.T = c->T;
-    p.tz = c->tz;
-    p.ntx = g.ntx;
-    p.nty = g.nty;
-    p.ntz = g.ntz;
-    p.capM = capM;
-    p.full_depth = (c->tz == c->Z) ? 1 : 0;
-    CU(cudaMemsetAsync(c->d_tmp_max, 0, sizeof(int), st));
-    mu_zero_kernel<<<B, 256, 0, st>>>(c->d_G, c->d_b, frame_ids_dev, c->K);
-    CU(cudaGetLastError());
-    const int mb = (capM + bs - 1) / bs;
-    const int nblk = mb * (mb + 1) / 2;
-    const int need = (nblk + kMuThreads - 1) / kMuThreads;
-    int rc;
-    if (bs == 8) {
-      if (need <= 1) rc = launch_mu<1, 8>(p, B * nt, smem, st);
-      else rc = launch_mu<2, 8>(p, B * nt, smem, st);
-    } else if (need <= 1) rc = launch_mu<1, 4>(p, B * nt, smem, st);
-    else if (need <= 2) rc = launch_mu<2, 4>(p, B * nt, smem, st);
-    else rc = launch_mu<4, 4>(p, B * nt, smem, st);
-    if (rc) return rc;
-    int over = 0;
-    CU(cudaMemcpyAsync(&over, c->d_tmp_max, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    c->counters[6] += 1;
+    if (stats_pass(c, 2, frames_dev, frame_ids_dev, B, beta_dev, st, &over)) return 1;
     if (over == 0) return 0;
-    // a tile's list outgrew the panel under the current deformation: grow once and redo
     c->mu_capM = (std::min(c->K + 1, over + over / 4 + 4) + 7) & ~7;
   }
   return fail("dnmf_mu_stats: neuron list longer than the A panel after regrowth");
@@ -722,8 +881,9 @@ extern "C" int dnmf_mu_path(dnmf_ctx* c, int force_panel, int* last_path_out) {
     c->mu_force_panel = (force_panel & 1) != 0;
     c->mu_dense_sweeps = (force_panel & 2) != 0;
     c->mu_sweep_per_launch = (force_panel & 4) != 0;
+    c->mu_prefer_tc = (force_panel & 8) != 0;
   }
-  if (last_path_out) *last_path_out = c->mu_last_path | (c->mu_last_sparse << 1);
+  if (last_path_out) *last_path_out = c->mu_last_path | (c->mu_last_sparse << 1) | (c->mu_last_tc << 2);
   return 0;
 }
 
@@ -883,14 +1043,20 @@ extern "C" int dnmf_iwarp(dnmf_ctx* c, const float* frames_dev, const int32_t* f
   if (!frames_dev && !c->d_video) return fail("dnmf_iwarp: no resident video and frames_dev is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(c->device));
+  if (check_sticky(c, "dnmf_iwarp") || sanitize_ids(c, frame_ids_dev, B, st, &frame_ids_dev)) return 1;
   const size_t total = c->N * (size_t)B;
-  if (ensure(&c->d_keys, &c->keys_cap, total)) return 1;
-  CU(cudaMemsetAsync(c->d_keys, 0xff, total * sizeof(unsigned long long), st));
+  if (c->N > 0xffffffffull) return fail("dnmf_iwarp: more than 2^32 voxels per frame");
+  if (ensure(&c->d_keys, &c->keys_cap, total + (total + 1) / 2)) return 1;  // fp64 distances + 32-bit winners
+  unsigned* winner = reinterpret_cast<unsigned*>(c->d_keys + total);
+  CU(cudaMemsetAsync(c->d_keys, 0xff, (total + (total + 1) / 2) * sizeof(unsigned long long), st));
   Geom g = geom_of(c);
-  iwarp_vote_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, frame_ids_dev, B, beta_dev, c->d_keys);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  iwarp_vote_kernel<0><<<blocks, 256, 0, st>>>(g, frame_ids_dev, B, beta_dev, c->d_keys, winner);
   CU(cudaGetLastError());
-  iwarp_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-      g, frames_dev ? frames_dev : c->d_video, frames_dev ? 1 : 0, frame_ids_dev, B, beta_dev, c->d_keys, out_dev);
+  iwarp_vote_kernel<1><<<blocks, 256, 0, st>>>(g, frame_ids_dev, B, beta_dev, c->d_keys, winner);
+  CU(cudaGetLastError());
+  iwarp_gather_kernel<<<blocks, 256, 0, st>>>(g, frames_dev ? frames_dev : c->d_video, frames_dev ? 1 : 0,
+                                             frame_ids_dev, B, beta_dev, c->d_keys, winner, out_dev);
   CU(cudaGetLastError());
   return 0;
 }

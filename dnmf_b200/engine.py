@@ -22,11 +22,13 @@ def _stream_ptr(device) -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def _check_dev(t: torch.Tensor, dtype, name: str, device=None):
-    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+def _check_dev(t: torch.Tensor, dtype, name: str, device=None, shape=None):
+    if not torch.is_tensor(t) or not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
         raise _lib.DnmfError("%s must be a contiguous CUDA %s tensor" % (name, dtype))
     if device is not None and t.device != device:
         raise _lib.DnmfError("%s is on %s, engine is on %s" % (name, t.device, device))
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise _lib.DnmfError("%s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
 
 
 class Engine:
@@ -62,6 +64,36 @@ class Engine:
     @property
     def stream(self):
         return _stream_ptr(self.device)
+
+    def _ids32(self, frame_ids, allow_duplicates: bool = True) -> torch.Tensor:
+        """int32 CUDA ids of this engine.  Ids that are still on the host are validated here (range, duplicates)
+        so that the error is immediate; ids already on the device are checked by the library's own kernel."""
+        t = torch.as_tensor(frame_ids)
+        if not t.is_cuda:
+            flat = t.reshape(-1).to(torch.int64)
+            if flat.numel() == 0:
+                raise _lib.DnmfError("empty frame id batch")
+            lo, hi = int(flat.min()), int(flat.max())
+            if lo < 0 or hi >= self.T:
+                raise _lib.DnmfError("frame id %d outside [0, %d) (ids index this engine's slab of T frames)"
+                                     % (lo if lo < 0 else hi, self.T))
+            if not allow_duplicates and int(torch.unique(flat).numel()) != int(flat.numel()):
+                raise _lib.DnmfError("a frame id occurs twice in the batch")
+        return t.reshape(-1).to(self.device, torch.int32).contiguous()
+
+    def _check_state(self, beta, m=None, v=None, C=None):
+        """Shape / dtype / device of the tensors whose raw pointers go to the library."""
+        _check_dev(beta, torch.float32, "beta", self.device, (10, 3, self.T))
+        if m is not None:
+            _check_dev(m, torch.float32, "exp_avg", self.device, (10, 3, self.T))
+        if v is not None:
+            _check_dev(v, torch.float32, "exp_avg_sq", self.device, (10, 3, self.T))
+        if C is not None:
+            _check_dev(C, torch.float32, "C", self.device, (self.K, self.T))
+
+    def check_status(self):
+        """Synchronises the stream and raises if an earlier asynchronous call found an error on the device."""
+        _lib.check(self.lib.dnmf_check_status(self._h, self.stream), "dnmf_check_status")
 
     # -- footprints / tiling ----------------------------------------------------------------------
     def set_footprints(self, pos, sigma, cutoff: float):
@@ -123,8 +155,8 @@ class Engine:
     # -- kernels ----------------------------------------------------------------------------------
     def bin_tiles(self, beta: torch.Tensor, frame_ids: torch.Tensor):
         """Stand-alone binning.  Returns (counts, offsets, ids, windows) as numpy arrays."""
-        _check_dev(beta, torch.float32, "beta")
-        ids32 = frame_ids.to(self.device, torch.int32).contiguous()
+        self._check_state(beta)
+        ids32 = self._ids32(frame_ids)
         B = int(ids32.numel())
         tl = self.tiling()
         nt = tl["ntx"] * tl["nty"] * tl["ntz"]
@@ -144,12 +176,11 @@ class Engine:
                   frames: Optional[torch.Tensor] = None, B_global: Optional[int] = None
                   ) -> Tuple[torch.Tensor, torch.Tensor]:
         """Returns (grad[10,3,T] float32 with only the batch columns non-zero, sse[B] float64)."""
-        _check_dev(beta, torch.float32, "beta")
-        _check_dev(C, torch.float32, "C")
-        ids32 = frame_ids.to(self.device, torch.int32).contiguous()
+        self._check_state(beta, C=C)
+        ids32 = self._ids32(frame_ids)
         B = int(ids32.numel())
         if frames is not None:
-            _check_dev(frames, torch.float32, "frames")
+            _check_dev(frames, torch.float32, "frames", self.device, (B, self.X, self.Y, self.Z))
         grad = torch.zeros(10, 3, self.T, dtype=torch.float32, device=self.device)
         sse = torch.zeros(B, dtype=torch.float64, device=self.device)
         _lib.check(self.lib.dnmf_loss_grad(self._h, _ptr(frames), _ptr(ids32), B, int(B_global or B), _ptr(beta),
@@ -167,7 +198,13 @@ class Engine:
                     frames: Optional[torch.Tensor] = None, B_global: Optional[int] = None,
                     loss_out: Optional[torch.Tensor] = None):
         """Device-resident step (frames=None reads the resident slab).  loss_out: float64 CUDA scalar."""
+        self._check_state(beta, m, v, C)
+        frame_ids32 = self._ids32(frame_ids32)
         B = int(frame_ids32.numel())
+        if frames is not None:
+            _check_dev(frames, torch.float32, "frames", self.device, (B, self.X, self.Y, self.Z))
+        if loss_out is not None:
+            _check_dev(loss_out, torch.float64, "loss_out", self.device)
         _lib.check(self.lib.dnmf_motion_step(self._h, _ptr(frames), _ptr(frame_ids32), B, int(B_global or B),
                                              _ptr(beta), _ptr(m), _ptr(v), _ptr(C), float(lr), float(betas[0]),
                                              float(betas[1]), float(eps), int(step), int(affine), _ptr(loss_out),
@@ -179,6 +216,12 @@ class Engine:
         the batches concatenated; offsets: nbatches+1 host ints; loss_out: float64 CUDA tensor [nbatches]."""
         off = np.ascontiguousarray(np.asarray(offsets, dtype=np.int32))
         nb = int(off.size) - 1
+        self._check_state(beta, m, v, C)
+        _check_dev(ids_dev, torch.int32, "ids_dev", self.device)
+        if nb < 0 or int(off[0]) < 0 or int(off[-1]) > int(ids_dev.numel()) or np.any(np.diff(off) < 1):
+            raise _lib.DnmfError("batch offsets must be increasing and stay inside the id array")
+        if loss_out is not None:
+            _check_dev(loss_out, torch.float64, "loss_out", self.device, (nb,))
         _lib.check(self.lib.dnmf_motion_epoch(self._h, _ptr(ids_dev), ctypes.c_void_p(off.ctypes.data), nb,
                                               int(global_batch_scale), _ptr(beta), _ptr(m), _ptr(v), _ptr(C),
                                               float(lr), float(betas[0]), float(betas[1]), float(eps),
@@ -195,7 +238,12 @@ class Engine:
     def motion_step_host(self, frames_host: torch.Tensor, ids_host: torch.Tensor, beta, m, v, C, lr, betas, eps,
                          step, affine=False, B_global: Optional[int] = None) -> float:
         """End-to-end step from HOST buffers (H2D copy + kernels + loss read-back)."""
+        self._check_state(beta, m, v, C)
         B = int(ids_host.numel())
+        if frames_host.is_cuda or frames_host.dtype != torch.float32 or not frames_host.is_contiguous() or \
+                tuple(frames_host.shape) != (B, self.X, self.Y, self.Z):
+            raise _lib.DnmfError("frames_host must be a contiguous float32 host tensor [B,X,Y,Z]")
+        ids_host = torch.as_tensor(ids_host).reshape(-1).to("cpu", torch.int32).contiguous()
         loss = ctypes.c_double(0.0)
         _lib.check(self.lib.dnmf_motion_step_host(self._h, _ptr(frames_host), _ptr(ids_host), B, int(B_global or B),
                                                   _ptr(beta), _ptr(m), _ptr(v), _ptr(C), float(lr), float(betas[0]),
@@ -204,9 +252,8 @@ class Engine:
         return loss.value
 
     def forward(self, frame_ids: torch.Tensor, beta, C, want_At=False, want_grid=False):
-        _check_dev(beta, torch.float32, "beta")
-        _check_dev(C, torch.float32, "C")
-        ids32 = frame_ids.to(self.device, torch.int32).contiguous()
+        self._check_state(beta, C=C)
+        ids32 = self._ids32(frame_ids)
         B = int(ids32.numel())
         AtC = torch.empty(B, self.X, self.Y, self.Z, dtype=torch.float32, device=self.device)
         At = torch.empty(B, self.K, self.X, self.Y, self.Z, dtype=torch.float32, device=self.device) if want_At else None
@@ -216,16 +263,18 @@ class Engine:
         return AtC, At, grid
 
     def mu_stats(self, frame_ids: torch.Tensor, beta, frames: Optional[torch.Tensor] = None):
-        ids32 = frame_ids.to(self.device, torch.int32).contiguous()
+        self._check_state(beta)
+        ids32 = self._ids32(frame_ids, allow_duplicates=False)
         if frames is not None:
-            _check_dev(frames, torch.float32, "frames")
+            _check_dev(frames, torch.float32, "frames", self.device, (int(ids32.numel()), self.X, self.Y, self.Z))
         _lib.check(self.lib.dnmf_mu_stats(self._h, _ptr(frames), _ptr(ids32), int(ids32.numel()), _ptr(beta),
                                           self.stream), "dnmf_mu_stats")
 
     def mu_path(self, flags: int = -1) -> int:
-        """Select (bit 0 = panel statistics kernel only, bit 1 = dense sweeps only, 0 = automatic) and/or query the
-        device paths of the trace update: returns bit 0 = the last `mu_stats` ran on the fused kernel's tiles,
-        bit 1 = the last `mu_begin` / `mu_sweeps` used the neighbour-compacted statistics."""
+        """Select (bit 0 = skip the fused tiles, bit 1 = dense sweeps only, bit 2 = one launch per sweep, bit 3 =
+        tensor-core panel kernel first, 0 = automatic) and/or query the device paths of the trace update: returns
+        bit 0 = the last `mu_stats` ran on the fused kernel's tiles, bit 1 = the last `mu_begin` / `mu_sweeps` used
+        the neighbour-compacted statistics, bit 2 = the last `mu_stats` ran on the tensor-core panel kernel."""
         last = ctypes.c_int(0)
         _lib.check(self.lib.dnmf_mu_path(self._h, int(flags), ctypes.byref(last)), "dnmf_mu_path")
         return int(last.value)
@@ -238,11 +287,12 @@ class Engine:
         return G, b
 
     def mu_sweeps(self, C: torch.Tensor, gamma, iters: int):
-        _check_dev(C, torch.float32, "C")
+        _check_dev(C, torch.float32, "C", self.device, (self.K, self.T))
         _lib.check(self.lib.dnmf_mu_sweeps(self._h, _ptr(C), float(gamma or 0.0), int(gamma is not None), int(iters),
                                            self.stream), "dnmf_mu_sweeps")
 
     def mu_begin(self, C):
+        _check_dev(C, torch.float32, "C", self.device, (self.K, self.T))
         _lib.check(self.lib.dnmf_mu_begin(self._h, _ptr(C), self.stream), "dnmf_mu_begin")
 
     def mu_sweep(self, gamma, halo_prev=None, halo_next=None):
@@ -256,11 +306,15 @@ class Engine:
         return first, last
 
     def mu_end(self, C):
+        _check_dev(C, torch.float32, "C", self.device, (self.K, self.T))
         _lib.check(self.lib.dnmf_mu_end(self._h, _ptr(C), self.stream), "dnmf_mu_end")
 
     def iwarp(self, frame_ids: torch.Tensor, beta, frames: Optional[torch.Tensor] = None) -> torch.Tensor:
-        ids32 = frame_ids.to(self.device, torch.int32).contiguous()
+        self._check_state(beta)
+        ids32 = self._ids32(frame_ids)
         B = int(ids32.numel())
+        if frames is not None:
+            _check_dev(frames, torch.float32, "frames", self.device, (B, self.X, self.Y, self.Z))
         out = torch.empty(B, self.X, self.Y, self.Z, dtype=torch.float32, device=self.device)
         _lib.check(self.lib.dnmf_iwarp(self._h, _ptr(frames), _ptr(ids32), B, _ptr(beta), _ptr(out), self.stream),
                    "dnmf_iwarp")
@@ -273,12 +327,11 @@ class Engine:
     def ext_loss_grad(self, frame_ids: torch.Tensor, beta, C, background: float = 0.0,
                       frames: Optional[torch.Tensor] = None, B_global: Optional[int] = None, grad_beta=None):
         """Returns (grad_beta[10,3,T], sse[B], gpos[K,3], gsig[K], gbg[1]) -- the last three in float64."""
-        _check_dev(beta, torch.float32, "beta")
-        _check_dev(C, torch.float32, "C")
-        ids32 = frame_ids.to(self.device, torch.int32).contiguous()
+        self._check_state(beta, C=C)
+        ids32 = self._ids32(frame_ids)
         B = int(ids32.numel())
         if frames is not None:
-            _check_dev(frames, torch.float32, "frames")
+            _check_dev(frames, torch.float32, "frames", self.device, (B, self.X, self.Y, self.Z))
         if grad_beta is None:
             grad_beta = torch.zeros(10, 3, self.T, dtype=torch.float32, device=self.device)
         sse = torch.zeros(B, dtype=torch.float64, device=self.device)

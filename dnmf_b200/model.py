@@ -205,8 +205,52 @@ def loader_index_batches(loader):
     if not (getattr(ds, "returns_frame_index", False) or
             type(ds).__name__ in ("SimulatedVideoDataset", "NeuroPALVideoDataset")):
         return None
+    # map-style datasets with a finite batch sampler only (an IterableDataset's sampler never ends), and only for
+    # the DataLoader internals this shortcut was checked against (tests/test_host.py compares it with real iteration)
+    if getattr(loader, "_dataset_kind", 0) != 0 or not hasattr(loader.batch_sampler, "__len__"):
+        return None
+    if not _loader_shortcut_ok():
+        return None
+    offset = int(getattr(ds, "offset", 0))
     torch.empty((), dtype=torch.int64).random_(generator=loader.generator)      # _BaseDataLoaderIter._base_seed
-    return [np.asarray(b, dtype=np.int64).reshape(-1) for b in loader.batch_sampler]
+    return [np.asarray(b, dtype=np.int64).reshape(-1) + offset for b in loader.batch_sampler]
+
+
+_LOADER_SHORTCUT = None
+
+
+def _loader_shortcut_ok() -> bool:
+    """One self-check per process: on a tiny shuffled DataLoader, walking the batch sampler after one int64 draw
+    must give the batches (and leave the global random stream in the state) that real iteration gives.  A torch
+    release that changes how the iterator consumes the stream makes this False and the loaders are walked the
+    ordinary way."""
+    global _LOADER_SHORTCUT
+    if _LOADER_SHORTCUT is None:
+        from torch.utils.data import DataLoader, Dataset
+
+        class _Probe(Dataset):
+            def __len__(self):
+                return 7
+
+            def __getitem__(self, i):
+                return torch.zeros(1), i
+
+        state = torch.get_rng_state()
+        try:
+            torch.manual_seed(12345)
+            real = [b[1].tolist() for b in DataLoader(_Probe(), batch_size=3, shuffle=True)]
+            after_real = torch.rand(1).item()
+            torch.manual_seed(12345)
+            dl = DataLoader(_Probe(), batch_size=3, shuffle=True)
+            torch.empty((), dtype=torch.int64).random_(generator=dl.generator)
+            mine = [list(b) for b in dl.batch_sampler]
+            after_mine = torch.rand(1).item()
+            _LOADER_SHORTCUT = real == mine and after_real == after_mine
+        except Exception:
+            _LOADER_SHORTCUT = False
+        finally:
+            torch.set_rng_state(state)
+    return _LOADER_SHORTCUT
 
 
 def collect_id_batches(loader):
@@ -333,6 +377,19 @@ class DeformableNMF:
         self.fp._A = None
         return loss
 
+    def _local_ids(self, ids) -> torch.Tensor:
+        """Frame ids as the loader yields them (global ids when this rank's slab starts at `frame_offset`) ->
+        int32 ids into the slab, validated on the host: an id outside the slab is an error, not a memory fault."""
+        t = torch.as_tensor(ids).reshape(-1)
+        if t.is_cuda:
+            return (t - self.frame_offset).to(torch.int32) if self.frame_offset else t.to(torch.int32)
+        t = t.to(torch.int64) - self.frame_offset
+        if t.numel() and (int(t.min()) < 0 or int(t.max()) >= self.fp.T):
+            bad = int(t.min()) if int(t.min()) < 0 else int(t.max())
+            raise DnmfError("frame id %d is outside this model's slab [%d, %d)"
+                            % (bad + self.frame_offset, self.frame_offset, self.frame_offset + self.fp.T))
+        return t.to(torch.int32)
+
     # -- Adam state shared with the caller's optimiser ---------------------------------------------
     def _adam_state(self, optimizer):
         if not isinstance(optimizer, torch.optim.Adam) or type(optimizer) is not torch.optim.Adam:
@@ -375,7 +432,7 @@ class DeformableNMF:
                 nbatches = int(offsets.size) - 1
                 if nbatches == 0:
                     continue
-                ids_dev = torch.from_numpy(ids_np).to(eng.device)
+                ids_dev = self._local_ids(torch.from_numpy(ids_np)).to(eng.device)
                 losses = torch.zeros(nbatches, dtype=torch.float64, device=eng.device)
                 first = int(st["step"]) + 1
                 eng.motion_epoch(ids_dev, offsets, beta, st["exp_avg"], st["exp_avg_sq"], self.C, group["lr"],
@@ -385,7 +442,7 @@ class DeformableNMF:
                 self.loss_history.extend(losses.unbind(0))
                 continue
             for batch_idx, data in enumerate(dataloader):
-                ids = torch.as_tensor(data[1]).to(torch.int32)
+                ids = self._local_ids(data[1])
                 step = int(st["step"]) + 1
                 lr, betas, eps = group["lr"], group["betas"], group["eps"]
                 if self.jacobian_regularizer and gamma and self._shared is None:
@@ -428,6 +485,7 @@ class DeformableNMF:
                 if self.verbose and batch_idx % 10 == 0:
                     print("Recon: " + str(float(loss)))
                     print("Reg: " + str(self.fp.regularizer_values(ids.tolist())))
+        eng.check_status()      # surfaces an error an asynchronous step found on the device (one sync per call)
 
     def losses(self) -> np.ndarray:
         """Per-step reconstruction losses recorded by update_motion (one device sync)."""
@@ -478,14 +536,14 @@ class DeformableNMF:
             if testloader is None:
                 ids = torch.arange(self.fp.T, dtype=torch.int32)
             else:
-                ids = torch.from_numpy(collect_id_batches(testloader)[0])
+                ids = self._local_ids(torch.from_numpy(collect_id_batches(testloader)[0]))
             ids = ids.to(eng.device)
             step = 512
             for i in range(0, int(ids.numel()), step):
                 eng.mu_stats(ids[i:i + step], beta)
         else:
             for data in testloader:
-                ids = torch.as_tensor(data[1]).to(torch.int32)
+                ids = self._local_ids(data[1])
                 fd = data[0].float().to(eng.device).contiguous()
                 eng.mu_stats(ids, beta, frames=fd)
         if halo_exchange is None:

@@ -148,7 +148,9 @@ class SimulatedVideoDataset(Dataset):
 
 
 class FrameDataset(Dataset):
-    """Wraps existing frames [T,X,Y,Z] (e.g. a golden fixture or a rank's slab) as (frame, idx) items."""
+    """Wraps existing frames [T,X,Y,Z] (e.g. a golden fixture or a rank's slab) as (frame, id) items.  `offset` is
+    the global id of the slab's first frame: items carry GLOBAL ids (idx + offset), which a model built with
+    `frame_offset=offset` maps back to its slab."""
     returns_frame_index = True
 
     def __init__(self, frames: torch.Tensor, offset: int = 0):
@@ -161,7 +163,7 @@ class FrameDataset(Dataset):
     def __getitem__(self, idx):
         if torch.is_tensor(idx):
             idx = idx.tolist()
-        return self.frames[idx], idx
+        return self.frames[idx], idx + self.offset
 
 
 class NeuroPALVideoDataset(Dataset):

@@ -14,6 +14,13 @@
  *   - layouts are the reference's own: beta[10][3][T], C[K][T] (T innermost), frames
  *     [n][X][Y][Z] (Z innermost, what the reference's DataLoader yields, Demix/dNMF.py:214).
  *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ *   - frame ids (frame_ids_dev / frame_ids_host) index this context's slab: 0 <= id < T.  Device ids are checked
+ *     on the device before any kernel indexes with them (the kernels read a copy clamped into the slab, so an id
+ *     out of range cannot touch memory outside it); asynchronous calls report such an id at the NEXT entry
+ *     point or at dnmf_check_status, synchronous ones (dnmf_mu_stats, dnmf_motion_step_host, the frame-parallel
+ *     dnmf_motion_epoch) immediately.  An id listed twice in one gradient batch gets the sum of its
+ *     occurrences' gradients, like the reference's autograd (index_put with accumulate); dnmf_mu_stats and
+ *     dnmf_motion_step_host reject duplicates.
  */
 #ifndef DNMF_B200_H
 #define DNMF_B200_H
@@ -26,7 +33,7 @@ extern "C" {
 
 typedef struct dnmf_ctx dnmf_ctx;
 
-#define DNMF_ABI_VERSION 4
+#define DNMF_ABI_VERSION 5
 
 int dnmf_abi_version(void);
 const char* dnmf_last_error(void);
@@ -130,9 +137,14 @@ int dnmf_get_mu_stats(dnmf_ctx* ctx, int t, double* G_host /* [K][K] */, double*
  * also the automatic redo when a list outgrows the staged capacity).  The sweeps read G either dense or
  * compacted to the static neighbour lists (neurons whose truncated supports overlap; the default when the
  * lists are shorter than K/2); without temporal coupling (gamma None or 0) dnmf_mu_sweeps runs all sweeps of
- * a frame in one CTA.  flags: bit 0 = always the panel kernel, bit 1 = always dense sweeps, bit 2 = one
- * launch per sweep, 0 = automatic, negative = leave unchanged.  last_path_out (may be NULL): bit 0 = the most recent
- * dnmf_mu_stats ran on the fused tiles, bit 1 = the most recent dnmf_mu_begin set up sparse sweeps. */
+ * a frame in one CTA.  A third statistics kernel takes the dense configurations (lists of up to 127 neurons per
+ * 8 x 8 x Z tile): the panel Gram on the tensor cores (tcgen05.mma.kind::tf32, 3xTF32 split, accumulators in TMEM);
+ * automatic order: fused tiles -> tensor-core panel -> SIMT panel.  Whatever the first stage, the per-frame sum
+ * over tiles is a fixed-order fp64 reduction (bitwise reproducible, G_t exactly symmetric).
+ * flags: bit 0 = skip the fused tiles (SIMT panel unless bit 3), bit 1 = always dense sweeps, bit 2 = one launch
+ * per sweep, bit 3 = tensor-core panel first, 0 = automatic, negative = leave unchanged.  last_path_out (may be
+ * NULL): bit 0 = the most recent dnmf_mu_stats ran on the fused tiles, bit 1 = the most recent dnmf_mu_begin set up
+ * sparse sweeps, bit 2 = the most recent dnmf_mu_stats ran on the tensor-core panel kernel. */
 int dnmf_mu_path(dnmf_ctx* ctx, int flags, int* last_path_out);
 
 /* Multiplicative sweeps C <- C (b + g nbr) / (G C + 2 g C + 1e-32) over all T frames in fp64
@@ -168,6 +180,10 @@ int dnmf_ext_loss_grad(dnmf_ctx* ctx, const float* frames_dev, const int32_t* fr
 /* FFMA microbenchmark: best-of-`repeats` dense FP32 throughput of the device in TFLOP/s (FMA = 2);
  * the roofline denominator for the FP32-bound fused kernel (MEASURED_PEAKS.json has no FP32 entry). */
 int dnmf_measure_fp32_peak(int device, int repeats, double* tflops_out);
+
+/* Waits for `stream` and reports an error that an earlier asynchronous call found on the device (see the
+ * conventions above); returns 0 when there is none.  The error is cleared by reporting it. */
+int dnmf_check_status(dnmf_ctx* ctx, void* stream);
 
 /* Counters for bench accounting: number of fused-kernel launches etc. since creation. */
 int dnmf_get_counters(dnmf_ctx* ctx, int64_t* out /* [8] */);

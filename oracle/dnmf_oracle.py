@@ -253,22 +253,58 @@ def axis_tables(pos, sigma, sz, cutoff) -> Tuple[List[np.ndarray], np.ndarray]:
     return tabs, rng
 
 
-def sample_coords(beta_t: np.ndarray, sz: Sequence[int]) -> np.ndarray:
-    """Un-normalised sample coordinates ix[3, X, Y, Z] in fp32 with the reference's op order
-    (Demix/dNMF.py:54-55 then ATen grid_sampler unnormalize, SURVEY F2 / Appendix A)."""
+def _fma(a, b, c):
+    """fp32 fused multiply-add of float32 arrays: the product of two float32 is exact in float64, so one float64
+    addition and one rounding to float32 reproduce the device's fmaf up to double rounding (probability ~2^-29
+    per operation)."""
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(f32)
+
+
+def deformed_coords(beta_t: np.ndarray, sz: Sequence[int], q_order: str = "sequential") -> List[np.ndarray]:
+    """q_d(p) = sum_a phi_a(p) beta_t[a, d] in fp32 for every voxel (Demix/dNMF.py:54).  The reference evaluates
+    this contraction with an MKL GEMM whose summation order is not specified; any fp32 order is a legitimate
+    realisation and they differ by a few ulp of |q| (3e-5 px at x = 255, 6e-5 px at x = 511).  Orders:
+      "sequential"  a = 0..9 with separate multiply and add (the oracle's default),
+      "horner"      the CUDA kernels' order: FMA chains over the (x, y) monomials, then Horner in z,
+      "exact"       float64 accumulation rounded once to fp32 (the correctly rounded value)."""
     X, Y, Z = (int(s) for s in sz)
     x = np.arange(X, dtype=f32)[:, None, None]
     y = np.arange(Y, dtype=f32)[None, :, None]
     z = np.arange(Z, dtype=f32)[None, None, :]
     one = np.ones((X, Y, Z), f32)
-    phi = [one, x * one, y * one, z * one, (x * x) * one, (y * y) * one, (z * z) * one,
-           (x * y) * one, (x * z) * one, (y * z) * one]
     b = np.asarray(beta_t, f32)
+    out = []
+    for d in range(3):
+        if q_order == "horner":
+            v = _fma(b[1, d], x, b[0, d])
+            v = _fma(b[2, d], y, v)
+            v = _fma(b[4, d], (x * x).astype(f32), v)
+            v = _fma(b[5, d], (y * y).astype(f32), v)
+            v = _fma(b[7, d], (x * y).astype(f32), v)
+            w = _fma(b[9, d], y, _fma(b[8, d], x, b[3, d]))
+            q = _fma(z * one, _fma(z * one, b[6, d], w * one), v * one)
+        elif q_order == "exact":
+            phi = [one, x * one, y * one, z * one, (x * x) * one, (y * y) * one, (z * z) * one, (x * y) * one,
+                   (x * z) * one, (y * z) * one]
+            q = sum(phi[a].astype(np.float64) * np.float64(b[a, d]) for a in range(10)).astype(f32)
+        else:
+            phi = [one, x * one, y * one, z * one, (x * x) * one, (y * y) * one, (z * z) * one, (x * y) * one,
+                   (x * z) * one, (y * z) * one]
+            q = np.zeros((X, Y, Z), f32)
+            for a in range(10):
+                q = (q + (phi[a] * b[a, d]).astype(f32)).astype(f32)
+        out.append(q)
+    return out
+
+
+def sample_coords(beta_t: np.ndarray, sz: Sequence[int], q_order: str = "sequential") -> np.ndarray:
+    """Un-normalised sample coordinates ix[3, X, Y, Z] in fp32 with the reference's op order
+    (Demix/dNMF.py:54-55 then ATen grid_sampler unnormalize, SURVEY F2 / Appendix A)."""
+    X, Y, Z = (int(s) for s in sz)
+    qs = deformed_coords(beta_t, sz, q_order)
     out = np.empty((3, X, Y, Z), f32)
     for d in range(3):
-        q = np.zeros((X, Y, Z), f32)
-        for a in range(10):
-            q = (q + (phi[a] * b[a, d]).astype(f32)).astype(f32)
+        q = qs[d]
         sm1 = f32(int(sz[d]) - 1)
         if int(sz[d]) == 1:
             # The reference divides by s-1 = 0 here (NaN everywhere, SURVEY App. B).  The CUDA path
@@ -400,6 +436,129 @@ def closed_form_mu_stats(frames: np.ndarray, times, beta, tabs, sz):
         At = ((a[0] * a[1]).astype(f32) * a[2]).astype(f32).reshape(K, -1).astype(np.float64)
         Gm[j] = At @ At.T
         bv[j] = At @ frames[j].reshape(-1).astype(np.float64)
+    return Gm, bv
+
+
+def _cells(beta_t, sz, q_order="sequential"):
+    """Cell index (+2: table row) and fraction of every voxel's sample, per axis, as closed_form_frame does."""
+    ix = sample_coords(beta_t, sz, q_order)
+    i_idx, fr = [], []
+    for d in range(3):
+        s = int(sz[d])
+        c = np.fmin(np.fmax(ix[d], f32(-2)), f32(s))
+        fl = np.floor(c)
+        i_idx.append(fl.astype(np.int32) + 2)
+        fr.append((c - fl).astype(f32))
+    return i_idx, fr
+
+
+def neuron_boxes(i_idx, rng):
+    """Voxel boxes [K,3,2] (inclusive, hi < lo when empty) outside which a neuron's resampled footprint is exactly
+    zero for this frame: table row i (= cell i - 2) is non-zero only for lo_k - 1 <= cell <= hi_k, so on axis d the
+    voxel coordinate is kept when some voxel of that coordinate plane has its cell in that interval.  A superset of
+    the support, which makes the boxed closed forms below bit-identical to the all-voxel ones (the skipped terms
+    are +0)."""
+    K = rng.shape[0]
+    out = np.zeros((K, 3, 2), np.int64)
+    for d in range(3):
+        other = tuple(a for a in range(3) if a != d)
+        cmin = i_idx[d].min(axis=other).astype(np.int64) - 2
+        cmax = i_idx[d].max(axis=other).astype(np.int64) - 2
+        for k in range(K):
+            lo, hi = int(rng[k, d, 0]), int(rng[k, d, 1])
+            live = np.nonzero((cmax >= lo - 1) & (cmin <= hi))[0] if lo <= hi else np.zeros(0, np.int64)
+            out[k, d] = (live[0], live[-1]) if live.size else (0, -1)
+    return out
+
+
+def _footprint_in_box(k, box, i_idx, fr, tabs):
+    """(a0, a1, a2, d0, d1, d2) of neuron k on its voxel box: per-axis lerped values and table differences."""
+    sl = tuple(slice(int(box[d, 0]), int(box[d, 1]) + 1) for d in range(3))
+    a, dd = [], []
+    for d in range(3):
+        e = tabs[d][k][i_idx[d][sl]]
+        a.append((e[..., 0] + fr[d][sl] * e[..., 1]).astype(f32))
+        dd.append(e[..., 1])
+    return sl, a, dd
+
+
+def closed_form_frame_boxed(frame, beta_t, c_t, tabs, rng, sz, q_order="sequential"):
+    """closed_form_frame evaluated neuron by neuron on `neuron_boxes` only: same values bit for bit, but the cost
+    is the number of in-support (voxel, neuron) pairs instead of N*K -- what makes the BASELINE configurations
+    (cfg2 256x128x21 K=150, cfg3 512x256x32 K=300, cfg4 K=1000 sigma=6) checkable in seconds."""
+    X, Y, Z = (int(s) for s in sz)
+    i_idx, fr = _cells(beta_t, sz, q_order)
+    boxes = neuron_boxes(i_idx, rng)
+    yhat = np.zeros((X, Y, Z), f32)
+    g = [np.zeros((X, Y, Z), f32) for _ in range(3)]
+    for k in range(tabs[0].shape[0]):
+        if boxes[k, :, 1].min() < 0 or (boxes[k, :, 1] < boxes[k, :, 0]).any():
+            continue
+        ck = f32(c_t[k])
+        sl, a, dd = _footprint_in_box(k, boxes[k], i_idx, fr, tabs)
+        yhat[sl] += ck * a[0] * a[1] * a[2]
+        g[0][sl] += ck * dd[0] * a[1] * a[2]
+        g[1][sl] += ck * a[0] * dd[1] * a[2]
+        g[2][sl] += ck * a[0] * a[1] * dd[2]
+    r = (yhat - frame.astype(f32)).astype(f32)
+    sse = float(np.sum(r.astype(np.float64) ** 2))
+    x = np.arange(X, dtype=np.float64)[:, None, None]
+    y = np.arange(Y, dtype=np.float64)[None, :, None]
+    z = np.arange(Z, dtype=np.float64)[None, None, :]
+    grad = np.zeros((10, 3))
+    for b in range(3):
+        h = r.astype(np.float64) * g[b].astype(np.float64)
+        hx, hy, hz = h.sum((1, 2)), h.sum((0, 2)), h.sum((0, 1))
+        xs, ys, zs = x.ravel(), y.ravel(), z.ravel()
+        grad[0, b] = 2.0 * h.sum()
+        grad[1, b], grad[2, b], grad[3, b] = 2.0 * (xs @ hx), 2.0 * (ys @ hy), 2.0 * (zs @ hz)
+        grad[4, b], grad[5, b], grad[6, b] = 2.0 * (xs * xs @ hx), 2.0 * (ys * ys @ hy), 2.0 * (zs * zs @ hz)
+        grad[7, b] = 2.0 * (xs @ h.sum(2) @ ys)
+        grad[8, b] = 2.0 * (xs @ h.sum(1) @ zs)
+        grad[9, b] = 2.0 * (ys @ h.sum(0) @ zs)
+    return yhat, sse, grad
+
+
+def closed_form_step_boxed(frames, times, beta, C, tabs, rng, sz, q_order="sequential"):
+    """closed_form_step on the neuron boxes (Demix/dNMF.py:187-190; mean over B*N)."""
+    B = len(times)
+    N = int(np.prod([int(s) for s in sz]))
+    grad = np.zeros(beta.shape, np.float64)
+    sse = 0.0
+    for j, t in enumerate(times):
+        _, s, g = closed_form_frame_boxed(frames[j], beta[:, :, t], C[:, t], tabs, rng, sz, q_order)
+        sse += s
+        grad[:, :, t] += g / (B * N)
+    return sse / (B * N), grad.astype(f32)
+
+
+def closed_form_mu_stats_boxed(frames, times, beta, tabs, rng, sz, slab: int = 16, q_order="sequential"):
+    """closed_form_mu_stats (G_t = A_t^T A_t, b_t = A_t^T Y_t in fp64 of fp32 footprint values,
+    Demix/dNMF.py:141-142) assembled x-slab by x-slab from the neuron boxes, with one BLAS product per slab over
+    the neurons that reach it."""
+    X, Y, Z = (int(s) for s in sz)
+    K = tabs[0].shape[0]
+    Gm = np.zeros((len(times), K, K))
+    bv = np.zeros((len(times), K))
+    for j, t in enumerate(times):
+        i_idx, fr = _cells(beta[:, :, t], sz, q_order)
+        boxes = neuron_boxes(i_idx, rng)
+        live = [k for k in range(K) if (boxes[k, :, 1] >= boxes[k, :, 0]).all()]
+        for x0 in range(0, X, slab):
+            x1 = min(x0 + slab, X)
+            act = [k for k in live if boxes[k, 0, 0] < x1 and boxes[k, 0, 1] >= x0]
+            if not act:
+                continue
+            panel = np.zeros((len(act), x1 - x0, Y, Z))
+            for r_, k in enumerate(act):
+                box = boxes[k].copy()
+                box[0, 0], box[0, 1] = max(box[0, 0], x0), min(box[0, 1], x1 - 1)
+                sl, a, _ = _footprint_in_box(k, box, i_idx, fr, tabs)
+                val = ((a[0] * a[1]).astype(f32) * a[2]).astype(f32)
+                panel[(r_, slice(sl[0].start - x0, sl[0].stop - x0), sl[1], sl[2])] = val
+            P = panel.reshape(len(act), -1)
+            Gm[j][np.ix_(act, act)] += P @ P.T
+            bv[j][act] += P @ frames[j][x0:x1].reshape(-1).astype(np.float64)
     return Gm, bv
 
 

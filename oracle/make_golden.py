@@ -13,6 +13,12 @@ CUDA path to outputs of the reference's own code.  Seeds: np.random.seed(0), tor
                   with torch.manual_seed(1000+epoch) before each of 2 epochs: batch order, losses, beta.
   random_beta.npz small 3-D case with random quadratic beta (44 % out-of-bounds samples):
                   forward A_tC, A_t, loss and d loss / d beta from the reference's autograd.
+  extras.npz      (python -m oracle.make_golden extras) outputs the first three files do not hold: the `reg`
+                  return of ExponentialFP.forward (Demix/dNMF.py:60-61) for the random-beta case and for the
+                  demo's beta after 250 steps; spatial_pushforward (Demix/dNMF.py:69-103) of the random-beta
+                  case -- a 3-D volume whose deformed points are in general position, so the nearest-neighbour
+                  registered video Y_i has no distance ties; the static update_spatial (Demix/dNMF.py:151-160)
+                  and update_temporal (:139-149) on small dense arrays.
 """
 import contextlib
 import io
@@ -131,13 +137,74 @@ def random_beta(ref):
     print("random_beta: loss %.6g, oob %.2f" % (float(loss), oob))
 
 
+def extras(ref):
+    g = dict(np.load(os.path.join(OUT, "random_beta.npz")))
+    d = dict(np.load(os.path.join(OUT, "demo_cfg1.npz")))
+    out = {}
+    # -- reg of forward (Demix/dNMF.py:60-61), random quadratic beta --
+    sz = torch.tensor(g["sz"])
+    K, T = g["pos"].shape[0], g["beta"].shape[2]
+    torch.manual_seed(5)
+    fp = ref.ExponentialFP(sz, K, T, positions=torch.tensor(g["pos"]), shape_std=2.5)
+    with torch.no_grad():
+        fp.beta.copy_(torch.tensor(g["beta"]))
+    C = torch.tensor(g["C"])
+    with quiet():
+        _, _, _, reg = fp(list(range(T)), C)
+    out["reg_random"] = reg.detach().numpy()
+    # -- reg for the demo's beta after 250 Adam steps, frames 0..7 --
+    szd = torch.tensor(d["sz"])
+    fpd = ref.ExponentialFP(szd, 10, 100, positions=torch.tensor(d["pos0"]))
+    with torch.no_grad():
+        fpd.beta.copy_(torch.tensor(d["beta250"]))
+    with quiet():
+        _, _, _, regd = fpd(list(range(8)), torch.tensor(d["C0"]))
+    out["reg_demo250_first8"] = regd.detach().numpy()
+    # -- spatial_pushforward of the random-beta case with a milder deformation (tie-free Y_i) --
+    class _Model:
+        pass
+    m = _Model()
+    m.fp, m.C = fp, C
+    with torch.no_grad():
+        ident = torch.cat((torch.zeros(1, 3), torch.eye(3), torch.zeros(6, 3)), 0)[:, :, None]
+        fp.beta.copy_(ident + 0.25 * (torch.tensor(g["beta"]) - ident))
+    out["pf_beta"] = fp.beta.detach().numpy().copy()
+    frames = torch.tensor(g["frames"])
+    batches = [(frames[i:i + 2], torch.arange(i, i + 2)) for i in range(0, T, 2)]
+    with quiet(), torch.no_grad():
+        A_t, Y_i, Y = ref.ExponentialFP.spatial_pushforward(batches, 2, sz.tolist(), "cpu", m)
+    out["pf_Y_i"] = Y_i.astype(np.float32)
+    out["pf_A_t_max2"] = A_t.max(2).astype(np.float32)          # demo.py:50-52 style max-projection along z
+    # -- static multiplicative updates on small dense arrays --
+    rs = np.random.RandomState(11)
+    Kd, Td, M, N = 4, 6, 7, 5
+    A = rs.rand(M, N, Kd)
+    Cs = rs.rand(Kd, Td)
+    Yi = rs.rand(M, N, Td)
+    D = rs.rand(M, N, Kd)
+    out.update(us_A=A, us_C=Cs, us_Yi=Yi, us_D=D, us_gamma=np.float64(0.7),
+               us_out_D=ref.DeformableNMF.update_spatial(A.copy(), Cs, Yi, D=D, gamma=0.7),
+               us_out_noD=ref.DeformableNMF.update_spatial(A.copy(), Cs, Yi))
+    At = rs.rand(5, 4, 3, Kd, Td)
+    Yt = rs.rand(5, 4, 3, Td)
+    out.update(ut_A_t=At, ut_Y=Yt, ut_out_none=ref.DeformableNMF.update_temporal(At, Cs.copy(), Yt),
+               ut_out_gamma=ref.DeformableNMF.update_temporal(At, Cs.copy(), Yt, gamma=1e-2))
+    np.savez_compressed(os.path.join(OUT, "extras.npz"), **out)
+    print("extras: reg_random", out["reg_random"], "reg_demo", out["reg_demo250_first8"][:3])
+
+
 def main():
+    import sys
     warnings.filterwarnings("ignore")
     os.makedirs(OUT, exist_ok=True)
     ref, _ = load_reference()
+    if "extras" in sys.argv[1:]:
+        extras(ref)
+        return
     demo_cfg1(ref)
     demo_shuffle(ref)
     random_beta(ref)
+    extras(ref)
 
 
 if __name__ == "__main__":

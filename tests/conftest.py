@@ -25,3 +25,9 @@ def golden_demo():
 def golden_random():
     import numpy as np
     return dict(np.load(os.path.join(GOLDEN, "random_beta.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_extras():
+    import numpy as np
+    return dict(np.load(os.path.join(GOLDEN, "extras.npz")))

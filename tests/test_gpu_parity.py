@@ -270,3 +270,154 @@ def test_opt_in_jacobian_regularizer_vs_autograd(golden_demo):
         m.update_motion(DataLoader(FrameDataset(frames), batch_size=4, shuffle=False),
                         torch.optim.Adam([m.fp.beta], lr=1e-4), gamma=gm, epochs=1)
     assert torch.equal(a.fp.beta, b.fp.beta)
+
+
+def test_reg_return_of_forward_matches_reference(golden_random, golden_demo, golden_extras):
+    """`reg` of ExponentialFP.forward (Demix/dNMF.py:60-61: log-det-Jacobian at two corners with the reference's
+    own cross-term indexing) against the real reference's output, for a random quadratic beta and for the demo's
+    beta after 250 Adam steps."""
+    from dnmf_b200 import ExponentialFP
+    g, d, x = golden_random, golden_demo, golden_extras
+    fp = ExponentialFP(g["sz"].tolist(), 5, 6, positions=torch.tensor(g["pos"]), shape_std=2.5, cutoff=0.0)
+    with torch.no_grad():
+        fp.beta.copy_(torch.tensor(g["beta"]).cuda())
+    _, _, _, reg = fp(list(range(6)), torch.tensor(g["C"]))
+    assert not reg.is_cuda and not reg.requires_grad          # detached, on the CPU, like the reference's (F3)
+    np.testing.assert_allclose(reg.numpy(), x["reg_random"], rtol=1e-5, atol=1e-9)
+    fpd = ExponentialFP(d["sz"].tolist(), 10, 100, positions=torch.tensor(d["pos0"]))
+    with torch.no_grad():
+        fpd.beta.copy_(torch.tensor(d["beta250"]).cuda())
+    _, _, _, regd = fpd(list(range(8)), torch.tensor(d["C0"]))
+    np.testing.assert_allclose(regd.numpy(), x["reg_demo250_first8"], rtol=1e-4, atol=1e-9)
+
+
+def test_registered_video_matches_reference_nearest_neighbour(golden_random, golden_extras):
+    """Y_i of spatial_pushforward (Demix/dNMF.py:81-83,90-103: scipy NearestNDInterpolator over the deformed
+    points) against the real reference on a 3-D volume whose deformed points are in general position.  Exact
+    equality is required wherever the nearest neighbour is unique; the voxels with a distance tie (counted with
+    a float64 brute force here) may differ, there the reference's KD-tree order is arbitrary."""
+    from dnmf_b200.engine import Engine
+    g, x = golden_random, golden_extras
+    sz = g["sz"].tolist()
+    X, Y, Z = sz
+    T = x["pf_beta"].shape[2]
+    e = Engine(sz, 5, T)
+    e.set_footprints(g["pos"], g["sigma"], 0.0)
+    frames = torch.tensor(g["frames"])
+    yi = e.iwarp(torch.arange(T), torch.tensor(x["pf_beta"]).cuda(), frames=frames.cuda()).cpu().numpy()
+    ref = np.moveaxis(x["pf_Y_i"], 3, 0)
+    grid = np.stack(np.meshgrid(np.arange(X), np.arange(Y), np.arange(Z), indexing="ij"), -1).reshape(-1, 3).astype(np.float64)
+    _, phi = O.voxel_basis(sz)
+    ties = mism = mism_unique = 0
+    for t in range(T):
+        q = torch.einsum("mnza,ab->mnzb", phi, torch.tensor(x["pf_beta"][:, :, t]))
+        u = 2 * q / (torch.tensor(sz)[None, None, None, :] - 1) - 1
+        P = (((u + 1) / 2) * torch.tensor(sz)[None, None, None, :].float()).reshape(-1, 3).numpy().astype(np.float64)
+        d2 = ((grid[:, None, :] - P[None, :, :]) ** 2).sum(-1)
+        tie = ((d2 <= d2.min(1)[:, None]).sum(1) > 1).reshape(X, Y, Z)
+        bad = yi[t] != ref[t]
+        ties += int(tie.sum())
+        mism += int(bad.sum())
+        mism_unique += int((bad & ~tie).sum())
+    print("\n[Y_i] %d voxels, %d with a distance tie, %d differ from the reference, %d of them where the nearest "
+          "neighbour is unique" % (T * X * Y * Z, ties, mism, mism_unique))
+    assert mism_unique == 0
+    assert mism <= ties
+
+
+def test_demo_registered_video_first_plane_matches_reference(golden_demo):
+    """Y_i at the demo size (50x50x2): the reference scales the deformed points by sz, not sz-1
+    (Demix/dNMF.py:83), which puts the z = 1 sources at z = 2: every z = 1 voxel is equidistant from both planes
+    (a tie, KD-tree order arbitrary), the z = 0 plane has unique neighbours and must match exactly."""
+    g = golden_demo
+    dn = _demo_model(g, 3.5, resident=False)
+    # the golden's Y_i was produced after the 250 Adam steps: use the reference's own beta for the comparison
+    with torch.no_grad():
+        dn.fp.beta.copy_(torch.tensor(g["beta250"]).cuda())
+    yi = dn.fp.engine.iwarp(torch.arange(4), dn.fp.beta.detach(), frames=torch.tensor(g["frames"][:4]).cuda()).cpu().numpy()
+    ref = np.moveaxis(g["Y_i_first4"], 3, 0)
+    same0 = float((yi[:, :, :, 0] == ref[:, :, :, 0]).mean())
+    same1 = float((yi[:, :, :, 1] == ref[:, :, :, 1]).mean())
+    print("\n[Y_i demo] plane z=0 equal %.4f, plane z=1 (all ties) equal %.4f" % (same0, same1))
+    assert same0 == 1.0
+
+
+def test_traces_from_the_references_own_beta(golden_demo):
+    """Trace update with the deformation taken from the reference's run (beta after its 250 Adam steps), so that
+    the only differences left are the closed-form footprint values and the accumulation of G_t, b_t: the margin
+    of the statistics themselves against the reference's fp64 einsum (Demix/dNMF.py:141-148), 50 sweeps."""
+    g = golden_demo
+    for cutoff in (0.0, 3.5):
+        dn = _demo_model(g, cutoff, resident=True)
+        with torch.no_grad():
+            dn.fp.beta.copy_(torch.tensor(g["beta250"]).cuda())
+        dn.update_traces(None, gamma_c=0, iter_c=50)
+        err = float((dn.C.cpu() - torch.tensor(g["C_mu0"])).abs().max() / np.abs(g["C_mu0"]).max())
+        print("\n[traces from the reference's beta, cutoff %.1f] max |C - C_ref| / max |C_ref| = %.2e" % (cutoff, err))
+        assert err <= (1e-5 if cutoff == 0.0 else 1e-4)
+
+
+def test_repeated_frame_in_a_batch_sums_its_gradients(golden_random):
+    """A sampler with replacement can list a frame twice in one minibatch: the reference's autograd adds both
+    contributions to the frame's gradient column and the loss averages over all B entries."""
+    g = golden_random
+    sz = g["sz"].tolist()
+    T = g["beta"].shape[2]
+    e = _engine(sz, 5, T, g["pos"], g["sigma"], 0.0, (1, 1, 0, 0, 2))
+    beta = torch.tensor(g["beta"]).cuda()
+    C = torch.tensor(g["C"]).cuda()
+    frames = torch.tensor(g["frames"])
+    ids = [2, 4, 2, 1, 2]
+    fb = frames[ids].clone()
+    fb[2] = frames[3]                      # the second occurrence of frame 2 even carries different data
+    grad, sse = e.loss_grad(torch.tensor(ids), beta, C, frames=fb.cuda())
+    port = O.TorchPort(sz, 5, T, positions=g["pos"], shape_std=2.5, C0=g["C"])
+    with torch.no_grad():
+        port.beta.copy_(torch.tensor(g["beta"]))
+    A_tC, _, _ = port.forward(ids)
+    loss = torch.nn.functional.mse_loss(A_tC, fb)
+    loss.backward()
+    ref = port.beta.grad.numpy()
+    N = int(np.prod(sz))
+    assert abs(float(sse.sum()) / (len(ids) * N) - float(loss)) <= 1e-5 * float(loss)
+    err = np.abs(grad.cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert err < 2e-5, err
+    g2, s2 = e.loss_grad(torch.tensor(ids), beta, C, frames=fb.cuda())
+    assert torch.equal(grad, g2) and torch.equal(sse, s2)
+    # statistics are stored per frame id: a repeated id is rejected
+    from dnmf_b200 import DnmfError
+    with pytest.raises(DnmfError):
+        e.mu_stats(torch.tensor(ids), beta, frames=fb.cuda())
+    with pytest.raises(DnmfError):
+        e.mu_stats(torch.tensor(ids).cuda(), beta, frames=fb.cuda())
+
+
+def test_frame_ids_outside_the_slab_are_errors_not_memory_faults(golden_random):
+    from dnmf_b200 import DnmfError
+    g = golden_random
+    sz = g["sz"].tolist()
+    T = g["beta"].shape[2]
+    e = _engine(sz, 5, T, g["pos"], g["sigma"], 0.0)
+    beta = torch.tensor(g["beta"]).cuda()
+    C = torch.tensor(g["C"]).cuda()
+    frames = torch.tensor(g["frames"])[:2].cuda()
+    with pytest.raises(DnmfError):                       # host ids: immediate
+        e.loss_grad(torch.tensor([0, T]), beta, C, frames=frames)
+    with pytest.raises(DnmfError):
+        e.forward(torch.tensor([-1, 0]), beta, C)
+    e.loss_grad(torch.tensor([0, T + 5]).cuda(), beta, C, frames=frames)   # device ids: asynchronous call ...
+    with pytest.raises(DnmfError):
+        e.check_status()                                 # ... reported at the next synchronising check
+    e.check_status()                                     # cleared by reporting
+    with pytest.raises(DnmfError):
+        e.mu_stats(torch.tensor([0, 99]).cuda(), beta, frames=frames)
+    grad, sse = e.loss_grad(torch.tensor([0, 1]), beta, C, frames=frames)  # the engine keeps working
+    assert torch.isfinite(grad).all() and torch.isfinite(sse).all()
+    # tensors the kernels would index blindly are validated before the call
+    with pytest.raises(DnmfError):
+        e.loss_grad(torch.tensor([0, 1]), beta[:, :, :3].contiguous(), C, frames=frames)
+    with pytest.raises(DnmfError):
+        e.loss_grad(torch.tensor([0, 1]), beta, C.cpu(), frames=frames)
+    with pytest.raises(DnmfError):
+        e.motion_step(torch.tensor([0, 1]), beta, torch.zeros(10, 3, T), torch.zeros_like(beta), C, 1e-3, (0.9, 0.999),
+                      1e-8, 1, frames=frames)

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "library does not export %s" % n
     lib2 = dnmf_b200.load()
-    assert lib2.dnmf_abi_version() == 4
+    assert lib2.dnmf_abi_version() == 5
     for n in names:                                   # every declared symbol has a ctypes signature
         assert n in lib2._signatures, n
 
@@ -271,6 +271,9 @@ def test_update_motion_and_traces_host_plumbing_with_a_recording_engine(monkeypa
         def mu_sweeps(self, C, gamma, iters):
             calls.append(("sweeps", gamma, iters))
 
+        def check_status(self):
+            calls.append(("check",))
+
     class NeverRead(Dataset):
         returns_frame_index = True
 
@@ -298,3 +301,4 @@ def test_update_motion_and_traces_host_plumbing_with_a_recording_engine(monkeypa
     stats = [c for c in calls if c[0] == "stats"]
     assert sum((c[1] for c in stats), []) == list(range(10))
     assert calls[-1] == ("sweeps", 0, 50)
+    assert ("check",) in calls                                      # update_motion ends with the device status check
