@@ -340,16 +340,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
     __syncwarp();
   }
 
-  // ---- epilogue: wait for every warp's last MMAs, add the four accumulators, write the partial block ----
-  int nacc = 0;
-#pragma unroll
-  for (int w = 0; w < 4; ++w) {
-    const int uw = nz > (w >> 1) ? (nz - (w >> 1) + 1) >> 1 : 0;
-    if (uw > 0) {
-      mbar_wait(smem_addr(&sBar[w]), (uint32_t)((uw - 1) & 1));
-      nacc = w + 1;  // warps with planes are 0..nacc-1 (warps 2, 3 have none when nz == 1)
-    }
-  }
+  // ---- epilogue: every warp waits for ITS OWN last commit (a barrier's phases can only be followed by a waiter
+  // that saw every one of them: a foreign warp asking for "parity of the last phase" would also be answered by an
+  // older phase of the same parity), then the CTA barrier makes all four completions known to everyone ----
+  if (uses > 0) mbar_wait(bar, (uint32_t)((uses - 1) & 1));
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  const int nacc = nz > 1 ? 4 : 2;  // warps 2, 3 (odd planes) have no plane when nz == 1
   asm volatile("tcgen05.fence::after_thread_sync;");
   {
     const int row = warp * 32 + lane;
