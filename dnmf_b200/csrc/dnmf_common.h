@@ -157,6 +157,8 @@ struct GramTcParams {
   int X, Y, Z, K, T;
   int ntx, nty;
   int b_base;  // batch position of this launch's first frame in the partial buffers
+  int fast_div;  // exact 3-instruction division verified for all three axes (verify_coord_kernel)
+  float rcp0, rcp1, rcp2;
 };
 int launch_gram_tc(const GramTcParams& p, int B, cudaStream_t st);
 size_t gram_tc_smem_bytes(int X, int Y, int Z);

@@ -7,15 +7,15 @@
 // tile's voxels.  One CTA (4 warps) per (frame, 8 x 8 x Z tile):
 //   * prologue: beta_t -> conservative window -> neuron list (same device code as the binning kernel) -> the
 //     listed neurons' table slices staged in shared memory, two slots per float4 (G_j, G_j+1, D_j, D_j+1);
-//   * producers: warp w owns the 8 x 4 (x, y) half `w & 1` of the tile and every second z plane (`w >> 1`).
-//     Per plane it evaluates the closed-form footprint value of every listed neuron at its 32 voxels from the
+//   * producers: panel stage s (4 of them) belongs to the 8 x 4 (x, y) half `s & 1` of the tile and the z planes
+//     of parity `s >> 1`; two warps (8 per CTA) share a stage and split its rows.  Per plane they evaluate the closed-form footprint value of every listed neuron at its 32 voxels from the
 //     staged slices (3 LDS.128 + 5 packed FP32x2 operations per slot pair and voxel, no global memory, no
 //     transcendental) and writes them as ONE K-major panel stage [128 rows][32 voxels] in the canonical
 //     SWIZZLE_128B layout -- twice: hi = tf32(a) and lo = tf32(a - hi);
-//   * tensor cores: lane 0 of the warp issues tcgen05.mma.cta_group::1.kind::tf32 (UMMA 128 x N x 8, N = list
+//   * tensor cores: one lane of the stage issues tcgen05.mma.cta_group::1.kind::tf32 (UMMA 128 x N x 8, N = list
 //     length rounded up to 16) on that stage: SYRK has ONE operand, so the same shared-memory panel serves the A
 //     and the B descriptor; fp32-accurate products come from the 3xTF32 split D += hi hi^T + hi lo^T + lo hi^T.
-//     Each warp accumulates into its OWN 128-column TMEM accumulator (4 x 128 = all 512 columns): no ordering is
+//     Each stage accumulates into its OWN 128-column TMEM accumulator (4 x 128 = all 512 columns): no ordering is
 //     needed between the issuing threads, and the truncating fp32 accumulation of the tensor pipe (measured with
 //     tools/experiments/syrk_tf32_umma.cu: relative error 3e-6 per 256 accumulated voxels, growing linearly)
 //     stays at a quarter of the chain length.  tcgen05.commit -> mbarrier hands the stage back to its producer;
@@ -28,7 +28,8 @@ namespace dnmf {
 
 namespace {
 
-constexpr int kTcThreads = 128;
+constexpr int kTcWarps = 9;                           // 8 producers (two per panel stage, they split the rows) + the MMA warp
+constexpr int kTcThreads = 32 * kTcWarps;
 constexpr int kTcStageBytes = kGramRows * 128;        // 128 rows x 32 voxels of tf32
 constexpr int kTcPairs = kGramRows / 2;               // slot pairs per slice entry
 constexpr int kTcEntryBytes = (kTcPairs + 1) * 16;    // padded: consecutive entries start 16 B apart mod 128
@@ -71,13 +72,28 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// The staged slices are read-only once the CTA barrier after staging has passed: the loads are plain (not
+// volatile, no memory clobber) so that the compiler may hoist them over the panel stores of the previous slot
+// pairs; the panel stores are volatile (ordered among themselves and with the fences) but do not clobber memory.
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+template <int OFF>
 __device__ __forceinline__ void sts32(uint32_t addr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+  asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(addr), "f"(v), "n"(OFF));
+}
+__device__ __forceinline__ void sts32r(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v));
+}
+
+// hi = the value rounded to tf32 (round to nearest, ties away: what cvt.rna.tf32.f32 does for finite inputs; two
+// integer instructions instead of the guarded conversion sequence), lo = the exact remainder.  lo is handed to the
+// tensor core as it is: the MMA reads the upper 19 bits, a truncation of 2^-11 |lo| <= 2^-22 |a|.
+__device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
+  lo = a - hi;
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -102,9 +118,9 @@ struct TcSmem {
 __host__ __device__ static TcSmem gram_tc_layout(int wsum, int Z) {
   TcSmem s;
   s.slices = (size_t)4 * 2 * kTcStageBytes;                        // panel stages come first (1024-byte aligned)
-  s.ytile = s.slices + (size_t)wsum * kTcEntryBytes;
+  s.ytile = s.slices + (size_t)(wsum + 1) * kTcEntryBytes;  // + one all-zero entry (x slice of lanes outside the volume)
   s.misc = s.ytile + (((size_t)kGramTX * kGramTY * Z + 3) & ~(size_t)3) * 4;
-  s.bytes = s.misc + kGramRows * 2 + 32 * 4 + 32 * 4 + 4 * 8 + 16 + 1024;  // list, beta, ints, barriers, tmem ptr, slack
+  s.bytes = s.misc + kGramRows * 2 * (2 + kTcWarps) + 32 * 4 + 32 * 4 + 8 * 8 + 16 + 1024;  // list + per-warp lists, beta, ints, barriers, tmem ptr, slack
   return s;
 }
 
@@ -117,14 +133,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
   const int wmax0 = min(kGramTX + 4, p.X + 3), wmax1 = min(kGramTY + 4, p.Y + 3), wmax2 = p.Z + 3;
-  const TcSmem lay = gram_tc_layout(wmax0 + wmax1 + wmax2, p.Z);
+  const int wsum = wmax0 + wmax1 + wmax2;
+  const TcSmem lay = gram_tc_layout(wsum, p.Z);
   unsigned char* sSl = base + lay.slices;
   float* sY = reinterpret_cast<float*>(base + lay.ytile);
   unsigned short* sList = reinterpret_cast<unsigned short*>(base + lay.misc);
-  float* sBeta = reinterpret_cast<float*>(sList + kGramRows);
+  unsigned short* sWList = sList + kGramRows;                        // [warps][kGramRows]: matches found by each warp
+  float* sBeta = reinterpret_cast<float*>(sWList + kTcWarps * kGramRows + (kTcWarps & 1) * kGramRows);
   int* sInt = reinterpret_cast<int*>(sBeta + 32);
-  unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sInt + 32);
-  uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 4);
+  unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sInt + 32);   // full[4], empty[4]
+  uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 8);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x, b = blockIdx.y;
@@ -137,15 +155,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
   const float* __restrict__ frame = p.frames + (size_t)(p.frames_are_batch ? b : t) * Nvox;
   const size_t tf = (size_t)(p.b_base + b) * nt + tile;  // tile-frame index in the partial buffers
 
-  // ---- beta, Y tile, window, neuron list ----
+  // ---- beta, Y tile, window ----
   if (tid < 30) sBeta[tid] = p.beta[(size_t)tid * p.T + t];
   {
     const int run = ny * p.Z;
-    for (int lx = warp; lx < nx; lx += 4) {
+    for (int lx = warp; lx < nx; lx += kTcWarps) {
       const float* src = frame + ((size_t)(x0 + lx) * p.Y + y0) * p.Z;
       for (int e = lane; e < run; e += 32) sY[lx * kGramTY * p.Z + e] = __ldg(src + e);
     }
   }
+  for (int e = tid; e < kTcEntryBytes / 16; e += kTcThreads)   // the all-zero slice entry
+    reinterpret_cast<float4*>(sSl + (size_t)wsum * kTcEntryBytes)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
   if (tid < 3) {
     const int s = tid == 0 ? p.X : (tid == 1 ? p.Y : p.Z);
@@ -162,21 +182,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
     wlo[d] = sInt[d];
     whi[d] = sInt[3 + d];
   }
-  const int per = ((p.K + kTcThreads - 1) / kTcThreads) * 32;
-  const int kb = warp * per;
+  // ---- neuron list (ascending k): every warp scans its share of the neurons ONCE into its own segment, the
+  // segments are then concatenated in warp order ----
   {
+    const int per = ((p.K + kTcThreads - 1) / kTcThreads) * 32;
+    const int kb = warp * per;
     int cnt = 0;
     for (int k0 = kb; k0 < kb + per; k0 += 32) {
       const int k = k0 + lane;
-      const bool ok = (k < p.K) && neuron_in_window(p.rng + (size_t)k * 6, wlo, whi);
-      cnt += __popc(__ballot_sync(0xffffffffu, ok));
+      bool ok = false;
+      if (k < p.K) {  // the six range bounds as three independent 8-byte loads, then the test
+        const int2* r2 = reinterpret_cast<const int2*>(p.rng + (size_t)k * 6);
+        const int2 rx = __ldg(r2), ry = __ldg(r2 + 1), rz = __ldg(r2 + 2);
+        const int r[6] = {rx.x, rx.y, ry.x, ry.y, rz.x, rz.y};
+        ok = neuron_in_window(r, wlo, whi);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+      if (ok && pos < kGramRows) sWList[warp * kGramRows + pos] = (unsigned short)k;
+      cnt += __popc(m);
     }
     if (lane == 0) sInt[8 + warp] = cnt;
   }
   __syncthreads();
   int L = 0, off = 0;
 #pragma unroll
-  for (int w = 0; w < 4; ++w) {
+  for (int w = 0; w < kTcWarps; ++w) {
     const int c = sInt[8 + w];
     if (w < warp) off += c;
     L += c;
@@ -188,27 +219,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
   }
   if (tid == 0) p.out.count[tf] = L;
   if (L == 0) return;
-  for (int k0 = kb; k0 < kb + per; k0 += 32) {
-    const int k = k0 + lane;
-    const bool ok = (k < p.K) && neuron_in_window(p.rng + (size_t)k * 6, wlo, whi);
-    const unsigned m = __ballot_sync(0xffffffffu, ok);
-    if (ok) {
-      const int pos = off + __popc(m & ((1u << lane) - 1u));
-      sList[pos] = (unsigned short)k;
-      p.out.ids[tf * p.out.capL + pos] = (unsigned short)k;
-      p.out.slot_of[((size_t)(p.b_base + b) * p.K + k) * nt + tile] = (unsigned short)pos;
-    }
-    off += __popc(m);
+  for (int i = lane; i < sInt[8 + warp]; i += 32) {
+    const int k = sWList[warp * kGramRows + i], pos = off + i;
+    sList[pos] = (unsigned short)k;
+    p.out.ids[tf * p.out.capL + pos] = (unsigned short)k;
+    p.out.slot_of[((size_t)(p.b_base + b) * p.K + k) * nt + tile] = (unsigned short)pos;
   }
 
-  // ---- TMEM (all 512 columns: one 128-column accumulator per warp), stage barriers ----
+  // ---- TMEM (all 512 columns: one 128-column accumulator per panel stage), stage barriers ----
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(sTmem)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
 #pragma unroll
-    for (int w = 0; w < 4; ++w) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sBar[w])));
+    for (int w = 0; w < 4; ++w) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"(smem_addr(&sBar[w])));      // full: both producer warps
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sBar[4 + w])));  // empty: tcgen05.commit
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
@@ -221,8 +249,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
   {
     const int sX3 = p.X + 3, sY3 = p.Y + 3, sZ3 = p.Z + 3;
     const int Wt = W0 + W1 + W2;
-    for (int item = tid; item < Wt * npair; item += kTcThreads) {
-      const int e = item / npair, pp = item - e * npair;
+    for (int e = warp; e < Wt; e += kTcWarps) {
       const float2* src;
       int row, ent;
       if (e < W0) {
@@ -238,123 +265,161 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
         row = sZ3;
         ent = wmax0 + wmax1 + (e - W0 - W1);
       }
-      const int j = 2 * pp;
-      float2 va = make_float2(0.f, 0.f), vb = va;
-      if (j < L) va = __ldg(src + (size_t)sList[j] * row);
-      if (j + 1 < L) vb = __ldg(src + (size_t)sList[j + 1] * row);
-      *reinterpret_cast<float4*>(sSl + (size_t)ent * kTcEntryBytes + (size_t)pp * 16) = make_float4(va.x, vb.x, va.y, vb.y);
+      float4* dst = reinterpret_cast<float4*>(sSl + (size_t)ent * kTcEntryBytes);
+      for (int pp = lane; pp < npair; pp += 32) {
+        const int j = 2 * pp;
+        float2 va = make_float2(0.f, 0.f), vb = va;
+        if (j < L) va = __ldg(src + (size_t)sList[j] * row);
+        if (j + 1 < L) vb = __ldg(src + (size_t)sList[j + 1] * row);
+        dst[pp] = make_float4(va.x, vb.x, va.y, vb.y);
+      }
     }
   }
   __syncthreads();
 
-  // ---- producers + MMA issue ----
-  const int sub = warp & 1, zpar = warp >> 1;
-  const int lx = lane & 7, ly = (lane >> 3) + 4 * sub;
-  const int gx = x0 + lx, gy = y0 + ly;
-  const bool valid = (gx < p.X) && (gy < p.Y);
-  const float vmask = valid ? 1.f : 0.f;
-  const float xf = (float)gx, yf = (float)gy;
-  float c0[3], c1[3], c2[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {  // same operation order as the fused kernel's Horner form in z
-    float v = sBeta[d];
-    v = fmaf(sBeta[3 + d], xf, v);
-    v = fmaf(sBeta[6 + d], yf, v);
-    v = fmaf(sBeta[12 + d], xf * xf, v);
-    v = fmaf(sBeta[15 + d], yf * yf, v);
-    v = fmaf(sBeta[21 + d], xf * yf, v);
-    c0[d] = v;
-    c1[d] = fmaf(sBeta[27 + d], yf, fmaf(sBeta[24 + d], xf, sBeta[9 + d]));
-    c2[d] = sBeta[18 + d];
-  }
-  const float sm1x = (float)(p.X - 1), sm1y = (float)(p.Y - 1), sm1z = (float)(p.Z - 1);
-  const uint32_t hi_base = smem_addr(base) + (uint32_t)warp * 2u * kTcStageBytes;
-  const uint32_t lo_base = hi_base + kTcStageBytes;
-  const uint32_t slx = smem_addr(sSl), sly = slx + (uint32_t)wmax0 * kTcEntryBytes,
-                 slz = sly + (uint32_t)wmax1 * kTcEntryBytes;
-  const uint32_t bar = smem_addr(&sBar[warp]);
-  // byte offset of this lane's column inside row r8 of an 8-row atom (16-byte chunks XOR-swizzled with the row)
-  uint32_t off8[8];
-#pragma unroll
-  for (int r8 = 0; r8 < 8; ++r8) off8[r8] = (uint32_t)(r8 * 128 + (((lane >> 2) ^ r8) << 4) + ((lane & 3) << 2));
+  // ---- producers (warps 0..7) and the MMA warp (warp 8).  Stage s = warp & 3 belongs to the 8 x 4 (x, y) half
+  // s & 1 and the z planes of parity s >> 1; its two producer warps (half = warp >> 2) split the 8-row atoms of
+  // the panel between them and arrive on full[s]; the MMA warp issues the stage's MMAs and tcgen05.commit hands
+  // the stage back through empty[s] ----
+  const int stg = warp & 3, half = (warp >> 2) & 1;
   const int npad = (L + 1 + 15) & ~15;  // MMA N
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(kGramRows >> 4) << 24);
-  const uint32_t acc = tmem + (uint32_t)warp * 128u;
-  const int uses = nz > zpar ? (nz - zpar + 1) >> 1 : 0;
-  const int natom = (npair + 3) >> 2;
-  const int yL_atom = L >> 3, yL_r8 = L & 7;
-  for (int u = 0; u < uses; ++u) {
-    const int z = zpar + 2 * u;
-    if (u > 0) mbar_wait(bar, (uint32_t)((u - 1) & 1));  // the MMAs that read this stage have completed
-    const float zf = (float)z;
-    int i0, i1, i2;
-    float f0, f1, f2;
-    split_coord(sample_coord(fmaf(zf, fmaf(zf, c2[0], c1[0]), c0[0]), sm1x), p.X, i0, f0);
-    split_coord(sample_coord(fmaf(zf, fmaf(zf, c2[1], c1[1]), c0[1]), sm1y), p.Y, i1, f1);
-    split_coord(sample_coord(fmaf(zf, fmaf(zf, c2[2], c1[2]), c0[2]), sm1z), p.Z, i2, f2);
-    const uint32_t ax = slx + (uint32_t)min(max(i0 - wlo[0], 0), W0 - 1) * kTcEntryBytes;
-    const uint32_t ay = sly + (uint32_t)min(max(i1 - wlo[1], 0), W1 - 1) * kTcEntryBytes;
-    const uint32_t az = slz + (uint32_t)min(max(i2 - wlo[2], 0), W2 - 1) * kTcEntryBytes;
-    const float2 ff0 = make_float2(f0, f0), ff1 = make_float2(f1, f1), ff2 = make_float2(f2, f2);
-    const float2 mm = make_float2(vmask, vmask);
-#pragma unroll 1
-    for (int at = 0; at < natom; ++at) {
-      const uint32_t rowh = hi_base + (uint32_t)at * 1024u, rowl = lo_base + (uint32_t)at * 1024u;
-      const uint32_t pofs = (uint32_t)at * 64u;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 ex = lds128(ax + pofs + q * 16), ey = lds128(ay + pofs + q * 16), ez = lds128(az + pofs + q * 16);
-        const float2 a0 = __ffma2_rn(ff0, make_float2(ex.z, ex.w), make_float2(ex.x, ex.y));
-        const float2 a1 = __ffma2_rn(ff1, make_float2(ey.z, ey.w), make_float2(ey.x, ey.y));
-        const float2 a2 = __ffma2_rn(ff2, make_float2(ez.z, ez.w), make_float2(ez.x, ez.y));
-        const float2 a = __fmul2_rn(__fmul2_rn(__fmul2_rn(a0, a1), a2), mm);
-        const float2 h = make_float2(to_tf32(a.x), to_tf32(a.y));
-        const float2 l = make_float2(to_tf32(a.x - h.x), to_tf32(a.y - h.y));
-        sts32(rowh + off8[2 * q], h.x);
-        sts32(rowh + off8[2 * q + 1], h.y);
-        sts32(rowl + off8[2 * q], l.x);
-        sts32(rowl + off8[2 * q + 1], l.y);
-      }
-    }
-    {  // the Y pseudo-neuron (row L): b_t = A_t^T Y_t rides in column L of the same product
-      const float y = valid ? sY[(lx * kGramTY + ly) * p.Z + z] : 0.f;
-      const float h = to_tf32(y), l = to_tf32(y - h);
-      const uint32_t o = (uint32_t)yL_atom * 1024u + (uint32_t)(yL_r8 * 128 + (((lane >> 2) ^ yL_r8) << 4) + ((lane & 3) << 2));
-      sts32(hi_base + o, h);
-      sts32(lo_base + o, l);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA's async proxy
-    __syncwarp();
+  const int nz0 = (nz + 1) >> 1, nz1 = nz >> 1;  // planes of parity 0 / 1
+  if (warp == 8) {
     if (lane == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;");
-      const uint64_t dh = make_desc(hi_base), dl = make_desc(lo_base);
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(kGramRows >> 4) << 24);
+      const uint32_t sbase = smem_addr(base), bar0 = smem_addr(&sBar[0]);
+      for (int u = 0; u < nz0; ++u) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {  // UMMA_K = 8 tf32 = 32 bytes along the swizzled row: +2 in the address field
-        const uint64_t ah = dh + (uint64_t)(2 * k), al = dl + (uint64_t)(2 * k);
-        umma_tf32(acc, ah, ah, idesc, (u > 0 || k > 0) ? 1u : 0u);
-        umma_tf32(acc, ah, al, idesc, 1u);
-        umma_tf32(acc, al, ah, idesc, 1u);
+        for (int sI = 0; sI < 4; ++sI) {
+          if (u >= ((sI >> 1) ? nz1 : nz0)) continue;
+          mbar_wait(bar0 + 8u * sI, (uint32_t)(u & 1));  // both producer warps have written plane u of this stage
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          const uint64_t dh = make_desc(sbase + (uint32_t)sI * 2u * kTcStageBytes);
+          const uint64_t dl = make_desc(sbase + (uint32_t)sI * 2u * kTcStageBytes + kTcStageBytes);
+          const uint32_t acc = tmem + (uint32_t)sI * 128u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // UMMA_K = 8 tf32 = 32 bytes along the swizzled row: +2 in the address field
+            const uint64_t ah = dh + (uint64_t)(2 * k), al = dl + (uint64_t)(2 * k);
+            umma_tf32(acc, ah, ah, idesc, (u > 0 || k > 0) ? 1u : 0u);
+            umma_tf32(acc, ah, al, idesc, 1u);
+            umma_tf32(acc, al, ah, idesc, 1u);
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 32u + 8u * sI)
+                       : "memory");
+        }
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
     }
     __syncwarp();
+  } else {
+    const int sub = stg & 1, zpar = stg >> 1;
+    const int lx = lane & 7, ly = (lane >> 3) + 4 * sub;
+    const int gx = x0 + lx, gy = y0 + ly;
+    const bool valid = (gx < p.X) && (gy < p.Y);
+    const float xf = (float)gx, yf = (float)gy;
+    float c0[3], c1[3], c2[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {  // same operation order as the fused kernel's Horner form in z
+      float v = sBeta[d];
+      v = fmaf(sBeta[3 + d], xf, v);
+      v = fmaf(sBeta[6 + d], yf, v);
+      v = fmaf(sBeta[12 + d], xf * xf, v);
+      v = fmaf(sBeta[15 + d], yf * yf, v);
+      v = fmaf(sBeta[21 + d], xf * yf, v);
+      c0[d] = v;
+      c1[d] = fmaf(sBeta[27 + d], yf, fmaf(sBeta[24 + d], xf, sBeta[9 + d]));
+      c2[d] = sBeta[18 + d];
+      if (p.fast_div) {  // exact doubling: the plane loop then evaluates 2q, what sample_coord_fast expects
+        c0[d] += c0[d];
+        c1[d] += c1[d];
+        c2[d] += c2[d];
+      }
+    }
+    const float sm1[3] = {(float)(p.X - 1), (float)(p.Y - 1), (float)(p.Z - 1)};
+    const float rcp[3] = {p.rcp0, p.rcp1, p.rcp2};
+    const int sz[3] = {p.X, p.Y, p.Z};
+    const uint32_t hi_base = smem_addr(base) + (uint32_t)stg * 2u * kTcStageBytes;
+    const uint32_t slx = smem_addr(sSl), sly = slx + (uint32_t)wmax0 * kTcEntryBytes,
+                   slz = sly + (uint32_t)wmax1 * kTcEntryBytes, slzero = slx + (uint32_t)wsum * kTcEntryBytes;
+    const uint32_t full = smem_addr(&sBar[stg]), empty = smem_addr(&sBar[4 + stg]);
+    const int uses = zpar ? nz1 : nz0;
+    const int natom = (npair + 3) >> 2;
+    const int at0 = half == 0 ? 0 : (natom + 1) >> 1, at1 = half == 0 ? (natom + 1) >> 1 : natom;
+    const bool owns_y = (natom == 1) ? half == 0 : half == 1;   // the Y pseudo-row lives in the last atom
+    // address of this lane's column in row r8 of atom at0 of the hi stage (16-byte chunks XOR-swizzled with the
+    // row); the lo stage is kTcStageBytes further, the next atom 1024 bytes further
+    uint32_t rowaddr[8];
+#pragma unroll
+    for (int r8 = 0; r8 < 8; ++r8)
+      rowaddr[r8] = hi_base + (uint32_t)at0 * 1024u + (uint32_t)(r8 * 128 + (((lane >> 2) ^ r8) << 4) + ((lane & 3) << 2));
+    const int yL_r8 = L & 7;
+    const uint32_t yaddr = hi_base + (uint32_t)(L >> 3) * 1024u + (uint32_t)(yL_r8 * 128 + (((lane >> 2) ^ yL_r8) << 4) + ((lane & 3) << 2));
+    for (int u = 0; u < uses; ++u) {
+      const int z = zpar + 2 * u;
+      const float zf = (float)z;
+      int ii[3];
+      float ff[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float q = fmaf(zf, fmaf(zf, c2[d], c1[d]), c0[d]);
+        const float ix = p.fast_div ? sample_coord_fast(q, sm1[d], rcp[d], 0.5f * sm1[d]) : sample_coord(q, sm1[d]);
+        split_coord(ix, sz[d], ii[d], ff[d]);
+      }
+      const uint32_t ax = (valid ? slx + (uint32_t)min(max(ii[0] - wlo[0], 0), W0 - 1) * kTcEntryBytes : slzero) + (uint32_t)at0 * 64u;
+      const uint32_t ay = sly + (uint32_t)min(max(ii[1] - wlo[1], 0), W1 - 1) * kTcEntryBytes + (uint32_t)at0 * 64u;
+      const uint32_t az = slz + (uint32_t)min(max(ii[2] - wlo[2], 0), W2 - 1) * kTcEntryBytes + (uint32_t)at0 * 64u;
+      const float2 ff0 = make_float2(ff[0], ff[0]), ff1 = make_float2(ff[1], ff[1]), ff2 = make_float2(ff[2], ff[2]);
+      if (u > 0) mbar_wait(empty, (uint32_t)((u - 1) & 1));  // the MMAs that read this stage have completed
+      uint32_t pofs = 0, rofs = 0;
+#pragma unroll 2
+      for (int at = at0; at < at1; ++at, pofs += 64u, rofs += 1024u) {
+        float4 ex[4], ey[4], ez[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          ex[q] = lds128(ax + pofs + q * 16);
+          ey[q] = lds128(ay + pofs + q * 16);
+          ez[q] = lds128(az + pofs + q * 16);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 a0 = __ffma2_rn(ff0, make_float2(ex[q].z, ex[q].w), make_float2(ex[q].x, ex[q].y));
+          const float2 a1 = __ffma2_rn(ff1, make_float2(ey[q].z, ey[q].w), make_float2(ey[q].x, ey[q].y));
+          const float2 a2 = __ffma2_rn(ff2, make_float2(ez[q].z, ez[q].w), make_float2(ez[q].x, ez[q].y));
+          const float2 a = __fmul2_rn(__fmul2_rn(a0, a1), a2);
+          float hx, lx_, hy, ly_;
+          split_tf32(a.x, hx, lx_);
+          split_tf32(a.y, hy, ly_);
+          sts32<0>(rowaddr[2 * q] + rofs, hx);
+          sts32<0>(rowaddr[2 * q + 1] + rofs, hy);
+          sts32<kTcStageBytes>(rowaddr[2 * q] + rofs, lx_);
+          sts32<kTcStageBytes>(rowaddr[2 * q + 1] + rofs, ly_);
+        }
+      }
+      if (owns_y) {  // the Y pseudo-neuron (row L): b_t = A_t^T Y_t rides in column L of the same product
+        const float y = valid ? sY[(lx * kGramTY + ly) * p.Z + z] : 0.f;
+        float h, l;
+        split_tf32(y, h, l);
+        sts32r(yaddr, h);
+        sts32<kTcStageBytes>(yaddr, l);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA's async proxy
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
+    }
+    // a stage's phases can only be followed by a waiter that saw every one of them: its own producers
+    if (uses > 0) mbar_wait(empty, (uint32_t)((uses - 1) & 1));
   }
-
-  // ---- epilogue: every warp waits for ITS OWN last commit (a barrier's phases can only be followed by a waiter
-  // that saw every one of them: a foreign warp asking for "parity of the last phase" would also be answered by an
-  // older phase of the same parity), then the CTA barrier makes all four completions known to everyone ----
-  if (uses > 0) mbar_wait(bar, (uint32_t)((uses - 1) & 1));
   asm volatile("tcgen05.fence::before_thread_sync;");
-  __syncthreads();
-  const int nacc = nz > 1 ? 4 : 2;  // warps 2, 3 (odd planes) have no plane when nz == 1
+  __syncthreads();  // all four stages' last commits are now known to every warp
+  const int nacc = nz > 1 ? 4 : 2;  // stages 2, 3 (odd planes) have no plane when nz == 1
   asm volatile("tcgen05.fence::after_thread_sync;");
-  {
-    const int row = warp * 32 + lane;
+  if (warp < 8) {
+    // a warp reads the TMEM lanes 32 * (warp % 4) ..: warps w and w + 4 share a row quadrant and split the columns
+    const int row = stg * 32 + lane;
     float* out = p.out.vals + tf * (size_t)p.out.capL * p.out.ld + (size_t)row * p.out.ld;
-    for (int cb = 0; cb < npad; cb += 32) {
+    for (int cb = 32 * half; cb < npad; cb += 64) {
       float sum[32];
       uint32_t r[32];
-      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb;
+      const uint32_t taddr = tmem + ((uint32_t)(stg * 32) << 16) + (uint32_t)cb;
       tmem_ld32(taddr, r);
 #pragma unroll
       for (int i = 0; i < 32; ++i) sum[i] = __uint_as_float(r[i]);

@@ -722,6 +722,10 @@ static int stats_pass(dnmf_ctx* c, int which, const float* frames_dev, const int
     tp.Z = c->Z;
     tp.K = c->K;
     tp.T = c->T;
+    tp.fast_div = c->fast_div;
+    tp.rcp0 = c->rcp[0];
+    tp.rcp1 = c->rcp[1];
+    tp.rcp2 = c->rcp[2];
     tp.ntx = (c->X + kGramTX - 1) / kGramTX;
     tp.nty = (c->Y + kGramTY - 1) / kGramTY;
     if (gram_tc_smem_bytes(c->X, c->Y, c->Z) > (size_t)c->max_smem_optin) {
