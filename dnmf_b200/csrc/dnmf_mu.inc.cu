@@ -302,24 +302,38 @@ __global__ void stats_reduce_kernel(StatsPartials sp, const int* __restrict__ fr
   double bsum = 0.0;
   __syncwarp();
   const unsigned short* slots = sp.slot_of + ((size_t)b * K + k) * nt;
-  for (int tile0 = 0; tile0 < nt; tile0 += 32) {
-    const int tl = tile0 + lane;
-    const unsigned s = tl < nt ? slots[tl] : 0xffffu;
-    unsigned mask = __ballot_sync(0xffffffffu, s != 0xffffu);
-    while (mask) {
-      const int src = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const int j = (int)__shfl_sync(0xffffffffu, s, src);
-      const size_t tf = (size_t)b * nt + tile0 + src;
-      const int L = sp.count[tf];
-      const float* blk = sp.vals + tf * (size_t)sp.capL * sp.ld;
-      const unsigned short* ids = sp.ids + tf * sp.capL;
-      for (int i = lane; i < L; i += 32) {
-        const float v = i >= j ? blk[(size_t)j * sp.ld + i] : blk[(size_t)i * sp.ld + j];
-        row[ids[i]] += (double)v;
+  constexpr int R = 8;  // tiles per lane and round: the slot and list-length loads of a round are all in flight together
+  for (int tile0 = 0; tile0 < nt; tile0 += 32 * R) {
+    unsigned s[R];
+    int cnt[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int tl = tile0 + r * 32 + lane;
+      s[r] = tl < nt ? slots[tl] : 0xffffu;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int tl = tile0 + r * 32 + lane;
+      cnt[r] = s[r] != 0xffffu ? sp.count[(size_t)b * nt + tl] : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      unsigned mask = __ballot_sync(0xffffffffu, s[r] != 0xffffu);
+      while (mask) {  // ascending tile order: the fixed summation order of every entry of the row
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int j = (int)__shfl_sync(0xffffffffu, s[r], src);
+        const int L = __shfl_sync(0xffffffffu, cnt[r], src);
+        const size_t tf = (size_t)b * nt + tile0 + r * 32 + src;
+        const float* blk = sp.vals + tf * (size_t)sp.capL * sp.ld;
+        const unsigned short* ids = sp.ids + tf * sp.capL;
+        for (int i = lane; i < L; i += 32) {
+          const float v = i >= j ? blk[(size_t)j * sp.ld + i] : blk[(size_t)i * sp.ld + j];
+          row[ids[i]] += (double)v;
+        }
+        if (lane == 0) bsum += (double)blk[(size_t)j * sp.ld + sp.capL];
+        __syncwarp();
       }
-      if (lane == 0) bsum += (double)blk[(size_t)j * sp.ld + sp.capL];
-      __syncwarp();
     }
   }
   const int t = frame_ids[b];
