@@ -69,6 +69,12 @@ def load(build_if_missing: bool = True):
         "dnmf_iwarp": (c_int, [P, P, P, c_int, P, P, P]),
         "dnmf_get_counters": (c_int, [P, P]),
         "dnmf_check_status": (c_int, [P, P]),
+        "dnmf_render_cells": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P]),
+        "dnmf_update_spatial": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_double, c_int, c_int64, c_int, c_int,
+                                        P, P, P]),
+        "dnmf_update_temporal_dense": (c_int, [P, P, P, c_double, c_int, c_int64, c_int, c_int, P, P, P]),
+        "dnmf_forward_maxz": (c_int, [P, P, c_int, P, P, P]),
+        "dnmf_frames_maxz": (c_int, [P, c_int64, c_int, P, P]),
         "dnmf_ext_enable": (c_int, [P]),
         "dnmf_ext_loss_grad": (c_int, [P, P, P, c_int, c_int, P, P, c_float, P, P, P, P, P, P]),
         "dnmf_measure_fp32_peak": (c_int, [c_int, c_int, POINTER(c_double)]),

@@ -327,11 +327,25 @@ __global__ void stats_reduce_kernel(StatsPartials sp, const int* __restrict__ fr
         const size_t tf = (size_t)b * nt + tile0 + r * 32 + src;
         const float* blk = sp.vals + tf * (size_t)sp.capL * sp.ld;
         const unsigned short* ids = sp.ids + tf * sp.capL;
-        for (int i = lane; i < L; i += 32) {
-          const float v = i >= j ? blk[(size_t)j * sp.ld + i] : blk[(size_t)i * sp.ld + j];
-          row[ids[i]] += (double)v;
+        const float bj = lane == 0 ? blk[(size_t)j * sp.ld + sp.capL] : 0.f;
+        for (int i0 = 0; i0 < L; i0 += 128) {  // four entries per lane in flight: one memory round trip per 128 entries
+          float v[4];
+          int id[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32 + lane;
+            id[u] = 0;
+            v[u] = 0.f;
+            if (i < L) {
+              id[u] = ids[i];
+              v[u] = i >= j ? blk[(size_t)j * sp.ld + i] : blk[(size_t)i * sp.ld + j];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (i0 + u * 32 + lane < L) row[id[u]] += (double)v[u];
         }
-        if (lane == 0) bsum += (double)blk[(size_t)j * sp.ld + sp.capL];
+        if (lane == 0) bsum += (double)bj;
         __syncwarp();
       }
     }

@@ -320,6 +320,24 @@ class Engine:
                    "dnmf_iwarp")
         return out
 
+    def forward_maxz(self, frame_ids: torch.Tensor, beta) -> torch.Tensor:
+        """max over z of the deformed footprints, [B,K,X,Y] (demo.py:50-52 `A_t.max(2)`), without the dense A_t."""
+        self._check_state(beta)
+        ids32 = self._ids32(frame_ids)
+        B = int(ids32.numel())
+        out = torch.empty(B, self.K, self.X, self.Y, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.dnmf_forward_maxz(self._h, _ptr(ids32), B, _ptr(beta), _ptr(out), self.stream),
+                   "dnmf_forward_maxz")
+        return out
+
+    def frames_maxz(self, frames: torch.Tensor) -> torch.Tensor:
+        """max over the last axis of a contiguous float32 CUDA tensor [..., Z] (Y.max(2), Y_i.max(2))."""
+        _check_dev(frames, torch.float32, "frames", self.device)
+        out = torch.empty(frames.shape[:-1], dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.dnmf_frames_maxz(_ptr(frames), int(out.numel()), int(frames.shape[-1]), _ptr(out),
+                                             self.stream), "dnmf_frames_maxz")
+        return out
+
     # -- extension: shared-parameter gradients (no reference counterpart) -----------------------------
     def ext_enable(self):
         _lib.check(self.lib.dnmf_ext_enable(self._h), "dnmf_ext_enable")
@@ -349,3 +367,86 @@ class Engine:
         keys = ("fit_launches", "reduce_launches", "bin_calls", "table_builds", "adam_launches",
                 "dense_forward_launches", "mu_stats_launches", "mu_sweep_launches")
         return dict(zip(keys, (int(v) for v in out)))
+
+
+# -- context-free entry points (dense fp64 multiplicative updates, synthetic generator) ---------------------
+def _cuda_device(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.DnmfError("dnmf_b200 needs a CUDA device: there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise _lib.DnmfError("device must be a CUDA device, got %s" % dev)
+    return torch.device("cuda", torch.cuda.current_device()) if dev.index is None else dev
+
+
+def update_spatial_dense(A, C, Y_i, D=None, gamma=None, positions=None, grid=None, device=None) -> torch.Tensor:
+    """A <- A * (Y_i C^T) / (A (C C^T) + gamma D + 1e-32) in fp64 on the GPU (Demix/dNMF.py:151-160).  A[..., K],
+    C[K, T], Y_i[..., T] with the same leading (voxel) axes.  D: array like A, or None; with `positions` [K,3] and
+    `grid` (X, Y, Z) the penalty D = 1 - exp(-0.01 |p - pos_k|) (:133-135) is computed on the fly instead."""
+    dev = _cuda_device(device)
+    lib = _lib.load()
+    Ad = torch.as_tensor(A, dtype=torch.float64).to(dev).contiguous()
+    Cd = torch.as_tensor(C, dtype=torch.float64).to(dev).contiguous()
+    Yd = torch.as_tensor(Y_i, dtype=torch.float64).to(dev).contiguous()
+    K, T = int(Cd.shape[0]), int(Cd.shape[1])
+    if Ad.shape[-1] != K or Yd.shape[-1] != T or Ad.shape[:-1] != Yd.shape[:-1]:
+        raise _lib.DnmfError("update_spatial: A[...,K], C[K,T], Y_i[...,T] do not fit together")
+    P = int(Ad.numel() // K)
+    use_D, Dd, pos, g = 0, None, None, (0, 0, 0)
+    if D is not None:
+        if gamma is None:
+            raise _lib.DnmfError("update_spatial: D needs gamma")   # the reference raises a TypeError here
+        Dd = torch.as_tensor(D, dtype=torch.float64).to(dev).contiguous()
+        if Dd.numel() != Ad.numel():
+            raise _lib.DnmfError("update_spatial: D must have the shape of A")
+        use_D = 1
+    elif positions is not None and gamma is not None:
+        g = tuple(int(v) for v in grid)
+        pos = torch.as_tensor(positions, dtype=torch.float32).to(dev).contiguous()
+        use_D = 2
+    scratch = torch.empty(K * K, dtype=torch.float64, device=dev)
+    out = torch.empty_like(Ad)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dnmf_update_spatial(_ptr(Ad), _ptr(Cd), _ptr(Yd), _ptr(Dd), _ptr(pos), g[0], g[1], g[2],
+                                           float(gamma or 0.0), use_D, P, K, T, _ptr(scratch), _ptr(out),
+                                           _stream_ptr(dev)), "dnmf_update_spatial")
+    return out
+
+
+def update_temporal_dense(A_t, C, Y, gamma=None, device=None) -> torch.Tensor:
+    """The static update_temporal on dense arrays (Demix/dNMF.py:139-149), fp64 on the GPU: A_t[..., K, T], C[K,T],
+    Y[..., T]."""
+    dev = _cuda_device(device)
+    lib = _lib.load()
+    Ad = torch.as_tensor(A_t, dtype=torch.float64).to(dev).contiguous()
+    Cd = torch.as_tensor(C, dtype=torch.float64).to(dev).contiguous()
+    Yd = torch.as_tensor(Y, dtype=torch.float64).to(dev).contiguous()
+    K, T = int(Cd.shape[0]), int(Cd.shape[1])
+    if tuple(Ad.shape[-2:]) != (K, T) or Yd.shape[-1] != T or Ad.shape[:-2] != Yd.shape[:-1]:
+        raise _lib.DnmfError("update_temporal: A_t[...,K,T], C[K,T], Y[...,T] do not fit together")
+    P = int(Yd.numel() // T)
+    scratch = torch.empty((K * K + K) * T, dtype=torch.float64, device=dev)
+    out = torch.empty_like(Cd)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dnmf_update_temporal_dense(_ptr(Ad), _ptr(Cd), _ptr(Yd), float(gamma or 0.0),
+                                                  int(gamma is not None), P, K, T, _ptr(scratch), _ptr(out),
+                                                  _stream_ptr(dev)), "dnmf_update_temporal_dense")
+    return out
+
+
+def render_cells(positions, traces, sz, shape_std, device=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Clean synthetic frames [T,X,Y,Z] = sum_k traces[k,t] exp(-|p - P_k(t)|^2 / (2 shape_std))
+    (WUtils/Simulator.py:66-77,197-203) with the hand-written generator kernel."""
+    dev = _cuda_device(device)
+    lib = _lib.load()
+    pos = torch.as_tensor(positions, dtype=torch.float32).to(dev).contiguous()
+    tr = torch.as_tensor(np.asarray(traces), dtype=torch.float32).to(dev).contiguous()
+    K, _, T = pos.shape
+    X, Y, Z = (int(v) for v in sz)
+    if out is None:
+        out = torch.empty(T, X, Y, Z, dtype=torch.float32, device=dev)
+    _check_dev(out, torch.float32, "out", dev, (T, X, Y, Z))
+    with torch.cuda.device(dev):
+        _lib.check(lib.dnmf_render_cells(_ptr(pos), _ptr(tr), int(K), int(T), 0, int(T), X, Y, Z, float(shape_std),
+                                         _ptr(out), _stream_ptr(dev)), "dnmf_render_cells")
+    return out

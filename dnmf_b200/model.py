@@ -160,6 +160,37 @@ class ExponentialFP(nn.Module):
         return b.grad
 
     @staticmethod
+    def pushforward_chunks(dl, model, want_At: bool = True):
+        """Lazy form of spatial_pushforward for volumes where the dense arrays cannot exist (825 GB at cfg2,
+        Demix/dNMF.py:72): yields per batch of the loader (ids, A_t[B,K,X,Y,Z] or None, Y_i[B,X,Y,Z], Y[B,X,Y,Z]) as
+        float32 CUDA tensors; nothing is kept between batches."""
+        eng = model.fp.engine
+        beta = model.fp.beta.detach()
+        local = getattr(model, "_local_ids", lambda v: torch.as_tensor(v).to(torch.int32))
+        for data in dl:
+            ids = local(data[1])
+            if data[0] is None:
+                fd = eng.video()[ids.long().to(eng.device)].contiguous()
+            else:
+                fd = data[0].float().to(eng.device).contiguous()
+            At = eng.forward(ids, beta, model.C, want_At=True)[1] if want_At else None
+            yield ids, At, eng.iwarp(ids, beta, frames=fd), fd
+
+    @staticmethod
+    def max_projections(dl, model):
+        """The projections demo.py:50-52 takes of the pushforward outputs, computed on the device without the dense
+        arrays: (A_t.max(2) [X,Y,K,T'], Y_i.max(2) [X,Y,T'], Y.max(2) [X,Y,T']) as float32 CUDA tensors."""
+        eng = model.fp.engine
+        beta = model.fp.beta.detach()
+        A_parts, Yi_parts, Y_parts = [], [], []
+        for ids, _, yi, y in ExponentialFP.pushforward_chunks(dl, model, want_At=False):
+            A_parts.append(eng.forward_maxz(ids, beta))        # [B,K,X,Y]
+            Yi_parts.append(eng.frames_maxz(yi))               # [B,X,Y]
+            Y_parts.append(eng.frames_maxz(y))
+        A_max = torch.cat(A_parts, 0).permute(2, 3, 1, 0)
+        return A_max, torch.cat(Yi_parts, 0).permute(1, 2, 0), torch.cat(Y_parts, 0).permute(1, 2, 0)
+
+    @staticmethod
     def spatial_pushforward(dl, batch_size, sz, device, model):
         """Dense outputs of Demix/dNMF.py:69-93: (A_t[X,Y,Z,K,T'] f64, Y_i[X,Y,Z,T'] f64, Y[X,Y,Z,T'] f64)
         as numpy arrays, computed on the GPU batch by batch."""
@@ -177,7 +208,7 @@ class ExponentialFP(nn.Module):
         beta = model.fp.beta.detach()
         for bi, data in enumerate(dl):
             frames = data[0].float()
-            ids = torch.as_tensor(data[1]).to(torch.int32)
+            ids = model._local_ids(data[1]) if hasattr(model, "_local_ids") else torch.as_tensor(data[1]).to(torch.int32)
             fd = frames.to(eng.device).contiguous()
             _, At, _ = eng.forward(ids, beta, model.C, want_At=True)
             yi = eng.iwarp(ids, beta, frames=fd)
@@ -496,35 +527,28 @@ class DeformableNMF:
 
     # -- traces -------------------------------------------------------------------------------------
     @staticmethod
-    def update_temporal(A_t, C, Y, gamma=None):
-        """Stand-alone multiplicative update on dense arrays (Demix/dNMF.py:139-149), fp64 on the GPU."""
-        dev = torch.device("cuda")
-        A = torch.as_tensor(A_t, dtype=torch.float64, device=dev)
-        Cd = torch.as_tensor(C, dtype=torch.float64, device=dev)
-        Yd = torch.as_tensor(Y, dtype=torch.float64, device=dev)
-        A_ts = torch.einsum("mnzkt,mnzlt->klt", A, A)
-        C1 = torch.einsum("mnzkt,mnzt->kt", A, Yd)
-        C2 = torch.einsum("klt,lt->kt", A_ts, Cd)
-        if gamma is not None:
-            reg = torch.cat((Cd[:, :1], Cd[:, :-1]), 1) + torch.cat((Cd[:, 1:], Cd[:, -1:]), 1)
-            C1 = C1 + gamma * reg
-            C2 = C2 + 2 * gamma * Cd
-        return (Cd * C1 / (C2 + 1e-32)).cpu().numpy()
+    def update_temporal(A_t, C, Y, gamma=None, device=None):
+        """Stand-alone multiplicative update on dense arrays (Demix/dNMF.py:139-149): fp64 kernels on the GPU
+        (`dnmf_update_temporal_dense`), numpy array back like the reference."""
+        from .engine import update_temporal_dense
+        return update_temporal_dense(A_t, C, Y, gamma=gamma, device=device).cpu().numpy()
 
     @staticmethod
-    def update_spatial(A, C, Y_i, D=None, gamma=None):
-        """Non-parametric footprint update of Demix/dNMF.py:151-160 (never called by the reference's
-        fit loop, :174), fp64 on the GPU."""
-        dev = torch.device("cuda")
-        Ad = torch.as_tensor(A, dtype=torch.float64, device=dev)
-        Cd = torch.as_tensor(C, dtype=torch.float64, device=dev)
-        Yd = torch.as_tensor(Y_i, dtype=torch.float64, device=dev)
-        C_s = torch.einsum("kt,pt->kp", Cd, Cd)
-        A1 = torch.einsum("mnt,kt->mnk", Yd, Cd)
-        A2 = torch.einsum("mnk,kp->mnp", Ad, C_s)
-        if D is not None:
-            A2 = A2 + gamma * torch.as_tensor(D, dtype=torch.float64, device=dev)
-        return (Ad * A1 / (A2 + 1e-32)).cpu().numpy()
+    def update_spatial(A, C, Y_i, D=None, gamma=None, device=None):
+        """Non-parametric footprint update of Demix/dNMF.py:151-160 (never called by the reference's fit loop,
+        :174): one fused fp64 pass over the registered video (`dnmf_update_spatial`), numpy array back."""
+        from .engine import update_spatial_dense
+        return update_spatial_dense(A, C, Y_i, D=D, gamma=gamma, device=device).cpu().numpy()
+
+    def update_spatial_on_grid(self, A, Y_i, gamma=1e0):
+        """update_spatial for this model's traces with the distance penalty of Demix/dNMF.py:133-135 computed on the
+        fly from the neuron positions (the reference stores it as a dense fp64 [X,Y,Z,K] array, 826 MB at cfg2):
+        A[X,Y,Z,K], Y_i[X,Y,Z,T] -> the updated A as a CUDA fp64 tensor."""
+        from .engine import update_spatial_dense
+        if self._positions is None:
+            raise DnmfError("update_spatial_on_grid needs the positions the model was built with")
+        return update_spatial_dense(A, self.C, Y_i, gamma=gamma, positions=self._positions, grid=self._size,
+                                    device=self.fp.engine.device)
 
     def update_traces(self, testloader=None, gamma_c=1e-2, iter_c=10, halo_exchange=None):
         """Device-only trace update: statistics kernel over all frames, then iter_c sweeps.

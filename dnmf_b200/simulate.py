@@ -1,10 +1,11 @@
 """Synthetic worm-video generator and dataset (input side of the hot path).
 
 Re-statement of the semantics of WUtils/Simulator.py::generate_video (:20-77) with the separable
-structure of its Gaussian cells exploited: video_t = sum_k traces[k,t] * gx_k (x) gy_k (x) gz_k is
-one batched GEMM per chunk of frames instead of K*T scipy pdf evaluations over all voxels
-(O(T*K*N) host work in the reference, unusable beyond the demo size).  Runs on the GPU when one is
-present (torch ops; this is input generation, not the fit path).
+structure of its Gaussian cells exploited: video_t = sum_k traces[k,t] * gx_k (x) gy_k (x) gz_k
+instead of K*T scipy pdf evaluations over all voxels (O(T*K*N) host work in the reference, unusable
+beyond the demo size).  On a GPU the clean frames come from the library's generator kernel
+(`dnmf_render_cells`, csrc/dnmf_aux.cu); on the CPU (tests, the reference arm's workload) from one
+batched GEMM per chunk of frames.
 
   * cells:   exp(-|p - P_k(t)|^2 / (2*shape_std))            Simulator.py:72,197-203 (cov = shape_std*I)
   * traces:  1 + Bernoulli(density) spikes (*) exp(-0.3 j), j < 10      Simulator.py:174-195
@@ -71,6 +72,10 @@ def render_clean(positions: torch.Tensor, traces, sz: Sequence[int], shape_std: 
     device = torch.device(device) if device is not None else positions.device
     X, Y, Z = (int(s) for s in sz)
     K, _, T = positions.shape
+    if device.type == "cuda" and Z <= 64:
+        # on the GPU the frames come from the hand-written generator kernel (dnmf_render_cells)
+        from .engine import render_cells
+        return render_cells(positions, traces, (X, Y, Z), shape_std, device=device, out=out)
     tr = torch.as_tensor(np.asarray(traces), dtype=torch.float32, device=device)
     pos = positions.to(device)
     ax = [torch.arange(n, device=device, dtype=torch.float32) for n in (X, Y, Z)]

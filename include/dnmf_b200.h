@@ -181,6 +181,36 @@ int dnmf_ext_loss_grad(dnmf_ctx* ctx, const float* frames_dev, const int32_t* fr
  * the roofline denominator for the FP32-bound fused kernel (MEASURED_PEAKS.json has no FP32 entry). */
 int dnmf_measure_fp32_peak(int device, int repeats, double* tflops_out);
 
+/* ---- callers and data formats either side of the fit path ---------------------------- */
+
+/* Synthetic generator, clean frames (WUtils/Simulator.py:66-77,197-203: every cell is a Gaussian with
+ * cov = shape_std * I rescaled to peak 1, weighted by its trace): out[nT][X][Y][Z] =
+ * sum_k traces[k][t] * exp(-|p - pos[k][:][t]|^2 / (2 * shape_std)) for t = t0 .. t0+nT-1.
+ * pos_dev[K][3][T], traces_dev[K][T] (float32, device).  Z <= 64.  No context needed. */
+int dnmf_render_cells(const float* pos_dev, const float* traces_dev, int K, int T, int t0, int nT, int X, int Y,
+                      int Z, float shape_std, float* out_dev, void* stream);
+
+/* DeformableNMF.update_spatial (Demix/dNMF.py:151-160), fp64 like the reference's numpy einsum, voxels P =
+ * the flattened leading axes: A[P][K], C[K][T], Y_i[P][T] -> out[P][K] = A * (Y_i C^T) / (A (C C^T) + gamma D + 1e-32).
+ * use_D: 0 = no penalty (D=None), 1 = D_dev[P][K] given, 2 = D computed on the fly from pos_dev[K][3] on the
+ * X*Y*Z = P grid, D = 1 - exp(-0.01 |p - pos_k|) (Demix/dNMF.py:133-135).  scratch_KK_dev: K*K doubles. */
+int dnmf_update_spatial(const double* A_dev, const double* C_dev, const double* Yi_dev, const double* D_dev,
+                        const float* pos_dev, int gX, int gY, int gZ, double gamma, int use_D, int64_t P, int K,
+                        int T, double* scratch_KK_dev, double* out_dev, void* stream);
+
+/* The static DeformableNMF.update_temporal on DENSE arrays (Demix/dNMF.py:139-149), fp64: A_t[P][K][T] (the
+ * reference's [X,Y,Z,K,T] array), C[K][T], Y[P][T] -> out[K][T].  scratch_dev: (K*K + K) * T doubles. */
+int dnmf_update_temporal_dense(const double* At_dev, const double* C_dev, const double* Y_dev, double gamma,
+                               int use_gamma, int64_t P, int K, int T, double* scratch_dev, double* out_dev,
+                               void* stream);
+
+/* Max-projection along z of the deformed footprints (demo.py:50-52, A_t.max(2)) for B frames, straight from the
+ * per-axis tables: out[B][K][X][Y]; the dense A_t[B][K][X][Y][Z] is never formed.  Z <= 64. */
+int dnmf_forward_maxz(dnmf_ctx* ctx, const int32_t* frame_ids_dev, int B, const float* beta_dev, float* out_dev,
+                      void* stream);
+/* The same for frames (Y.max(2), Y_i.max(2)): frames_dev[columns][Z] -> out_dev[columns]. */
+int dnmf_frames_maxz(const float* frames_dev, int64_t columns, int Z, float* out_dev, void* stream);
+
 /* Waits for `stream` and reports an error that an earlier asynchronous call found on the device (see the
  * conventions above); returns 0 when there is none.  The error is cleared by reporting it. */
 int dnmf_check_status(dnmf_ctx* ctx, void* stream);

@@ -157,6 +157,50 @@ def mu_sweep(Gm: np.ndarray, bv: np.ndarray, C: np.ndarray, gamma) -> np.ndarray
     return C * C1 / (C2 + 1e-32)
 
 
+def update_spatial(A: np.ndarray, C: np.ndarray, Y_i: np.ndarray, D=None, gamma=None) -> np.ndarray:
+    """Non-parametric footprint update (Demix/dNMF.py:151-160), numpy fp64; the voxel axes of A[..., K] and
+    Y_i[..., T] may be any leading shape (the reference's einsum strings fix two)."""
+    A = np.asarray(A, np.float64)
+    C = np.asarray(C, np.float64)
+    Y_i = np.asarray(Y_i, np.float64)
+    C_s = np.einsum("kt,pt->kp", C, C)
+    A1 = np.einsum("...t,kt->...k", Y_i, C)
+    A2 = np.einsum("...k,kp->...p", A, C_s)
+    if D is not None:
+        A2 = A2 + gamma * np.asarray(D, np.float64)
+    return A * A1 / (A2 + 1e-32)
+
+
+def distance_penalty(sz: Sequence[int], positions: np.ndarray) -> np.ndarray:
+    """D = 1 - exp(-0.01 * cdist(grid, positions)) reshaped to [X,Y,Z,K] (Demix/dNMF.py:133-135)."""
+    X, Y, Z = (int(s) for s in sz)
+    g = np.stack(np.meshgrid(np.arange(X), np.arange(Y), np.arange(Z), indexing="ij"), -1).reshape(-1, 3).astype(np.float64)
+    d = np.sqrt(((g[:, None, :] - np.asarray(positions, np.float64)[None, :, :]) ** 2).sum(-1))
+    return (1 - np.exp(-.01 * d)).reshape(X, Y, Z, -1)
+
+
+def update_temporal_dense(A_t: np.ndarray, C: np.ndarray, Y: np.ndarray, gamma=None) -> np.ndarray:
+    """The static update_temporal on dense arrays (Demix/dNMF.py:139-149), numpy fp64."""
+    A_t = np.asarray(A_t, np.float64)
+    Gm, bv = mu_stats_dense(A_t, np.asarray(Y, np.float64))
+    return mu_sweep(Gm, bv, np.asarray(C, np.float64), gamma)
+
+
+def render_cells(positions: np.ndarray, traces: np.ndarray, sz: Sequence[int], shape_std: float) -> np.ndarray:
+    """Clean frames [T,X,Y,Z] of the synthetic generator in fp64: sum_k traces[k,t] * pdf_k / max(pdf_k) with
+    pdf_k the normal density of cov = shape_std * I centred at positions[k,:,t] (WUtils/Simulator.py:66-73,197-203:
+    the density is rescaled to peak 1, i.e. exp(-|p - P|^2 / (2 shape_std)))."""
+    X, Y, Z = (int(s) for s in sz)
+    K, _, T = positions.shape
+    ax = [np.arange(n, dtype=np.float64) for n in (X, Y, Z)]
+    out = np.zeros((T, X, Y, Z))
+    for t in range(T):
+        for k in range(K):
+            g = [np.exp(-(ax[d] - float(positions[k, d, t])) ** 2 / (2.0 * shape_std)) for d in range(3)]
+            out[t] += float(traces[k, t]) * g[0][:, None, None] * g[1][None, :, None] * g[2][None, None, :]
+    return out
+
+
 def log_det_jac_consistent(Bm: torch.Tensor, P) -> torch.Tensor:
     """log|det J| with cross-term rows matching the basis order (xy=7, xz=8, yz=9); opt-in fix of F3."""
     x, y, z = P[0], P[1], P[2]
