@@ -229,7 +229,7 @@ def build_model(cfg, T, dev, world, tiling=None, seed=100):
     dn = DeformableNMF(cfg["sz"], cfg["K"], T, positions=positions[:, :, 0], cutoff=CUTOFF,
                        deformation=cfg["deformation"], shape_std=cfg["sigma"], device=dev, tiling=tiling, verbose=False,
                        global_batch_scale=world)
-    dn.attach_video(vid, layout="TXYZ")
+    dn.attach_video(vid, layout="TXYZ", copy=False)     # the context reads the generated slab in place
     return dn, vid
 
 
@@ -513,11 +513,9 @@ def run_b200(args, cfg):
     for i in range(args.steps):
         one_step(args.warmup + i)
     evk.record()                           # the rank's own K steps are enqueued up to here
-    t_w0 = time.perf_counter()
     drain(final=True)                      # the timed region ends after the last loss reduction
     ev1.record()
     torch.cuda.synchronize()
-    t_wait = (time.perf_counter() - t_w0) * 1e3
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     ms_steps_only = ev0.elapsed_time(evk)
@@ -546,7 +544,7 @@ def run_b200(args, cfg):
             clk = float(torch.cuda.clock_rate(dev))
         except Exception:
             clk = 0.0
-        mine = torch.tensor([ms_own / args.steps, ms_steps_only / args.steps, t_wait, listed, clk],
+        mine = torch.tensor([ms_own / args.steps, ms_steps_only / args.steps, ms_own - ms_steps_only, listed, clk],
                             dtype=torch.float64, device=dev)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
@@ -554,7 +552,7 @@ def run_b200(args, cfg):
             rows = torch.stack(allr).cpu().numpy()
             scaling_detail = {"per_rank_ms_per_step": rows[:, 0].tolist(),
                               "per_rank_ms_per_step_kernels_only": rows[:, 1].tolist(),
-                              "per_rank_host_ms_in_final_loss_reduction": rows[:, 2].tolist(),
+                              "per_rank_device_ms_from_last_step_to_end_of_final_loss_reduction": rows[:, 2].tolist(),
                               "per_rank_listed_pairs_per_voxel": rows[:, 3].tolist(),
                               "per_rank_sm_clock_mhz_after": rows[:, 4].tolist(),
                               "workloads": "identical on every rank (same seed): differences are the hardware's",

@@ -46,6 +46,7 @@ def load(build_if_missing: bool = True):
         "dnmf_get_tiling": (c_int, [P, P]),
         "dnmf_upload_frames": (c_int, [P, P, c_int, c_int, c_int, P]),
         "dnmf_video_devptr": (c_int, [P, POINTER(c_void_p)]),
+        "dnmf_attach_frames": (c_int, [P, P, c_int, P]),
         "dnmf_bin_tiles": (c_int, [P, P, P, c_int, P, P, P, P, c_int64, POINTER(c_int64), P]),
         "dnmf_loss_grad": (c_int, [P, P, P, c_int, c_int, P, P, P, P, P]),
         "dnmf_adam_step": (c_int, [P, P, P, P, P, c_double, c_double, c_double, c_double, c_int64, c_int, P,

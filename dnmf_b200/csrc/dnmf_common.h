@@ -208,6 +208,7 @@ struct dnmf_ctx {
   void* encode_tiled = nullptr;
   // video
   float* d_video = nullptr;
+  bool video_owned = true;  // false: the slab belongs to the caller (dnmf_attach_frames)
   // scratch
   float* d_partials = nullptr;
   size_t partials_cap = 0;

@@ -578,7 +578,7 @@ extern "C" void dnmf_destroy(dnmf_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   void* ptrs[] = {c->d_pos,     c->d_sigma, c->d_rng,        c->d_tab[0],      c->d_tab[1],
-                  c->d_tab[2],  c->d_video, c->d_partials,   c->d_grad,        c->d_sse,
+                  c->d_tab[2],  c->video_owned ? c->d_video : nullptr, c->d_partials,   c->d_grad,        c->d_sse,
                   c->d_batch,   c->d_ids,   c->d_loss,       c->d_tmp_counts,  c->d_tmp_offsets,
                   c->d_tmp_max, c->d_G,     c->d_b,          c->d_identity_beta,
                   c->d_Cd[0],   c->d_Cd[1], c->d_keys,       c->d_cand_off,    c->d_cand_ids,
@@ -853,11 +853,33 @@ extern "C" int dnmf_upload_frames(dnmf_ctx* c, const float* frames_host, int t0,
   if (t0 < 0 || n < 0 || t0 + n > c->T) return fail("dnmf_upload_frames: frame range outside [0,T)");
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(c->device));
+  if (c->d_video && !c->video_owned) {  // a slab attached by the caller is left alone: the context gets its own
+    c->d_video = nullptr;
+    c->video_owned = true;
+    c->tmap_valid = false;
+    c->tmap_ptr = nullptr;
+  }
   if (!c->d_video) CU(cudaMalloc((void**)&c->d_video, c->N * (size_t)c->T * sizeof(float)));
   float* dst = c->d_video + (size_t)t0 * c->N;
   CU(cudaMemcpyAsync(dst, frames_host, c->N * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, st));
   if (clamp_negative && n > 0) {
     clamp_negative_kernel<<<c->num_sms * 8, 256, 0, st>>>(dst, c->N * (size_t)n);
+    CU(cudaGetLastError());
+  }
+  return 0;
+}
+
+extern "C" int dnmf_attach_frames(dnmf_ctx* c, float* frames_dev, int clamp_negative, void* stream) {
+  if (!c) return fail("dnmf_attach_frames: ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  if (c->d_video && c->video_owned) CU(cudaFree(c->d_video));
+  c->d_video = frames_dev;             // NULL detaches
+  c->video_owned = frames_dev == nullptr;
+  c->tmap_valid = false;
+  c->tmap_ptr = nullptr;
+  if (frames_dev && clamp_negative) {
+    if (((uintptr_t)frames_dev & 3) != 0) return fail("dnmf_attach_frames: misaligned pointer");
+    clamp_negative_kernel<<<c->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(frames_dev, c->N * (size_t)c->T);
     CU(cudaGetLastError());
   }
   return 0;

@@ -49,11 +49,13 @@ class Engine:
                                         self.device.index), "dnmf_create")
         self._h = h
         self._has_video = False
+        self._attached = None
 
     def close(self):
         if getattr(self, "_h", None):
             self.lib.dnmf_destroy(self._h)
             self._h = None
+        self._attached = None
 
     def __del__(self):
         try:
@@ -137,6 +139,16 @@ class Engine:
             _lib.check(self.lib.dnmf_upload_frames(self._h, _ptr(frames), int(t0), int(frames.shape[0]),
                                                    int(clamp_negative), self.stream), "dnmf_upload_frames")
             torch.cuda.current_stream(self.device).synchronize()
+            self._attached = None      # the library switched to a slab of its own
+        self._has_video = True
+
+    def attach_frames(self, frames: torch.Tensor, clamp_negative: bool = True):
+        """Zero-copy: the engine reads the caller's CUDA slab [T,X,Y,Z] in place (clamped in place when asked, like
+        the reference's dataset does to its own video, Demix/dNMF.py:215).  The engine keeps a reference."""
+        _check_dev(frames, torch.float32, "frames", self.device, (self.T, self.X, self.Y, self.Z))
+        _lib.check(self.lib.dnmf_attach_frames(self._h, _ptr(frames), int(clamp_negative), self.stream),
+                   "dnmf_attach_frames")
+        self._attached = frames
         self._has_video = True
 
     def video(self) -> torch.Tensor:

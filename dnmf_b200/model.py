@@ -346,9 +346,10 @@ class DeformableNMF:
         return self._D
 
     # -- resident video (extension: keeps the frames in HBM so steps only send frame ids) ----------
-    def attach_video(self, video: torch.Tensor, layout: str = "XYZT"):
+    def attach_video(self, video: torch.Tensor, layout: str = "XYZT", copy: bool = True):
         """Upload this rank's frames once.  layout 'XYZT' is SimulatedVideoDataset.video
-        (Demix/dNMF.py:203), 'TXYZ' is frame-major."""
+        (Demix/dNMF.py:203), 'TXYZ' is frame-major.  copy=False adopts a frame-major float32 CUDA tensor in place
+        (no second slab in HBM; negatives are clamped in place like the reference's dataset does, :215)."""
         if layout == "XYZT":
             frames = video.permute(3, 0, 1, 2)
         elif layout == "TXYZ":
@@ -357,6 +358,12 @@ class DeformableNMF:
             raise ValueError("layout must be 'XYZT' or 'TXYZ'")
         if frames.shape[0] != self.fp.T:
             raise DnmfError("video has %d frames, model has T=%d" % (frames.shape[0], self.fp.T))
+        if not copy:
+            if not (frames.is_cuda and frames.dtype == torch.float32 and frames.is_contiguous()):
+                raise DnmfError("attach_video(copy=False) needs a contiguous frame-major float32 CUDA tensor")
+            self.fp.engine.attach_frames(frames, clamp_negative=True)
+            self._video_resident = True
+            return
         self.fp.engine.upload_frames(frames.float().contiguous(), 0, clamp_negative=True)
         self._video_resident = True
 

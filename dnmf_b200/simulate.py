@@ -116,12 +116,17 @@ def generate_video(K, T, sz=(20, 20, 1), shape_std=3, density=.1, bg_snr=-1, tra
     gen = torch.Generator(device=video.device)
     gen.manual_seed(int(rng.integers(0, 2 ** 31 - 1)))
     bg_std = float(np.sqrt(10 ** (bg_snr / 10)))
-    video /= (video.double() ** 2).sum().float()
-    chunk = 64
+    chunk = 64                                   # chunked passes: no second copy of the slab (110 GB at T = 40k)
+    ssq = sum((video[t0:t0 + chunk].double() ** 2).sum() for t0 in range(0, T, chunk))
+    ssq = ssq.float()
+    vmax = torch.zeros((), device=video.device)
     for t0 in range(0, T, chunk):
         v = video[t0:t0 + chunk]
+        v /= ssq
         v += bg_std * torch.randn(v.shape, generator=gen, device=video.device)
-    video /= video.max()
+        vmax = torch.maximum(vmax, v.max())
+    for t0 in range(0, T, chunk):
+        video[t0:t0 + chunk] /= vmax
     if not frame_major:
         video = video.permute(1, 2, 3, 0)
     return video, positions, traces

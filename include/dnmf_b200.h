@@ -65,6 +65,10 @@ int dnmf_get_tiling(dnmf_ctx* ctx, int32_t* out /* tx,ty,tz,ntx,nty,ntz,warps_x,
 int dnmf_upload_frames(dnmf_ctx* ctx, const float* frames_host, int t0, int n, int clamp_negative,
                        void* stream);
 int dnmf_video_devptr(dnmf_ctx* ctx, float** out_dev);
+/* Zero-copy alternative for frames that are already on the device: the context reads the caller's slab
+ * frames_dev[T][X][Y][Z] in place (the caller keeps it alive and owns it; NULL detaches).  clamp_negative != 0
+ * clamps it IN PLACE, which is what the reference's dataset does to its own video (Demix/dNMF.py:215). */
+int dnmf_attach_frames(dnmf_ctx* ctx, float* frames_dev, int clamp_negative, void* stream);
 
 /* Kernel 1b (stand-alone form): deterministic neuron-to-tile binning for B frames; the fused
  * kernel runs the same device code in its prologue.  Outputs are device arrays:
