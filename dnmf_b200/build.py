@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 UNITS = ["dnmf_kernels.cu", "fit_mode0.cu", "fit_mode1.cu", "fit_mode2.cu", "fit_mode3.cu", "dnmf_gram_tc.cu",
          "dnmf_aux.cu"]
-OUT_DIR = os.path.join(HERE, "_C")
+OUT_DIR = os.environ.get("DNMF_B200_OUT_DIR") or os.path.join(HERE, "_C")   # kernel experiments build elsewhere
 OBJ_DIR = os.path.join(OUT_DIR, "obj")
 OUT = os.path.join(OUT_DIR, "libdnmf_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

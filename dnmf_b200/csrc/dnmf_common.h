@@ -31,6 +31,27 @@ constexpr int kZUnroll = DNMF_ZUNROLL;
                              // (4 bodies instead of 6; measured at cfg2: identity beta 2.65 ms either way, a different
                              // deformation per frame 3.40 -> 2.94 ms per 1000 frames)
 #endif
+#ifndef DNMF_AFFINE_BODIES
+#define DNMF_AFFINE_BODIES 1  // 1: affine frames with frozen quadratic rows (FitParams::skip_quad) take main loops without
+                              // the z^2 Horner term and the z^2 gradient moments (6 packed + 1 scalar op per z step fewer)
+#endif
+#ifndef DNMF_FLAT_RESTAGE
+#define DNMF_FLAT_RESTAGE 0  // bit 0: the slice gathers, bit 1: the x-slice rescale deal (slot pair, entry) items to all
+                             // lanes instead of one thread per entry.  Measured at cfg2 / cfg3, both on: 8-20 % SLOWER
+                             // (128 registers, larger prologue), so off.
+#endif
+#ifndef DNMF_RESTAGE_BATCH
+#define DNMF_RESTAGE_BATCH 4
+#endif
+#ifndef DNMF_DYN_TAIL_BODIES
+#define DNMF_DYN_TAIL_BODIES 0  // 1: also compile the single-body main loops with a run-time tail kind (march_rolled TAIL 3)
+                                // and the per-launch choice from restage counters (DNMF_DYN_TAIL).  Measured slower than the
+                                // default four bodies in both states (2.77 / 3.05 vs 2.65 / 2.94 ms); 4 unused loop bodies
+                                // (13 KB of SASS) and a counter round trip per launch otherwise.
+#endif
+#ifndef DNMF_FMA_MOMENTS
+#define DNMF_FMA_MOMENTS 1  // 1: gradient z-moments as fma(z^m r, g, S) in the specialised main loops
+#endif
 #ifndef DNMF_ALWAYS_SAFE
 #define DNMF_ALWAYS_SAFE 0  // 1: every tile takes the clamped main loop (one loop body fewer in the instruction cache)
 #endif
@@ -104,6 +125,7 @@ struct FitParams {
   int fpc;       // consecutive frames walked by one CTA (<= 32)
   StatsPartials stats;  // MODE 3 (trace statistics): partial blocks of this launch's tile-frames
   int* mu_overflow;  // MODE 3: set when a tile's list is not fully staged (the caller reruns the generic kernel)
+  int skip_quad;  // != 0: gradient rows 4..9 are not wanted (affine fit: Adam freezes them) and are returned as zero
   int dyn_tail;  // != 0: main loop with the run-time tail kind (one loop body per SAFE; see march_rolled TAIL 3)
   unsigned* restage_count;  // [32] frames whose slices were rebuilt, counted per CTA (MODE 0; may be NULL)
   int y_pitch;   // floats between x rows of the Y tile in shared memory (>= ty * tile depth)
@@ -197,6 +219,8 @@ struct dnmf_ctx {
   int* d_cand_ids = nullptr;
   int cand_expand = 6;
   int cand_cap = 0;
+  int affine_grad = 0;   // dnmf_set_affine: dnmf_loss_grad leaves the quadratic gradient rows zero
+  int affine_call = 0;   // the same for the duration of one step call made with affine != 0
   int fpc_override = 0;  // DNMF_FPC environment override of the frames-per-CTA heuristic (tuning)
   int y_pitch = 0, z_skew = 0;  // shared-memory layout of the Y tile (bank conflicts, configure_tiling_fixed)
   // tensor map of the frame buffer the fused kernel last ran on (resident slab or caller's batch)

@@ -86,6 +86,21 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
   return v[0];
 }
 
+// The same for 16 values: afterwards lanes l and l ^ 16 hold the total of v[l & 15] (16 shuffles).
+__device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Specialised main loop of the fused kernel for the common case (two y-adjacent sub-tiles per warp, the
 // whole list staged): each lane carries voxel A = (x, y, z) and voxel B = (x, y+4, z) through the z march
@@ -340,12 +355,17 @@ __device__ __forceinline__ void tail_slot(const unsigned (&adA)[3], const unsign
 // DNMF_MERGE_TAIL01).  FitParams::dyn_tail selects TAIL 3 per launch (DNMF_DYN_TAIL=1, or -1: from the counters).
 // SKEW: the lanes of a warp walk z in rotated order (lane-dependent start, wrap-around), which spreads their
 // reads of the Y tile over the banks when the tile's y/x pitches are multiples of 32 floats (Z = 32).
-template <bool SAFE, int MODE, int TAIL, bool SKEW>
+// AFF: the frame's quadratic coefficients (rows 4..9 of beta_t) are all zero and their gradient rows are not wanted
+// (FitParams::skip_quad): 2q = c1 z + c0 exactly as Horner with c2 = 0 would give it, and the z^2 moments are dropped.
+template <bool SAFE, int MODE, int TAIL, bool SKEW, bool AFF = false>
 __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOut& o, int tail = 0) {
   const float oz = a.oz;
   const float2 zero2 = make_float2(oz, oz);
 #pragma unroll
-  for (int d = 0; d < 3; ++d) o.S0[d] = o.S1[d] = o.S2[d] = zero2;
+  for (int d = 0; d < 3; ++d) {
+    o.S0[d] = o.S1[d] = zero2;
+    if (!AFF) o.S2[d] = zero2;  // AFF: set after the loop (kept live across it they were re-materialised every z step)
+  }
   float2 sse = zero2, sum_r = zero2;
   unsigned bias[3];
 #pragma unroll
@@ -374,7 +394,8 @@ __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOu
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       const float2 rcp2 = make_float2(a.rcp[d], a.rcp[d]);
-      const float2 q = __ffma2_rn(z2, __ffma2_rn(z2, make_float2(a.c2[d], a.c2[d]), a.c1[d]), a.c0[d]);  // = 2q
+      const float2 q = AFF ? __ffma2_rn(z2, a.c1[d], a.c0[d])
+                           : __ffma2_rn(z2, __ffma2_rn(z2, make_float2(a.c2[d], a.c2[d]), a.c1[d]), a.c0[d]);  // = 2q
       const float2 t0 = __fmul2_rn(q, rcp2);
       const float2 r = __ffma2_rn(make_float2(-t0.x, -t0.y), make_float2(a.sm1[d], a.sm1[d]), q);
       const float2 v = __ffma2_rn(r, rcp2, t0);  // = fl(2q / (s-1)), verified exact (verify_coord_kernel)
@@ -443,18 +464,47 @@ __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOu
       sum_r = __fadd2_rn(sum_r, r);
     }
     sse = __ffma2_rn(r, r, sse);
-    const float zq = zf * zf;
-    const float2 zq2 = make_float2(zq, zq);
+#if DNMF_FMA_MOMENTS
+    // z-moments of r * dYhat/dix_d accumulated as fma(z^m r, g_d, S): one packed op per moment and axis
+    // (the product-first form S + fl(r g) z^m needs an extra multiply per axis)
+    const float2 zr = __fmul2_rn(z2, r);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      const float2 h = __fmul2_rn(r, g[d]);
-      o.S0[d] = __fadd2_rn(o.S0[d], h);
-      o.S1[d] = __ffma2_rn(z2, h, o.S1[d]);
-      o.S2[d] = __ffma2_rn(zq2, h, o.S2[d]);
+      o.S0[d] = __ffma2_rn(r, g[d], o.S0[d]);
+      o.S1[d] = __ffma2_rn(zr, g[d], o.S1[d]);
     }
+    if constexpr (!AFF) {
+      const float2 zzr = __fmul2_rn(z2, zr);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) o.S2[d] = __ffma2_rn(zzr, g[d], o.S2[d]);
+    }
+#else
+    if constexpr (AFF) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float2 h = __fmul2_rn(r, g[d]);
+        o.S0[d] = __fadd2_rn(o.S0[d], h);
+        o.S1[d] = __ffma2_rn(z2, h, o.S1[d]);
+      }
+    } else {
+      const float zq = zf * zf;
+      const float2 zq2 = make_float2(zq, zq);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float2 h = __fmul2_rn(r, g[d]);
+        o.S0[d] = __fadd2_rn(o.S0[d], h);
+        o.S1[d] = __ffma2_rn(z2, h, o.S1[d]);
+        o.S2[d] = __ffma2_rn(zq2, h, o.S2[d]);
+      }
+    }
+#endif
   }
   o.sse = sse;
   o.sum_r = sum_r;
+  if (AFF) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) o.S2[d] = make_float2(0.f, 0.f);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -809,8 +859,13 @@ __device__ __forceinline__ void march_generic(const GenericArgs& a, float (&S0)[
 // staged table slices are kept across frames: they are gathered again from the L2-resident tables only when
 // the frame's window or neuron list differs from the previous frame's; otherwise only the x slice is rescaled
 // by the frame's traces.  In the steady state no global-memory latency sits between two main loops.
-template <int NWX, int NWY, int SUB, int MODE, bool FAST_DIV>
+// AFFK (MODE 0, launched only with FitParams::skip_quad): the instantiation for affine fits.  Its specialised main
+// loops are the AFF ones only (march_rolled); a frame that does carry quadratic coefficients takes the generic loop.
+// A separate instantiation rather than more bodies in one kernel: the hot code of either kernel stays as small as
+// before (instruction cache; with both families in one kernel cfg3 lost 6 % to code placement alone).
+template <int NWX, int NWY, int SUB, int MODE, bool FAST_DIV, bool AFFK = false>
 __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 ? DNMF_MU_MINB : DNMF_MINB) : 1) fit_tile_kernel(const __grid_constant__ FitParams p) {
+  static_assert(!AFFK || (MODE == 0 && SUB == 2 && FAST_DIV), "affine instantiation: fit, two sub-tiles, fast division");
   constexpr bool WRITE_YHAT = MODE == 1;
   constexpr bool WRITE_RES = MODE == 2;
   constexpr int NW = NWX * NWY;
@@ -1010,6 +1065,9 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
       whi[d] = sInt[3 + d];
     }
     const bool window_clipped = (sInt[24] | sInt[25] | sInt[26]) != 0;
+    // affine frame (rows 4..9 of beta_t all zero) whose quadratic gradient rows the caller does not want
+    bool quad_zero = false;
+    if constexpr (AFFK) quad_zero = __all_sync(0xffffffffu, lane >= 18 || sBeta[12 + lane] == 0.f);
 
     // ---- neuron list: ascending k, ballot compaction (single pass for one warp, two passes else).
     // Candidates come from the tile's static list (in shared memory) when the window stays inside the
@@ -1113,11 +1171,57 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
     if ((nst & 1) && tid == 0) sCk[nst] = 0.f;  // partner of the last neuron of an odd list: zero footprint
     if (changed) {
       ++n_restaged;
-      // One thread owns table entry e of every slot.  Slot pairs (2p, 2p+1) share one float4
-      // (G_2p, G_2p+1, D_2p, D_2p+1) = the packed operands of FFMA2; an odd list is completed with a zero
-      // footprint.  Loads are issued four pairs at a time ahead of the stores.  The x slice is kept without
-      // the traces (they change with the frame, the slices usually do not).
+      // Slot pairs (2p, 2p+1) share one float4 (G_2p, G_2p+1, D_2p, D_2p+1) = the packed operands of FFMA2; an odd
+      // list is completed with a zero footprint.  The x slice is kept without the traces (they change with the
+      // frame, the slices usually do not).
       const int Wt = W0 + W1 + W2;
+#if (DNMF_FLAT_RESTAGE & 1)
+      // Work items (slot pair, table entry), the entry running fastest, dealt to the threads round-robin: every lane
+      // is busy whatever the window size (one thread per entry left 14 of 46 entries to a second, mostly idle
+      // round), consecutive lanes read consecutive entries of one table row, and the loads of four items are in
+      // flight before the first store.
+      const int items = Wt * npair;
+      const unsigned recW = 0xFFFFFFFFu / (unsigned)Wt + 1u;  // Wt >= 3: floor(i / Wt) == umulhi(i, recW) for i < 2^32 / Wt
+      constexpr int kBatch = DNMF_RESTAGE_BATCH;
+      for (int i0 = tid; i0 < items; i0 += kBatch * NT) {
+        float2 va[kBatch], vb[kBatch];
+        float4* dst[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int i = i0 + u * NT;
+          va[u] = vb[u] = make_float2(0.f, 0.f);
+          dst[u] = nullptr;
+          if (i < items) {
+            const int pp = (int)__umulhi((unsigned)i, recW);
+            const int e = i - pp * Wt;
+            const float2* src;
+            int row;
+            float2* d;
+            if (e < W0) {
+              src = p.tab0 + (wlo[0] + 2 + e);
+              row = sX3;
+              d = sXraw + (size_t)e * CAP;
+            } else if (e < W0 + W1) {
+              src = p.tab1 + (wlo[1] + 2 + (e - W0));
+              row = sY3;
+              d = sTab + (size_t)(p.wmax0 + (e - W0)) * CAP;
+            } else {
+              src = p.tab2 + (wlo[2] + 2 + (e - W0 - W1));
+              row = sZ3;
+              d = sTab + (size_t)(p.wmax0 + p.wmax1 + (e - W0 - W1)) * CAP;
+            }
+            const int j = 2 * pp;
+            va[u] = __ldg(src + (size_t)sList[j] * row);
+            if (j + 1 < nst) vb[u] = __ldg(src + (size_t)sList[j + 1] * row);
+            dst[u] = reinterpret_cast<float4*>(d) + pp;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u)
+          if (dst[u]) *dst[u] = make_float4(va[u].x, vb[u].x, va[u].y, vb[u].y);
+      }
+#else
+      // One thread owns table entry e of every slot; loads are issued four pairs at a time ahead of the stores.
       for (int e = tid; e < Wt; e += NT) {
         const float2* src;
         int row;
@@ -1150,9 +1254,23 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
             if (p0 + u < npair) dst[p0 + u] = make_float4(va[u].x, vb[u].x, va[u].y, vb[u].y);
         }
       }
+#endif
     }
     cta_sync();
     // x slice of this frame: C[k,t] folded in
+#if (DNMF_FLAT_RESTAGE & 2)
+    {
+      const int itemsx = W0 * npair;
+      const unsigned rec0 = W0 > 1 ? 0xFFFFFFFFu / (unsigned)W0 + 1u : 0u;
+      for (int i = tid; i < itemsx; i += NT) {
+        const int pp = W0 > 1 ? (int)__umulhi((unsigned)i, rec0) : i;
+        const int e = i - pp * W0;
+        const float4 v = reinterpret_cast<const float4*>(sXraw + (size_t)e * CAP)[pp];
+        const float2 c = MODE == 3 ? make_float2(1.f, 1.f) : *reinterpret_cast<const float2*>(sCk + 2 * pp);
+        reinterpret_cast<float4*>(sTab + (size_t)e * CAP)[pp] = make_float4(v.x * c.x, v.y * c.y, v.z * c.x, v.w * c.y);
+      }
+    }
+#else
     for (int e = tid; e < W0; e += NT) {
       const float4* src = reinterpret_cast<const float4*>(sXraw + (size_t)e * CAP);
       float4* dst = reinterpret_cast<float4*>(sTab + (size_t)e * CAP);
@@ -1162,6 +1280,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
         dst[pp] = make_float4(v.x * c.x, v.y * c.y, v.z * c.x, v.w * c.y);
       }
     }
+#endif
     cta_sync();
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -1286,7 +1405,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
     const bool has_overflow = L > nst;
     bool marched = false;
     if constexpr (SUB == 2 && FAST_DIV) {
-      if (!has_overflow && (npair <= kMaxNP || !DNMF_UNROLLED_MARCH)) {
+      if (!has_overflow && (npair <= kMaxNP || !DNMF_UNROLLED_MARCH) && (!AFFK || quad_zero)) {
         MarchArgs a;
         fill_march_args(a);
         MarchOut o;
@@ -1322,24 +1441,24 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
         } else {
           const int npf = nst >> 1;  // full slot pairs; an odd list ends with a single slot
           const int tail = (nst & 1) ? (npf == 0 ? 2 : 1) : 0;
-          if (p.dyn_tail) {
+          if (DNMF_DYN_TAIL_BODIES && p.dyn_tail) {
             switch ((p.z_skew != 0 ? 2 : 0) + (safe ? 1 : 0)) {
-              case 0: march_rolled<false, MODE, 3, false>(a, npf, o, tail); break;
-              case 1: march_rolled<true, MODE, 3, false>(a, npf, o, tail); break;
-              case 2: march_rolled<false, MODE, 3, true>(a, npf, o, tail); break;
-              default: march_rolled<true, MODE, 3, true>(a, npf, o, tail); break;
+              case 0: march_rolled<false, MODE, 3, false, AFFK>(a, npf, o, tail); break;
+              case 1: march_rolled<true, MODE, 3, false, AFFK>(a, npf, o, tail); break;
+              case 2: march_rolled<false, MODE, 3, true, AFFK>(a, npf, o, tail); break;
+              default: march_rolled<true, MODE, 3, true, AFFK>(a, npf, o, tail); break;
             }
           } else
 #if DNMF_MERGE_TAIL01
           switch ((p.z_skew != 0 ? 4 : 0) + (tail == 2 ? 2 : 0) + (safe ? 1 : 0)) {
-            case 0: march_rolled<false, MODE, 4, false>(a, npf, o, tail); break;
-            case 1: march_rolled<true, MODE, 4, false>(a, npf, o, tail); break;
-            case 2: march_rolled<false, MODE, 2, false>(a, npf, o); break;
-            case 3: march_rolled<true, MODE, 2, false>(a, npf, o); break;
-            case 4: march_rolled<false, MODE, 4, true>(a, npf, o, tail); break;
-            case 5: march_rolled<true, MODE, 4, true>(a, npf, o, tail); break;
-            case 6: march_rolled<false, MODE, 2, true>(a, npf, o); break;
-            default: march_rolled<true, MODE, 2, true>(a, npf, o); break;
+            case 0: march_rolled<false, MODE, 4, false, AFFK>(a, npf, o, tail); break;
+            case 1: march_rolled<true, MODE, 4, false, AFFK>(a, npf, o, tail); break;
+            case 2: march_rolled<false, MODE, 2, false, AFFK>(a, npf, o); break;
+            case 3: march_rolled<true, MODE, 2, false, AFFK>(a, npf, o); break;
+            case 4: march_rolled<false, MODE, 4, true, AFFK>(a, npf, o, tail); break;
+            case 5: march_rolled<true, MODE, 4, true, AFFK>(a, npf, o, tail); break;
+            case 6: march_rolled<false, MODE, 2, true, AFFK>(a, npf, o); break;
+            default: march_rolled<true, MODE, 2, true, AFFK>(a, npf, o); break;
           }
 #else
           switch ((p.z_skew != 0 ? 6 : 0) + tail * 2 + (safe ? 1 : 0)) {
@@ -1391,7 +1510,30 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
 
     // ---- expand z-moments with this lane's (x,y) monomials, transposing warp reduction ----
     const unsigned cta_linear = ((unsigned)(b * p.ntz + bz) * p.nty + by) * p.ntx + bx;
-    {
+    if constexpr (AFFK && NW == 1) {
+      // affine fit: rows 0..3 only (12 moments) + SSE -> a 16-value reduction; rows 4..9 are stored as zero
+      float v[16];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        float t0 = 0.f, t1 = 0.f, y0s = 0.f;
+#pragma unroll
+        for (int h = 0; h < SUB; ++h) {
+          const float yh_ = (float)(y0 + ly0 + h * kWarpY);
+          t0 += S0[h][d];
+          t1 += S1[h][d];
+          y0s = fmaf(yh_, S0[h][d], y0s);
+        }
+        v[0 * 3 + d] = t0;
+        v[1 * 3 + d] = xf * t0;
+        v[2 * 3 + d] = y0s;
+        v[3 * 3 + d] = t1;
+      }
+      v[12] = sse;
+      v[13] = v[14] = v[15] = 0.f;
+      const float tot = warp_transpose_sum16(v, lane);
+      const float sse_tot = __shfl_sync(0xffffffffu, tot, 12);
+      p.partials[(size_t)cta_linear * kNumPartials + lane] = lane < 12 ? tot : (lane == 30 ? sse_tot : 0.f);
+    } else {
       float v[32];
       const float xx = xf * xf;
 #pragma unroll
@@ -1416,6 +1558,10 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
         v[7 * 3 + d] = xf * y0s;
         v[8 * 3 + d] = xf * t1;
         v[9 * 3 + d] = y1s;
+      }
+      if (MODE == 0 && p.skip_quad) {  // frozen quadratic rows: returned as zero whichever main loop ran
+#pragma unroll
+        for (int i = 12; i < 30; ++i) v[i] = 0.f;
       }
       v[30] = sse;
       v[31] = sum_r;  // sum of residuals (gradient of the scalar background), MODE 2 only
@@ -1457,13 +1603,13 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
     cta_sync();
     if (bulk && fi + 1 < nb) load_tile(fi + 1);
   }
-  if (MODE == 0 && p.restage_count != nullptr && tid == 0 && n_restaged > 0)
+  if (DNMF_DYN_TAIL_BODIES && MODE == 0 && p.restage_count != nullptr && tid == 0 && n_restaged > 0)
     atomicAdd(p.restage_count + ((blockIdx.x + blockIdx.y) & 31), (unsigned)n_restaged);
 }
 
-template <int NWX, int NWY, int SUB, int MD_, bool FD_>
+template <int NWX, int NWY, int SUB, int MD_, bool FD_, bool AFFK_ = false>
 static int launch_fit(const FitParams& p0, int B, size_t smem, cudaStream_t st) {
-  auto kern = fit_tile_kernel<NWX, NWY, SUB, MD_, FD_>;
+  auto kern = fit_tile_kernel<NWX, NWY, SUB, MD_, FD_, AFFK_>;
   static size_t configured[64] = {0};  // per device: the attribute is a per-device property of the function
   int dev = 0;
   CU(cudaGetDevice(&dev));

@@ -628,6 +628,12 @@ extern "C" int dnmf_set_tiling(dnmf_ctx* c, int warps_x, int warps_y, int tz, in
   return 0;
 }
 
+extern "C" int dnmf_set_affine(dnmf_ctx* c, int affine) {
+  if (!c) return fail("dnmf_set_affine: ctx is NULL");
+  c->affine_grad = affine ? 1 : 0;
+  return 0;
+}
+
 extern "C" int dnmf_get_tiling(dnmf_ctx* c, int32_t* out) {
   if (!c || !out) return fail("dnmf_get_tiling: NULL argument");
   int32_t v[11] = {c->tx, c->ty, c->tz, c->ntx, c->nty, c->ntz, c->nwx, c->nwy, c->cap, c->sub, c->fast_div};
@@ -1012,6 +1018,7 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
               (((size_t)c->ty * c->Z) % 4 == 0);
   memset(&p.stats, 0, sizeof(p.stats));
   p.mu_overflow = nullptr;
+  p.skip_quad = (c->affine_grad || c->affine_call) ? 1 : 0;
   p.dyn_tail = 0;
   p.restage_count = nullptr;
   p.y_pitch = c->y_pitch;
@@ -1085,6 +1092,7 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
 // synchronisation (read one or two launches late), and above half of all tile-frames the single-body main loop
 // is used (march_rolled TAIL 3).  Both variants execute the same arithmetic: results do not depend on the choice.
 static int launch_fused_fit(dnmf_ctx* c, FitParams& p, int B, cudaStream_t st) {
+  if (!DNMF_DYN_TAIL_BODIES) return dispatch_fit<0>(c, p, B, st);
   if (!c->d_restage) {
     CU(cudaMalloc((void**)&c->d_restage, 32 * sizeof(unsigned)));
     CU(cudaMemset(c->d_restage, 0, 32 * sizeof(unsigned)));
@@ -1174,8 +1182,10 @@ extern "C" int dnmf_motion_step(dnmf_ctx* c, const float* frames_dev, const int3
   if (!c) return fail("dnmf_motion_step: ctx is NULL");
   CU(cudaSetDevice(c->device));
   if (ensure(&c->d_sse, &c->sse_cap, (size_t)B)) return 1;
-  if (dnmf_loss_grad(c, frames_dev, frame_ids_dev, B, B_global, beta_dev, C_dev, c->d_grad, c->d_sse, stream))
-    return 1;
+  c->affine_call = affine;  // Adam freezes rows 4..9: the fused kernel need not produce their gradient
+  const int rc = dnmf_loss_grad(c, frames_dev, frame_ids_dev, B, B_global, beta_dev, C_dev, c->d_grad, c->d_sse, stream);
+  c->affine_call = 0;
+  if (rc) return 1;
   return dnmf_adam_step(c, beta_dev, c->d_grad, m_dev, v_dev, lr, beta1, beta2, eps, step, affine, c->d_sse, B,
                         B_global, loss_dev, stream);
 }
@@ -1235,7 +1245,10 @@ extern "C" int dnmf_motion_epoch(dnmf_ctx* c, const int32_t* frame_ids_dev, cons
                                                        epsf, c->d_epoch_scalars, nbatches, c->d_epoch_batch_of, 0);
     CU(cudaGetLastError());
     FitParams p;
-    if (fill_fit_params(c, p, nullptr, frame_ids_dev + b_first, (int)Btot, beta_dev, C_dev)) return 1;
+    c->affine_call = affine;
+    const int frc = fill_fit_params(c, p, nullptr, frame_ids_dev + b_first, (int)Btot, beta_dev, C_dev);
+    c->affine_call = 0;
+    if (frc) return 1;
     const int nt = c->ntx * c->nty * c->ntz;
     if (launch_fused_fit(c, p, (int)Btot, st)) return 1;
     reduce_partials_kernel<<<(unsigned)Btot, 256, 0, st>>>(c->d_partials, frame_ids_dev + b_first, (int)Btot, nt, c->T,
@@ -1320,8 +1333,10 @@ extern "C" int dnmf_motion_step_host(dnmf_ctx* c, const float* frames_host, cons
                        cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaEventRecord(c->ev_copied[slot], c->copy_stream));
     CU(cudaStreamWaitEvent(st, c->ev_copied[slot], 0));
-    if (dnmf_loss_grad(c, buf, c->d_ids + b0, nb, B_global, beta_dev, C_dev, c->d_grad, c->d_sse + b0, stream))
-      return 1;
+    c->affine_call = affine;
+    const int rc = dnmf_loss_grad(c, buf, c->d_ids + b0, nb, B_global, beta_dev, C_dev, c->d_grad, c->d_sse + b0, stream);
+    c->affine_call = 0;
+    if (rc) return 1;
     CU(cudaEventRecord(c->ev_done[slot], st));
   }
   if (dnmf_adam_step(c, beta_dev, c->d_grad, m_dev, v_dev, lr, beta1, beta2, eps, step, affine, c->d_sse, B,

@@ -122,6 +122,11 @@ class Engine:
         _lib.check(self.lib.dnmf_set_tiling(self._h, warps_x, warps_y, tz, slot_capacity, subtiles_y),
                    "dnmf_set_tiling")
 
+    def set_affine(self, affine: bool):
+        """Affine fit: loss_grad leaves the (frozen) quadratic gradient rows zero and affine frames take the shorter
+        main loop (dnmf_set_affine)."""
+        _lib.check(self.lib.dnmf_set_affine(self._h, int(bool(affine))), "dnmf_set_affine")
+
     def tiling(self) -> dict:
         out = np.zeros(11, np.int32)
         _lib.check(self.lib.dnmf_get_tiling(self._h, out.ctypes.data_as(ctypes.c_void_p)), "dnmf_get_tiling")

@@ -319,6 +319,7 @@ class DeformableNMF:
         self._size = size
         self._D = None
         self.affine = deformation == "affine"
+        self.fp.engine.set_affine(self.affine)
         # opt-in: make `gamma` of update_motion act (differentiable, index-consistent log-det-Jacobian
         # penalty).  OFF reproduces the reference, where the regulariser is a detached constant (F3).
         self.jacobian_regularizer = bool(jacobian_regularizer)

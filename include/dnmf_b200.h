@@ -33,7 +33,7 @@ extern "C" {
 
 typedef struct dnmf_ctx dnmf_ctx;
 
-#define DNMF_ABI_VERSION 5
+#define DNMF_ABI_VERSION 6
 
 int dnmf_abi_version(void);
 const char* dnmf_last_error(void);
@@ -86,6 +86,13 @@ int dnmf_bin_tiles(dnmf_ctx* ctx, const float* beta_dev, const int32_t* frame_id
 int dnmf_loss_grad(dnmf_ctx* ctx, const float* frames_dev, const int32_t* frame_ids_dev, int B,
                    int B_global, const float* beta_dev, const float* C_dev, float* grad_dev,
                    double* sse_dev, void* stream);
+
+/* Affine fits (rows 4..9 of beta frozen, the `affine` argument of the step calls below): with affine != 0
+ * dnmf_loss_grad no longer produces the gradient rows 4..9 (they are returned as zero, which is what the Adam step
+ * of an affine fit makes of them) and frames whose quadratic coefficients are all zero take main loops without the
+ * z^2 terms.  The step calls do the same for the duration of a call made with affine != 0.  The reference has no
+ * such switch (Demix/dNMF.py:53-58 always carries the full basis); 0 (the default) is its behaviour. */
+int dnmf_set_affine(dnmf_ctx* ctx, int affine);
 
 /* Kernel 3a: dense Adam over all 30*T entries (torch.optim.Adam step at Demix/dNMF.py:191,
  * demo.py:42).  `step` is the 1-based step count; affine != 0 freezes rows 4..9.  grad_dev is

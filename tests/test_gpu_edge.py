@@ -88,6 +88,39 @@ def test_neurons_outside_volume_and_empty_ranges():
     assert abs(float(sse.sum()) / (2 * 768) - loss) <= 1e-6 * loss
 
 
+@pytest.mark.parametrize("sz,tiling", [([40, 24, 9], (1, 1, 0, 0, 2)), ([33, 18, 32], (1, 1, 0, 0, 2)),
+                                       ([40, 24, 9], (2, 2, 0, 0, 2)), ([24, 20, 5], (2, 2, 0, 0, 1))])
+def test_affine_main_loops_bit_equal(sz, tiling):
+    """dnmf_set_affine: affine frames take main loops without the z^2 Horner term and the z^2 gradient moments.
+    Same arithmetic per voxel; the affine instantiation reduces 16 instead of 32 values per tile-frame, so the lane
+    sums are taken in another order: rows 0..3 and the SSE agree to fp32 summation noise, rows 4..9 are zero.  A frame
+    with quadratic coefficients takes the generic loop; its rows 4..9 are still returned as zero."""
+    from dnmf_b200.engine import Engine
+    K, T = 12, 6
+    pos, sig, beta, C, frames = _case(sz, K, T, seed=21)
+    beta[4:, :, :T - 1] = 0.0                      # frames 0..T-2 affine, the last one keeps its quadratic terms
+    e = Engine(sz, K, T)
+    e.set_tiling(*tiling)
+    e.set_footprints(pos, sig, 3.5)
+    ids = torch.arange(T)
+    g0, s0 = e.loss_grad(ids, beta.cuda(), C.cuda(), frames=frames.cuda())
+    e.set_affine(True)
+    g1, s1 = e.loss_grad(ids, beta.cuda(), C.cuda(), frames=frames.cuda())
+    e.set_affine(False)
+    g2, s2 = e.loss_grad(ids, beta.cuda(), C.cuda(), frames=frames.cuda())
+    assert torch.equal(s0, s2) and torch.equal(g0, g2)
+    assert float(((s0 - s1).abs() / s0).max()) < 1e-6
+    assert float((g0[:4] - g1[:4]).abs().max() / g0[:4].abs().max()) < 2e-6
+    assert float(g1[4:].abs().max()) == 0.0 and float(g0[4:].abs().max()) > 0.0
+    # the step calls do the same for the duration of a call made with affine != 0
+    m, v = torch.zeros(10, 3, T).cuda(), torch.zeros(10, 3, T).cuda()
+    b_a, b_b = beta.clone().cuda(), beta.clone().cuda()
+    e.motion_step(ids.int().cuda(), b_a, m, v, C.cuda(), 1e-3, (0.9, 0.999), 1e-8, 1, True, frames=frames.cuda())
+    gz = g1.clone()
+    e.adam_step(b_b, gz, torch.zeros_like(m), torch.zeros_like(v), 1e-3, (0.9, 0.999), 1e-8, 1, affine=True)
+    assert torch.equal(b_a, b_b)
+
+
 def test_affine_freezes_quadratic_rows():
     from dnmf_b200.engine import Engine
     e = Engine([8, 8, 2], 2, 3)

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "library does not export %s" % n
     lib2 = dnmf_b200.load()
-    assert lib2.dnmf_abi_version() == 5
+    assert lib2.dnmf_abi_version() == 6
     for n in names:                                   # every declared symbol has a ctypes signature
         assert n in lib2._signatures, n
 
@@ -251,6 +251,9 @@ def test_update_motion_and_traces_host_plumbing_with_a_recording_engine(monkeypa
 
         def set_tiling(self, *a):
             pass
+
+        def set_affine(self, affine):
+            calls.append(("set_affine", bool(affine)))
 
         def set_footprints(self, *a):
             pass
