@@ -52,6 +52,10 @@ constexpr int kZUnroll = DNMF_ZUNROLL;
 #ifndef DNMF_FMA_MOMENTS
 #define DNMF_FMA_MOMENTS 1  // 1: gradient z-moments as fma(z^m r, g, S) in the specialised main loops
 #endif
+#ifndef DNMF_WINDOW_PREPASS
+#define DNMF_WINDOW_PREPASS 1  // 1: tile windows of a batch come from tile_windows_kernel (one thread per tile-frame) instead
+                               // of three lanes of the fused kernel's per-frame prologue
+#endif
 #ifndef DNMF_ALWAYS_SAFE
 #define DNMF_ALWAYS_SAFE 0  // 1: every tile takes the clamped main loop (one loop body fewer in the instruction cache)
 #endif
@@ -125,6 +129,7 @@ struct FitParams {
   int fpc;       // consecutive frames walked by one CTA (<= 32)
   StatsPartials stats;  // MODE 3 (trace statistics): partial blocks of this launch's tile-frames
   int* mu_overflow;  // MODE 3: set when a tile's list is not fully staged (the caller reruns the generic kernel)
+  const int4* windows;  // [B][tiles][2]: (wlo0, wlo1, wlo2, whi0), (whi1, whi2, clipped, 0) from tile_windows_kernel, or NULL
   int skip_quad;  // != 0: gradient rows 4..9 are not wanted (affine fit: Adam freezes them) and are returned as zero
   int dyn_tail;  // != 0: main loop with the run-time tail kind (one loop body per SAFE; see march_rolled TAIL 3)
   unsigned* restage_count;  // [32] frames whose slices were rebuilt, counted per CTA (MODE 0; may be NULL)
@@ -236,6 +241,8 @@ struct dnmf_ctx {
   // scratch
   float* d_partials = nullptr;
   size_t partials_cap = 0;
+  int4* d_windows = nullptr;  // tile windows of the current batch (tile_windows_kernel)
+  size_t windows_cap = 0;
   float* d_grad = nullptr;  // [10][3][T]
   double* d_sse = nullptr;
   size_t sse_cap = 0;

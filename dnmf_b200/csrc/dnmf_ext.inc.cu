@@ -191,7 +191,7 @@ extern "C" int dnmf_ext_loss_grad(dnmf_ctx* c, const float* frames_dev, const in
   CU(cudaSetDevice(c->device));
   if (check_sticky(c, "dnmf_ext_loss_grad") || sanitize_ids(c, frame_ids_dev, B, st, &frame_ids_dev)) return 1;
   FitParams p;
-  if (fill_fit_params(c, p, frames_dev, frame_ids_dev, B, beta_dev, C_dev)) return 1;
+  if (fill_fit_params(c, p, frames_dev, frame_ids_dev, B, beta_dev, C_dev, st)) return 1;
   if (ensure(&c->d_resid, &c->resid_cap, (size_t)B * c->N)) return 1;
   if (ensure(&c->d_sumr, &c->sumr_cap, (size_t)B)) return 1;
   p.yhat = c->d_resid;

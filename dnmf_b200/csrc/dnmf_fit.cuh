@@ -1001,9 +1001,18 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
 
   // ---- requested one frame ahead: beta_t and the candidates' traces ----
   float beta_next = 0.f, cc_next[2] = {0.f, 0.f};
+#if DNMF_WINDOW_PREPASS
+  // ... and the tile's sample window under beta_t (tile_windows_kernel: eight ints per tile-frame)
+  int win_next = 0;
+  const size_t win_row0 = ((size_t)(p.b_base + b_first) * (p.ntx * p.nty * p.ntz) + (size_t)((bz * p.nty + by) * p.ntx + bx)) * 8;
+  const size_t win_step = (size_t)(p.ntx * p.nty * p.ntz) * 8;
+#endif
   auto prefetch_frame = [&](int fi) {
     const int t = __shfl_sync(0xffffffffu, my_frame, fi);
     if (tid < 30) beta_next = p.beta[(size_t)tid * p.T + t];
+#if DNMF_WINDOW_PREPASS
+    if (tid < 8) win_next = reinterpret_cast<const int*>(p.windows)[win_row0 + (size_t)fi * win_step + tid];
+#endif
     if (prefetch_c) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -1035,6 +1044,9 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
     const int b = b_first + fi;
     const int t = __shfl_sync(0xffffffffu, my_frame, fi);
     if (tid < 30) sBeta[tid] = beta_next;
+#if DNMF_WINDOW_PREPASS
+    if (tid < 8) sInt[tid] = win_next;
+#endif
     if (prefetch_c) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -1046,6 +1058,16 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
     cta_sync();
     if (fi + 1 < nb) prefetch_frame(fi + 1);
 
+#if DNMF_WINDOW_PREPASS
+    // ---- conservative window of this tile under beta_t: fetched one frame ahead, broadcast through shared memory ----
+    int wlo[3], whi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      wlo[d] = sInt[d];
+      whi[d] = sInt[3 + d];
+    }
+    const bool window_clipped = sInt[6] != 0;
+#else
     // ---- conservative window of this tile under beta_t (same code as the binning kernel) ----
     if (tid < 3) {
       const int s = tid == 0 ? p.X : (tid == 1 ? p.Y : p.Z);
@@ -1065,6 +1087,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
       whi[d] = sInt[3 + d];
     }
     const bool window_clipped = (sInt[24] | sInt[25] | sInt[26]) != 0;
+#endif
     // affine frame (rows 4..9 of beta_t all zero) whose quadratic gradient rows the caller does not want
     bool quad_zero = false;
     if constexpr (AFFK) quad_zero = __all_sync(0xffffffffu, lane >= 18 || sBeta[12 + lane] == 0.f);

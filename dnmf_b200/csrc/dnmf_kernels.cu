@@ -104,6 +104,31 @@ __device__ __forceinline__ void tile_box(const Geom& g, int tile, int& x0, int& 
   z1 = min(z0 + g.tz, g.Z) - 1;
 }
 
+// Kernel 1b, window part, for the fused kernel: one THREAD per (batch position, tile) evaluates the tile's
+// conservative sample window under beta_t (tile_window_axis: the device code of the binning kernel, bit-exact twin
+// of oracle.tile_window) and stores (wlo[3], whi[3], clipped, 0).  The fused kernel used to run this in its
+// per-frame prologue on three lanes of a warp (~130 warp instructions per tile-frame for three lanes of work);
+// here the lanes are all busy and the fused kernel fetches eight ints one frame ahead.
+__global__ void tile_windows_kernel(Geom g, const float* __restrict__ beta, const int* __restrict__ frame_ids,
+                                    long long items, int4* __restrict__ out) {
+  const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= items) return;
+  const int nt = g.ntx * g.nty * g.ntz;
+  const int b = (int)(item / nt), tile = (int)(item - (long long)b * nt);
+  const int t = frame_ids[b];
+  int x0, y0, z0, x1, y1, z1;
+  tile_box(g, tile, x0, y0, z0, x1, y1, z1);
+  int wlo[3], whi[3];
+  bool clipped[3];
+  const int sz[3] = {g.X, g.Y, g.Z};
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    tile_window_axis(beta + (size_t)d * g.T + t, 3 * g.T, (float)x0, (float)y0, (float)z0, (float)x1,
+                     (float)y1, (float)z1, sz[d], wlo[d], whi[d], clipped[d]);
+  out[2 * item] = make_int4(wlo[0], wlo[1], wlo[2], whi[0]);
+  out[2 * item + 1] = make_int4(whi[1], whi[2], (clipped[0] || clipped[1] || clipped[2]) ? 1 : 0, 0);
+}
+
 template <bool FILL>
 __global__ void bin_tiles_kernel(Geom g, const float* __restrict__ beta, const int* __restrict__ frame_ids,
                                  int B, const int* __restrict__ rng, int* __restrict__ counts,
@@ -579,6 +604,7 @@ extern "C" void dnmf_destroy(dnmf_ctx* c) {
   cudaSetDevice(c->device);
   void* ptrs[] = {c->d_pos,     c->d_sigma, c->d_rng,        c->d_tab[0],      c->d_tab[1],
                   c->d_tab[2],  c->video_owned ? c->d_video : nullptr, c->d_partials,   c->d_grad,        c->d_sse,
+                  c->d_windows,
                   c->d_batch,   c->d_ids,   c->d_loss,       c->d_tmp_counts,  c->d_tmp_offsets,
                   c->d_tmp_max, c->d_G,     c->d_b,          c->d_identity_beta,
                   c->d_Cd[0],   c->d_Cd[1], c->d_keys,       c->d_cand_off,    c->d_cand_ids,
@@ -987,7 +1013,7 @@ static int dispatch_stats(dnmf_ctx* c, const FitParams& p, int B, size_t smem, c
 }
 
 static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, const int32_t* ids, int B,
-                           const float* beta, const float* C) {
+                           const float* beta, const float* C, cudaStream_t st) {
   if (!c->have_footprints) return fail("fit: call dnmf_set_footprints first");
   if (!frames_dev && !c->d_video) return fail("fit: no resident video (dnmf_upload_frames) and frames_dev is NULL");
   if ((long long)B * c->ntx * c->nty * c->ntz > 2147483647LL) return fail("fit: too many tiles in one launch");
@@ -1084,6 +1110,17 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
   const size_t need = (size_t)B * c->ntx * c->nty * c->ntz * kNumPartials;
   if (ensure(&c->d_partials, &c->partials_cap, need)) return 1;
   p.partials = c->d_partials;
+  p.windows = nullptr;
+#if DNMF_WINDOW_PREPASS
+  {  // the tiles' sample windows of this batch, computed by all lanes ahead of the fused launch (same stream)
+    const long long items = (long long)B * c->ntx * c->nty * c->ntz;
+    if (ensure(&c->d_windows, &c->windows_cap, (size_t)items * 2)) return 1;
+    tile_windows_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(geom_of(c), beta, ids, items, c->d_windows);
+    CU(cudaGetLastError());
+    p.windows = c->d_windows;
+    c->counters[2] += 1;  // binning launches
+  }
+#endif
   return 0;
 }
 
@@ -1137,7 +1174,7 @@ extern "C" int dnmf_loss_grad(dnmf_ctx* c, const float* frames_dev, const int32_
   CU(cudaSetDevice(c->device));
   if (check_sticky(c, "dnmf_loss_grad") || sanitize_ids(c, frame_ids_dev, B, st, &frame_ids_dev)) return 1;
   FitParams p;
-  if (fill_fit_params(c, p, frames_dev, frame_ids_dev, B, beta_dev, C_dev)) return 1;
+  if (fill_fit_params(c, p, frames_dev, frame_ids_dev, B, beta_dev, C_dev, st)) return 1;
   const int nt = c->ntx * c->nty * c->ntz;
   if (launch_fused_fit(c, p, B, st)) return 1;
   const double scale = 2.0 / ((double)B_global * (double)c->N);
@@ -1246,7 +1283,7 @@ extern "C" int dnmf_motion_epoch(dnmf_ctx* c, const int32_t* frame_ids_dev, cons
     CU(cudaGetLastError());
     FitParams p;
     c->affine_call = affine;
-    const int frc = fill_fit_params(c, p, nullptr, frame_ids_dev + b_first, (int)Btot, beta_dev, C_dev);
+    const int frc = fill_fit_params(c, p, nullptr, frame_ids_dev + b_first, (int)Btot, beta_dev, C_dev, st);
     c->affine_call = 0;
     if (frc) return 1;
     const int nt = c->ntx * c->nty * c->ntz;
@@ -1358,7 +1395,7 @@ extern "C" int dnmf_forward(dnmf_ctx* c, const int32_t* frame_ids_dev, int B, co
   if (AtC_dev) {
     // Yhat does not depend on the video: the WRITE_YHAT instantiation never reads `frames`.
     FitParams p;
-    if (fill_fit_params(c, p, AtC_dev, frame_ids_dev, B, beta_dev, C_dev)) return 1;
+    if (fill_fit_params(c, p, AtC_dev, frame_ids_dev, B, beta_dev, C_dev, st)) return 1;
     p.yhat = AtC_dev;
     if (dispatch_fit<1>(c, p, B, st)) return 1;
     c->counters[0] += 1;

@@ -819,7 +819,7 @@ static int stats_pass(dnmf_ctx* c, int which, const float* frames_dev, const int
     const float* fr = frames_dev ? frames_dev + (size_t)b0 * c->N : nullptr;
     if (which == 0) {
       FitParams q;
-      if (fill_fit_params(c, q, fr, ids_dev + b0, nb, beta_dev, nullptr)) return 1;
+      if (fill_fit_params(c, q, fr, ids_dev + b0, nb, beta_dev, nullptr, st)) return 1;
       q.mu_overflow = c->d_tmp_max;
       q.cap = fused_cap;
       q.stats = sp;
