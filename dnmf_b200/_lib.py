@@ -42,7 +42,7 @@ def load(build_if_missing: bool = True):
         "dnmf_set_footprints": (c_int, [P, P, P, c_float, P]),
         "dnmf_get_ranges": (c_int, [P, P]),
         "dnmf_get_table": (c_int, [P, c_int, P]),
-        "dnmf_set_tiling": (c_int, [P, c_int, c_int, c_int, c_int, c_int]),
+        "dnmf_set_tiling": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int]),
         "dnmf_get_tiling": (c_int, [P, P]),
         "dnmf_set_affine": (c_int, [P, c_int]),
         "dnmf_upload_frames": (c_int, [P, P, c_int, c_int, c_int, P]),

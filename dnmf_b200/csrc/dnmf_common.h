@@ -115,6 +115,7 @@ struct FitParams {
   int frames_are_batch;
   int X, Y, Z, K, T;
   int tz, ntx, nty, ntz;
+  int nwz;  // warp groups splitting the tile's z range (1, 2 or 4)
   int cap;  // staged slot capacity, even
   int wmax0, wmax1, wmax2;
   int full_depth;
@@ -210,7 +211,7 @@ struct dnmf_ctx {
   bool have_footprints = false;
   float cutoff = 0.f;
   // tiling
-  int nwx = 1, nwy = 1, tz = 0, cap = 0, user_cap = 0;
+  int nwx = 1, nwy = 1, nwz = 1, tz = 0, cap = 0, user_cap = 0;
   int sub = 1;  // y-adjacent sub-tiles per warp (fit kernel only)
   bool auto_tiling = true;  // until dnmf_set_tiling is called: pick the warp layout from the list lengths
   int tx = 8, ty = 4, ntx = 0, nty = 0, ntz = 0;

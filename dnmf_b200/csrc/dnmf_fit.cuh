@@ -863,12 +863,18 @@ __device__ __forceinline__ void march_generic(const GenericArgs& a, float (&S0)[
 // loops are the AFF ones only (march_rolled); a frame that does carry quadratic coefficients takes the generic loop.
 // A separate instantiation rather than more bodies in one kernel: the hot code of either kernel stays as small as
 // before (instruction cache; with both families in one kernel cfg3 lost 6 % to code placement alone).
-template <int NWX, int NWY, int SUB, int MODE, bool FAST_DIV, bool AFFK = false>
-__global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 ? DNMF_MU_MINB : DNMF_MINB) : 1) fit_tile_kernel(const __grid_constant__ FitParams p) {
+// NWZ > 1 (dense configurations): NWZ groups of NWX*NWY warps share one tile and its staged slices, each group marching
+// its own part of the tile's z range.  The tile stays 8*NWX x 4*NWY*SUB voxels wide -- the list length follows the
+// tile's x, y extent, (8+s)(8+s) against (16+s)(16+s) for a footprint s nodes wide -- while the CTA still brings enough
+// warps per SM for its shared memory (the staged slices of ~85 neurons take 40 KB).
+template <int NWX, int NWY, int SUB, int MODE, bool FAST_DIV, bool AFFK = false, int NWZ = 1>
+__global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ? (MODE == 3 ? DNMF_MU_MINB : DNMF_MINB) : (NWZ > 1 ? 512 / (32 * NWX * NWY * NWZ) : 1)) fit_tile_kernel(const __grid_constant__ FitParams p) {
   static_assert(!AFFK || (MODE == 0 && SUB == 2 && FAST_DIV), "affine instantiation: fit, two sub-tiles, fast division");
+  static_assert(NWZ == 1 || MODE != 3, "the fused trace statistics do not split z");
   constexpr bool WRITE_YHAT = MODE == 1;
   constexpr bool WRITE_RES = MODE == 2;
-  constexpr int NW = NWX * NWY;
+  constexpr int NWXY = NWX * NWY;
+  constexpr int NW = NWXY * NWZ;
   constexpr int NT = 32 * NW;
   constexpr int TX = kWarpX * NWX, TY = kWarpY * NWY * SUB;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1024,8 +1030,12 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
   prefetch_frame(0);
 
   // lane geometry (frame independent)
-  const int lx = (warp % NWX) * kWarpX + (lane & 7);
-  const int ly0 = (warp / NWX) * (kWarpY * SUB) + (lane >> 3);
+  const int wxy = NWZ == 1 ? warp : warp % NWXY, wz = NWZ == 1 ? 0 : warp / NWXY;
+  const int lx = (wxy % NWX) * kWarpX + (lane & 7);
+  const int ly0 = (wxy / NWX) * (kWarpY * SUB) + (lane >> 3);
+  // this warp's part of the tile's z range
+  const int zb = NWZ == 1 ? 0 : (nz * wz) / NWZ;
+  const int nzw = NWZ == 1 ? nz : (nz * (wz + 1)) / NWZ - zb;
   const int gx = x0 + lx;
   const float xf = (float)gx;
   const int sX3 = p.X + 3, sY3 = p.Y + 3, sZ3 = p.Z + 3;
@@ -1357,14 +1367,14 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
       }
       a.wl[0] = wlo[0], a.wl[1] = wlo[1], a.wl[2] = wlo[2];
       a.wm1[0] = W0 - 1, a.wm1[1] = W1 - 1, a.wm1[2] = W2 - 1;
-      a.yaddrA = smem_u32(sY + lx * RS + ly0 * zs);
-      a.zf0 = (float)z0;
-      a.nz = nz;
+      a.yaddrA = smem_u32(sY + lx * RS + ly0 * zs + zb);
+      a.zf0 = (float)(z0 + zb);
+      a.nz = nzw;
       a.validA = (gx < p.X) && (y0 + ly0 < p.Y);
       a.validB = (gx < p.X) && (y0 + ly0 + kWarpY < p.Y);
       a.bg = bg;
       a.zskew = 0;
-      if (p.z_skew != 0 && nz >= 4) a.zskew = ((lane >> 3) * p.z_skew) & 3;
+      if (p.z_skew != 0 && nzw >= 4) a.zskew = ((lane >> 3) * p.z_skew) & 3;
     };
 
     if constexpr (MODE == 3) {
@@ -1519,9 +1529,9 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
       a.p = &p;
       a.sBeta = sBeta;
       a.sList = sList;
-      a.sY = sY;
+      a.sY = sY + zb;
       a.t = t, a.L = L, a.nst = nst;
-      a.x0 = x0, a.y0 = y0, a.z0 = z0, a.nz = nz;
+      a.x0 = x0, a.y0 = y0, a.z0 = z0 + zb, a.nz = nzw;
       a.lx = lx, a.ly0 = ly0, a.RS = RS, a.zs = zs;
       a.wl[0] = wlo[0], a.wl[1] = wlo[1], a.wl[2] = wlo[2];
       a.wm1[0] = W0 - 1, a.wm1[1] = W1 - 1, a.wm1[2] = W2 - 1;
@@ -1630,9 +1640,9 @@ __global__ void __launch_bounds__(32 * NWX * NWY, (NWX * NWY == 1) ? (MODE == 3 
     atomicAdd(p.restage_count + ((blockIdx.x + blockIdx.y) & 31), (unsigned)n_restaged);
 }
 
-template <int NWX, int NWY, int SUB, int MD_, bool FD_, bool AFFK_ = false>
+template <int NWX, int NWY, int SUB, int MD_, bool FD_, bool AFFK_ = false, int NWZ_ = 1>
 static int launch_fit(const FitParams& p0, int B, size_t smem, cudaStream_t st) {
-  auto kern = fit_tile_kernel<NWX, NWY, SUB, MD_, FD_, AFFK_>;
+  auto kern = fit_tile_kernel<NWX, NWY, SUB, MD_, FD_, AFFK_, NWZ_>;
   static size_t configured[64] = {0};  // per device: the attribute is a per-device property of the function
   int dev = 0;
   CU(cudaGetDevice(&dev));
@@ -1658,7 +1668,7 @@ static int launch_fit(const FitParams& p0, int B, size_t smem, cudaStream_t st) 
     if (p0.yhat) p.yhat = p0.yhat + (size_t)b0 * N;
     const int chunks = (nb + fpc - 1) / fpc;
     dim3 grid((unsigned)p0.ntx, (unsigned)p0.nty, (unsigned)(chunks * p0.ntz));
-    kern<<<grid, 32 * NWX * NWY, smem, st>>>(p);
+    kern<<<grid, 32 * NWX * NWY * NWZ_, smem, st>>>(p);
     CU(cudaGetLastError());
   }
   return 0;
@@ -1667,6 +1677,12 @@ static int launch_fit(const FitParams& p0, int B, size_t smem, cudaStream_t st) 
 // layout dispatch shared by the per-MODE translation units
 #define DNMF_FIT_DISPATCH(MD_)                                                                                 \
   do {                                                                                                         \
+    if (p.nwz > 1) {  /* z-split CTAs: the 8 x 8 tile of the one-warp layout, two sub-tiles, fast division */    \
+      if (!(nwx == 1 && nwy == 1 && sub == 2 && fd)) return fail("dispatch_fit: warps_z > 1 needs the 1x1 layout with two sub-tiles"); \
+      if (p.nwz == 2) return launch_fit<1, 1, 2, MD_, true, false, 2>(p, B, smem, st);                          \
+      if (p.nwz == 4) return launch_fit<1, 1, 2, MD_, true, false, 4>(p, B, smem, st);                          \
+      return fail("dispatch_fit: warps_z must be 1, 2 or 4");                                                  \
+    }                                                                                                          \
     if (nwx == 1 && nwy == 1 && sub == 1) return fd ? launch_fit<1, 1, 1, MD_, true>(p, B, smem, st) : launch_fit<1, 1, 1, MD_, false>(p, B, smem, st); \
     if (nwx == 1 && nwy == 1 && sub == 2) return fd ? launch_fit<1, 1, 2, MD_, true>(p, B, smem, st) : launch_fit<1, 1, 2, MD_, false>(p, B, smem, st); \
     if (nwx == 2 && nwy == 1 && sub == 1) return fd ? launch_fit<2, 1, 1, MD_, true>(p, B, smem, st) : launch_fit<2, 1, 1, MD_, false>(p, B, smem, st); \

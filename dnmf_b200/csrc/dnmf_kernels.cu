@@ -634,9 +634,13 @@ extern "C" void dnmf_destroy(dnmf_ctx* c) {
 // ---- tiling -----------------------------------------------------------------------------------
 static int configure_tiling(dnmf_ctx* c, cudaStream_t st);
 
-extern "C" int dnmf_set_tiling(dnmf_ctx* c, int warps_x, int warps_y, int tz, int slot_capacity, int subtiles_y) {
+extern "C" int dnmf_set_tiling(dnmf_ctx* c, int warps_x, int warps_y, int tz, int slot_capacity, int subtiles_y,
+                               int warps_z) {
   if (!c) return fail("dnmf_set_tiling: ctx is NULL");
   if (subtiles_y < 1) subtiles_y = 1;
+  if (warps_z < 1) warps_z = 1;
+  if (warps_z != 1 && !((warps_z == 2 || warps_z == 4) && warps_x == 1 && warps_y == 1 && subtiles_y == 2))
+    return fail("dnmf_set_tiling: warps_z = 2 or 4 is supported for the 1x1 warp layout with subtiles_y = 2");
   if (subtiles_y > 2 || (subtiles_y == 2 && warps_y > 2))
     return fail("dnmf_set_tiling: subtiles_y = 2 is supported for the 1x1, 2x1 and 2x2 warp layouts");
   const bool ok = (warps_x == 1 && warps_y == 1) || (warps_x == 2 && warps_y == 1) ||
@@ -645,6 +649,7 @@ extern "C" int dnmf_set_tiling(dnmf_ctx* c, int warps_x, int warps_y, int tz, in
   if (tz < 0) return fail("dnmf_set_tiling: tz must be >= 0");
   c->nwx = warps_x;
   c->nwy = warps_y;
+  c->nwz = warps_z;
   c->tz = tz;
   c->user_cap = slot_capacity;
   c->sub = subtiles_y;
@@ -662,7 +667,7 @@ extern "C" int dnmf_set_affine(dnmf_ctx* c, int affine) {
 
 extern "C" int dnmf_get_tiling(dnmf_ctx* c, int32_t* out) {
   if (!c || !out) return fail("dnmf_get_tiling: NULL argument");
-  int32_t v[11] = {c->tx, c->ty, c->tz, c->ntx, c->nty, c->ntz, c->nwx, c->nwy, c->cap, c->sub, c->fast_div};
+  int32_t v[12] = {c->tx, c->ty, c->tz, c->ntx, c->nty, c->ntz, c->nwx, c->nwy, c->cap, c->sub, c->fast_div, c->nwz};
   memcpy(out, v, sizeof(v));
   return 0;
 }
@@ -689,26 +694,34 @@ static int configure_tiling(dnmf_ctx* c, cudaStream_t st) {
   // Instruction-count model of the fused kernel per 32-voxel row (from the ncu source pages, profiles/):
   // ~85 fixed + ~9.5 per listed neuron (one sub-tile per warp; the packed two-sub-tile march: 42 + 7.3) + the tile
   // prologue/epilogue amortised over the rows of the tile, inflated when shared memory leaves too few warps per SM.
-  static const int layouts[7][3] = {{1, 1, 2}, {1, 1, 1}, {2, 1, 2}, {2, 2, 2}, {2, 1, 1}, {2, 2, 1}, {2, 4, 1}};
+  // {warps_x, warps_y, sub-tiles, warps_z}; the z-split layouts keep the 8 x 8 tile of the one-warp layout (shortest
+  // lists) and put 2 or 4 warps on it (long lists: shared memory would leave a one-warp CTA too few warps per SM)
+  constexpr int kLayouts = 9;
+  static const int layouts[kLayouts][4] = {{1, 1, 2, 1}, {1, 1, 1, 1}, {2, 1, 2, 1}, {2, 2, 2, 1}, {2, 1, 1, 1},
+                                          {2, 2, 1, 1}, {2, 4, 1, 1}, {1, 1, 2, 2}, {1, 1, 2, 4}};
   int best = 0;
   double best_cost = 1e300;
-  for (int i = 0; i < 7; ++i) {
+  for (int i = 0; i < kLayouts; ++i) {
     c->nwx = layouts[i][0];
     c->nwy = layouts[i][1];
     c->sub = layouts[i][2];
+    c->nwz = layouts[i][3];
+    if (c->nwz > 1 && c->Z / c->nwz < 4) continue;  // a few z planes per warp: the per-frame setup is not amortised
     if (configure_tiling_fixed(c, st)) return 1;
-    const int nw = c->nwx * c->nwy;
+    const int nw = c->nwx * c->nwy * c->nwz;
     const int ctas = std::min(32, (int)((size_t)227 * 1024 / (c->fit_smem + 1024)));
     const double warps = std::min(64, ctas * nw);
-    const double rows = (double)c->sub * c->tz;
+    const double rows = (double)c->sub * c->tz / c->nwz;
     // two sub-tiles per warp run the packed (A, B) march: ~42 fixed + ~7.3 per listed neuron per row
     const double fixed = c->sub == 2 ? 42.0 : 85.0, per = c->sub == 2 ? 7.3 : 9.5;
     // fewer than ~8 resident warps per SM cannot keep the FP32 pipe fed (cfg4, measured: 16 warps 1.0, 8 warps
     // 1.04, 6 warps 1.6, 4 warps 2.0 relative cost)
     // lanes past the volume edge still cost: padded volume / volume
     const double edge = ((double)c->ntx * c->tx / c->X) * ((double)c->nty * c->ty / c->Y);
+    // fewer than ~16 resident warps leave the FP32 pipe idle part of the time (cfg4, 8 x 8 tile, measured: 4 CTAs of 4
+    // warps 2.80 ms, 4 CTAs of 2 warps 3.31 ms per 100 frames)
     double cost = (fixed + per * c->mean_list_identity + (300.0 + 600.0 / nw) / rows) *
-                  std::pow(std::max(1.0, 8.0 / warps), 1.5) * edge;
+                  std::pow(std::max(1.0, 8.0 / warps), 1.5) * (1.0 + 0.25 * std::max(0.0, 16.0 - warps) / 8.0) * edge;
     if (nw > 1 && c->mean_list_identity < 16.0) cost *= 1.25;  // sharing the staged slices only pays for long lists
     if (cost < best_cost) {
       best_cost = cost;
@@ -718,6 +731,7 @@ static int configure_tiling(dnmf_ctx* c, cudaStream_t st) {
   c->nwx = layouts[best][0];
   c->nwy = layouts[best][1];
   c->sub = layouts[best][2];
+  c->nwz = layouts[best][3];
   return configure_tiling_fixed(c, st);
 }
 
@@ -819,7 +833,7 @@ static int configure_tiling_fixed(dnmf_ctx* c, cudaStream_t st) {
   cap = (cap + 1) & ~1;               // slots are consumed in pairs (LDS.128)
   if ((cap & 3) == 0) cap += 2;       // slot-row stride = 2 (mod 4) float2: spreads entries over banks
   const int wsum = c->wmax[0] + c->wmax[1] + c->wmax[2];
-  const int nw = c->nwx * c->nwy;
+  const int nw = c->nwx * c->nwy * c->nwz;
   // keep at least ~2 CTAs per SM worth of shared memory when possible
   const size_t budget = std::min<size_t>((size_t)c->max_smem_optin, (size_t)113 * 1024);
   while (cap > 2 && fit_smem_layout(nw, c->tx, c->ty, c->tz, cap, wsum, c->K, c->wmax[0], c->cand_cap, c->y_pitch).bytes > budget)
@@ -1004,7 +1018,7 @@ static int dispatch_fit(dnmf_ctx* c, const FitParams& p, int B, cudaStream_t st)
 
 // MODE 3 (trace statistics) exists for the two-sub-tile layouts with the verified fast division only
 static bool fused_stats_available(const dnmf_ctx* c) {
-  return c->sub == 2 && c->fast_div != 0 && ((c->nwx == 1 && c->nwy == 1) || (c->nwx == 2 && c->nwy <= 2));
+  return c->sub == 2 && c->fast_div != 0 && c->nwz == 1 && ((c->nwx == 1 && c->nwy == 1) || (c->nwx == 2 && c->nwy <= 2));
 }
 static int dispatch_stats(dnmf_ctx* c, const FitParams& p, int B, size_t smem, cudaStream_t st) {
   if (c->nty > 65535) return fail("dispatch_stats: more than 65535 tiles along y");
@@ -1035,6 +1049,8 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
   p.ntx = c->ntx;
   p.nty = c->nty;
   p.ntz = c->ntz;
+  // z-split warp groups exist for the verified fast division only (a singleton axis has none): same tile, one warp
+  p.nwz = (c->fast_div != 0 && c->nwx == 1 && c->nwy == 1 && c->sub == 2) ? c->nwz : 1;
   p.cap = c->cap;
   p.wmax0 = c->wmax[0];
   p.wmax1 = c->wmax[1];

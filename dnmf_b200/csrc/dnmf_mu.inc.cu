@@ -723,7 +723,7 @@ static int stats_pass(dnmf_ctx* c, int which, const float* frames_dev, const int
     if ((cap & 3) == 0) cap += 2;
     if (cap > c->cap) {
       const int wsum = c->wmax[0] + c->wmax[1] + c->wmax[2];
-      const size_t need = fit_smem_layout(c->nwx * c->nwy, c->tx, c->ty, c->tz, cap, wsum, c->K, c->wmax[0],
+      const size_t need = fit_smem_layout(c->nwx * c->nwy * c->nwz, c->tx, c->ty, c->tz, cap, wsum, c->K, c->wmax[0],
                                           c->cand_cap, c->y_pitch).bytes;
       if (need <= std::min<size_t>((size_t)c->max_smem_optin, (size_t)113 * 1024)) {
         fused_cap = cap;

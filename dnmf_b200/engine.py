@@ -118,8 +118,9 @@ class Engine:
         _lib.check(self.lib.dnmf_get_table(self._h, axis, out.ctypes.data_as(ctypes.c_void_p)), "dnmf_get_table")
         return out
 
-    def set_tiling(self, warps_x: int = 1, warps_y: int = 1, tz: int = 0, slot_capacity: int = 0, subtiles_y: int = 1):
-        _lib.check(self.lib.dnmf_set_tiling(self._h, warps_x, warps_y, tz, slot_capacity, subtiles_y),
+    def set_tiling(self, warps_x: int = 1, warps_y: int = 1, tz: int = 0, slot_capacity: int = 0, subtiles_y: int = 1,
+                   warps_z: int = 1):
+        _lib.check(self.lib.dnmf_set_tiling(self._h, warps_x, warps_y, tz, slot_capacity, subtiles_y, warps_z),
                    "dnmf_set_tiling")
 
     def set_affine(self, affine: bool):
@@ -128,9 +129,9 @@ class Engine:
         _lib.check(self.lib.dnmf_set_affine(self._h, int(bool(affine))), "dnmf_set_affine")
 
     def tiling(self) -> dict:
-        out = np.zeros(11, np.int32)
+        out = np.zeros(12, np.int32)
         _lib.check(self.lib.dnmf_get_tiling(self._h, out.ctypes.data_as(ctypes.c_void_p)), "dnmf_get_tiling")
-        keys = ("tx", "ty", "tz", "ntx", "nty", "ntz", "warps_x", "warps_y", "cap", "subtiles_y", "fast_div")
+        keys = ("tx", "ty", "tz", "ntx", "nty", "ntz", "warps_x", "warps_y", "cap", "subtiles_y", "fast_div", "warps_z")
         return dict(zip(keys, (int(v) for v in out)))
 
     # -- video ------------------------------------------------------------------------------------

@@ -54,11 +54,14 @@ int dnmf_get_table(dnmf_ctx* ctx, int axis, float* table_host /* [K][s_axis+3][2
 /* Launch geometry of the fused kernel: warps per CTA along x and y (warp footprint is 8x4 voxels),
  * tile depth tz (0 = whole Z), staged-slot capacity (0 = automatic), y-adjacent sub-tiles carried by each
  * warp (1, or 2 for the 1x1, 2x1 and 2x2 warp layouts: the two sub-tiles then run as one packed FP32x2 stream).
+ * warps_z = 2 or 4 (1x1 layout with two sub-tiles only) puts that many warps on the one 8 x 8 tile, each marching its
+ * part of the z range: the short lists of the small tile with enough warps per SM for dense configurations.
  * Without this call the library picks a layout from the list lengths.  One CTA walks up to 8 consecutive
  * frames of the batch through its tile (environment override for tuning: DNMF_FPC=<1..32>). */
-int dnmf_set_tiling(dnmf_ctx* ctx, int warps_x, int warps_y, int tz, int slot_capacity, int subtiles_y);
-int dnmf_get_tiling(dnmf_ctx* ctx, int32_t* out /* tx,ty,tz,ntx,nty,ntz,warps_x,warps_y,cap,subtiles_y,
-                                                     exact_fast_division_verified */);
+int dnmf_set_tiling(dnmf_ctx* ctx, int warps_x, int warps_y, int tz, int slot_capacity, int subtiles_y,
+                    int warps_z);
+int dnmf_get_tiling(dnmf_ctx* ctx, int32_t* out /* [12]: tx,ty,tz,ntx,nty,ntz,warps_x,warps_y,cap,subtiles_y,
+                                                     exact_fast_division_verified,warps_z */);
 
 /* Resident video slab [T][X][Y][Z] on the device (ingest of SimulatedVideoDataset.video,
  * Demix/dNMF.py:203,214-215; negative values are clamped to 0 like __getitem__ does). */

@@ -44,9 +44,11 @@ def _check(sz, K, T, seed, cutoff, tiling, sigma=2.5, beta_scale=1.0, tol=3e-5):
 
 
 @pytest.mark.parametrize("sz", [[13, 7, 5], [8, 4, 1], [33, 9, 2], [17, 30, 11], [50, 50, 2]])
-@pytest.mark.parametrize("tiling", [(1, 1, 0, 0), (2, 2, 0, 0), (1, 1, 0, 0, 2), (2, 1, 0, 0, 2), (2, 2, 0, 0, 2)])
+@pytest.mark.parametrize("tiling", [(1, 1, 0, 0), (2, 2, 0, 0), (1, 1, 0, 0, 2), (2, 1, 0, 0, 2), (2, 2, 0, 0, 2),
+                                    (1, 1, 0, 0, 2, 2), (1, 1, 0, 0, 2, 4)])
 def test_ragged_sizes(sz, tiling):
-    """volumes that do not divide into tiles, odd depths (no bulk-copy alignment), singleton z."""
+    """volumes that do not divide into tiles, odd depths (no bulk-copy alignment), singleton z; z-split warp groups
+    (warps_z = 2, 4) with fewer z planes than warps."""
     _check(sz, 4, 3, seed=sum(sz), cutoff=3.5, tiling=tiling)
 
 

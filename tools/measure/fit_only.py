@@ -19,7 +19,8 @@ def run(name, frames, reps):
     cfg = bench.CONFIGS[name]
     T = frames or cfg.get("T_single", cfg["T"])
     dev = torch.device("cuda:0")
-    dn, vid = bench.build_model(cfg, T, dev, 1)
+    tiling = tuple(int(v) for v in os.environ["DNMF_TILING"].split(",")) if os.environ.get("DNMF_TILING") else None
+    dn, vid = bench.build_model(cfg, T, dev, 1, tiling)
     eng = dn.fp.engine
     beta = dn.fp.beta.detach()
     ids = torch.arange(T, dtype=torch.int32, device=dev)
@@ -45,9 +46,9 @@ def run(name, frames, reps):
         ev1.record()
         torch.cuda.synchronize()
         step_ms = ev0.elapsed_time(ev1) / reps
-        print("%s %-8s T=%d fit %.4f ms  step %.4f ms  (%.3f us/frame)  sse %.10e  |g| %.10e  g[0:4] %.8e loss %.10e tiling %dx%dx%d cap %d"
+        print("%s %-8s T=%d fit %.4f ms  step %.4f ms  (%.3f us/frame)  sse %.10e  |g| %.10e  g[0:4] %.8e loss %.10e tiling %dx%dx%d z%d cap %d"
               % (name, state, T, ms, step_ms, 1e3 * ms / T, float(sse.sum()), float(g.double().norm()),
-                 float(g[:4].double().abs().sum()), float(loss), tl["warps_x"], tl["warps_y"], tl["subtiles_y"], tl["cap"]),
+                 float(g[:4].double().abs().sum()), float(loss), tl["warps_x"], tl["warps_y"], tl["subtiles_y"], tl["warps_z"], tl["cap"]),
               flush=True)
         if keep is not None:
             beta.copy_(keep)
