@@ -56,6 +56,10 @@ constexpr int kZUnroll = DNMF_ZUNROLL;
 #define DNMF_WINDOW_PREPASS 1  // 1: tile windows of a batch come from tile_windows_kernel (one thread per tile-frame) instead
                                // of three lanes of the fused kernel's per-frame prologue
 #endif
+#ifndef DNMF_LANE_YFAST
+#define DNMF_LANE_YFAST 0  // 1: lane = 4 * x + y inside the warp's 8 x 4 footprint (0: lane = 8 * y + x).  Tried for the
+                           // shared-memory wavefronts of the slice loads; measured no difference at cfg2 / cfg3 / cfg4.
+#endif
 #ifndef DNMF_ALWAYS_SAFE
 #define DNMF_ALWAYS_SAFE 0  // 1: every tile takes the clamped main loop (one loop body fewer in the instruction cache)
 #endif

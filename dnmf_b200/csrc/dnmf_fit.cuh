@@ -1031,8 +1031,14 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
 
   // lane geometry (frame independent)
   const int wxy = NWZ == 1 ? warp : warp % NWXY, wz = NWZ == 1 ? 0 : warp / NWXY;
-  const int lx = (wxy % NWX) * kWarpX + (lane & 7);
-  const int ly0 = (wxy / NWX) * (kWarpY * SUB) + (lane >> 3);
+  // lane -> (x, y) of the warp's 8 x 4 footprint (DNMF_LANE_YFAST: y fastest; no measurable difference)
+#if DNMF_LANE_YFAST
+  const int lane_x = lane >> 2, lane_y = lane & 3;
+#else
+  const int lane_x = lane & 7, lane_y = lane >> 3;
+#endif
+  const int lx = (wxy % NWX) * kWarpX + lane_x;
+  const int ly0 = (wxy / NWX) * (kWarpY * SUB) + lane_y;
   // this warp's part of the tile's z range
   const int zb = NWZ == 1 ? 0 : (nz * wz) / NWZ;
   const int nzw = NWZ == 1 ? nz : (nz * (wz + 1)) / NWZ - zb;
@@ -1374,7 +1380,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
       a.validB = (gx < p.X) && (y0 + ly0 + kWarpY < p.Y);
       a.bg = bg;
       a.zskew = 0;
-      if (p.z_skew != 0 && nzw >= 4) a.zskew = ((lane >> 3) * p.z_skew) & 3;
+      if (p.z_skew != 0 && nzw >= 4) a.zskew = (lane_y * p.z_skew) & 3;
     };
 
     if constexpr (MODE == 3) {

@@ -754,7 +754,11 @@ static int configure_tiling_fixed(dnmf_ctx* c, cudaStream_t st) {
     const int zs = c->tz;
     const int dense = c->ty * zs;
     int worst = 0, hist[32] = {0};
+#if DNMF_LANE_YFAST
+    for (int l = 0; l < 32; ++l) worst = std::max(worst, ++hist[((l >> 2) * dense + (l & 3) * zs) & 31]);
+#else
     for (int l = 0; l < 32; ++l) worst = std::max(worst, ++hist[((l & 7) * dense + (l >> 3) * zs) & 31]);
+#endif
     c->y_pitch = dense;
     c->z_skew = 0;
     if (worst > 2) {
