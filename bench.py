@@ -16,6 +16,7 @@ The JSON line carries, next to the contract's keys:
   e2e_reference_batch the same from HOST frames (4-frame steps: what --impl reference steps)
   e2e_resident        host frames uploaded once (attach_video) + the same steps from ids (public API, amortised)
   trace_update        dnmf_mu_stats + 50 sweeps (update_footprints), frame-MU-iterations/s
+  shared_learning     EXTENSION: iterations that also learn positions / widths / background (one all-reduce per step)
   configs             compact legs of the other BASELINE configurations (cfg3, cfg4): value, frac, trace update
   scaling_detail      N > 1: per-rank step times, list lengths, time inside the final loss reduction
   strong_scaling      N > 1: a fixed T_global split over the ranks (BASELINE configuration 5)
@@ -317,6 +318,40 @@ def time_trace_update(eng, dn, beta, ids_all, T, chunk=250, iters=50):
             "stats_kernel": "fused tiles" if path & 1 else ("tensor-core panel (tcgen05 tf32)" if path & 4 else "SIMT panel"),
             "what": "dnmf_mu_stats over all frames + %d multiplicative sweeps (update_footprints without the dense "
                     "returns); reference: 1 035 frame-MU-iters/s on the 8-core CPU at cfg1" % iters}
+
+
+def shared_learning_leg(cfg, dev, world, dist, steps, frames=250):
+    """EXTENSION leg (no reference counterpart, flag OFF by default): full-batch iterations that also learn the shared
+    parameters -- positions, widths, background -- through DeformableNMF.update_motion after enable_shared_learning:
+    fused kernel with the residual written, parameter-gradient kernel, ONE all-reduce of the packed shared gradients
+    over the ranks (NCCL), device Adam on beta and on pos / sigma / b, tables and candidate lists rebuilt by kernels."""
+    T = min(frames, cfg["T"])
+    dn, vid = build_model(cfg, T, dev, world)
+    dn.enable_shared_learning(lr_pos=1e-4, lr_sigma=1e-5, lr_background=1e-5)
+    opt = torch.optim.Adam([dn.fp.beta], lr=cfg.get("lr", LR))
+    ids = torch.arange(T, dtype=torch.int32)
+    dn.update_motion(Loader([(None, ids)] * 2), opt, epochs=1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    dn.update_motion(Loader([(None, ids)] * steps), opt, epochs=1)
+    ev1.record()
+    torch.cuda.synchronize()
+    t_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    moved = float((dn.fp.pos.detach().cpu() - dn._positions).abs().max())
+    out = {"value": T * steps * world / (float(t_ms) * 1e-3), "unit": "frame-iterations/s", "frames_per_gpu": T,
+           "steps": steps, "ms_per_step": float(t_ms) / steps, "collective": "all_reduce of 4K+2 doubles per iteration"
+           if world > 1 else "none (one rank)", "max_position_change_px": moved,
+           "what": "EXTENSION (no reference counterpart): update_motion after enable_shared_learning -- beta, positions, "
+                   "widths and background learned together, device-resident step (dnmf_ext_step_begin / _end)"}
+    dn.fp.engine.close()
+    del dn, vid
+    torch.cuda.empty_cache()
+    return out
 
 
 def fp32_peak(eng, local):
@@ -663,6 +698,15 @@ def run_b200(args, cfg):
         del host_frames
         host_frames = None
 
+    # ---- extension: shared-parameter learning (all ranks: it carries the path's one real collective) ----
+    shared = None
+    if not args.no_legs:
+        try:
+            shared = shared_learning_leg(cfg, dev, world, dist, max(3, min(args.steps, 10)))
+        except Exception as ex:  # pragma: no cover
+            shared = {"error": repr(ex)[:300]}
+        barrier()
+
     # ---- roofline of the dominant kernel (fit_tile_kernel), timed live with CUDA events (rank 0) ----
     roofline = deformed = ref_batch = mu = None
     peak = 0.0
@@ -780,7 +824,7 @@ def run_b200(args, cfg):
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "final_loss": final_loss, "trace_update": mu,
             "reference_batch": ref_batch, "e2e_reference_batch": e2e_b4, "e2e_resident": e2e_res,
-            "deformed_beta": deformed, "configs": legs, "scaling_detail": scaling_detail, "strong_scaling": strong}
+            "deformed_beta": deformed, "shared_learning": shared, "configs": legs, "scaling_detail": scaling_detail, "strong_scaling": strong}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -79,6 +79,11 @@ def load(build_if_missing: bool = True):
         "dnmf_frames_maxz": (c_int, [P, c_int64, c_int, P, P]),
         "dnmf_ext_enable": (c_int, [P]),
         "dnmf_ext_loss_grad": (c_int, [P, P, P, c_int, c_int, P, P, c_float, P, P, P, P, P, P]),
+        "dnmf_ext_step_begin": (c_int, [P, P, P, c_int, c_int, P, P, P, P]),
+        "dnmf_ext_step_end": (c_int, [P, P, P, P, c_double, c_double, c_double, c_double, c_int64, c_int, P, c_int,
+                                      c_double, c_double, c_double, c_float, P, P]),
+        "dnmf_ext_set_params": (c_int, [P, c_float, c_int, P]),
+        "dnmf_ext_get_params": (c_int, [P, P, P, P, P]),
         "dnmf_measure_fp32_peak": (c_int, [c_int, c_int, POINTER(c_double)]),
     }
     for name, (res, args) in sig.items():

@@ -26,11 +26,6 @@ constexpr int kZUnroll = DNMF_ZUNROLL;
 #ifndef DNMF_UNROLLED_MARCH
 #define DNMF_UNROLLED_MARCH 0  // 1: one fully unrolled main loop per slot-pair count (more code than the I-cache holds)
 #endif
-#ifndef DNMF_MERGE_TAIL01
-#define DNMF_MERGE_TAIL01 1  // 1: the specialised main loops keep "single slot" apart and merge even / odd lists
-                             // (4 bodies instead of 6; measured at cfg2: identity beta 2.65 ms either way, a different
-                             // deformation per frame 3.40 -> 2.94 ms per 1000 frames)
-#endif
 #ifndef DNMF_AFFINE_BODIES
 #define DNMF_AFFINE_BODIES 1  // 1: affine frames with frozen quadratic rows (FitParams::skip_quad) take main loops without
                               // the z^2 Horner term and the z^2 gradient moments (6 packed + 1 scalar op per z step fewer)
@@ -43,12 +38,6 @@ constexpr int kZUnroll = DNMF_ZUNROLL;
 #ifndef DNMF_RESTAGE_BATCH
 #define DNMF_RESTAGE_BATCH 4
 #endif
-#ifndef DNMF_DYN_TAIL_BODIES
-#define DNMF_DYN_TAIL_BODIES 0  // 1: also compile the single-body main loops with a run-time tail kind (march_rolled TAIL 3)
-                                // and the per-launch choice from restage counters (DNMF_DYN_TAIL).  Measured slower than the
-                                // default four bodies in both states (2.77 / 3.05 vs 2.65 / 2.94 ms); 4 unused loop bodies
-                                // (13 KB of SASS) and a counter round trip per launch otherwise.
-#endif
 #ifndef DNMF_FMA_MOMENTS
 #define DNMF_FMA_MOMENTS 1  // 1: gradient z-moments as fma(z^m r, g, S) in the specialised main loops
 #endif
@@ -59,6 +48,16 @@ constexpr int kZUnroll = DNMF_ZUNROLL;
 #ifndef DNMF_LANE_YFAST
 #define DNMF_LANE_YFAST 0  // 1: lane = 4 * x + y inside the warp's 8 x 4 footprint (0: lane = 8 * y + x).  Tried for the
                            // shared-memory wavefronts of the slice loads; measured no difference at cfg2 / cfg3 / cfg4.
+#endif
+#ifndef DNMF_DYN_TAIL_BODIES
+#define DNMF_DYN_TAIL_BODIES 0  // 1: also compile the single-body main loops with a run-time tail kind (march_rolled TAIL 3;
+                                // FitParams::dyn_tail would select them).  Measured slower than the default four bodies in
+                                // both states (2.77 / 3.05 vs 2.65 / 2.94 ms per 1000 cfg2 frames) and four more loop bodies
+                                // in the instruction cache; the per-launch choice from restage counters is gone.
+#endif
+#ifndef DNMF_MERGE_TAIL01
+#define DNMF_MERGE_TAIL01 1  // 1: the specialised main loops keep "single slot" apart and merge even / odd lists
+                             // (4 bodies instead of 6; a deformation per frame 3.40 -> 2.94 ms per 1000 cfg2 frames)
 #endif
 #ifndef DNMF_ALWAYS_SAFE
 #define DNMF_ALWAYS_SAFE 0  // 1: every tile takes the clamped main loop (one loop body fewer in the instruction cache)
@@ -136,12 +135,16 @@ struct FitParams {
   int* mu_overflow;  // MODE 3: set when a tile's list is not fully staged (the caller reruns the generic kernel)
   const int4* windows;  // [B][tiles][2]: (wlo0, wlo1, wlo2, whi0), (whi1, whi2, clipped, 0) from tile_windows_kernel, or NULL
   int skip_quad;  // != 0: gradient rows 4..9 are not wanted (affine fit: Adam freezes them) and are returned as zero
-  int dyn_tail;  // != 0: main loop with the run-time tail kind (one loop body per SAFE; see march_rolled TAIL 3)
-  unsigned* restage_count;  // [32] frames whose slices were rebuilt, counted per CTA (MODE 0; may be NULL)
+  int dyn_tail;  // DNMF_DYN_TAIL_BODIES builds only: main loop with the run-time tail kind
+  unsigned* restage_count;  // DNMF_DYN_TAIL_BODIES builds only: [32] frames whose slices were rebuilt, or NULL
   int y_pitch;   // floats between x rows of the Y tile in shared memory (>= ty * tile depth)
   int z_skew;    // != 0: lane (lx, ly) starts its z march at ((ly * z_skew) & 3), see march_rolled<SKEW>
   int tmap_ok;   // the frame tile can be fetched with ONE tensor TMA copy (3-D map over [frame][x][y*Z])
   int b_base;    // index of this launch's first frame in the buffer the tensor map describes
+  // New fields go HERE, behind everything the kernels have always read: the offsets of the fields above decide which
+  // parameters ptxas fetches in pairs, and moving them changed the generated main loops (cfg3 / cfg4 lost 6-7 %
+  // when an 8-byte pointer was inserted next to `bg`).
+  const float* bg_dev;  // MODE 2: the background is read from the device instead (dnmf_ext_step_begin), or NULL
   alignas(64) CUtensorMap tmap;
 };
 
@@ -227,6 +230,12 @@ struct dnmf_ctx {
   float rcp[3] = {0.f, 0.f, 0.f};
   long long* d_cand_off = nullptr;  // static candidate lists per tile (identity windows +- cand_expand)
   int* d_cand_ids = nullptr;
+  long long cand_ids_cap = 0;
+  // extension, device-resident shared parameters (dnmf_ext_step_begin / _end): background, Adam state of
+  // pos[K][3], sigma[K], b
+  float* d_bg = nullptr;
+  float* d_ext_m = nullptr;   // [4K+1]
+  float* d_ext_v = nullptr;   // [4K+1]
   int cand_expand = 6;
   int cand_cap = 0;
   int affine_grad = 0;   // dnmf_set_affine: dnmf_loss_grad leaves the quadratic gradient rows zero
@@ -290,13 +299,6 @@ struct dnmf_ctx {
   int mu_sweep_per_launch = 0; // DNMF_MU_SWEEP_PER_LAUNCH / dnmf_mu_path bit 2: one launch per sweep even without coupling
   int mu_block4 = 0;           // DNMF_MU_BLOCK4: keep the 4x4 register blocks of the panel kernel for every list length
   int mu_capM = 0;
-  // adaptive main-loop variant (FitParams::dyn_tail): restage counts of the previous fused launch
-  unsigned* d_restage = nullptr;   // [32]
-  unsigned* h_restage = nullptr;   // pinned [32], refreshed asynchronously after every fused launch
-  long long restage_den_pending = 0;  // tile-frames of the launch the pending copy of the counters describes
-  cudaEvent_t ev_restage = nullptr;
-  int dyn_tail_mode = 0;           // DNMF_DYN_TAIL: 0 (default) / 1 force a variant, -1 automatic from the counters
-  int dyn_tail_cur = 0;
   // frame-parallel epoch (dnmf_motion_epoch)
   int* d_epoch_batch_of = nullptr;
   size_t epoch_batch_of_cap = 0;

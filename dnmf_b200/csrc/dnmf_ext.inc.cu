@@ -179,15 +179,13 @@ extern "C" int dnmf_ext_enable(dnmf_ctx* c) {
   return 0;
 }
 
-extern "C" int dnmf_ext_loss_grad(dnmf_ctx* c, const float* frames_dev, const int32_t* frame_ids_dev, int B,
-                                  int B_global, const float* beta_dev, const float* C_dev, float background,
-                                  float* grad_beta_dev, double* sse_dev, double* gpos_dev, double* gsig_dev,
-                                  double* gbg_dev, void* stream) {
-  if (!c || !frame_ids_dev || !beta_dev || !C_dev || !grad_beta_dev || !sse_dev || !gpos_dev || !gsig_dev || !gbg_dev)
-    return fail("dnmf_ext_loss_grad: NULL argument");
+// background_dev != NULL: the scalar background is read from the device (the context's own, dnmf_ext_step_begin)
+static int ext_loss_grad_impl(dnmf_ctx* c, const float* frames_dev, const int32_t* frame_ids_dev, int B, int B_global,
+                              const float* beta_dev, const float* C_dev, float background, const float* background_dev,
+                              float* grad_beta_dev, double* sse_dev, double* gpos_dev, double* gsig_dev,
+                              double* gbg_dev, cudaStream_t st) {
   if (!c->d_tab_dpos[0]) return fail("dnmf_ext_loss_grad: call dnmf_ext_enable (then dnmf_set_footprints) first");
   if (B < 1 || B_global < B) return fail("dnmf_ext_loss_grad: need 1 <= B <= B_global");
-  cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(c->device));
   if (check_sticky(c, "dnmf_ext_loss_grad") || sanitize_ids(c, frame_ids_dev, B, st, &frame_ids_dev)) return 1;
   FitParams p;
@@ -196,6 +194,7 @@ extern "C" int dnmf_ext_loss_grad(dnmf_ctx* c, const float* frames_dev, const in
   if (ensure(&c->d_sumr, &c->sumr_cap, (size_t)B)) return 1;
   p.yhat = c->d_resid;
   p.bg = background;
+  p.bg_dev = background_dev;
   if (dispatch_fit<2>(c, p, B, st)) return 1;
   const int nt = c->ntx * c->nty * c->ntz;
   const double scale = 2.0 / ((double)B_global * (double)c->N);
@@ -244,4 +243,172 @@ extern "C" int dnmf_ext_loss_grad(dnmf_ctx* c, const float* frames_dev, const in
   c->counters[0] += 1;
   c->counters[1] += 1;
   return 0;
+}
+
+extern "C" int dnmf_ext_loss_grad(dnmf_ctx* c, const float* frames_dev, const int32_t* frame_ids_dev, int B,
+                                  int B_global, const float* beta_dev, const float* C_dev, float background,
+                                  float* grad_beta_dev, double* sse_dev, double* gpos_dev, double* gsig_dev,
+                                  double* gbg_dev, void* stream) {
+  if (!c || !frame_ids_dev || !beta_dev || !C_dev || !grad_beta_dev || !sse_dev || !gpos_dev || !gsig_dev || !gbg_dev)
+    return fail("dnmf_ext_loss_grad: NULL argument");
+  return ext_loss_grad_impl(c, frames_dev, frame_ids_dev, B, B_global, beta_dev, C_dev, background, nullptr,
+                            grad_beta_dev, sse_dev, gpos_dev, gsig_dev, gbg_dev, (cudaStream_t)stream);
+}
+
+// ---- device-resident iteration of the extension: no host round trip between the gradient kernels, the caller's
+// all-reduce of ONE packed buffer, the Adam steps and the table rebuild ------------------------------------------
+namespace dnmf {
+
+// packed[0 .. 3K) = dL/dpos, [3K .. 4K) = dL/dsigma, [4K] = dL/db (already in place), [4K+1] = sum of the batch SSE
+__global__ void ext_pack_sse_kernel(const double* __restrict__ sse, int B, double* __restrict__ packed_sse) {
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < B; j += 32) acc += sse[j];
+  acc = warp_sum_d(acc);
+  if (threadIdx.x == 0) *packed_sse = acc;
+}
+
+// Adam (torch.optim._single_tensor_adam's formula, fp32 state) on pos[K][3], sigma[K] and the background, gradients
+// from the packed (all-reduced) buffer; sigma is kept >= sigma_min.
+__global__ void ext_adam_kernel(float* __restrict__ pos, float* __restrict__ sigma, float* __restrict__ bg,
+                                float* __restrict__ m, float* __restrict__ v, const double* __restrict__ packed, int K,
+                                float w1, float b2, float w2, float bc2_sqrt, float eps, float ss_pos,
+                                float ss_sigma, float ss_bg, float sigma_min) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > 4 * K) return;
+  float* prm = i < 3 * K ? pos + i : (i < 4 * K ? sigma + (i - 3 * K) : bg);
+  const float ss = i < 3 * K ? ss_pos : (i < 4 * K ? ss_sigma : ss_bg);
+  const float g = (float)packed[i];
+  float x = *prm, mi = m[i], vi = v[i];
+  adam_update(x, mi, vi, g, w1, b2, w2, ss, bc2_sqrt, eps);   // the arithmetic of adam_kernel
+  m[i] = mi;
+  v[i] = vi;
+  if (i >= 3 * K && i < 4 * K) x = fmaxf(x, sigma_min);
+  *prm = x;
+}
+
+// The refreshed candidate lists must fit the id buffer they were first sized for (+50 %): if they do not, the offsets
+// are emptied (no kernel reads past the buffer) and the context's sticky error is raised -- the next call fails loudly
+// and dnmf_set_footprints re-sizes everything.
+__global__ void ext_guard_candidates_kernel(long long* __restrict__ cand_off, int nt, long long cap, int* sticky) {
+  const long long total = cand_off[nt];
+  if (total <= cap) return;
+  for (int i = threadIdx.x; i <= nt; i += blockDim.x) cand_off[i] = 0;
+  if (threadIdx.x == 0) atomicOr(sticky, 8);
+}
+
+// Ranges, tables and the static candidate lists from the device-resident pos / sigma at the CURRENT launch geometry
+// (no layout search, no synchronisation).
+static int ext_rebuild_tables(dnmf_ctx* c, cudaStream_t st) {
+  build_ranges_kernel<<<(c->K + 127) / 128, 128, 0, st>>>(c->d_pos, c->d_sigma, c->K, c->X, c->Y, c->Z, c->cutoff,
+                                                          c->d_rng);
+  CU(cudaGetLastError());
+  const int s[3] = {c->X, c->Y, c->Z};
+  for (int d = 0; d < 3; ++d) {
+    dim3 grid((s[d] + 3 + 127) / 128, c->K);
+    build_tables_kernel<<<grid, 128, 0, st>>>(c->d_pos, c->d_sigma, c->d_rng, c->K, s[d], d, c->d_tab[d],
+                                              c->d_tab_dpos[d], c->d_tab_dsig[d]);
+    CU(cudaGetLastError());
+  }
+  const int nt = c->ntx * c->nty * c->ntz;
+  if (run_bin_count(c, c->d_identity_beta, 1, c->d_ids_zero, 1, c->d_tmp_counts, nullptr, st, c->cand_expand)) return 1;
+  scan_counts_kernel<<<1, 1024, 0, st>>>(c->d_tmp_counts, nt, c->d_cand_off, nullptr);
+  CU(cudaGetLastError());
+  ext_guard_candidates_kernel<<<1, 256, 0, st>>>(c->d_cand_off, nt, c->cand_ids_cap, c->d_sticky);
+  CU(cudaGetLastError());
+  Geom g1 = geom_of(c);
+  g1.T = 1;
+  const int wpb = 8;
+  bin_tiles_kernel<true><<<(unsigned)((nt + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+      g1, c->d_identity_beta, c->d_ids_zero, 1, c->d_rng, c->d_tmp_counts, c->d_cand_off, nullptr, c->d_cand_ids,
+      c->cand_ids_cap, c->cand_expand);
+  CU(cudaGetLastError());
+  c->mu_capM = 0;
+  c->mu_nbr_built = false;
+  c->gc_valid = false;
+  c->mu_fused_need = 0;
+  c->mu_fused_off = 0;
+  c->counters[3]++;
+  return 0;
+}
+
+static int ext_state(dnmf_ctx* c) {
+  if (!c->d_tab_dpos[0] || !c->have_footprints)
+    return fail("dnmf_ext_step: call dnmf_ext_enable and dnmf_set_footprints first");
+  if (!c->d_bg) {
+    CU(cudaMalloc((void**)&c->d_bg, sizeof(float)));
+    CU(cudaMemset(c->d_bg, 0, sizeof(float)));
+    CU(cudaMalloc((void**)&c->d_ext_m, ((size_t)4 * c->K + 1) * sizeof(float)));
+    CU(cudaMalloc((void**)&c->d_ext_v, ((size_t)4 * c->K + 1) * sizeof(float)));
+    CU(cudaMemset(c->d_ext_m, 0, ((size_t)4 * c->K + 1) * sizeof(float)));
+    CU(cudaMemset(c->d_ext_v, 0, ((size_t)4 * c->K + 1) * sizeof(float)));
+  }
+  return 0;
+}
+
+}  // namespace dnmf
+
+extern "C" int dnmf_ext_set_params(dnmf_ctx* c, float background, int reset_adam_state, void* stream) {
+  if (!c) return fail("dnmf_ext_set_params: ctx is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaSetDevice(c->device));
+  if (ext_state(c)) return 1;
+  CU(cudaMemcpyAsync(c->d_bg, &background, sizeof(float), cudaMemcpyHostToDevice, st));
+  if (reset_adam_state) {
+    CU(cudaMemsetAsync(c->d_ext_m, 0, ((size_t)4 * c->K + 1) * sizeof(float), st));
+    CU(cudaMemsetAsync(c->d_ext_v, 0, ((size_t)4 * c->K + 1) * sizeof(float), st));
+  }
+  CU(cudaStreamSynchronize(st));  // `background` is a stack value
+  return 0;
+}
+
+extern "C" int dnmf_ext_get_params(dnmf_ctx* c, float* pos_dev_out, float* sigma_dev_out, float* background_dev_out,
+                                   void* stream) {
+  if (!c) return fail("dnmf_ext_get_params: ctx is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaSetDevice(c->device));
+  if (ext_state(c)) return 1;
+  if (pos_dev_out) CU(cudaMemcpyAsync(pos_dev_out, c->d_pos, (size_t)c->K * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (sigma_dev_out) CU(cudaMemcpyAsync(sigma_dev_out, c->d_sigma, (size_t)c->K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (background_dev_out) CU(cudaMemcpyAsync(background_dev_out, c->d_bg, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+extern "C" int dnmf_ext_step_begin(dnmf_ctx* c, const float* frames_dev, const int32_t* frame_ids_dev, int B,
+                                   int B_global, const float* beta_dev, const float* C_dev, double* packed_dev,
+                                   void* stream) {
+  if (!c || !frame_ids_dev || !beta_dev || !C_dev || !packed_dev) return fail("dnmf_ext_step_begin: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaSetDevice(c->device));
+  if (ext_state(c)) return 1;
+  if (ensure(&c->d_sse, &c->sse_cap, (size_t)B)) return 1;
+  const int K = c->K;
+  if (ext_loss_grad_impl(c, frames_dev, frame_ids_dev, B, B_global, beta_dev, C_dev, 0.f, c->d_bg, c->d_grad, c->d_sse,
+                         packed_dev, packed_dev + 3 * (size_t)K, packed_dev + 4 * (size_t)K, st))
+    return 1;
+  ext_pack_sse_kernel<<<1, 32, 0, st>>>(c->d_sse, B, packed_dev + 4 * (size_t)K + 1);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dnmf_ext_step_end(dnmf_ctx* c, float* beta_dev, float* m_dev, float* v_dev, double lr, double beta1,
+                                 double beta2, double eps, int64_t step, int affine, const double* packed_dev,
+                                 int B_global, double lr_pos, double lr_sigma, double lr_background, float sigma_min,
+                                 double* loss_dev, void* stream) {
+  if (!c || !beta_dev || !m_dev || !v_dev || !packed_dev) return fail("dnmf_ext_step_end: NULL argument");
+  if (step < 1) return fail("dnmf_ext_step_end: step is 1-based");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaSetDevice(c->device));
+  if (ext_state(c)) return 1;
+  const int K = c->K;
+  // Adam on beta with the gradient dnmf_ext_step_begin left in the context; the loss is the all-reduced SSE sum
+  if (dnmf_adam_step(c, beta_dev, c->d_grad, m_dev, v_dev, lr, beta1, beta2, eps, step, affine, packed_dev + 4 * (size_t)K + 1,
+                     1, B_global, loss_dev, stream))
+    return 1;
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  ext_adam_kernel<<<(4 * K + 1 + 127) / 128, 128, 0, st>>>(
+      c->d_pos, c->d_sigma, c->d_bg, c->d_ext_m, c->d_ext_v, packed_dev, K, (float)(1.0 - beta1),
+      (float)beta2, (float)(1.0 - beta2), (float)sqrt(bc2), (float)eps, (float)(lr_pos / bc1), (float)(lr_sigma / bc1),
+      (float)(lr_background / bc1), sigma_min);
+  CU(cudaGetLastError());
+  return ext_rebuild_tables(c, st);
 }

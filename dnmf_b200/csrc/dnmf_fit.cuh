@@ -1049,7 +1049,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
   const unsigned baseX = smem_u32(sTab);
   const unsigned baseY = baseX + (unsigned)p.wmax0 * strideB;
   const unsigned baseZ = baseY + (unsigned)p.wmax1 * strideB;
-  const float bg = WRITE_RES ? p.bg : 0.f;
+  const float bg = WRITE_RES ? (p.bg_dev != nullptr ? *p.bg_dev : p.bg) : 0.f;
 
   // state carried from frame to frame: what the staged slices were built for
   int pw_lo[3] = {0x7fffffff, 0, 0}, pw_hi[3] = {0, 0, 0}, prev_L = -1;

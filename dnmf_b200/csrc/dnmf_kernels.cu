@@ -535,7 +535,6 @@ static int create_impl(dnmf_ctx* c, int X, int Y, int Z, int K, int T, int devic
   c->num_sms = prop.multiProcessorCount;
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (const char* ev = getenv("DNMF_FPC")) c->fpc_override = atoi(ev);
-  if (const char* ev = getenv("DNMF_DYN_TAIL")) c->dyn_tail_mode = atoi(ev);
   if (const char* ev = getenv("DNMF_MU_PANEL")) c->mu_force_panel = atoi(ev) != 0;
   if (const char* ev = getenv("DNMF_MU_SWEEP_PER_LAUNCH")) c->mu_sweep_per_launch = atoi(ev) != 0;
   if (const char* ev = getenv("DNMF_MU_BLOCK4")) c->mu_block4 = atoi(ev) != 0;
@@ -604,14 +603,14 @@ extern "C" void dnmf_destroy(dnmf_ctx* c) {
   cudaSetDevice(c->device);
   void* ptrs[] = {c->d_pos,     c->d_sigma, c->d_rng,        c->d_tab[0],      c->d_tab[1],
                   c->d_tab[2],  c->video_owned ? c->d_video : nullptr, c->d_partials,   c->d_grad,        c->d_sse,
-                  c->d_windows,
+                  c->d_windows, c->d_bg, c->d_ext_m, c->d_ext_v,
                   c->d_batch,   c->d_ids,   c->d_loss,       c->d_tmp_counts,  c->d_tmp_offsets,
                   c->d_tmp_max, c->d_G,     c->d_b,          c->d_identity_beta,
                   c->d_Cd[0],   c->d_Cd[1], c->d_keys,       c->d_cand_off,    c->d_cand_ids,
                   c->d_tab_dpos[0], c->d_tab_dpos[1], c->d_tab_dpos[2], c->d_tab_dsig[0], c->d_tab_dsig[1],
                   c->d_tab_dsig[2], c->d_resid, c->d_sumr, c->d_ids_zero,
                   c->d_epoch_batch_of, c->d_epoch_offsets, c->d_epoch_scalars, c->d_epoch_scale,
-                  c->d_mu_nbr, c->d_Gc, c->d_restage, c->d_ids_safe, c->d_id_mark, c->d_id_flags,
+                  c->d_mu_nbr, c->d_Gc, c->d_ids_safe, c->d_id_mark, c->d_id_flags,
                   c->d_pb_vals, c->d_pb_ids, c->d_pb_count, c->d_pb_slot};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -622,11 +621,6 @@ extern "C" void dnmf_destroy(dnmf_ctx* c) {
       cudaEventDestroy(c->ev_done[i]);
     }
   }
-  if (c->ev_restage) {
-    cudaEventSynchronize(c->ev_restage);  // a copy into the pinned counters may still be in flight
-    cudaEventDestroy(c->ev_restage);
-  }
-  if (c->h_restage) cudaFreeHost(c->h_restage);
   if (c->h_sticky) cudaFreeHost(c->h_sticky);
   delete c;
 }
@@ -795,7 +789,8 @@ static int configure_tiling_fixed(dnmf_ctx* c, cudaStream_t st) {
     long long total = 0;
     CU(cudaMemcpyAsync(&total, c->d_cand_off + nt, sizeof(long long), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    CU(cudaMalloc((void**)&c->d_cand_ids, (size_t)std::max<long long>(total, 1) * sizeof(int)));
+    c->cand_ids_cap = total + total / 2 + 1024;  // slack: the extension refreshes the lists in place as positions move
+    CU(cudaMalloc((void**)&c->d_cand_ids, (size_t)c->cand_ids_cap * sizeof(int)));
     {  // longest static candidate list -> shared-memory capacity of the fused kernel's candidate cache
       std::vector<long long> h_off((size_t)nt + 1);
       CU(cudaMemcpy(h_off.data(), c->d_cand_off, ((size_t)nt + 1) * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -953,7 +948,8 @@ static int check_sticky(dnmf_ctx* c, const char* who) {
   *(volatile int*)c->h_sticky = 0;
   std::string what;
   if (bits & 2) what += " a frame id outside [0, T) was passed (the call ran on ids clamped into the slab; its results are invalid)";
-  if (bits & ~2) what += " device status " + std::to_string(bits);
+  if (bits & 8) what += " the candidate lists rebuilt on the device outgrew their buffer (extension: positions moved far; call dnmf_set_footprints)";
+  if (bits & ~(2 | 8)) what += " device status " + std::to_string(bits);
   return fail(std::string(who) + ": an earlier asynchronous call failed:" + what);
 }
 
@@ -1127,6 +1123,7 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
   }
   p.yhat = nullptr;
   p.bg = 0.f;
+  p.bg_dev = nullptr;
   const size_t need = (size_t)B * c->ntx * c->nty * c->ntz * kNumPartials;
   if (ensure(&c->d_partials, &c->partials_cap, need)) return 1;
   p.partials = c->d_partials;
@@ -1144,45 +1141,7 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
   return 0;
 }
 
-// Fused fit launch (MODE 0) with the main-loop variant picked from what the previous launches did: the kernel
-// counts the tile-frames whose slices were (re)built, the counters come back through pinned memory without a
-// synchronisation (read one or two launches late), and above half of all tile-frames the single-body main loop
-// is used (march_rolled TAIL 3).  Both variants execute the same arithmetic: results do not depend on the choice.
-static int launch_fused_fit(dnmf_ctx* c, FitParams& p, int B, cudaStream_t st) {
-  if (!DNMF_DYN_TAIL_BODIES) return dispatch_fit<0>(c, p, B, st);
-  if (!c->d_restage) {
-    CU(cudaMalloc((void**)&c->d_restage, 32 * sizeof(unsigned)));
-    CU(cudaMemset(c->d_restage, 0, 32 * sizeof(unsigned)));
-    CU(cudaMallocHost((void**)&c->h_restage, 32 * sizeof(unsigned)));
-    CU(cudaEventCreateWithFlags(&c->ev_restage, cudaEventDisableTiming));
-  }
-  bool can_enqueue = true;
-  if (c->restage_den_pending > 0) {
-    const cudaError_t q = cudaEventQuery(c->ev_restage);
-    if (q == cudaSuccess) {
-      unsigned long long sum = 0;
-      for (int i = 0; i < 32; ++i) sum += c->h_restage[i];
-      const double frac = (double)sum / (double)c->restage_den_pending;
-      if (frac > 0.5) c->dyn_tail_cur = 1;
-      else if (frac < 0.35) c->dyn_tail_cur = 0;
-      c->restage_den_pending = 0;
-    } else if (q == cudaErrorNotReady) {
-      can_enqueue = false;  // the pinned buffer is still owed a copy
-    } else {
-      CU(q);
-    }
-  }
-  p.dyn_tail = c->dyn_tail_mode >= 0 ? (c->dyn_tail_mode != 0) : c->dyn_tail_cur;
-  p.restage_count = c->d_restage;
-  if (dispatch_fit<0>(c, p, B, st)) return 1;
-  if (can_enqueue) {
-    CU(cudaMemcpyAsync(c->h_restage, c->d_restage, 32 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemsetAsync(c->d_restage, 0, 32 * sizeof(unsigned), st));
-    CU(cudaEventRecord(c->ev_restage, st));
-    c->restage_den_pending = (long long)B * c->ntx * c->nty * c->ntz;
-  }
-  return 0;
-}
+static int launch_fused_fit(dnmf_ctx* c, FitParams& p, int B, cudaStream_t st) { return dispatch_fit<0>(c, p, B, st); }
 
 extern "C" int dnmf_loss_grad(dnmf_ctx* c, const float* frames_dev, const int32_t* frame_ids_dev, int B,
                               int B_global, const float* beta_dev, const float* C_dev, float* grad_dev,

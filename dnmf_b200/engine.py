@@ -379,6 +379,44 @@ class Engine:
                                                _ptr(gsig), _ptr(gbg), self.stream), "dnmf_ext_loss_grad")
         return grad_beta, sse, gpos, gsig, gbg
 
+    # device-resident iteration of the extension (no host round trip; the caller all-reduces `packed` in between)
+    def ext_step_begin(self, frame_ids: torch.Tensor, beta, C, packed: torch.Tensor,
+                       frames: Optional[torch.Tensor] = None, B_global: Optional[int] = None):
+        """packed: float64 CUDA tensor of 4K+2 entries <- (dL/dpos[K,3], dL/dsigma[K], dL/db, sum of the batch SSE)."""
+        self._check_state(beta, C=C)
+        ids32 = self._ids32(frame_ids)
+        B = int(ids32.numel())
+        if frames is not None:
+            _check_dev(frames, torch.float32, "frames", self.device, (B, self.X, self.Y, self.Z))
+        _check_dev(packed, torch.float64, "packed", self.device, (4 * self.K + 2,))
+        _lib.check(self.lib.dnmf_ext_step_begin(self._h, _ptr(frames), _ptr(ids32), B, int(B_global or B), _ptr(beta),
+                                                _ptr(C), _ptr(packed), self.stream), "dnmf_ext_step_begin")
+
+    def ext_step_end(self, beta, m, v, lr, betas, eps, step, affine, packed: torch.Tensor, B_global: int,
+                     lr_pos: float, lr_sigma: float, lr_background: float, sigma_min: float = 0.5,
+                     loss_out: Optional[torch.Tensor] = None):
+        self._check_state(beta, m, v)
+        _check_dev(packed, torch.float64, "packed", self.device, (4 * self.K + 2,))
+        if loss_out is not None:
+            _check_dev(loss_out, torch.float64, "loss_out", self.device)
+        _lib.check(self.lib.dnmf_ext_step_end(self._h, _ptr(beta), _ptr(m), _ptr(v), float(lr), float(betas[0]),
+                                              float(betas[1]), float(eps), int(step), int(affine), _ptr(packed),
+                                              int(B_global), float(lr_pos), float(lr_sigma), float(lr_background),
+                                              float(sigma_min), _ptr(loss_out), self.stream), "dnmf_ext_step_end")
+
+    def ext_set_params(self, background: float = 0.0, reset_adam_state: bool = False):
+        _lib.check(self.lib.dnmf_ext_set_params(self._h, float(background), int(reset_adam_state), self.stream),
+                   "dnmf_ext_set_params")
+
+    def ext_get_params(self):
+        """(pos[K,3], sigma[K], background[]) as the context holds them now (float32 CUDA tensors, copies)."""
+        pos = torch.empty(self.K, 3, dtype=torch.float32, device=self.device)
+        sigma = torch.empty(self.K, dtype=torch.float32, device=self.device)
+        bg = torch.empty((), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.dnmf_ext_get_params(self._h, _ptr(pos), _ptr(sigma), _ptr(bg), self.stream),
+                   "dnmf_ext_get_params")
+        return pos, sigma, bg
+
     def counters(self) -> dict:
         out = np.zeros(8, np.int64)
         _lib.check(self.lib.dnmf_get_counters(self._h, out.ctypes.data_as(ctypes.c_void_p)), "dnmf_get_counters")

@@ -369,12 +369,20 @@ class DeformableNMF:
         self._video_resident = True
 
     # -- EXTENSION (no reference counterpart, off by default) ---------------------------------------
-    def enable_shared_learning(self, lr_pos=0.0, lr_sigma=0.0, lr_background=0.0, process_group=None):
+    def enable_shared_learning(self, lr_pos=0.0, lr_sigma=0.0, lr_background=0.0, process_group=None,
+                               device_step: bool = True, sigma_min: float = 0.5):
         """Also learn the SHARED parameters -- neuron positions, widths and a scalar background added to the
         model -- with Adam next to the per-frame deformation.  Their gradients come from
         dnmf_ext_loss_grad; with frames sharded over GPUs they are the only gradients that are all-reduced
         (one small NCCL all-reduce per iteration).  The reference keeps pos/sigma fixed and has no background
-        (Demix/dNMF.py:29-33), so this has no reference oracle: it is tested against torch autograd."""
+        (Demix/dNMF.py:29-33), so this has no reference oracle: it is tested against torch autograd.
+
+        device_step=True (default): the whole iteration stays on the device (dnmf_ext_step_begin / _end): one packed
+        gradient buffer for the all-reduce, Adam on pos / sigma / b with the library's kernel (betas and eps of the
+        optimiser handed to update_motion), sigma clamped to >= sigma_min, ranges / tables / candidate lists rebuilt by
+        kernels.  `fp.pos`, `fp.sigma`, `background` are refreshed from the device at the end of every update_motion
+        call.  device_step=False keeps the first implementation (torch.optim.Adam on the three tensors and a table
+        rebuild through the host per step); the two are tested against each other."""
         eng = self.fp.engine
         eng.ext_enable()
         self.fp.pos = self.fp.pos.detach().clone().requires_grad_(True)
@@ -382,8 +390,12 @@ class DeformableNMF:
         self.background = self.background.detach().clone().requires_grad_(True)
         groups = [{"params": [self.fp.pos], "lr": lr_pos}, {"params": [self.fp.sigma], "lr": lr_sigma},
                   {"params": [self.background], "lr": lr_background}]
-        self._shared = {"opt": torch.optim.Adam(groups), "group": process_group}
+        self._shared = {"opt": torch.optim.Adam(groups), "group": process_group, "device_step": bool(device_step),
+                        "lr": (float(lr_pos), float(lr_sigma), float(lr_background)), "sigma_min": float(sigma_min),
+                        "packed": torch.zeros(4 * eng.K + 2, dtype=torch.float64, device=eng.device), "step": 0}
         eng.set_footprints(self.fp.pos, self.fp.sigma, self.fp.cutoff)
+        if device_step:
+            eng.ext_set_params(float(self.background.detach()), reset_adam_state=True)
 
     def _shared_step(self, ids, frames_dev, optimizer_group, st, step, B_global):
         """One iteration with shared-parameter learning: fused kernel (residual written) + parameter
@@ -392,6 +404,21 @@ class DeformableNMF:
         import torch.distributed as dist
         eng = self.fp.engine
         beta = self.fp.beta.detach()
+        sh = self._shared
+        if sh["device_step"]:
+            packed, group = sh["packed"], sh["group"]
+            eng.ext_step_begin(ids, beta, self.C, packed, frames=frames_dev, B_global=B_global)
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+                dist.all_reduce(packed, group=group)         # the one collective of the extension
+            if self._loss_buf is None:
+                self._loss_buf = torch.zeros(1024, dtype=torch.float64, device=eng.device)
+            slot = self._loss_buf[(step - 1) % 1024:(step - 1) % 1024 + 1]
+            sh["step"] += 1
+            eng.ext_step_end(beta, st["exp_avg"], st["exp_avg_sq"], optimizer_group["lr"], optimizer_group["betas"],
+                             optimizer_group["eps"], step, self.affine, packed, B_global, *sh["lr"],
+                             sigma_min=sh["sigma_min"], loss_out=slot)
+            self.fp._A = None
+            return slot
         grad = getattr(self, "_ext_grad", None)
         if grad is None:
             grad = self._ext_grad = torch.zeros_like(beta)
@@ -524,7 +551,17 @@ class DeformableNMF:
                 if self.verbose and batch_idx % 10 == 0:
                     print("Recon: " + str(float(loss)))
                     print("Reg: " + str(self.fp.regularizer_values(ids.tolist())))
+        if self._shared is not None and self._shared["device_step"]:
+            self._refresh_shared_params()
         eng.check_status()      # surfaces an error an asynchronous step found on the device (one sync per call)
+
+    def _refresh_shared_params(self):
+        """fp.pos / fp.sigma / background <- what the device-resident shared step has made of them."""
+        pos, sigma, bg = self.fp.engine.ext_get_params()
+        with torch.no_grad():
+            self.fp.pos.copy_(pos)
+            self.fp.sigma.copy_(sigma)
+            self.background.copy_(bg)
 
     def losses(self) -> np.ndarray:
         """Per-step reconstruction losses recorded by update_motion (one device sync)."""

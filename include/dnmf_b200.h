@@ -191,6 +191,26 @@ int dnmf_ext_loss_grad(dnmf_ctx* ctx, const float* frames_dev, const int32_t* fr
                        float* grad_beta_dev, double* sse_dev, double* gpos_dev, double* gsig_dev,
                        double* gbg_dev, void* stream);
 
+/* The same iteration without leaving the device (what DeformableNMF.update_motion runs after
+ * enable_shared_learning): dnmf_ext_step_begin = the two gradient kernels with the context's own background, the
+ * beta gradient kept in the context and ONE packed buffer for the caller's all-reduce,
+ *   packed[0..3K) = dL/dpos, [3K..4K) = dL/dsigma, [4K] = dL/db, [4K+1] = sum of the batch's SSE    (doubles);
+ * dnmf_ext_step_end (after the all-reduce) = Adam on beta (dnmf_adam_step), Adam with the same formula on
+ * pos / sigma / b from the packed buffer (state kept in the context; sigma is clamped to >= sigma_min), then ranges,
+ * tables and the static candidate lists rebuilt on the device at the current launch geometry.  No host
+ * synchronisation in either call; loss_dev (optional) = packed[4K+1] / (B_global * N).
+ * dnmf_ext_set_params sets the background (and optionally clears the Adam state of the shared parameters),
+ * dnmf_ext_get_params copies pos[K][3], sigma[K], b into the caller's device buffers. */
+int dnmf_ext_step_begin(dnmf_ctx* ctx, const float* frames_dev, const int32_t* frame_ids_dev, int B, int B_global,
+                        const float* beta_dev, const float* C_dev, double* packed_dev, void* stream);
+int dnmf_ext_step_end(dnmf_ctx* ctx, float* beta_dev, float* m_dev, float* v_dev, double lr, double beta1,
+                      double beta2, double eps, int64_t step, int affine, const double* packed_dev, int B_global,
+                      double lr_pos, double lr_sigma, double lr_background, float sigma_min, double* loss_dev,
+                      void* stream);
+int dnmf_ext_set_params(dnmf_ctx* ctx, float background, int reset_adam_state, void* stream);
+int dnmf_ext_get_params(dnmf_ctx* ctx, float* pos_dev_out, float* sigma_dev_out, float* background_dev_out,
+                        void* stream);
+
 /* FFMA microbenchmark: best-of-`repeats` dense FP32 throughput of the device in TFLOP/s (FMA = 2);
  * the roofline denominator for the FP32-bound fused kernel (MEASURED_PEAKS.json has no FP32 entry). */
 int dnmf_measure_fp32_peak(int device, int repeats, double* tflops_out);

@@ -598,29 +598,20 @@ def test_mu_stats_panel_kernel_8x8_blocks_long_lists(monkeypatch, K):
 
 
 @pytest.mark.parametrize("tiling", [(1, 1, 0, 0, 2), (2, 2, 0, 0, 2), (1, 1, 0, 3, 2)])
-def test_main_loop_variants_are_bit_identical(monkeypatch, tiling):
-    """The fused kernel picks its main-loop variant per launch (three bodies specialised on the list's tail kind,
-    or one body with a run-time tail kind, chosen from how often the previous launches rebuilt their slices).
-    Both execute the same arithmetic: forcing either gives bit-identical gradients and losses, also against the
-    automatic choice over several launches with changing deformations; lists of every tail kind (cap 3: odd
-    lists, single slots, overflow)."""
+def test_main_loop_bodies_every_tail_kind(tiling):
+    """Lists of every tail kind (slot capacity 3: even and odd lists, single slots, overflow through the global tables)
+    through the specialised main-loop bodies: against the closed form, and bit-identical over repeated launches."""
     from dnmf_b200.engine import Engine
     sz, K, T = [40, 24, 9], 10, 12
     pos, sig, beta, C, frames = _case(sz, K, T, 17, sigma=2.5, beta_scale=0.6)
     tabs, _ = O.axis_tables(pos, sig, sz, 3.5)
     loss, gref = O.closed_form_step(frames.numpy(), list(range(T)), beta.numpy(), C.numpy(), tabs, sz)
-    res = []
-    for mode in ("0", "1", "-1"):
-        monkeypatch.setenv("DNMF_DYN_TAIL", mode)
-        e = Engine(sz, K, T)
-        e.set_tiling(*tiling)
-        e.set_footprints(pos, sig, 3.5)
-        out = [e.loss_grad(torch.arange(T), beta.cuda(), C.cuda(), frames=frames.cuda()) for _ in range(4)]
-        torch.cuda.synchronize()
-        for g, s_ in out[1:]:
-            assert torch.equal(g, out[0][0]) and torch.equal(s_, out[0][1])
-        res.append(out[0])
-    err = np.abs(res[0][0].cpu().numpy() - gref).max() / np.abs(gref).max()
+    e = Engine(sz, K, T)
+    e.set_tiling(*tiling)
+    e.set_footprints(pos, sig, 3.5)
+    out = [e.loss_grad(torch.arange(T), beta.cuda(), C.cuda(), frames=frames.cuda()) for _ in range(4)]
+    torch.cuda.synchronize()
+    for g, s_ in out[1:]:
+        assert torch.equal(g, out[0][0]) and torch.equal(s_, out[0][1])
+    err = np.abs(out[0][0].cpu().numpy() - gref).max() / np.abs(gref).max()
     assert err < 3e-5, err
-    for g, s_ in res[1:]:
-        assert torch.equal(g, res[0][0]) and torch.equal(s_, res[0][1])

@@ -84,6 +84,44 @@ def test_learning_positions_reduces_loss():
     assert abs(float(dn.background.detach()) - 0.05) < 0.04
 
 
+def test_device_resident_shared_step_matches_the_torch_optimiser_route():
+    """(extension, not reference parity)  dnmf_ext_step_begin / _end -- device Adam on pos / sigma / b, tables and
+    candidate lists rebuilt by kernels, no host round trip -- against the first implementation (torch.optim.Adam on
+    the three tensors, dnmf_set_footprints through the host every step): same parameters after 6 iterations."""
+    from dnmf_b200 import DeformableNMF, FrameDataset
+    from torch.utils.data import DataLoader
+    sz, K, T = [28, 20, 5], 6, 8
+    rng = np.random.default_rng(3)
+    pos = (rng.random((K, 3)) * (np.asarray(sz) - 1)).astype(np.float32)
+    frames = torch.tensor(rng.random((T, *sz)).astype(np.float32))
+    C0 = torch.tensor(rng.random((K, T)).astype(np.float32))
+    out = []
+    for device_step in (True, False):
+        dn = DeformableNMF(sz, K, T, positions=torch.tensor(pos), cutoff=3.5, verbose=False)
+        dn.C = C0.clone().cuda()
+        dn.enable_shared_learning(lr_pos=0.03, lr_sigma=0.01, lr_background=0.01, device_step=device_step)
+        opt = torch.optim.Adam([dn.fp.beta], lr=1e-4)
+        loader = DataLoader(FrameDataset(frames), batch_size=4, shuffle=False)
+        dn.update_motion(loader, opt, epochs=3)
+        out.append((dn.fp.pos.detach().cpu().numpy(), dn.fp.sigma.detach().cpu().numpy(), float(dn.background.detach()),
+                    dn.fp.beta.detach().cpu().numpy(), dn.losses()))
+        # the context's tables follow the learned parameters: a fresh context built from them gives the same forward
+        ref = DeformableNMF(sz, K, T, positions=dn.fp.pos.detach().cpu(), cutoff=3.5, verbose=False,
+                            shape_std=dn.fp.sigma.detach().cpu())
+        with torch.no_grad():
+            ref.fp.beta.copy_(dn.fp.beta)
+        y0 = dn.fp([0, 3], dn.C)[0]
+        y1 = ref.fp([0, 3], dn.C)[0]
+        assert float((y0 - y1).abs().max()) <= 1e-6 * float(y1.abs().max())
+    a, b = out
+    assert np.abs(a[0] - pos).max() > 1e-3                                 # the positions did move
+    np.testing.assert_allclose(a[0], b[0], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(a[1], b[1], rtol=0, atol=2e-5)
+    assert abs(a[2] - b[2]) < 2e-5
+    np.testing.assert_allclose(a[3], b[3], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(a[4], b[4], rtol=1e-5)
+
+
 def test_two_rank_shared_learning_matches_single_rank(tmp_path):
     """2 processes (one GPU, gloo), each owning half the frames, all-reduce the shared gradients every
     iteration: positions / widths / background end up equal to the single-process full-batch run."""
