@@ -59,6 +59,10 @@ constexpr int kZUnroll = DNMF_ZUNROLL;
 #define DNMF_MERGE_TAIL01 1  // 1: the specialised main loops keep "single slot" apart and merge even / odd lists
                              // (4 bodies instead of 6; a deformation per frame 3.40 -> 2.94 ms per 1000 cfg2 frames)
 #endif
+#ifndef DNMF_SKEW_KERNELS
+#define DNMF_SKEW_KERNELS 0  // 1: the rotated z order (Z = 32) gets its own kernel instantiations: four main-loop bodies
+                             // per kernel instead of eight
+#endif
 #ifndef DNMF_ALWAYS_SAFE
 #define DNMF_ALWAYS_SAFE 0  // 1: every tile takes the clamped main loop (one loop body fewer in the instruction cache)
 #endif
@@ -194,6 +198,9 @@ struct GramTcParams {
   int b_base;  // batch position of this launch's first frame in the partial buffers
   int fast_div;  // exact 3-instruction division verified for all three axes (verify_coord_kernel)
   float rcp0, rcp1, rcp2;
+  const long long* cand_off;  // the fit kernel's static per-tile candidate lists when its tiles are these 8 x 8 x Z
+  const int* cand_ids;        // tiles (NULL otherwise: every CTA scans all K neurons)
+  int cand_expand;
 };
 int launch_gram_tc(const GramTcParams& p, int B, cudaStream_t st);
 size_t gram_tc_smem_bytes(int X, int Y, int Z);

@@ -867,7 +867,7 @@ __device__ __forceinline__ void march_generic(const GenericArgs& a, float (&S0)[
 // its own part of the tile's z range.  The tile stays 8*NWX x 4*NWY*SUB voxels wide -- the list length follows the
 // tile's x, y extent, (8+s)(8+s) against (16+s)(16+s) for a footprint s nodes wide -- while the CTA still brings enough
 // warps per SM for its shared memory (the staged slices of ~85 neurons take 40 KB).
-template <int NWX, int NWY, int SUB, int MODE, bool FAST_DIV, bool AFFK = false, int NWZ = 1>
+template <int NWX, int NWY, int SUB, int MODE, bool FAST_DIV, bool AFFK = false, int NWZ = 1, bool SKEWK = false>
 __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ? (MODE == 3 ? DNMF_MU_MINB : DNMF_MINB) : (NWZ > 1 ? 512 / (32 * NWX * NWY * NWZ) : 1)) fit_tile_kernel(const __grid_constant__ FitParams p) {
   static_assert(!AFFK || (MODE == 0 && SUB == 2 && FAST_DIV), "affine instantiation: fit, two sub-tiles, fast division");
   static_assert(NWZ == 1 || MODE != 3, "the fused trace statistics do not split z");
@@ -1380,7 +1380,11 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
       a.validB = (gx < p.X) && (y0 + ly0 + kWarpY < p.Y);
       a.bg = bg;
       a.zskew = 0;
+#if DNMF_SKEW_KERNELS
+      if ((SKEWK || (MODE == 3 && p.z_skew != 0)) && nzw >= 4) a.zskew = (lane_y * p.z_skew) & 3;
+#else
       if (p.z_skew != 0 && nzw >= 4) a.zskew = (lane_y * p.z_skew) & 3;
+#endif
     };
 
     if constexpr (MODE == 3) {
@@ -1488,7 +1492,16 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
               default: march_rolled<true, MODE, 3, true, AFFK>(a, npf, o, tail); break;
             }
           } else
-#if DNMF_MERGE_TAIL01
+#if DNMF_SKEW_KERNELS
+          // the skew of the z order is a property of the launch (shared-memory pitch of the Y tile): SKEWK kernels hold
+          // the rotated-order bodies only, the others the plain ones -- four bodies per kernel instead of eight
+          switch ((tail == 2 ? 2 : 0) + (safe ? 1 : 0)) {
+            case 0: march_rolled<false, MODE, 4, SKEWK, AFFK>(a, npf, o, tail); break;
+            case 1: march_rolled<true, MODE, 4, SKEWK, AFFK>(a, npf, o, tail); break;
+            case 2: march_rolled<false, MODE, 2, SKEWK, AFFK>(a, npf, o); break;
+            default: march_rolled<true, MODE, 2, SKEWK, AFFK>(a, npf, o); break;
+          }
+#elif DNMF_MERGE_TAIL01
           switch ((p.z_skew != 0 ? 4 : 0) + (tail == 2 ? 2 : 0) + (safe ? 1 : 0)) {
             case 0: march_rolled<false, MODE, 4, false, AFFK>(a, npf, o, tail); break;
             case 1: march_rolled<true, MODE, 4, false, AFFK>(a, npf, o, tail); break;
@@ -1646,9 +1659,9 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
     atomicAdd(p.restage_count + ((blockIdx.x + blockIdx.y) & 31), (unsigned)n_restaged);
 }
 
-template <int NWX, int NWY, int SUB, int MD_, bool FD_, bool AFFK_ = false, int NWZ_ = 1>
+template <int NWX, int NWY, int SUB, int MD_, bool FD_, bool AFFK_ = false, int NWZ_ = 1, bool SKEWK_ = false>
 static int launch_fit(const FitParams& p0, int B, size_t smem, cudaStream_t st) {
-  auto kern = fit_tile_kernel<NWX, NWY, SUB, MD_, FD_, AFFK_, NWZ_>;
+  auto kern = fit_tile_kernel<NWX, NWY, SUB, MD_, FD_, AFFK_, NWZ_, SKEWK_>;
   static size_t configured[64] = {0};  // per device: the attribute is a per-device property of the function
   int dev = 0;
   CU(cudaGetDevice(&dev));

@@ -185,13 +185,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
   // ---- neuron list (ascending k): every warp scans its share of the neurons ONCE into its own segment, the
   // segments are then concatenated in warp order ----
   {
-    const int per = ((p.K + kTcThreads - 1) / kTcThreads) * 32;
+    // candidates: the fit kernel's static per-tile lists (identity windows expanded by cand_expand nodes, ascending k)
+    // when they were built for these very tiles and the window stays inside the expanded box; else all K neurons
+    long long r0 = 0;
+    int r1 = p.K;
+    const int* __restrict__ cand = nullptr;
+    if (p.cand_off != nullptr) {
+      const int e = p.cand_expand;
+      const bool inside = wlo[0] >= max(x0 - 1, -2) - e && whi[0] <= min(x0 + nx, p.X) + e &&
+                          wlo[1] >= max(y0 - 1, -2) - e && whi[1] <= min(y0 + ny, p.Y) + e &&
+                          wlo[2] >= -1 - e && whi[2] <= p.Z + e;
+      if (inside) {
+        r0 = p.cand_off[tile];
+        r1 = (int)(p.cand_off[tile + 1] - r0);
+        cand = p.cand_ids + r0;
+      }
+    }
+    const int per = ((r1 + kTcThreads - 1) / kTcThreads) * 32;
     const int kb = warp * per;
     int cnt = 0;
     for (int k0 = kb; k0 < kb + per; k0 += 32) {
-      const int k = k0 + lane;
+      const int idx = k0 + lane;
       bool ok = false;
-      if (k < p.K) {  // the six range bounds as three independent 8-byte loads, then the test
+      int k = 0;
+      if (idx < r1) {  // the six range bounds as three independent 8-byte loads, then the test
+        k = cand ? __ldg(cand + idx) : idx;
         const int2* r2 = reinterpret_cast<const int2*>(p.rng + (size_t)k * 6);
         const int2 rx = __ldg(r2), ry = __ldg(r2 + 1), rz = __ldg(r2 + 2);
         const int r[6] = {rx.x, rx.y, ry.x, ry.y, rz.x, rz.y};
@@ -249,30 +267,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
   {
     const int sX3 = p.X + 3, sY3 = p.Y + 3, sZ3 = p.Z + 3;
     const int Wt = W0 + W1 + W2;
-    for (int e = warp; e < Wt; e += kTcWarps) {
-      const float2* src;
-      int row, ent;
-      if (e < W0) {
-        src = p.tab0 + (wlo[0] + 2 + e);
-        row = sX3;
-        ent = e;
-      } else if (e < W0 + W1) {
-        src = p.tab1 + (wlo[1] + 2 + (e - W0));
-        row = sY3;
-        ent = wmax0 + (e - W0);
-      } else {
-        src = p.tab2 + (wlo[2] + 2 + (e - W0 - W1));
-        row = sZ3;
-        ent = wmax0 + wmax1 + (e - W0 - W1);
+    // work items (table entry, slot pair) dealt round-robin to all threads, four items (eight 8-byte gathers) in flight
+    // per thread before the first store: two dependent rounds of L2 latency instead of the eleven of one entry per
+    // warp and 32 pairs per pass
+    const int items = Wt * npair;
+    const unsigned recN = npair > 1 ? 0xFFFFFFFFu / (unsigned)npair + 1u : 0u;  // floor(i / npair) == umulhi(i, recN)
+    constexpr int kBatch = 4;
+    for (int i0 = tid; i0 < items; i0 += kBatch * kTcThreads) {
+      float2 va[kBatch], vb[kBatch];
+      float4* dst[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int i = i0 + u * kTcThreads;
+        va[u] = vb[u] = make_float2(0.f, 0.f);
+        dst[u] = nullptr;
+        if (i < items) {
+          const int e = npair > 1 ? (int)__umulhi((unsigned)i, recN) : i;
+          const int pp = i - e * npair;
+          const float2* src;
+          int row, ent;
+          if (e < W0) {
+            src = p.tab0 + (wlo[0] + 2 + e);
+            row = sX3;
+            ent = e;
+          } else if (e < W0 + W1) {
+            src = p.tab1 + (wlo[1] + 2 + (e - W0));
+            row = sY3;
+            ent = wmax0 + (e - W0);
+          } else {
+            src = p.tab2 + (wlo[2] + 2 + (e - W0 - W1));
+            row = sZ3;
+            ent = wmax0 + wmax1 + (e - W0 - W1);
+          }
+          const int j = 2 * pp;
+          if (j < L) va[u] = __ldg(src + (size_t)sList[j] * row);
+          if (j + 1 < L) vb[u] = __ldg(src + (size_t)sList[j + 1] * row);
+          dst[u] = reinterpret_cast<float4*>(sSl + (size_t)ent * kTcEntryBytes) + pp;
+        }
       }
-      float4* dst = reinterpret_cast<float4*>(sSl + (size_t)ent * kTcEntryBytes);
-      for (int pp = lane; pp < npair; pp += 32) {
-        const int j = 2 * pp;
-        float2 va = make_float2(0.f, 0.f), vb = va;
-        if (j < L) va = __ldg(src + (size_t)sList[j] * row);
-        if (j + 1 < L) vb = __ldg(src + (size_t)sList[j + 1] * row);
-        dst[pp] = make_float4(va.x, vb.x, va.y, vb.y);
-      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u)
+        if (dst[u]) *dst[u] = make_float4(va[u].x, vb[u].x, va[u].y, vb[u].y);
     }
   }
   __syncthreads();

@@ -756,6 +756,10 @@ static int stats_pass(dnmf_ctx* c, int which, const float* frames_dev, const int
     tp.rcp2 = c->rcp[2];
     tp.ntx = (c->X + kGramTX - 1) / kGramTX;
     tp.nty = (c->Y + kGramTY - 1) / kGramTY;
+    const bool same_tiles = c->tx == kGramTX && c->ty == kGramTY && c->ntz == 1 && c->d_cand_off && c->d_cand_ids;
+    tp.cand_off = same_tiles ? c->d_cand_off : nullptr;
+    tp.cand_ids = same_tiles ? c->d_cand_ids : nullptr;
+    tp.cand_expand = c->cand_expand;
     if (gram_tc_smem_bytes(c->X, c->Y, c->Z) > (size_t)c->max_smem_optin) {
       *over = 1 << 30;  // volume too deep for whole-depth tiles in shared memory
       return 0;
