@@ -59,6 +59,13 @@ constexpr int kZUnroll = DNMF_ZUNROLL;
 #define DNMF_MERGE_TAIL01 1  // 1: the specialised main loops keep "single slot" apart and merge even / odd lists
                              // (4 bodies instead of 6; a deformation per frame 3.40 -> 2.94 ms per 1000 cfg2 frames)
 #endif
+#ifndef DNMF_RESTAGE_U32
+#define DNMF_RESTAGE_U32 0
+#endif
+#ifndef DNMF_SHARE_XZ
+#define DNMF_SHARE_XZ 1  // 1: the z-split (dense-list) kernels load the x and z slice entries of a slot pair once for the
+                         // voxels A and B of a lane when they coincide (march_rolled SHARE)
+#endif
 #ifndef DNMF_SKEW_KERNELS
 #define DNMF_SKEW_KERNELS 0  // 1: the rotated z order (Z = 32) gets its own kernel instantiations: four main-loop bodies
                              // per kernel instead of eight

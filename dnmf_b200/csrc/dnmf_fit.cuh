@@ -50,6 +50,20 @@ __device__ __forceinline__ void pair2_accumulate(float2 exG, float2 exD, float2 
   g2 = __ffma2_rn(__fmul2_rn(ca0, a1), ezD, g2);
 }
 
+// the same, producing the accumulators (the first slot pair of a list): exactly slot_pair<0, true>'s arithmetic
+__device__ __forceinline__ void pair2_first(float2 exG, float2 exD, float2 eyG, float2 eyD, float2 ezG, float2 ezD,
+                                            float2 f0, float2 f1, float2 f2, float2& yh, float2& g0, float2& g1,
+                                            float2& g2) {
+  const float2 ca0 = __ffma2_rn(f0, exD, exG);
+  const float2 a1 = __ffma2_rn(f1, eyD, eyG);
+  const float2 a2 = __ffma2_rn(f2, ezD, ezG);
+  const float2 t12 = __fmul2_rn(a1, a2);
+  yh = __fmul2_rn(ca0, t12);
+  g0 = __fmul2_rn(exD, t12);
+  g1 = __fmul2_rn(__fmul2_rn(ca0, a2), eyD);
+  g2 = __fmul2_rn(__fmul2_rn(ca0, a1), ezD);
+}
+
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 // Loop-invariant values the compiler would otherwise rematerialise inside the hot loop (constant-bank
@@ -357,7 +371,12 @@ __device__ __forceinline__ void tail_slot(const unsigned (&adA)[3], const unsign
 // reads of the Y tile over the banks when the tile's y/x pitches are multiples of 32 floats (Z = 32).
 // AFF: the frame's quadratic coefficients (rows 4..9 of beta_t) are all zero and their gradient rows are not wanted
 // (FitParams::skip_quad): 2q = c1 z + c0 exactly as Horner with c2 = 0 would give it, and the z^2 moments are dropped.
-template <bool SAFE, int MODE, int TAIL, bool SKEW, bool AFF = false>
+// SHARE (dense lists, NWZ kernels): when every lane's voxels A and B fall on the same x and z table entries -- B is
+// A four rows further in y, so they do unless the deformation's y-coupling carries a lane across a node -- the slot
+// pairs' x and z slice entries are loaded once for both voxels: four LDS.128 per slot pair and voxel pair instead of
+// six.  Dense lists are bound by the shared-memory pipe (79 % of its wavefront peak at cfg4), not by the FP32 pipe.
+// The test is one warp vote per z step; the arithmetic is unchanged (same operands, same order).
+template <bool SAFE, int MODE, int TAIL, bool SKEW, bool AFF = false, bool SHARE = false>
 __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOut& o, int tail = 0) {
   const float oz = a.oz;
   const float2 zero2 = make_float2(oz, oz);
@@ -422,6 +441,30 @@ __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOu
     if (TAIL == 3 ? (tail != 2) : (TAIL != 2)) {  // TAIL 4: np >= 1, run-time choice between kinds 0 and 1
       // first slot pair produces the accumulators, the rest of the list updates them
       float2 yA, gA0, gA1, gA2, yB, gB0, gB1, gB2;
+      bool shared_xz = false;
+      if constexpr (SHARE) shared_xz = __all_sync(0xffffffffu, adA[0] == adB[0] && adA[2] == adB[2]);
+      if (SHARE && shared_xz) {
+        {
+          const float4 ex = lds128r(adA[0]), ez = lds128r(adA[2]), eyA = lds128r(adA[1]), eyB = lds128r(adB[1]);
+          pair2_first(make_float2(ex.x, ex.y), make_float2(ex.z, ex.w), make_float2(eyA.x, eyA.y),
+                      make_float2(eyA.z, eyA.w), make_float2(ez.x, ez.y), make_float2(ez.z, ez.w), fA0, fA1, fA2, yA, gA0,
+                      gA1, gA2);
+          pair2_first(make_float2(ex.x, ex.y), make_float2(ex.z, ex.w), make_float2(eyB.x, eyB.y),
+                      make_float2(eyB.z, eyB.w), make_float2(ez.x, ez.y), make_float2(ez.z, ez.w), fB0, fB1, fB2, yB, gB0,
+                      gB1, gB2);
+        }
+#pragma unroll 1
+        for (unsigned off = 16u; off < pair_bytes; off += 16u) {
+          const float4 ex = lds128r(adA[0] + off), ez = lds128r(adA[2] + off);
+          const float4 eyA = lds128r(adA[1] + off), eyB = lds128r(adB[1] + off);
+          pair2_accumulate(make_float2(ex.x, ex.y), make_float2(ex.z, ex.w), make_float2(eyA.x, eyA.y),
+                           make_float2(eyA.z, eyA.w), make_float2(ez.x, ez.y), make_float2(ez.z, ez.w), fA0, fA1, fA2,
+                           yA, gA0, gA1, gA2);
+          pair2_accumulate(make_float2(ex.x, ex.y), make_float2(ex.z, ex.w), make_float2(eyB.x, eyB.y),
+                           make_float2(eyB.z, eyB.w), make_float2(ez.x, ez.y), make_float2(ez.z, ez.w), fB0, fB1, fB2,
+                           yB, gB0, gB1, gB2);
+        }
+      } else {
       slot_pair<0, true>(adA[0], adA[1], adA[2], fA0, fA1, fA2, yA, gA0, gA1, gA2);
       slot_pair<0, true>(adB[0], adB[1], adB[2], fB0, fB1, fB2, yB, gB0, gB1, gB2);
 #pragma unroll 1
@@ -439,6 +482,7 @@ __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOu
                            yB, gB0, gB1, gB2);
         }
       }
+      }  // !shared_xz
       yh = make_float2(yA.x + yA.y, yB.x + yB.y);
       g[0] = make_float2(gA0.x + gA0.y, gB0.x + gB0.y);
       g[1] = make_float2(gA1.x + gA1.y, gB1.x + gB1.y);
@@ -1285,8 +1329,15 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
           for (int u = 0; u < kBatch; ++u) {
             const int j = 2 * (p0 + u);
             va[u] = vb[u] = make_float2(0.f, 0.f);
+#if DNMF_RESTAGE_U32
+            // row offsets in 32 bits (K * (s + 3) < 2^31 float2 entries): one IMAD.WIDE per gather instead of a 64-bit
+            // multiply-add chain of four
+            if (j < nst) va[u] = __ldg(src + (unsigned)sList[j] * (unsigned)row);
+            if (j + 1 < nst) vb[u] = __ldg(src + (unsigned)sList[j + 1] * (unsigned)row);
+#else
             if (j < nst) va[u] = __ldg(src + (size_t)sList[j] * row);
             if (j + 1 < nst) vb[u] = __ldg(src + (size_t)sList[j + 1] * row);
+#endif
           }
 #pragma unroll
           for (int u = 0; u < kBatch; ++u)
@@ -1484,6 +1535,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
         } else {
           const int npf = nst >> 1;  // full slot pairs; an odd list ends with a single slot
           const int tail = (nst & 1) ? (npf == 0 ? 2 : 1) : 0;
+          constexpr bool kShare = DNMF_SHARE_XZ == 2 || (DNMF_SHARE_XZ && NWZ > 1);  // dense lists: x / z slice entries shared by voxels A and B
           if (DNMF_DYN_TAIL_BODIES && p.dyn_tail) {
             switch ((p.z_skew != 0 ? 2 : 0) + (safe ? 1 : 0)) {
               case 0: march_rolled<false, MODE, 3, false, AFFK>(a, npf, o, tail); break;
@@ -1503,12 +1555,12 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
           }
 #elif DNMF_MERGE_TAIL01
           switch ((p.z_skew != 0 ? 4 : 0) + (tail == 2 ? 2 : 0) + (safe ? 1 : 0)) {
-            case 0: march_rolled<false, MODE, 4, false, AFFK>(a, npf, o, tail); break;
-            case 1: march_rolled<true, MODE, 4, false, AFFK>(a, npf, o, tail); break;
+            case 0: march_rolled<false, MODE, 4, false, AFFK, kShare>(a, npf, o, tail); break;
+            case 1: march_rolled<true, MODE, 4, false, AFFK, kShare>(a, npf, o, tail); break;
             case 2: march_rolled<false, MODE, 2, false, AFFK>(a, npf, o); break;
             case 3: march_rolled<true, MODE, 2, false, AFFK>(a, npf, o); break;
-            case 4: march_rolled<false, MODE, 4, true, AFFK>(a, npf, o, tail); break;
-            case 5: march_rolled<true, MODE, 4, true, AFFK>(a, npf, o, tail); break;
+            case 4: march_rolled<false, MODE, 4, true, AFFK, kShare>(a, npf, o, tail); break;
+            case 5: march_rolled<true, MODE, 4, true, AFFK, kShare>(a, npf, o, tail); break;
             case 6: march_rolled<false, MODE, 2, true, AFFK>(a, npf, o); break;
             default: march_rolled<true, MODE, 2, true, AFFK>(a, npf, o); break;
           }

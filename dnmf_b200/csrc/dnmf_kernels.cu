@@ -961,6 +961,7 @@ static int sanitize_ids(dnmf_ctx* c, const int32_t* ids_dev, int B, cudaStream_t
   check_ids_kernel<<<1, 256, 0, st>>>(ids_dev, B, c->T, c->d_id_mark, c->id_stamp, c->d_ids_safe, c->d_id_flags,
                                       c->d_sticky);
   CU(cudaGetLastError());
+  c->counters[2] += 1;  // pre-pass launches (id check, tile windows, stand-alone binning)
   *out = c->d_ids_safe;
   return 0;
 }

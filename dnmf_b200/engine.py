@@ -420,7 +420,7 @@ class Engine:
     def counters(self) -> dict:
         out = np.zeros(8, np.int64)
         _lib.check(self.lib.dnmf_get_counters(self._h, out.ctypes.data_as(ctypes.c_void_p)), "dnmf_get_counters")
-        keys = ("fit_launches", "reduce_launches", "bin_calls", "table_builds", "adam_launches",
+        keys = ("fit_launches", "reduce_launches", "prepass_launches", "table_builds", "adam_launches",
                 "dense_forward_launches", "mu_stats_launches", "mu_sweep_launches")
         return dict(zip(keys, (int(v) for v in out)))
 
