@@ -23,55 +23,13 @@
 namespace dnmf {
 constexpr int kZUnroll = DNMF_ZUNROLL;
 }
-#ifndef DNMF_UNROLLED_MARCH
-#define DNMF_UNROLLED_MARCH 0  // 1: one fully unrolled main loop per slot-pair count (more code than the I-cache holds)
-#endif
 #ifndef DNMF_AFFINE_BODIES
 #define DNMF_AFFINE_BODIES 1  // 1: affine frames with frozen quadratic rows (FitParams::skip_quad) take main loops without
                               // the z^2 Horner term and the z^2 gradient moments (6 packed + 1 scalar op per z step fewer)
 #endif
-#ifndef DNMF_FLAT_RESTAGE
-#define DNMF_FLAT_RESTAGE 0  // bit 0: the slice gathers, bit 1: the x-slice rescale deal (slot pair, entry) items to all
-                             // lanes instead of one thread per entry.  Measured at cfg2 / cfg3, both on: 8-20 % SLOWER
-                             // (128 registers, larger prologue), so off.
-#endif
-#ifndef DNMF_RESTAGE_BATCH
-#define DNMF_RESTAGE_BATCH 4
-#endif
-#ifndef DNMF_FMA_MOMENTS
-#define DNMF_FMA_MOMENTS 1  // 1: gradient z-moments as fma(z^m r, g, S) in the specialised main loops
-#endif
-#ifndef DNMF_WINDOW_PREPASS
-#define DNMF_WINDOW_PREPASS 1  // 1: tile windows of a batch come from tile_windows_kernel (one thread per tile-frame) instead
-                               // of three lanes of the fused kernel's per-frame prologue
-#endif
-#ifndef DNMF_LANE_YFAST
-#define DNMF_LANE_YFAST 0  // 1: lane = 4 * x + y inside the warp's 8 x 4 footprint (0: lane = 8 * y + x).  Tried for the
-                           // shared-memory wavefronts of the slice loads; measured no difference at cfg2 / cfg3 / cfg4.
-#endif
-#ifndef DNMF_DYN_TAIL_BODIES
-#define DNMF_DYN_TAIL_BODIES 0  // 1: also compile the single-body main loops with a run-time tail kind (march_rolled TAIL 3;
-                                // FitParams::dyn_tail would select them).  Measured slower than the default four bodies in
-                                // both states (2.77 / 3.05 vs 2.65 / 2.94 ms per 1000 cfg2 frames) and four more loop bodies
-                                // in the instruction cache; the per-launch choice from restage counters is gone.
-#endif
-#ifndef DNMF_MERGE_TAIL01
-#define DNMF_MERGE_TAIL01 1  // 1: the specialised main loops keep "single slot" apart and merge even / odd lists
-                             // (4 bodies instead of 6; a deformation per frame 3.40 -> 2.94 ms per 1000 cfg2 frames)
-#endif
-#ifndef DNMF_RESTAGE_U32
-#define DNMF_RESTAGE_U32 0
-#endif
 #ifndef DNMF_SHARE_XZ
 #define DNMF_SHARE_XZ 1  // 1: the z-split (dense-list) kernels load the x and z slice entries of a slot pair once for the
                          // voxels A and B of a lane when they coincide (march_rolled SHARE)
-#endif
-#ifndef DNMF_SKEW_KERNELS
-#define DNMF_SKEW_KERNELS 0  // 1: the rotated z order (Z = 32) gets its own kernel instantiations: four main-loop bodies
-                             // per kernel instead of eight
-#endif
-#ifndef DNMF_ALWAYS_SAFE
-#define DNMF_ALWAYS_SAFE 0  // 1: every tile takes the clamped main loop (one loop body fewer in the instruction cache)
 #endif
 #ifndef DNMF_MU_MINB
 #define DNMF_MU_MINB 10  // the same for the trace-statistics variant (MODE 3) of the single-warp layout: 167 registers
@@ -146,8 +104,8 @@ struct FitParams {
   int* mu_overflow;  // MODE 3: set when a tile's list is not fully staged (the caller reruns the generic kernel)
   const int4* windows;  // [B][tiles][2]: (wlo0, wlo1, wlo2, whi0), (whi1, whi2, clipped, 0) from tile_windows_kernel, or NULL
   int skip_quad;  // != 0: gradient rows 4..9 are not wanted (affine fit: Adam freezes them) and are returned as zero
-  int dyn_tail;  // DNMF_DYN_TAIL_BODIES builds only: main loop with the run-time tail kind
-  unsigned* restage_count;  // DNMF_DYN_TAIL_BODIES builds only: [32] frames whose slices were rebuilt, or NULL
+  int reserved0;  // (was: run-time tail kind switch; kept so that the offsets below do not move, see the note at the end)
+  unsigned* reserved1;
   int y_pitch;   // floats between x rows of the Y tile in shared memory (>= ty * tile depth)
   int z_skew;    // != 0: lane (lx, ly) starts its z march at ((ly * z_skew) & 3), see march_rolled<SKEW>
   int tmap_ok;   // the frame tile can be fetched with ONE tensor TMA copy (3-D map over [frame][x][y*Z])

@@ -127,7 +127,6 @@ __device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) 
 // conservative window was not clipped by the table domain (tile_window_axis), where every sample is known to
 // index inside the staged slices.  Same IEEE operations per value as the generic loop below.
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxNP = 8;  // unrolled variants up to 16 staged neurons; longer lists take the generic loop
 
 struct MarchArgs {
   float2 c0[3], c1[3];      // Horner coefficients of 2q for (A, B), per axis
@@ -190,27 +189,6 @@ __device__ __forceinline__ void slot_pair(unsigned ax, unsigned ay, unsigned az,
   }
 }
 
-// All NP slot pairs of one voxel -> (Yhat, dYhat/dix_0..2).
-template <int NP>
-__device__ __forceinline__ void voxel_pairs(unsigned ax, unsigned ay, unsigned az, float f0s, float f1s, float f2s,
-                                            float& yh, float& g0, float& g1, float& g2) {
-  static_assert(NP >= 1 && NP <= 8, "unrolled slot pairs");
-  const float2 f0 = make_float2(f0s, f0s), f1 = make_float2(f1s, f1s), f2 = make_float2(f2s, f2s);
-  float2 y2, a2, b2, c2;
-  slot_pair<0, true>(ax, ay, az, f0, f1, f2, y2, a2, b2, c2);
-  if (NP > 1) slot_pair<16, false>(ax, ay, az, f0, f1, f2, y2, a2, b2, c2);
-  if (NP > 2) slot_pair<32, false>(ax, ay, az, f0, f1, f2, y2, a2, b2, c2);
-  if (NP > 3) slot_pair<48, false>(ax, ay, az, f0, f1, f2, y2, a2, b2, c2);
-  if (NP > 4) slot_pair<64, false>(ax, ay, az, f0, f1, f2, y2, a2, b2, c2);
-  if (NP > 5) slot_pair<80, false>(ax, ay, az, f0, f1, f2, y2, a2, b2, c2);
-  if (NP > 6) slot_pair<96, false>(ax, ay, az, f0, f1, f2, y2, a2, b2, c2);
-  if (NP > 7) slot_pair<112, false>(ax, ay, az, f0, f1, f2, y2, a2, b2, c2);
-  yh = y2.x + y2.y;
-  g0 = a2.x + a2.y;
-  g1 = b2.x + b2.y;
-  g2 = c2.x + c2.y;
-}
-
 __device__ __forceinline__ float lds32(unsigned addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -222,8 +200,9 @@ __device__ __forceinline__ void sts32(unsigned addr, float v) {
 
 // MODE as in fit_tile_kernel: 0 fit, 1 forward only (Yhat replaces the Y tile in shared memory), 2 fit with
 // scalar background, residual written back to the Y tile.
-template <int NP, bool SAFE, int MODE>
-__device__ __forceinline__ void march_pairs(const MarchArgs& a, MarchOut& o) {
+// Empty list: Yhat = 0, no gradient; only the loss term.
+template <bool SAFE, int MODE>
+__device__ __forceinline__ void march_empty(const MarchArgs& a, MarchOut& o) {
   // accumulators start from an opaque zero (read back from shared memory): with a literal 0 ptxas peels the first z step
   // into a straight-line copy of the whole loop body (fold of 0 + x), which costs instruction-cache footprint
   const float oz = a.oz;
@@ -232,97 +211,31 @@ __device__ __forceinline__ void march_pairs(const MarchArgs& a, MarchOut& o) {
   for (int d = 0; d < 3; ++d) o.S0[d] = o.S1[d] = o.S2[d] = zero2;
   float2 sse = zero2, sum_r = zero2;
   unsigned yaddr = a.yaddrA;
-  if constexpr (NP == 0) {  // empty list: Yhat = 0, no gradient; only the loss term
 #pragma unroll 1
-    for (int zz = 0; zz < a.nz; ++zz, yaddr += 4u) {
-      if (MODE == 1) {
-        sts32(yaddr, 0.f);
-        sts32(yaddr + a.yoffB, 0.f);
-        continue;
-      }
-      float2 r = make_float2(-lds32(yaddr), -lds32(yaddr + a.yoffB));
-      if (MODE == 2) r = __fadd2_rn(r, make_float2(a.bg, a.bg));
-      if (SAFE) {
-        r.x = a.validA ? r.x : 0.f;
-        r.y = a.validB ? r.y : 0.f;
-      }
-      if (MODE == 2) {
-        sts32(yaddr, r.x);
-        sts32(yaddr + a.yoffB, r.y);
-        sum_r = __fadd2_rn(sum_r, r);
-      }
-      sse = __ffma2_rn(r, r, sse);
+  for (int zz = 0; zz < a.nz; ++zz, yaddr += 4u) {
+    if (MODE == 1) {
+      sts32(yaddr, 0.f);
+      sts32(yaddr + a.yoffB, 0.f);
+      continue;
     }
-  } else {
-    // address of entry i of axis d: (i - wl) * strideB + base  ==  i * strideB + bias   (mod 2^32)
-    unsigned bias[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) bias[d] = a.base[d] - (unsigned)a.wl[d] * a.strideB;
-    float zf = a.zf0;
-#pragma unroll 1
-    for (int zz = 0; zz < a.nz; ++zz, zf += 1.f, yaddr += 4u) {
-      const float2 z2 = make_float2(zf, zf);
-      float2 ix[3];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const float2 rcp2 = make_float2(a.rcp[d], a.rcp[d]);
-        const float2 q = __ffma2_rn(z2, __ffma2_rn(z2, make_float2(a.c2[d], a.c2[d]), a.c1[d]), a.c0[d]);  // = 2q
-        const float2 t0 = __fmul2_rn(q, rcp2);
-        const float2 r = __ffma2_rn(make_float2(-t0.x, -t0.y), make_float2(a.sm1[d], a.sm1[d]), q);
-        const float2 v = __ffma2_rn(r, rcp2, t0);  // = fl(2q / (s-1)), verified exact (verify_coord_kernel)
-        const float2 u = __fadd2_rn(v, make_float2(-1.f, -1.f));
-        ix[d] = __fmul2_rn(__fadd2_rn(u, make_float2(1.f, 1.f)), make_float2(a.hsm1[d], a.hsm1[d]));
-      }
-      unsigned adA[3], adB[3];
-      float2 f[3];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const int iA = __float2int_rd(ix[d].x), iB = __float2int_rd(ix[d].y);
-        f[d] = __fadd2_rn(ix[d], make_float2(-(float)iA, -(float)iB));
-        if (SAFE) {
-          adA[d] = (unsigned)min(max(iA - a.wl[d], 0), a.wm1[d]) * a.strideB + a.base[d];
-          adB[d] = (unsigned)min(max(iB - a.wl[d], 0), a.wm1[d]) * a.strideB + a.base[d];
-        } else {
-          adA[d] = (unsigned)iA * a.strideB + bias[d];
-          adB[d] = (unsigned)iB * a.strideB + bias[d];
-        }
-      }
-      float2 yh, g[3];
-      voxel_pairs<NP>(adA[0], adA[1], adA[2], f[0].x, f[1].x, f[2].x, yh.x, g[0].x, g[1].x, g[2].x);
-      voxel_pairs<NP>(adB[0], adB[1], adB[2], f[0].y, f[1].y, f[2].y, yh.y, g[0].y, g[1].y, g[2].y);
-      if (MODE == 1) {
-        sts32(yaddr, yh.x);
-        sts32(yaddr + a.yoffB, yh.y);
-        continue;
-      }
-      if (MODE == 2) yh = __fadd2_rn(yh, make_float2(a.bg, a.bg));
-      float2 r = __fadd2_rn(yh, make_float2(-lds32(yaddr), -lds32(yaddr + a.yoffB)));
-      if (SAFE) {
-        r.x = a.validA ? r.x : 0.f;
-        r.y = a.validB ? r.y : 0.f;
-      }
-      if (MODE == 2) {
-        sts32(yaddr, r.x);
-        sts32(yaddr + a.yoffB, r.y);
-        sum_r = __fadd2_rn(sum_r, r);
-      }
-      sse = __ffma2_rn(r, r, sse);
-      const float zq = zf * zf;
-      const float2 zq2 = make_float2(zq, zq);
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const float2 h = __fmul2_rn(r, g[d]);
-        o.S0[d] = __fadd2_rn(o.S0[d], h);
-        o.S1[d] = __ffma2_rn(z2, h, o.S1[d]);
-        o.S2[d] = __ffma2_rn(zq2, h, o.S2[d]);
-      }
+    float2 r = make_float2(-lds32(yaddr), -lds32(yaddr + a.yoffB));
+    if (MODE == 2) r = __fadd2_rn(r, make_float2(a.bg, a.bg));
+    if (SAFE) {
+      r.x = a.validA ? r.x : 0.f;
+      r.y = a.validB ? r.y : 0.f;
     }
+    if (MODE == 2) {
+      sts32(yaddr, r.x);
+      sts32(yaddr + a.yoffB, r.y);
+      sum_r = __fadd2_rn(sum_r, r);
+    }
+    sse = __ffma2_rn(r, r, sse);
   }
   o.sse = sse;
   o.sum_r = sum_r;
 }
 
-// Rolled form of march_pairs: the slot-pair count is a run-time (tile-uniform) value and the pair loop is a
+// Main loop of the two-sub-tile layouts: the slot-pair count is a run-time (tile-uniform) value and the pair loop is a
 // real loop, A and B interleaved inside it.  A few more integer/branch instructions per pair than the
 // unrolled variants, but ONE loop body for every list length: the kernel's hot code then fits the 32 KB
 // L1.5 instruction cache (the unrolled family did not, and the SMs starved on instruction fetch).
@@ -359,14 +272,12 @@ __device__ __forceinline__ void tail_slot(const unsigned (&adA)[3], const unsign
   }
 }
 
-// TAIL 0: even list, np >= 1 full slot pairs.  TAIL 1: np >= 1 full pairs and one last slot.  TAIL 2: a single
-// slot (np == 0).  TAIL 3: the kind is the run-time value `tail` (warp-uniform branches inside the z loop): one
-// loop body per SAFE instead of three.  TAIL 4: np >= 1 and a run-time choice between kinds 0 and 1 only.
-// Why: with three specialised bodies per SAFE, once every frame of a CTA has its own deformation the per-frame
-// list / restage code joins the hot set, the 32 KB instruction cache thrashes (stall_no_instruction 1.7 per issue,
-// profiles/README.md) and the kernel loses 20-25 %.  Measured at cfg2, ms per 1000 frames, identity beta / a
-// different deformation per frame: TAIL {0,1,2} 2.65 / 3.40, TAIL 3 2.77 / 3.05, TAIL {4,2} 2.65 / 2.94 (default,
-// DNMF_MERGE_TAIL01).  FitParams::dyn_tail selects TAIL 3 per launch (DNMF_DYN_TAIL=1, or -1: from the counters).
+// TAIL 4: np >= 1 full slot pairs, and a run-time (warp-uniform) test per z step for one last slot of an odd list.
+// TAIL 2: a single slot (np == 0).  Two bodies per (SAFE, SKEW) and not more: with even / odd lists as separate bodies
+// (three per SAFE) the per-frame list / restage code of a late fit pushes the hot set past the 32 KB instruction cache
+// (stall_no_instruction 1.7 per issue, profiles/README.md); one body with a fully run-time tail kind is slower at
+// identity.  Measured at cfg2, ms per 1000 frames, identity beta / a deformation per frame: three bodies 2.65 / 3.40,
+// one body 2.77 / 3.05, these two 2.65 / 2.94 (round 1).
 // SKEW: the lanes of a warp walk z in rotated order (lane-dependent start, wrap-around), which spreads their
 // reads of the Y tile over the banks when the tile's y/x pitches are multiples of 32 floats (Z = 32).
 // AFF: the frame's quadratic coefficients (rows 4..9 of beta_t) are all zero and their gradient rows are not wanted
@@ -438,7 +349,7 @@ __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOu
     const float2 fA0 = make_float2(f[0].x, f[0].x), fA1 = make_float2(f[1].x, f[1].x), fA2 = make_float2(f[2].x, f[2].x);
     const float2 fB0 = make_float2(f[0].y, f[0].y), fB1 = make_float2(f[1].y, f[1].y), fB2 = make_float2(f[2].y, f[2].y);
     float2 yh, g[3];
-    if (TAIL == 3 ? (tail != 2) : (TAIL != 2)) {  // TAIL 4: np >= 1, run-time choice between kinds 0 and 1
+    if (TAIL != 2) {
       // first slot pair produces the accumulators, the rest of the list updates them
       float2 yA, gA0, gA1, gA2, yB, gB0, gB1, gB2;
       bool shared_xz = false;
@@ -487,7 +398,7 @@ __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOu
       g[0] = make_float2(gA0.x + gA0.y, gB0.x + gB0.y);
       g[1] = make_float2(gA1.x + gA1.y, gB1.x + gB1.y);
       g[2] = make_float2(gA2.x + gA2.y, gB2.x + gB2.y);
-      if ((TAIL == 3 || TAIL == 4) ? (tail == 1) : (TAIL == 1)) tail_slot<false>(adA, adB, pair_bytes, f, oz, yh, g);
+      if (tail == 1) tail_slot<false>(adA, adB, pair_bytes, f, oz, yh, g);
     } else {
       tail_slot<true>(adA, adB, 0u, f, oz, yh, g);
     }
@@ -508,7 +419,6 @@ __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOu
       sum_r = __fadd2_rn(sum_r, r);
     }
     sse = __ffma2_rn(r, r, sse);
-#if DNMF_FMA_MOMENTS
     // z-moments of r * dYhat/dix_d accumulated as fma(z^m r, g_d, S): one packed op per moment and axis
     // (the product-first form S + fl(r g) z^m needs an extra multiply per axis)
     const float2 zr = __fmul2_rn(z2, r);
@@ -522,26 +432,6 @@ __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOu
 #pragma unroll
       for (int d = 0; d < 3; ++d) o.S2[d] = __ffma2_rn(zzr, g[d], o.S2[d]);
     }
-#else
-    if constexpr (AFF) {
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const float2 h = __fmul2_rn(r, g[d]);
-        o.S0[d] = __fadd2_rn(o.S0[d], h);
-        o.S1[d] = __ffma2_rn(z2, h, o.S1[d]);
-      }
-    } else {
-      const float zq = zf * zf;
-      const float2 zq2 = make_float2(zq, zq);
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const float2 h = __fmul2_rn(r, g[d]);
-        o.S0[d] = __fadd2_rn(o.S0[d], h);
-        o.S1[d] = __ffma2_rn(z2, h, o.S1[d]);
-        o.S2[d] = __ffma2_rn(zq2, h, o.S2[d]);
-      }
-    }
-#endif
   }
   o.sse = sse;
   o.sum_r = sum_r;
@@ -911,7 +801,7 @@ __device__ __forceinline__ void march_generic(const GenericArgs& a, float (&S0)[
 // its own part of the tile's z range.  The tile stays 8*NWX x 4*NWY*SUB voxels wide -- the list length follows the
 // tile's x, y extent, (8+s)(8+s) against (16+s)(16+s) for a footprint s nodes wide -- while the CTA still brings enough
 // warps per SM for its shared memory (the staged slices of ~85 neurons take 40 KB).
-template <int NWX, int NWY, int SUB, int MODE, bool FAST_DIV, bool AFFK = false, int NWZ = 1, bool SKEWK = false>
+template <int NWX, int NWY, int SUB, int MODE, bool FAST_DIV, bool AFFK = false, int NWZ = 1>
 __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ? (MODE == 3 ? DNMF_MU_MINB : DNMF_MINB) : (NWZ > 1 ? 512 / (32 * NWX * NWY * NWZ) : 1)) fit_tile_kernel(const __grid_constant__ FitParams p) {
   static_assert(!AFFK || (MODE == 0 && SUB == 2 && FAST_DIV), "affine instantiation: fit, two sub-tiles, fast division");
   static_assert(NWZ == 1 || MODE != 3, "the fused trace statistics do not split z");
@@ -1051,18 +941,14 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
 
   // ---- requested one frame ahead: beta_t and the candidates' traces ----
   float beta_next = 0.f, cc_next[2] = {0.f, 0.f};
-#if DNMF_WINDOW_PREPASS
   // ... and the tile's sample window under beta_t (tile_windows_kernel: eight ints per tile-frame)
   int win_next = 0;
   const size_t win_row0 = ((size_t)(p.b_base + b_first) * (p.ntx * p.nty * p.ntz) + (size_t)((bz * p.nty + by) * p.ntx + bx)) * 8;
   const size_t win_step = (size_t)(p.ntx * p.nty * p.ntz) * 8;
-#endif
   auto prefetch_frame = [&](int fi) {
     const int t = __shfl_sync(0xffffffffu, my_frame, fi);
     if (tid < 30) beta_next = p.beta[(size_t)tid * p.T + t];
-#if DNMF_WINDOW_PREPASS
     if (tid < 8) win_next = reinterpret_cast<const int*>(p.windows)[win_row0 + (size_t)fi * win_step + tid];
-#endif
     if (prefetch_c) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -1075,12 +961,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
 
   // lane geometry (frame independent)
   const int wxy = NWZ == 1 ? warp : warp % NWXY, wz = NWZ == 1 ? 0 : warp / NWXY;
-  // lane -> (x, y) of the warp's 8 x 4 footprint (DNMF_LANE_YFAST: y fastest; no measurable difference)
-#if DNMF_LANE_YFAST
-  const int lane_x = lane >> 2, lane_y = lane & 3;
-#else
-  const int lane_x = lane & 7, lane_y = lane >> 3;
-#endif
+  const int lane_x = lane & 7, lane_y = lane >> 3;  // lane -> (x, y) of the warp's 8 x 4 footprint
   const int lx = (wxy % NWX) * kWarpX + lane_x;
   const int ly0 = (wxy / NWX) * (kWarpY * SUB) + lane_y;
   // this warp's part of the tile's z range
@@ -1097,16 +978,13 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
 
   // state carried from frame to frame: what the staged slices were built for
   int pw_lo[3] = {0x7fffffff, 0, 0}, pw_hi[3] = {0, 0, 0}, prev_L = -1;
-  int n_restaged = 0;  // frames whose slices had to be (re)built
   bool prev_fast = false;  // previous list came from the cached candidates with prefetched traces
 
   for (int fi = 0; fi < nb; ++fi) {
     const int b = b_first + fi;
     const int t = __shfl_sync(0xffffffffu, my_frame, fi);
     if (tid < 30) sBeta[tid] = beta_next;
-#if DNMF_WINDOW_PREPASS
     if (tid < 8) sInt[tid] = win_next;
-#endif
     if (prefetch_c) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -1118,7 +996,6 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
     cta_sync();
     if (fi + 1 < nb) prefetch_frame(fi + 1);
 
-#if DNMF_WINDOW_PREPASS
     // ---- conservative window of this tile under beta_t: fetched one frame ahead, broadcast through shared memory ----
     int wlo[3], whi[3];
 #pragma unroll
@@ -1127,27 +1004,6 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
       whi[d] = sInt[3 + d];
     }
     const bool window_clipped = sInt[6] != 0;
-#else
-    // ---- conservative window of this tile under beta_t (same code as the binning kernel) ----
-    if (tid < 3) {
-      const int s = tid == 0 ? p.X : (tid == 1 ? p.Y : p.Z);
-      int wlo, whi;
-      bool clipped;
-      tile_window_axis(sBeta + tid, 3, (float)x0, (float)y0, (float)z0, (float)(x0 + nx - 1),
-                       (float)(y0 + ny - 1), (float)(z0 + nz - 1), s, wlo, whi, clipped);
-      sInt[tid] = wlo;
-      sInt[3 + tid] = whi;
-      sInt[24 + tid] = clipped ? 1 : 0;
-    }
-    cta_sync();
-    int wlo[3], whi[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      wlo[d] = sInt[d];
-      whi[d] = sInt[3 + d];
-    }
-    const bool window_clipped = (sInt[24] | sInt[25] | sInt[26]) != 0;
-#endif
     // affine frame (rows 4..9 of beta_t all zero) whose quadratic gradient rows the caller does not want
     bool quad_zero = false;
     if constexpr (AFFK) quad_zero = __all_sync(0xffffffffu, lane >= 18 || sBeta[12 + lane] == 0.f);
@@ -1253,58 +1109,12 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
     const int npair = (nst + 1) >> 1;
     if ((nst & 1) && tid == 0) sCk[nst] = 0.f;  // partner of the last neuron of an odd list: zero footprint
     if (changed) {
-      ++n_restaged;
       // Slot pairs (2p, 2p+1) share one float4 (G_2p, G_2p+1, D_2p, D_2p+1) = the packed operands of FFMA2; an odd
       // list is completed with a zero footprint.  The x slice is kept without the traces (they change with the
-      // frame, the slices usually do not).
+      // frame, the slices usually do not).  One thread owns table entry e of every slot; loads are issued four
+      // pairs at a time ahead of the stores.  (Dealing (pair, entry) items to all lanes instead was measured 7 %
+      // slower with a deformation per frame: more address arithmetic per gather than it saves in idle lanes.)
       const int Wt = W0 + W1 + W2;
-#if (DNMF_FLAT_RESTAGE & 1)
-      // Work items (slot pair, table entry), the entry running fastest, dealt to the threads round-robin: every lane
-      // is busy whatever the window size (one thread per entry left 14 of 46 entries to a second, mostly idle
-      // round), consecutive lanes read consecutive entries of one table row, and the loads of four items are in
-      // flight before the first store.
-      const int items = Wt * npair;
-      const unsigned recW = 0xFFFFFFFFu / (unsigned)Wt + 1u;  // Wt >= 3: floor(i / Wt) == umulhi(i, recW) for i < 2^32 / Wt
-      constexpr int kBatch = DNMF_RESTAGE_BATCH;
-      for (int i0 = tid; i0 < items; i0 += kBatch * NT) {
-        float2 va[kBatch], vb[kBatch];
-        float4* dst[kBatch];
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-          const int i = i0 + u * NT;
-          va[u] = vb[u] = make_float2(0.f, 0.f);
-          dst[u] = nullptr;
-          if (i < items) {
-            const int pp = (int)__umulhi((unsigned)i, recW);
-            const int e = i - pp * Wt;
-            const float2* src;
-            int row;
-            float2* d;
-            if (e < W0) {
-              src = p.tab0 + (wlo[0] + 2 + e);
-              row = sX3;
-              d = sXraw + (size_t)e * CAP;
-            } else if (e < W0 + W1) {
-              src = p.tab1 + (wlo[1] + 2 + (e - W0));
-              row = sY3;
-              d = sTab + (size_t)(p.wmax0 + (e - W0)) * CAP;
-            } else {
-              src = p.tab2 + (wlo[2] + 2 + (e - W0 - W1));
-              row = sZ3;
-              d = sTab + (size_t)(p.wmax0 + p.wmax1 + (e - W0 - W1)) * CAP;
-            }
-            const int j = 2 * pp;
-            va[u] = __ldg(src + (size_t)sList[j] * row);
-            if (j + 1 < nst) vb[u] = __ldg(src + (size_t)sList[j + 1] * row);
-            dst[u] = reinterpret_cast<float4*>(d) + pp;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u)
-          if (dst[u]) *dst[u] = make_float4(va[u].x, vb[u].x, va[u].y, vb[u].y);
-      }
-#else
-      // One thread owns table entry e of every slot; loads are issued four pairs at a time ahead of the stores.
       for (int e = tid; e < Wt; e += NT) {
         const float2* src;
         int row;
@@ -1329,38 +1139,17 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
           for (int u = 0; u < kBatch; ++u) {
             const int j = 2 * (p0 + u);
             va[u] = vb[u] = make_float2(0.f, 0.f);
-#if DNMF_RESTAGE_U32
-            // row offsets in 32 bits (K * (s + 3) < 2^31 float2 entries): one IMAD.WIDE per gather instead of a 64-bit
-            // multiply-add chain of four
-            if (j < nst) va[u] = __ldg(src + (unsigned)sList[j] * (unsigned)row);
-            if (j + 1 < nst) vb[u] = __ldg(src + (unsigned)sList[j + 1] * (unsigned)row);
-#else
             if (j < nst) va[u] = __ldg(src + (size_t)sList[j] * row);
             if (j + 1 < nst) vb[u] = __ldg(src + (size_t)sList[j + 1] * row);
-#endif
           }
 #pragma unroll
           for (int u = 0; u < kBatch; ++u)
             if (p0 + u < npair) dst[p0 + u] = make_float4(va[u].x, vb[u].x, va[u].y, vb[u].y);
         }
       }
-#endif
     }
     cta_sync();
     // x slice of this frame: C[k,t] folded in
-#if (DNMF_FLAT_RESTAGE & 2)
-    {
-      const int itemsx = W0 * npair;
-      const unsigned rec0 = W0 > 1 ? 0xFFFFFFFFu / (unsigned)W0 + 1u : 0u;
-      for (int i = tid; i < itemsx; i += NT) {
-        const int pp = W0 > 1 ? (int)__umulhi((unsigned)i, rec0) : i;
-        const int e = i - pp * W0;
-        const float4 v = reinterpret_cast<const float4*>(sXraw + (size_t)e * CAP)[pp];
-        const float2 c = MODE == 3 ? make_float2(1.f, 1.f) : *reinterpret_cast<const float2*>(sCk + 2 * pp);
-        reinterpret_cast<float4*>(sTab + (size_t)e * CAP)[pp] = make_float4(v.x * c.x, v.y * c.y, v.z * c.x, v.w * c.y);
-      }
-    }
-#else
     for (int e = tid; e < W0; e += NT) {
       const float4* src = reinterpret_cast<const float4*>(sXraw + (size_t)e * CAP);
       float4* dst = reinterpret_cast<float4*>(sTab + (size_t)e * CAP);
@@ -1370,7 +1159,6 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
         dst[pp] = make_float4(v.x * c.x, v.y * c.y, v.z * c.x, v.w * c.y);
       }
     }
-#endif
     cta_sync();
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -1431,11 +1219,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
       a.validB = (gx < p.X) && (y0 + ly0 + kWarpY < p.Y);
       a.bg = bg;
       a.zskew = 0;
-#if DNMF_SKEW_KERNELS
-      if ((SKEWK || (MODE == 3 && p.z_skew != 0)) && nzw >= 4) a.zskew = (lane_y * p.z_skew) & 3;
-#else
       if (p.z_skew != 0 && nzw >= 4) a.zskew = (lane_y * p.z_skew) & 3;
-#endif
     };
 
     if constexpr (MODE == 3) {
@@ -1499,61 +1283,20 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
     const bool has_overflow = L > nst;
     bool marched = false;
     if constexpr (SUB == 2 && FAST_DIV) {
-      if (!has_overflow && (npair <= kMaxNP || !DNMF_UNROLLED_MARCH) && (!AFFK || quad_zero)) {
+      if (!has_overflow && (!AFFK || quad_zero)) {
         MarchArgs a;
         fill_march_args(a);
         MarchOut o;
-        const bool safe = DNMF_ALWAYS_SAFE || window_clipped || nx < TX || ny < TY;
-#if DNMF_UNROLLED_MARCH
-        switch (npair * 2 + (safe ? 1 : 0)) {
-#define DNMF_MARCH(n)                   \
-  case 2 * n:                           \
-    march_pairs<n, false, MODE>(a, o);  \
-    break;                              \
-  case 2 * n + 1:                       \
-    march_pairs<n, true, MODE>(a, o);   \
-    break;
-          DNMF_MARCH(0)
-          DNMF_MARCH(1)
-          DNMF_MARCH(2)
-          DNMF_MARCH(3)
-          DNMF_MARCH(4)
-          DNMF_MARCH(5)
-          DNMF_MARCH(6)
-          DNMF_MARCH(7)
-          DNMF_MARCH(8)
-#undef DNMF_MARCH
-          default:
-            break;
-        }
-#else
+        const bool safe = window_clipped || nx < TX || ny < TY;
         if (npair == 0) {
           if (safe)
-            march_pairs<0, true, MODE>(a, o);
+            march_empty<true, MODE>(a, o);
           else
-            march_pairs<0, false, MODE>(a, o);
+            march_empty<false, MODE>(a, o);
         } else {
           const int npf = nst >> 1;  // full slot pairs; an odd list ends with a single slot
           const int tail = (nst & 1) ? (npf == 0 ? 2 : 1) : 0;
           constexpr bool kShare = DNMF_SHARE_XZ == 2 || (DNMF_SHARE_XZ && NWZ > 1);  // dense lists: x / z slice entries shared by voxels A and B
-          if (DNMF_DYN_TAIL_BODIES && p.dyn_tail) {
-            switch ((p.z_skew != 0 ? 2 : 0) + (safe ? 1 : 0)) {
-              case 0: march_rolled<false, MODE, 3, false, AFFK>(a, npf, o, tail); break;
-              case 1: march_rolled<true, MODE, 3, false, AFFK>(a, npf, o, tail); break;
-              case 2: march_rolled<false, MODE, 3, true, AFFK>(a, npf, o, tail); break;
-              default: march_rolled<true, MODE, 3, true, AFFK>(a, npf, o, tail); break;
-            }
-          } else
-#if DNMF_SKEW_KERNELS
-          // the skew of the z order is a property of the launch (shared-memory pitch of the Y tile): SKEWK kernels hold
-          // the rotated-order bodies only, the others the plain ones -- four bodies per kernel instead of eight
-          switch ((tail == 2 ? 2 : 0) + (safe ? 1 : 0)) {
-            case 0: march_rolled<false, MODE, 4, SKEWK, AFFK>(a, npf, o, tail); break;
-            case 1: march_rolled<true, MODE, 4, SKEWK, AFFK>(a, npf, o, tail); break;
-            case 2: march_rolled<false, MODE, 2, SKEWK, AFFK>(a, npf, o); break;
-            default: march_rolled<true, MODE, 2, SKEWK, AFFK>(a, npf, o); break;
-          }
-#elif DNMF_MERGE_TAIL01
           switch ((p.z_skew != 0 ? 4 : 0) + (tail == 2 ? 2 : 0) + (safe ? 1 : 0)) {
             case 0: march_rolled<false, MODE, 4, false, AFFK, kShare>(a, npf, o, tail); break;
             case 1: march_rolled<true, MODE, 4, false, AFFK, kShare>(a, npf, o, tail); break;
@@ -1564,24 +1307,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
             case 6: march_rolled<false, MODE, 2, true, AFFK>(a, npf, o); break;
             default: march_rolled<true, MODE, 2, true, AFFK>(a, npf, o); break;
           }
-#else
-          switch ((p.z_skew != 0 ? 6 : 0) + tail * 2 + (safe ? 1 : 0)) {
-            case 0: march_rolled<false, MODE, 0, false>(a, npf, o); break;
-            case 1: march_rolled<true, MODE, 0, false>(a, npf, o); break;
-            case 2: march_rolled<false, MODE, 1, false>(a, npf, o); break;
-            case 3: march_rolled<true, MODE, 1, false>(a, npf, o); break;
-            case 4: march_rolled<false, MODE, 2, false>(a, npf, o); break;
-            case 5: march_rolled<true, MODE, 2, false>(a, npf, o); break;
-            case 6: march_rolled<false, MODE, 0, true>(a, npf, o); break;
-            case 7: march_rolled<true, MODE, 0, true>(a, npf, o); break;
-            case 8: march_rolled<false, MODE, 1, true>(a, npf, o); break;
-            case 9: march_rolled<true, MODE, 1, true>(a, npf, o); break;
-            case 10: march_rolled<false, MODE, 2, true>(a, npf, o); break;
-            default: march_rolled<true, MODE, 2, true>(a, npf, o); break;
-          }
-#endif
         }
-#endif
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
           S0[0][d] = o.S0[d].x;
@@ -1707,13 +1433,11 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
     cta_sync();
     if (bulk && fi + 1 < nb) load_tile(fi + 1);
   }
-  if (DNMF_DYN_TAIL_BODIES && MODE == 0 && p.restage_count != nullptr && tid == 0 && n_restaged > 0)
-    atomicAdd(p.restage_count + ((blockIdx.x + blockIdx.y) & 31), (unsigned)n_restaged);
 }
 
-template <int NWX, int NWY, int SUB, int MD_, bool FD_, bool AFFK_ = false, int NWZ_ = 1, bool SKEWK_ = false>
+template <int NWX, int NWY, int SUB, int MD_, bool FD_, bool AFFK_ = false, int NWZ_ = 1>
 static int launch_fit(const FitParams& p0, int B, size_t smem, cudaStream_t st) {
-  auto kern = fit_tile_kernel<NWX, NWY, SUB, MD_, FD_, AFFK_, NWZ_, SKEWK_>;
+  auto kern = fit_tile_kernel<NWX, NWY, SUB, MD_, FD_, AFFK_, NWZ_>;
   static size_t configured[64] = {0};  // per device: the attribute is a per-device property of the function
   int dev = 0;
   CU(cudaGetDevice(&dev));

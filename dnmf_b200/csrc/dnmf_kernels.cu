@@ -748,11 +748,7 @@ static int configure_tiling_fixed(dnmf_ctx* c, cudaStream_t st) {
     const int zs = c->tz;
     const int dense = c->ty * zs;
     int worst = 0, hist[32] = {0};
-#if DNMF_LANE_YFAST
-    for (int l = 0; l < 32; ++l) worst = std::max(worst, ++hist[((l >> 2) * dense + (l & 3) * zs) & 31]);
-#else
     for (int l = 0; l < 32; ++l) worst = std::max(worst, ++hist[((l & 7) * dense + (l >> 3) * zs) & 31]);
-#endif
     c->y_pitch = dense;
     c->z_skew = 0;
     if (worst > 2) {
@@ -1062,8 +1058,8 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
   memset(&p.stats, 0, sizeof(p.stats));
   p.mu_overflow = nullptr;
   p.skip_quad = (c->affine_grad || c->affine_call) ? 1 : 0;
-  p.dyn_tail = 0;
-  p.restage_count = nullptr;
+  p.reserved0 = 0;
+  p.reserved1 = nullptr;
   p.y_pitch = c->y_pitch;
   p.z_skew = c->z_skew;
   p.b_base = 0;
@@ -1128,17 +1124,14 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
   const size_t need = (size_t)B * c->ntx * c->nty * c->ntz * kNumPartials;
   if (ensure(&c->d_partials, &c->partials_cap, need)) return 1;
   p.partials = c->d_partials;
-  p.windows = nullptr;
-#if DNMF_WINDOW_PREPASS
   {  // the tiles' sample windows of this batch, computed by all lanes ahead of the fused launch (same stream)
     const long long items = (long long)B * c->ntx * c->nty * c->ntz;
     if (ensure(&c->d_windows, &c->windows_cap, (size_t)items * 2)) return 1;
     tile_windows_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(geom_of(c), beta, ids, items, c->d_windows);
     CU(cudaGetLastError());
     p.windows = c->d_windows;
-    c->counters[2] += 1;  // binning launches
+    c->counters[2] += 1;  // pre-pass launches
   }
-#endif
   return 0;
 }
 

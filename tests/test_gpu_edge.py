@@ -168,12 +168,16 @@ def test_forward_is_linear_in_traces_and_zero_for_zero_traces():
     np.testing.assert_allclose(y2.cpu().numpy(), 2 * y1.cpu().numpy(), rtol=1e-6, atol=1e-7)
 
 
-def test_perfect_model_has_zero_loss_and_gradient():
-    """Y := model output  =>  sse == 0 and gradient == 0 exactly (encode -> decode round trip)."""
+@pytest.mark.parametrize("tiling", [None, (1, 1, 0, 0, 2, 2), (1, 1, 0, 0, 2, 4), (2, 2, 0, 0, 2)])
+def test_perfect_model_has_zero_loss_and_gradient(tiling):
+    """Y := model output  =>  sse == 0 and gradient == 0 exactly (encode -> decode round trip): the forward-only and the
+    fit instantiations round Yhat identically, also in the z-split layouts (shared x / z slice loads)."""
     from dnmf_b200.engine import Engine
     sz, K, T = [32, 20, 7], 9, 3
     pos, sig, beta, C, _ = _case(sz, K, T, 35)
     e = Engine(sz, K, T)
+    if tiling:
+        e.set_tiling(*tiling)
     e.set_footprints(pos, sig, 3.5)
     b, c = beta.cuda(), C.cuda()
     y, _, _ = e.forward(torch.arange(T), b, c)

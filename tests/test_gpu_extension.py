@@ -27,7 +27,7 @@ def _setup(sz, K, T, seed, tiling=None):
     return e, pos, sig, beta, C, frames
 
 
-@pytest.mark.parametrize("tiling", [None, (1, 1, 0, 0, 1), (2, 2, 0, 0, 1)])
+@pytest.mark.parametrize("tiling", [None, (1, 1, 0, 0, 1), (2, 2, 0, 0, 1), (1, 1, 0, 0, 2, 2)])
 def test_shared_parameter_gradients_vs_autograd(tiling):
     sz, K, T = [20, 14, 5], 6, 4
     e, pos, sig, beta, C, frames = _setup(sz, K, T, 3, tiling)
