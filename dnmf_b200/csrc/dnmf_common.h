@@ -27,6 +27,9 @@ constexpr int kZUnroll = DNMF_ZUNROLL;
 #define DNMF_AFFINE_BODIES 1  // 1: affine frames with frozen quadratic rows (FitParams::skip_quad) take main loops without
                               // the z^2 Horner term and the z^2 gradient moments (6 packed + 1 scalar op per z step fewer)
 #endif
+#ifndef DNMF_RESTAGE_BATCH
+#define DNMF_RESTAGE_BATCH 4  // slot pairs whose gathers are in flight per thread while the slices are rebuilt
+#endif
 #ifndef DNMF_SHARE_XZ
 #define DNMF_SHARE_XZ 1  // 1: the z-split (dense-list) kernels load the x and z slice entries of a slot pair once for the
                          // voxels A and B of a lane when they coincide (march_rolled SHARE)

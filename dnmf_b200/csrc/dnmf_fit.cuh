@@ -1132,7 +1132,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
           row = sZ3;
           dst = reinterpret_cast<float4*>(sTab + (size_t)(p.wmax0 + p.wmax1 + (e - W0 - W1)) * CAP);
         }
-        constexpr int kBatch = 4;
+        constexpr int kBatch = DNMF_RESTAGE_BATCH;
         for (int p0 = 0; p0 < npair; p0 += kBatch) {
           float2 va[kBatch], vb[kBatch];
 #pragma unroll
