@@ -85,6 +85,8 @@ def load(build_if_missing: bool = True):
         "dnmf_ext_set_params": (c_int, [P, c_float, c_int, P]),
         "dnmf_ext_get_params": (c_int, [P, P, P, P, P]),
         "dnmf_measure_fp32_peak": (c_int, [c_int, c_int, POINTER(c_double)]),
+        "dnmf_build_info": (c_int, []),
+        "dnmf_debug_trip_assert": (c_int, [c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -1,6 +1,8 @@
 """Build the CUDA shared library in-tree with nvcc for sm_100a (no JIT cache, no torch extension).
 
     python -m dnmf_b200.build [--force] [-v]      # -> dnmf_b200/_C/libdnmf_b200.so
+    python -m dnmf_b200.build --checked           # -> dnmf_b200/_C/libdnmf_b200_checked.so  (-DDNMF_CHECKED: device-side
+                                                  #    assertions on every unclamped index; tests/test_gpu_checked.py)
 
 Every translation unit under csrc/ is compiled to its own object (in parallel; an object is rebuilt only when
 its source or one of the headers is newer) and the objects are linked into one shared library.  The fused
@@ -19,6 +21,7 @@ UNITS = ["dnmf_kernels.cu", "fit_mode0.cu", "fit_mode1.cu", "fit_mode2.cu", "fit
 OUT_DIR = os.environ.get("DNMF_B200_OUT_DIR") or os.path.join(HERE, "_C")   # kernel experiments build elsewhere
 OBJ_DIR = os.path.join(OUT_DIR, "obj")
 OUT = os.path.join(OUT_DIR, "libdnmf_b200.so")
+OUT_CHECKED = os.path.join(OUT_DIR, "libdnmf_b200_checked.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-std=c++17", "--fmad=true", "-Xcompiler", "-fPIC,-O2"]
 
@@ -40,8 +43,8 @@ def _units():
     return [u for u in UNITS if os.path.isfile(os.path.join(CSRC, u))]
 
 
-def _obj(unit: str) -> str:
-    return os.path.join(OBJ_DIR, os.path.splitext(unit)[0] + ".o")
+def _obj(unit: str, checked: bool = False) -> str:
+    return os.path.join(OBJ_DIR + ("_checked" if checked else ""), os.path.splitext(unit)[0] + ".o")
 
 
 def _stale(target: str, deps) -> bool:
@@ -51,14 +54,15 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def up_to_date() -> bool:
+def up_to_date(checked: bool = False) -> bool:
     hs = _headers()
     srcs = [os.path.join(CSRC, u) for u in _units()]
-    return not _stale(OUT, srcs + hs)
+    return not _stale(OUT_CHECKED if checked else OUT, srcs + hs)
 
 
-def _compile(unit: str, verbose: bool) -> str:
-    cmd = [nvcc_path()] + ARCH + FLAGS + ["-c", "-o", _obj(unit), os.path.join(CSRC, unit)]
+def _compile(unit: str, verbose: bool, checked: bool = False) -> str:
+    cmd = [nvcc_path()] + ARCH + FLAGS + (["-DDNMF_CHECKED"] if checked else []) + \
+          ["-c", "-o", _obj(unit, checked), os.path.join(CSRC, unit)]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     extra = os.environ.get("DNMF_NVCC_FLAGS")
@@ -70,22 +74,23 @@ def _compile(unit: str, verbose: bool) -> str:
     return res.stderr
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
-        return OUT
-    os.makedirs(OBJ_DIR, exist_ok=True)
+def build(force: bool = False, verbose: bool = False, checked: bool = False) -> str:
+    out = OUT_CHECKED if checked else OUT
+    if not force and up_to_date(checked):
+        return out
+    os.makedirs(os.path.dirname(_obj("x.cu", checked)), exist_ok=True)
     hs = _headers()
-    todo = [u for u in _units() if force or _stale(_obj(u), [os.path.join(CSRC, u)] + hs)]
+    todo = [u for u in _units() if force or _stale(_obj(u, checked), [os.path.join(CSRC, u)] + hs)]
     with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 1) or 1) as pool:
-        for u, log in zip(todo, pool.map(lambda u: _compile(u, verbose), todo)):
+        for u, log in zip(todo, pool.map(lambda u: _compile(u, verbose, checked), todo)):
             if verbose:
                 sys.stderr.write("== %s\n%s" % (u, log))
-    cmd = [nvcc_path()] + ARCH + ["-shared", "-o", OUT] + [_obj(u) for u in _units()]
+    cmd = [nvcc_path()] + ARCH + ["-shared", "-o", out] + [_obj(u, checked) for u in _units()]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, checked="--checked" in sys.argv))

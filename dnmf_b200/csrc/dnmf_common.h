@@ -27,6 +27,16 @@ constexpr int kZUnroll = DNMF_ZUNROLL;
 #define DNMF_AFFINE_BODIES 1  // 1: affine frames with frozen quadratic rows (FitParams::skip_quad) take main loops without
                               // the z^2 Horner term and the z^2 gradient moments (6 packed + 1 scalar op per z step fewer)
 #endif
+// Checked build (python -m dnmf_b200.build --checked -> _C/libdnmf_b200_checked.so, -DDNMF_CHECKED): device-side
+// assertions on every index the kernels form without a clamp -- frame ids, list lengths, the staged-window index of
+// the unclamped main loops, table rows of the slice gathers, partial-block slots.  compute-sanitizer is closed on the
+// GPU pool this was developed on; tests/test_gpu_checked.py runs a cross-section of the suite through this library.
+#ifdef DNMF_CHECKED
+#include <cassert>
+#define DNMF_DASSERT(cond) assert(cond)
+#else
+#define DNMF_DASSERT(cond) ((void)0)
+#endif
 #ifndef DNMF_RESTAGE_BATCH
 #define DNMF_RESTAGE_BATCH 4  // slot pairs whose gathers are in flight per thread while the slices are rebuilt
 #endif

@@ -338,6 +338,8 @@ __device__ __forceinline__ void march_rolled(const MarchArgs& a, int np, MarchOu
     for (int d = 0; d < 3; ++d) {
       const int iA = __float2int_rd(ix[d].x), iB = __float2int_rd(ix[d].y);
       f[d] = __fadd2_rn(ix[d], make_float2(-(float)iA, -(float)iB));
+      // the unclamped loop is chosen only when the conservative window covers every sample of the tile
+      DNMF_DASSERT(SAFE || (iA >= a.wl[d] && iA - a.wl[d] <= a.wm1[d] && iB >= a.wl[d] && iB - a.wl[d] <= a.wm1[d]));
       if (SAFE) {
         adA[d] = (unsigned)min(max(iA - a.wl[d], 0), a.wm1[d]) * a.strideB + a.base[d];
         adB[d] = (unsigned)min(max(iB - a.wl[d], 0), a.wm1[d]) * a.strideB + a.base[d];
@@ -593,6 +595,7 @@ __device__ __forceinline__ void flush_stats(const float2 (&G)[3][6], const float
         const int pc = idx >> 1, pp = pc / NCS, cc = pc % NCS;
         const int j = 6 * pb + 2 * pp + (idx & 1), l = 6 * lb + cc;
         if (j < nst && l < nst) {
+          DNMF_DASSERT(j < capL && l < capL && capL < ld);
           blk[(size_t)j * ld + l] = tot;
           if (TWO) blk[(size_t)l * ld + j] = tot;
         }
@@ -983,6 +986,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
   for (int fi = 0; fi < nb; ++fi) {
     const int b = b_first + fi;
     const int t = __shfl_sync(0xffffffffu, my_frame, fi);
+    DNMF_DASSERT(t >= 0 && t < p.T);
     if (tid < 30) sBeta[tid] = beta_next;
     if (tid < 8) sInt[tid] = win_next;
     if (prefetch_c) {
@@ -1106,6 +1110,8 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
     const int W0 = whi[0] - wlo[0] + 1, W1 = whi[1] - wlo[1] + 1, W2 = whi[2] - wlo[2] + 1;
     const bool fits = (W0 <= p.wmax0) && (W1 <= p.wmax1) && (W2 <= p.wmax2);
     const int nst = fits ? min(L, CAP) : 0;
+    DNMF_DASSERT(L >= 0 && L <= p.K && W0 >= 1 && W1 >= 1 && W2 >= 1);
+    DNMF_DASSERT(wlo[0] >= -2 && whi[0] <= p.X && wlo[1] >= -2 && whi[1] <= p.Y && wlo[2] >= -2 && whi[2] <= p.Z);  // table rows
     const int npair = (nst + 1) >> 1;
     if ((nst & 1) && tid == 0) sCk[nst] = 0.f;  // partner of the last neuron of an odd list: zero footprint
     if (changed) {
@@ -1139,6 +1145,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
           for (int u = 0; u < kBatch; ++u) {
             const int j = 2 * (p0 + u);
             va[u] = vb[u] = make_float2(0.f, 0.f);
+            DNMF_DASSERT(j >= nst || sList[j] < p.K);
             if (j < nst) va[u] = __ldg(src + (size_t)sList[j] * row);
             if (j + 1 < nst) vb[u] = __ldg(src + (size_t)sList[j + 1] * row);
           }
@@ -1231,6 +1238,7 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
         if (L > nst || L > p.stats.capL) {
           if (tid == 0) atomicMax(p.mu_overflow, L);  // not fully staged: the caller reruns a panel kernel
         } else {
+          DNMF_DASSERT(b >= 0 && b < p.B && L <= p.stats.capL);
           if (tid == 0) p.stats.count[tf] = L;
           for (int pos = tid; pos < L; pos += NT) {
             const int k = sList[pos];

@@ -4,31 +4,36 @@
 //
 // With ~100 neurons reaching every tile (BASELINE configuration 4: K = 1000, sigma = 6) the per-tile Gram
 // [A|Y]^T [A|Y] is a real dense contraction: M = N = listed neurons + the Y pseudo-neuron (<= 128), K = the
-// tile's voxels.  One CTA (4 warps) per (frame, 8 x 8 x Z tile):
+// tile's voxels.  One CTA (9 warps) per (frame, 8 x 8 x Z tile):
 //   * prologue: beta_t -> conservative window -> neuron list (same device code as the binning kernel) -> the
 //     listed neurons' table slices staged in shared memory, two slots per float4 (G_j, G_j+1, D_j, D_j+1);
-//   * producers: panel stage s (4 of them) belongs to the 8 x 4 (x, y) half `s & 1` of the tile and the z planes
-//     of parity `s >> 1`; two warps (8 per CTA) share a stage and split its rows.  Per plane they evaluate the closed-form footprint value of every listed neuron at its 32 voxels from the
-//     staged slices (3 LDS.128 + 5 packed FP32x2 operations per slot pair and voxel, no global memory, no
-//     transcendental) and writes them as ONE K-major panel stage [128 rows][32 voxels] in the canonical
-//     SWIZZLE_128B layout -- twice: hi = tf32(a) and lo = tf32(a - hi);
-//   * tensor cores: one lane of the stage issues tcgen05.mma.cta_group::1.kind::tf32 (UMMA 128 x N x 8, N = list
-//     length rounded up to 16) on that stage: SYRK has ONE operand, so the same shared-memory panel serves the A
-//     and the B descriptor; fp32-accurate products come from the 3xTF32 split D += hi hi^T + hi lo^T + lo hi^T.
-//     Each stage accumulates into its OWN 128-column TMEM accumulator (4 x 128 = all 512 columns): no ordering is
-//     needed between the issuing threads, and the truncating fp32 accumulation of the tensor pipe (measured with
-//     tools/experiments/syrk_tf32_umma.cu: relative error 3e-6 per 256 accumulated voxels, growing linearly)
-//     stays at a quarter of the chain length.  tcgen05.commit -> mbarrier hands the stage back to its producer;
-//   * epilogue: every thread reads its row of the four accumulators with tcgen05.ld, adds them in a fixed order
-//     and writes the tile-frame's partial block; the row-owner second stage (stats_reduce_kernel) sums the
-//     blocks of a frame in ascending tile order in fp64: deterministic, no atomics.
+//   * producers: four warps per 8 x 4 (x, y) half of the tile walk the z planes in ascending order and split the
+//     rows.  Per plane they evaluate the closed-form footprint value of every listed neuron at the half's 32 voxels
+//     from the staged slices (3 LDS.128 + 5 packed FP32x2 operations per slot pair and voxel, no global memory, no
+//     transcendental) and write them as ONE K-major panel stage [128 rows][32 voxels] in the canonical
+//     SWIZZLE_128B layout -- twice: hi = tf32(a) and lo = a - hi.  A half alternates between two stages (even / odd
+//     planes; four stages in all), so the tensor pipe reads plane z while plane z + 1 is being written;
+//   * tensor cores: one thread issues tcgen05.mma.cta_group::1.kind::tf32 (UMMA 128 x N x 8, N = list length
+//     rounded up to 16) on each stage-plane: SYRK has ONE operand, so the same shared-memory panel serves the A and
+//     the B descriptor.  fp32-accurate products come from the 3xTF32 split hi hi^T + hi lo^T + lo hi^T, of which the
+//     last term is the transpose of the second: P = hi hi^T and Q = hi lo^T are accumulated (two MMAs per 8 voxels,
+//     not three) and the epilogue forms P + Q + Q^T.  The stage-planes are dealt round-robin over nP = 4 (N <= 96) or 3
+//     TMEM accumulators for P, Q has one: the truncating fp32 accumulation of the tensor pipe (measured with
+//     tools/experiments/syrk_tf32_umma.cu: relative error 3e-6 per 256 accumulated voxels, growing linearly) stays
+//     at 1/nP of the chain length; Q is 2^-11 of P and its chain length does not matter.  tcgen05.commit ->
+//     mbarrier hands the stage back to its producers;
+//   * epilogue: Q is transposed through shared memory (the panel stages are free by then); every thread reads its
+//     row of the accumulators with tcgen05.ld, adds them in a fixed order and writes the tile-frame's partial block;
+//     the row-owner second stage (stats_reduce_kernel) sums the blocks of a frame in ascending tile order in fp64:
+//     deterministic, no atomics.
 #include "dnmf_common.h"
 
 namespace dnmf {
 
 namespace {
 
-constexpr int kTcWarps = 9;                           // 8 producers (two per panel stage, they split the rows) + the MMA warp
+constexpr int kTcProducers = 8;                       // four per (x, y) half of the tile, they split the rows
+constexpr int kTcWarps = kTcProducers + 1;            // + the MMA warp
 constexpr int kTcThreads = 32 * kTcWarps;
 constexpr int kTcStageBytes = kGramRows * 128;        // 128 rows x 32 voxels of tf32
 constexpr int kTcPairs = kGramRows / 2;               // slot pairs per slice entry
@@ -149,6 +154,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
   const int nt = p.ntx * p.nty;
   const int bx = tile % p.ntx, by = tile / p.ntx;
   const int t = p.frame_ids[b];
+  DNMF_DASSERT(t >= 0 && t < p.T);
   const int x0 = bx * kGramTX, y0 = by * kGramTY;
   const int nx = min(kGramTX, p.X - x0), ny = min(kGramTY, p.Y - y0), nz = p.Z;
   const size_t Nvox = (size_t)p.X * p.Y * p.Z;
@@ -235,6 +241,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
     if (tid == 0) atomicMax(p.overflow, max(L + 1, kGramRows + 1));
     return;
   }
+  DNMF_DASSERT(wlo[0] >= -2 && whi[0] <= p.X && wlo[1] >= -2 && whi[1] <= p.Y && wlo[2] >= -2 && whi[2] <= p.Z);  // table rows
+  DNMF_DASSERT(L + 1 <= p.out.capL + 1 && p.out.capL < p.out.ld);
   if (tid == 0) p.out.count[tf] = L;
   if (L == 0) return;
   for (int i = lane; i < sInt[8 + warp]; i += 32) {
@@ -252,7 +260,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
   if (tid == 0) {
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"(smem_addr(&sBar[w])));      // full: both producer warps
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&sBar[w])), "n"(4));  // full: the four producer warps of the stage's (x, y) half
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sBar[4 + w])));  // empty: tcgen05.commit
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -300,6 +308,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
             ent = wmax0 + wmax1 + (e - W0 - W1);
           }
           const int j = 2 * pp;
+          DNMF_DASSERT(j >= L || sList[j] < p.K);
           if (j < L) va[u] = __ldg(src + (size_t)sList[j] * row);
           if (j + 1 < L) vb[u] = __ldg(src + (size_t)sList[j + 1] * row);
           dst[u] = reinterpret_cast<float4*>(sSl + (size_t)ent * kTcEntryBytes) + pp;
@@ -312,17 +321,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
   }
   __syncthreads();
 
-  // ---- producers (warps 0..7) and the MMA warp (warp 8).  Stage s = warp & 3 belongs to the 8 x 4 (x, y) half
-  // s & 1 and the z planes of parity s >> 1; its two producer warps (half = warp >> 2) split the 8-row atoms of
-  // the panel between them and arrive on full[s]; the MMA warp issues the stage's MMAs and tcgen05.commit hands
-  // the stage back through empty[s] ----
-  const int stg = warp & 3, half = (warp >> 2) & 1;
+  // ---- producers (warps 0..7) and the MMA warp (warp 8).  Stage s belongs to the 8 x 4 (x, y) half s & 1 and the z
+  // planes of parity s >> 1; the four producer warps of the half arrive on full[s], the MMA warp issues the stage's
+  // MMAs and tcgen05.commit hands the stage back through empty[s].  (stg, colq) are the epilogue's roles: TMEM lane
+  // quadrant and column half ----
+  const int stg = warp & 3, colq = (warp >> 2) & 1;
   const int npad = (L + 1 + 15) & ~15;  // MMA N
+  // TMEM: nP accumulators for P = hi hi^T (the truncating fp32 accumulation of the tensor pipe makes the chain length
+  // matter: the stage-planes are dealt over nP chains) + ONE for the cross term Q = hi lo^T (2^-11 of P: its chain
+  // length does not matter).  The third product of the 3xTF32 split, lo hi^T, is Q^T: the epilogue adds it from a
+  // shared-memory transpose, and the tensor pipe and its shared-memory operand reads do 2/3 of the work.
+  const int accStride = npad <= 96 ? 96 : 128;
+  const int nP = npad <= 96 ? 4 : 3;
   const int nz0 = (nz + 1) >> 1, nz1 = nz >> 1;  // planes of parity 0 / 1
-  if (warp == 8) {
+  if (warp == kTcProducers) {
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(kGramRows >> 4) << 24);
       const uint32_t sbase = smem_addr(base), bar0 = smem_addr(&sBar[0]);
+      const uint32_t accQ = tmem + (uint32_t)(nP * accStride);
+      int chain = 0;  // stage-planes are dealt round-robin to the P accumulators: nP chains of equal length
       for (int u = 0; u < nz0; ++u) {
 #pragma unroll
         for (int sI = 0; sI < 4; ++sI) {
@@ -331,13 +348,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
           asm volatile("tcgen05.fence::after_thread_sync;");
           const uint64_t dh = make_desc(sbase + (uint32_t)sI * 2u * kTcStageBytes);
           const uint64_t dl = make_desc(sbase + (uint32_t)sI * 2u * kTcStageBytes + kTcStageBytes);
-          const uint32_t acc = tmem + (uint32_t)sI * 128u;
+          const int a = chain % nP;
+          const uint32_t accP = tmem + (uint32_t)(a * accStride);
+          const bool first_p = chain < nP, first_q = chain == 0;
+          ++chain;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // UMMA_K = 8 tf32 = 32 bytes along the swizzled row: +2 in the address field
             const uint64_t ah = dh + (uint64_t)(2 * k), al = dl + (uint64_t)(2 * k);
-            umma_tf32(acc, ah, ah, idesc, (u > 0 || k > 0) ? 1u : 0u);
-            umma_tf32(acc, ah, al, idesc, 1u);
-            umma_tf32(acc, al, ah, idesc, 1u);
+            umma_tf32(accP, ah, ah, idesc, (!first_p || k > 0) ? 1u : 0u);
+            umma_tf32(accQ, ah, al, idesc, (!first_q || k > 0) ? 1u : 0u);
           }
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 32u + 8u * sI)
                        : "memory");
@@ -346,7 +365,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
     }
     __syncwarp();
   } else {
-    const int sub = stg & 1, zpar = stg >> 1;
+    // Producer warp (sub, quarter): the 8 x 4 (x, y) half `sub` of the tile, every z plane in ascending order, a quarter
+    // of the 8-row atoms.  Plane z goes to panel stage sub + 2 (z & 1): the four warps of a half alternate between two
+    // stages, so the tensor pipe works on plane z while they write plane z + 1.
+    const int sub = warp & 1, quarter = warp >> 1;
     const int lx = lane & 7, ly = (lane >> 3) + 4 * sub;
     const int gx = x0 + lx, gy = y0 + ly;
     const bool valid = (gx < p.X) && (gy < p.Y);
@@ -372,14 +394,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
     const float sm1[3] = {(float)(p.X - 1), (float)(p.Y - 1), (float)(p.Z - 1)};
     const float rcp[3] = {p.rcp0, p.rcp1, p.rcp2};
     const int sz[3] = {p.X, p.Y, p.Z};
-    const uint32_t hi_base = smem_addr(base) + (uint32_t)stg * 2u * kTcStageBytes;
+    const uint32_t hi_base = smem_addr(base) + (uint32_t)sub * 2u * kTcStageBytes;  // stage `sub` (even planes)
+    constexpr uint32_t kOddPlanes = 4u * kTcStageBytes;                                 // stage sub + 2 is this much further
     const uint32_t slx = smem_addr(sSl), sly = slx + (uint32_t)wmax0 * kTcEntryBytes,
                    slz = sly + (uint32_t)wmax1 * kTcEntryBytes, slzero = slx + (uint32_t)wsum * kTcEntryBytes;
-    const uint32_t full = smem_addr(&sBar[stg]), empty = smem_addr(&sBar[4 + stg]);
-    const int uses = zpar ? nz1 : nz0;
+    const uint32_t full0 = smem_addr(&sBar[sub]), empty0 = smem_addr(&sBar[4 + sub]);  // odd planes: + 16 bytes (stage + 2)
     const int natom = (npair + 3) >> 2;
-    const int at0 = half == 0 ? 0 : (natom + 1) >> 1, at1 = half == 0 ? (natom + 1) >> 1 : natom;
-    const bool owns_y = (natom == 1) ? half == 0 : half == 1;   // the Y pseudo-row lives in the last atom
+    const int at0 = (natom * quarter) >> 2, at1 = (natom * (quarter + 1)) >> 2;
+    const bool owns_y = quarter == 3;   // the Y pseudo-row lives in the last atom
     // address of this lane's column in row r8 of atom at0 of the hi stage (16-byte chunks XOR-swizzled with the
     // row); the lo stage is kTcStageBytes further, the next atom 1024 bytes further
     uint32_t rowaddr[8];
@@ -388,8 +410,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
       rowaddr[r8] = hi_base + (uint32_t)at0 * 1024u + (uint32_t)(r8 * 128 + (((lane >> 2) ^ r8) << 4) + ((lane & 3) << 2));
     const int yL_r8 = L & 7;
     const uint32_t yaddr = hi_base + (uint32_t)(L >> 3) * 1024u + (uint32_t)(yL_r8 * 128 + (((lane >> 2) ^ yL_r8) << 4) + ((lane & 3) << 2));
-    for (int u = 0; u < uses; ++u) {
-      const int z = zpar + 2 * u;
+    for (int z = 0; z < nz; ++z) {
+      const int u = z >> 1;
+      const uint32_t zoff = (z & 1) ? kOddPlanes : 0u, boff = (z & 1) ? 16u : 0u;
       const float zf = (float)z;
       int ii[3];
       float ff[3];
@@ -403,8 +426,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
       const uint32_t ay = sly + (uint32_t)min(max(ii[1] - wlo[1], 0), W1 - 1) * kTcEntryBytes + (uint32_t)at0 * 64u;
       const uint32_t az = slz + (uint32_t)min(max(ii[2] - wlo[2], 0), W2 - 1) * kTcEntryBytes + (uint32_t)at0 * 64u;
       const float2 ff0 = make_float2(ff[0], ff[0]), ff1 = make_float2(ff[1], ff[1]), ff2 = make_float2(ff[2], ff[2]);
-      if (u > 0) mbar_wait(empty, (uint32_t)((u - 1) & 1));  // the MMAs that read this stage have completed
-      uint32_t pofs = 0, rofs = 0;
+      if (u > 0) mbar_wait(empty0 + boff, (uint32_t)((u - 1) & 1));  // the MMAs that read this stage have completed
+      uint32_t pofs = 0, rofs = zoff;
 #pragma unroll 2
       for (int at = at0; at < at1; ++at, pofs += 64u, rofs += 1024u) {
         float4 ex[4], ey[4], ez[4];
@@ -433,25 +456,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
         const float y = valid ? sY[(lx * kGramTY + ly) * p.Z + z] : 0.f;
         float h, l;
         split_tf32(y, h, l);
-        sts32r(yaddr, h);
-        sts32<kTcStageBytes>(yaddr, l);
+        sts32r(yaddr + zoff, h);
+        sts32<kTcStageBytes>(yaddr + zoff, l);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA's async proxy
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full0 + boff) : "memory");
     }
     // a stage's phases can only be followed by a waiter that saw every one of them: its own producers
-    if (uses > 0) mbar_wait(empty, (uint32_t)((uses - 1) & 1));
+    if (nz0 > 0) mbar_wait(empty0, (uint32_t)((nz0 - 1) & 1));
+    if (nz1 > 0) mbar_wait(empty0 + 16u, (uint32_t)((nz1 - 1) & 1));
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();  // all four stages' last commits are now known to every warp
-  const int nacc = nz > 1 ? 4 : 2;  // stages 2, 3 (odd planes) have no plane when nz == 1
+  const int nacc = min(nP, 2 * (nz0 + nz1));  // P accumulators that received a stage-plane
   asm volatile("tcgen05.fence::after_thread_sync;");
-  if (warp < 8) {
-    // a warp reads the TMEM lanes 32 * (warp % 4) ..: warps w and w + 4 share a row quadrant and split the columns
-    const int row = stg * 32 + lane;
+  // a warp reads the TMEM lanes 32 * (warp % 4) ..: warps w and w + 4 share a row quadrant and split the columns
+  const int row = stg * 32 + lane;
+  float* sQ = reinterpret_cast<float*>(base);  // [128][kQPitch]: the panel stages are free (every MMA has completed)
+  constexpr int kQPitch = 129;
+  const uint32_t tq = tmem + ((uint32_t)(stg * 32) << 16) + (uint32_t)(nP * accStride);
+  if (warp < kTcProducers) {
+    for (int cb = 32 * colq; cb < npad; cb += 32 * (kTcProducers / 4)) {
+      uint32_t r[32];
+      tmem_ld32(tq + (uint32_t)cb, r);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sQ[row * kQPitch + cb + i] = __uint_as_float(r[i]);
+    }
+  }
+  __syncthreads();
+  if (warp < kTcProducers) {
     float* out = p.out.vals + tf * (size_t)p.out.capL * p.out.ld + (size_t)row * p.out.ld;
-    for (int cb = 32 * half; cb < npad; cb += 64) {
+    for (int cb = 32 * colq; cb < npad; cb += 32 * (kTcProducers / 4)) {
       float sum[32];
       uint32_t r[32];
       const uint32_t taddr = tmem + ((uint32_t)(stg * 32) << 16) + (uint32_t)cb;
@@ -459,10 +495,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
 #pragma unroll
       for (int i = 0; i < 32; ++i) sum[i] = __uint_as_float(r[i]);
       for (int w = 1; w < nacc; ++w) {
-        tmem_ld32(taddr + (uint32_t)w * 128u, r);
+        tmem_ld32(taddr + (uint32_t)(w * accStride), r);
 #pragma unroll
         for (int i = 0; i < 32; ++i) sum[i] += __uint_as_float(r[i]);
       }
+      // the cross terms, Q[row][col] + Q[col][row] first: commutative, so that the block stays bitwise symmetric
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sum[i] += sQ[row * kQPitch + cb + i] + sQ[(cb + i) * kQPitch + row];
       if (row < L) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {

@@ -276,6 +276,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, const
   __shared__ int s_rel[2];
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int t = frame_ids[b];
+  DNMF_DASSERT(t >= 0 && t < T);
   int last = b;  // positions b..last may hold further occurrences of t
   if (flags != nullptr && (flags[0] & 1)) {
     if (threadIdx.x < 2) s_rel[threadIdx.x] = 0;
@@ -496,6 +497,26 @@ __global__ void dense_forward_kernel(Geom g, const int* __restrict__ frame_ids, 
 using namespace dnmf;
 
 extern "C" int dnmf_abi_version(void) { return DNMF_ABI_VERSION; }
+
+namespace dnmf {
+__global__ void trip_assert_kernel(int never) { DNMF_DASSERT(never == 12345); }
+}  // namespace dnmf
+
+extern "C" int dnmf_build_info(void) {
+#ifdef DNMF_CHECKED
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+extern "C" int dnmf_debug_trip_assert(int device) {
+  CU(cudaSetDevice(device));
+  dnmf::trip_assert_kernel<<<1, 32>>>(0);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  return 0;
+}
 extern "C" const char* dnmf_last_error(void) { return g_err.c_str(); }
 
 static int create_impl(dnmf_ctx* c, int X, int Y, int Z, int K, int T, int device);

@@ -338,6 +338,7 @@ __global__ void stats_reduce_kernel(StatsPartials sp, const int* __restrict__ fr
             v[u] = 0.f;
             if (i < L) {
               id[u] = ids[i];
+              DNMF_DASSERT(id[u] < K && j < L && L <= sp.capL);
               v[u] = i >= j ? blk[(size_t)j * sp.ld + i] : blk[(size_t)i * sp.ld + j];
             }
           }
@@ -351,6 +352,7 @@ __global__ void stats_reduce_kernel(StatsPartials sp, const int* __restrict__ fr
     }
   }
   const int t = frame_ids[b];
+  DNMF_DASSERT(t >= 0);
   double* g = G + ((size_t)t * K + k) * K;
   for (int l = lane; l < K; l += 32) g[l] = row[l];
   if (lane == 0) bvec[(size_t)t * K + k] = bsum;
@@ -438,7 +440,10 @@ __global__ void mu_compact_kernel(const double* __restrict__ G, const int* __res
 // consecutive frames of its (k, list slot): the neighbour id is loaded once and the kMuTB (G, C) pairs are
 // independent loads in flight (one row per warp and frame was latency-bound: nbr -> C gather -> reduce -> store).
 // grid = (ceil(T / kMuTB), ceil(K / rows per block)).
-constexpr int kMuTB = 4;
+#ifndef DNMF_MU_TB
+#define DNMF_MU_TB 4
+#endif
+constexpr int kMuTB = DNMF_MU_TB;
 __global__ void mu_sweep_sparse_kernel(const double* __restrict__ Gc, const int* __restrict__ nbr, int W, int Ws,
                                        const double* __restrict__ bvec, const double* __restrict__ Cin,
                                        double* __restrict__ Cout, int T, int K, double gamma, int use_gamma,
@@ -466,6 +471,7 @@ __global__ void mu_sweep_sparse_kernel(const double* __restrict__ Gc, const int*
   if (live) {
     for (int s_ = sub; s_ < W; s_ += Ws) {
       const int l = max(nbr[(size_t)k * W + s_], 0);  // padding slots hold G = 0
+      DNMF_DASSERT(l < K);
 #pragma unroll
       for (int u = 0; u < kMuTB; ++u) {
         const int t = min(t0 + u, T - 1);

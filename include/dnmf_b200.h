@@ -33,7 +33,7 @@ extern "C" {
 
 typedef struct dnmf_ctx dnmf_ctx;
 
-#define DNMF_ABI_VERSION 6
+#define DNMF_ABI_VERSION 7
 
 int dnmf_abi_version(void);
 const char* dnmf_last_error(void);
@@ -214,6 +214,14 @@ int dnmf_ext_get_params(dnmf_ctx* ctx, float* pos_dev_out, float* sigma_dev_out,
 /* FFMA microbenchmark: best-of-`repeats` dense FP32 throughput of the device in TFLOP/s (FMA = 2);
  * the roofline denominator for the FP32-bound fused kernel (MEASURED_PEAKS.json has no FP32 entry). */
 int dnmf_measure_fp32_peak(int device, int repeats, double* tflops_out);
+
+/* Build variant of the library: bit 0 = checked build (-DDNMF_CHECKED: device-side assertions on every unclamped
+ * index of the kernels; `python -m dnmf_b200.build --checked`).  No reference counterpart (test infrastructure). */
+int dnmf_build_info(void);
+/* Launches a kernel whose only statement is a failing device assertion and synchronises: returns non-zero in a
+ * checked build (the context is unusable afterwards: call it from a throw-away process), 0 in the normal build.
+ * Proves that the checked build's assertions are live.  No reference counterpart (test infrastructure). */
+int dnmf_debug_trip_assert(int device);
 
 /* ---- callers and data formats either side of the fit path ---------------------------- */
 

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "library does not export %s" % n
     lib2 = dnmf_b200.load()
-    assert lib2.dnmf_abi_version() == 6
+    assert lib2.dnmf_abi_version() == 7
     for n in names:                                   # every declared symbol has a ctypes signature
         assert n in lib2._signatures, n
 
