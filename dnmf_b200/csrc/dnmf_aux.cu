@@ -17,7 +17,8 @@ namespace dnmf {
 // every (t, k) and rescales it to peak 1 (:203); the cell is separable, so a block of 16 x 16 (x, y) columns
 // stages the three 1-D factors of a chunk of neurons for its frame (the x factor carries the trace) and every
 // thread marches its column along z.  Neurons whose x or y factor underflows to zero over the whole tile are
-// dropped while staging (their contribution is below 1e-38).
+// dropped while staging (their contribution is below 1e-38).  Every neuron of a chunk has its own slot and the columns
+// add the live ones in ascending k: the video is bitwise reproducible (slots handed out by an atomic counter were not).
 // ------------------------------------------------------------------------------------------------
 constexpr int kRenTX = 16, kRenTY = 16, kRenChunk = 96, kRenMaxZ = 64;
 
@@ -27,7 +28,7 @@ __global__ void __launch_bounds__(256) render_cells_kernel(const float* __restri
                                                            float* __restrict__ out /*[nT][X][Y][Z]*/) {
   __shared__ float sGX[kRenChunk][kRenTX], sGY[kRenChunk][kRenTY];
   __shared__ __align__(16) float sGZ[kRenChunk][kRenMaxZ];
-  __shared__ int sCount;
+  __shared__ unsigned char sLive[kRenChunk];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lx = tid & 15, ly = tid >> 4;
   const int x0 = blockIdx.x * kRenTX, y0 = blockIdx.y * kRenTY, tl = blockIdx.z, t = t0 + tl;
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(256) render_cells_kernel(const float* __restri
   for (int z = 0; z < kRenMaxZ; ++z) acc[z] = 0.f;
   for (int k0 = 0; k0 < K; k0 += kRenChunk) {
     __syncthreads();
-    if (tid == 0) sCount = 0;
+    if (tid < kRenChunk) sLive[tid] = 0;
     __syncthreads();
     // one warp per candidate neuron: factors of the tile, kept when the neuron reaches it at all
     for (int kk = warp; kk < kRenChunk && k0 + kk < K; kk += 8) {
@@ -55,9 +56,8 @@ __global__ void __launch_bounds__(256) render_cells_kernel(const float* __restri
       }
       const bool live = __any_sync(0xffffffffu, gx != 0.f) && __any_sync(0xffffffffu, gy != 0.f);
       if (!live) continue;
-      int slot = 0;
-      if (lane == 0) slot = atomicAdd(&sCount, 1);
-      slot = __shfl_sync(0xffffffffu, slot, 0);
+      const int slot = kk;
+      if (lane == 0) sLive[kk] = 1;
       if (lane < 16) sGX[slot][lane] = gx; else sGY[slot][lane - 16] = gy;
       for (int z = lane; z < Z4; z += 32) {
         const float d = (float)z - pz;
@@ -65,8 +65,9 @@ __global__ void __launch_bounds__(256) render_cells_kernel(const float* __restri
       }
     }
     __syncthreads();
-    const int n = sCount;
+    const int n = min(kRenChunk, K - k0);
     for (int j = 0; j < n; ++j) {
+      if (!sLive[j]) continue;  // block-uniform
       const float gxy = sGX[j][lx] * sGY[j][ly];
       const float4* gz = reinterpret_cast<const float4*>(sGZ[j]);
 #pragma unroll

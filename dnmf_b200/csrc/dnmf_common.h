@@ -117,7 +117,7 @@ struct FitParams {
   int* mu_overflow;  // MODE 3: set when a tile's list is not fully staged (the caller reruns the generic kernel)
   const int4* windows;  // [B][tiles][2]: (wlo0, wlo1, wlo2, whi0), (whi1, whi2, clipped, 0) from tile_windows_kernel, or NULL
   int skip_quad;  // != 0: gradient rows 4..9 are not wanted (affine fit: Adam freezes them) and are returned as zero
-  int reserved0;  // (was: run-time tail kind switch; kept so that the offsets below do not move, see the note at the end)
+  int chunks_main;  // the first chunks_main chunks of a launch walk fpc frames each, the rest fpc_tail (set by launch_fit)
   unsigned* reserved1;
   int y_pitch;   // floats between x rows of the Y tile in shared memory (>= ty * tile depth)
   int z_skew;    // != 0: lane (lx, ly) starts its z march at ((ly * z_skew) & 3), see march_rolled<SKEW>
@@ -127,6 +127,8 @@ struct FitParams {
   // parameters ptxas fetches in pairs, and moving them changed the generated main loops (cfg3 / cfg4 lost 6-7 %
   // when an 8-byte pointer was inserted next to `bg`).
   const float* bg_dev;  // MODE 2: the background is read from the device instead (dnmf_ext_step_begin), or NULL
+  int fpc_tail;         // frames per CTA of the last chunks of a launch (short CTAs at the end: the SMs run dry together)
+  int cta_slots;        // CTAs resident on the device at once (host-side input of that split)
   alignas(64) CUtensorMap tmap;
 };
 
@@ -226,6 +228,7 @@ struct dnmf_ctx {
   int affine_grad = 0;   // dnmf_set_affine: dnmf_loss_grad leaves the quadratic gradient rows zero
   int affine_call = 0;   // the same for the duration of one step call made with affine != 0
   int fpc_override = 0;  // DNMF_FPC environment override of the frames-per-CTA heuristic (tuning)
+  int fpc_tail_off = 0;  // DNMF_FPC_TAIL_OFF: every chunk fpc frames long (A/B of the short-tail split)
   int y_pitch = 0, z_skew = 0;  // shared-memory layout of the Y tile (bank conflicts, configure_tiling_fixed)
   // tensor map of the frame buffer the fused kernel last ran on (resident slab or caller's batch)
   alignas(64) CUtensorMap tmap;

@@ -843,8 +843,10 @@ __global__ void __launch_bounds__(32 * NWX * NWY * NWZ, (NWX * NWY * NWZ == 1) ?
   const int bx = blockIdx.x, by = blockIdx.y;
   const int chunk = p.ntz == 1 ? (int)blockIdx.z : (int)blockIdx.z / p.ntz;
   const int bz = p.ntz == 1 ? 0 : (int)blockIdx.z - chunk * p.ntz;
-  const int b_first = chunk * p.fpc;
-  const int nb = min(p.fpc, p.B - b_first);  // frames this CTA walks (<= 32)
+  // the last chunks of a launch are short (launch_fit): the tail of the grid then ends within a fraction of a CTA's time
+  const bool main_chunk = chunk < p.chunks_main;
+  const int b_first = main_chunk ? chunk * p.fpc : p.chunks_main * p.fpc + (chunk - p.chunks_main) * p.fpc_tail;
+  const int nb = main_chunk ? p.fpc : min(p.fpc_tail, p.B - b_first);  // frames this CTA walks (<= 32)
   const int x0 = bx * TX, y0 = by * TY, z0 = bz * p.tz;
   const int nx = min(TX, p.X - x0), ny = min(TY, p.Y - y0), nz = min(p.tz, p.Z - z0);
   const size_t Nvox = (size_t)p.X * p.Y * p.Z;
@@ -1456,7 +1458,7 @@ static int launch_fit(const FitParams& p0, int B, size_t smem, cudaStream_t st) 
   // grid = (ntx, nty, chunks*ntz), one chunk = fpc consecutive frames; gridDim.z <= 65535, so very large
   // batches go out in several launches
   const int fpc = std::max(1, std::min(p0.fpc, 32));
-  const int maxB = std::max(1, 65535 / p0.ntz) * fpc;
+  const int maxB = std::max(1, 65535 / p0.ntz / 2) * fpc;  // half: the short chunks at the end of a launch add to the count
   const size_t N = (size_t)p0.X * p0.Y * p0.Z;
   const size_t nt = (size_t)p0.ntx * p0.nty * p0.ntz;
   for (int b0 = 0; b0 < B; b0 += maxB) {
@@ -1469,7 +1471,22 @@ static int launch_fit(const FitParams& p0, int B, size_t smem, cudaStream_t st) 
     p.partials = p0.partials + (size_t)b0 * nt * kNumPartials;
     if (p0.frames_are_batch) p.frames = p0.frames + (size_t)b0 * N;
     if (p0.yhat) p.yhat = p0.yhat + (size_t)b0 * N;
-    const int chunks = (nb + fpc - 1) / fpc;
+    // chunk sizes: fpc frames per CTA, except for the frames of (about) the last wave of CTAs, which go out in chunks
+    // a quarter as long -- the grid is dispatched in chunk order, so the short CTAs run last and the SMs run dry
+    // within a quarter of a long CTA's time of each other instead of a whole one.
+    int fpc_tail = std::max(1, fpc / 4);
+    int tail_frames = 0;
+    if (p0.cta_slots > 0 && fpc_tail < fpc) {
+      const long long tiles = (long long)nt;
+      const long long wave_chunks = (p0.cta_slots + tiles - 1) / tiles;  // chunks resident at once
+      tail_frames = (int)std::min<long long>(nb, wave_chunks * fpc);
+    }
+    const int n_main = (nb - tail_frames) / fpc;
+    const int rest = nb - n_main * fpc;
+    if (rest == 0) fpc_tail = fpc;
+    p.chunks_main = n_main;
+    p.fpc_tail = fpc_tail;
+    const int chunks = n_main + (rest + fpc_tail - 1) / fpc_tail;
     dim3 grid((unsigned)p0.ntx, (unsigned)p0.nty, (unsigned)(chunks * p0.ntz));
     kern<<<grid, 32 * NWX * NWY * NWZ_, smem, st>>>(p);
     CU(cudaGetLastError());

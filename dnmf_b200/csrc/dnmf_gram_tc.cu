@@ -151,6 +151,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x, b = blockIdx.y;
+#ifdef DNMF_TC_TIMING
+  const bool tprint = blockIdx.x == 200 && (blockIdx.y == 3 || blockIdx.y == 17);
+  const long long T0 = clock64();
+  long long Twait = 0, Tmma0 = 0, Tloop0 = 0, Tloop1 = 0;
+#define TC_T(x) x
+#else
+#define TC_T(x)
+#endif
   const int nt = p.ntx * p.nty;
   const int bx = tile % p.ntx, by = tile / p.ntx;
   const int t = p.frame_ids[b];
@@ -320,6 +328,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
     }
   }
   __syncthreads();
+  TC_T(const long long T1 = clock64();)
 
   // ---- producers (warps 0..7) and the MMA warp (warp 8).  Stage s belongs to the 8 x 4 (x, y) half s & 1 and the z
   // planes of parity s >> 1; the four producer warps of the half arrive on full[s], the MMA warp issues the stage's
@@ -344,7 +353,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
 #pragma unroll
         for (int sI = 0; sI < 4; ++sI) {
           if (u >= ((sI >> 1) ? nz1 : nz0)) continue;
-          mbar_wait(bar0 + 8u * sI, (uint32_t)(u & 1));  // both producer warps have written plane u of this stage
+          TC_T(const long long w0 = clock64();)
+          mbar_wait(bar0 + 8u * sI, (uint32_t)(u & 1));  // the producer warps have written plane u of this stage
+          TC_T(Twait += clock64() - w0; if (u == 0 && sI == 0) Tmma0 = clock64();)
           asm volatile("tcgen05.fence::after_thread_sync;");
           const uint64_t dh = make_desc(sbase + (uint32_t)sI * 2u * kTcStageBytes);
           const uint64_t dl = make_desc(sbase + (uint32_t)sI * 2u * kTcStageBytes + kTcStageBytes);
@@ -426,7 +437,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
       const uint32_t ay = sly + (uint32_t)min(max(ii[1] - wlo[1], 0), W1 - 1) * kTcEntryBytes + (uint32_t)at0 * 64u;
       const uint32_t az = slz + (uint32_t)min(max(ii[2] - wlo[2], 0), W2 - 1) * kTcEntryBytes + (uint32_t)at0 * 64u;
       const float2 ff0 = make_float2(ff[0], ff[0]), ff1 = make_float2(ff[1], ff[1]), ff2 = make_float2(ff[2], ff[2]);
+      TC_T(const long long w0 = clock64();)
       if (u > 0) mbar_wait(empty0 + boff, (uint32_t)((u - 1) & 1));  // the MMAs that read this stage have completed
+      TC_T(Twait += clock64() - w0; if (z == 0) Tloop0 = clock64();)
       uint32_t pofs = 0, rofs = zoff;
 #pragma unroll 2
       for (int at = at0; at < at1; ++at, pofs += 64u, rofs += 1024u) {
@@ -464,11 +477,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full0 + boff) : "memory");
     }
     // a stage's phases can only be followed by a waiter that saw every one of them: its own producers
+    TC_T(Tloop1 = clock64();)
     if (nz0 > 0) mbar_wait(empty0, (uint32_t)((nz0 - 1) & 1));
     if (nz1 > 0) mbar_wait(empty0 + 16u, (uint32_t)((nz1 - 1) & 1));
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();  // all four stages' last commits are now known to every warp
+  TC_T(const long long T2 = clock64();)
   const int nacc = min(nP, 2 * (nz0 + nz1));  // P accumulators that received a stage-plane
   asm volatile("tcgen05.fence::after_thread_sync;");
   // a warp reads the TMEM lanes 32 * (warp % 4) ..: warps w and w + 4 share a row quadrant and split the columns
@@ -522,6 +537,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+  TC_T(if (tprint && lane == 0 && (warp == 0 || warp == 3 || warp == 8)) printf("tc-timing frame %d warp %d L %d: prologue %lld, loop %lld (first plane at +%lld, producer done at +%lld), waits %lld, epilogue %lld\n", (int)blockIdx.y, warp, L, T1 - T0, T2 - T1, (warp == 8 ? Tmma0 : Tloop0) - T1, Tloop1 - T1, Twait, clock64() - T2);)
 }
 
 int launch_gram_tc(const GramTcParams& p, int B, cudaStream_t st) {

@@ -556,6 +556,7 @@ static int create_impl(dnmf_ctx* c, int X, int Y, int Z, int K, int T, int devic
   c->num_sms = prop.multiProcessorCount;
   c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (const char* ev = getenv("DNMF_FPC")) c->fpc_override = atoi(ev);
+  if (const char* ev = getenv("DNMF_FPC_TAIL_OFF")) c->fpc_tail_off = atoi(ev) != 0;
   if (const char* ev = getenv("DNMF_MU_PANEL")) c->mu_force_panel = atoi(ev) != 0;
   if (const char* ev = getenv("DNMF_MU_SWEEP_PER_LAUNCH")) c->mu_sweep_per_launch = atoi(ev) != 0;
   if (const char* ev = getenv("DNMF_MU_BLOCK4")) c->mu_block4 = atoi(ev) != 0;
@@ -1079,7 +1080,9 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
   memset(&p.stats, 0, sizeof(p.stats));
   p.mu_overflow = nullptr;
   p.skip_quad = (c->affine_grad || c->affine_call) ? 1 : 0;
-  p.reserved0 = 0;
+  p.chunks_main = 0;  // launch_fit sets the chunk split
+  p.fpc_tail = 1;
+  p.cta_slots = 0;
   p.reserved1 = nullptr;
   p.y_pitch = c->y_pitch;
   p.z_skew = c->z_skew;
@@ -1138,6 +1141,7 @@ static int fill_fit_params(dnmf_ctx* c, FitParams& p, const float* frames_dev, c
     const long long slots = (long long)c->num_sms * 16 * 8;
     p.fpc = (int)std::max<long long>(1, std::min<long long>(8, (long long)B * tiles / std::max<long long>(slots, 1)));
     if (c->fpc_override > 0) p.fpc = std::min(c->fpc_override, 32);
+    p.cta_slots = c->fpc_tail_off ? 0 : c->num_sms * std::max(1, std::min(c->nwx * c->nwy * c->nwz == 1 ? 16 : 32, (int)((size_t)227 * 1024 / (c->fit_smem + 1024))));
   }
   p.yhat = nullptr;
   p.bg = 0.f;

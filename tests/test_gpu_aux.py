@@ -67,6 +67,19 @@ def test_generator_kernel_matches_the_separable_cells(sz, K, T, shape_std):
     np.testing.assert_allclose(got, ref, rtol=2e-5, atol=1e-6 * ref.max())
 
 
+def test_generator_kernel_is_bitwise_reproducible():
+    """Every neuron of a staged chunk has its own slot and the columns add the live ones in ascending k: rendering the
+    same cells twice (many neurons per tile, several chunks) gives the same bits."""
+    from dnmf_b200.engine import render_cells
+    sz, K, T = [48, 40, 9], 230, 3
+    rs = np.random.RandomState(5)
+    pos = (rs.rand(K, 3, T) * np.asarray(sz)[None, :, None]).astype(np.float32)
+    tr = (1 + rs.rand(K, T)).astype(np.float32)
+    first = render_cells(torch.tensor(pos), tr, sz, 9.0)
+    for _ in range(5):
+        assert torch.equal(first, render_cells(torch.tensor(pos), tr, sz, 9.0))
+
+
 def test_generate_video_on_the_gpu_uses_the_kernel_and_matches_the_cpu_path():
     from dnmf_b200.simulate import generate_video, render_clean
     args = (6, 4, [24, 20, 5], 3, .2, -120, "exp", "gp", {"sigma": [5, 5, .01], "ls": [10, 10, 10]})
