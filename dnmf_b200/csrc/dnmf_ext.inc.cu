@@ -315,8 +315,8 @@ __global__ void __launch_bounds__(32, 16) param_grad_kernel(const __grid_constan
               const float2 fg = __fmul2_rn(ff[d], __fadd2_rn(G, D));            // f G_{i+1}
               const float2 dd = __fadd2_rn(nn[d], make_float2(-pos[pp][d].x, -pos[pp][d].y));  // d_i = i - pos
               pn[d] = __ffma2_rn(dd, a[d], fg);                                 // (sigma^2 / 2) lerp(dG/dpos)
-              const float2 t2 = __ffma2_rn(dd, make_float2(2.f, 2.f), make_float2(1.f, 1.f));
-              sn[d] = __ffma2_rn(__fmul2_rn(dd, dd), a[d], __fmul2_rn(fg, t2));  // (sigma^3 / 2) lerp(dG/dsigma)
+              // (sigma^3 / 2) lerp(dG/dsigma) = d^2 a + f G_{i+1} (2 d + 1) = d (d a + f G_{i+1}) + f G_{i+1} (d + 1)
+              sn[d] = __ffma2_rn(dd, pn[d], __fmul2_rn(fg, __fadd2_rn(dd, make_float2(1.f, 1.f))));
             }
             const float2 a12 = __fmul2_rn(a[1], a[2]), a02 = __fmul2_rn(a[0], a[2]), a01 = __fmul2_rn(a[0], a[1]);
             const float2 w = __fmul2_rn(rr, ck[pp]);
