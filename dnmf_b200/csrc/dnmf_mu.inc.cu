@@ -441,6 +441,7 @@ __global__ void mu_compact_kernel(const double* __restrict__ G, const int* __res
 // independent loads in flight (one row per warp and frame was latency-bound: nbr -> C gather -> reduce -> store).
 // grid = (ceil(T / kMuTB), ceil(K / rows per block)).
 constexpr int kMuTB = 4;  // 8 frames per thread measured slower (cfg4 50 sweeps 3.78 -> 4.32 ms per 100 frames)
+template <int kMuSB>
 __global__ void mu_sweep_sparse_kernel(const double* __restrict__ Gc, const int* __restrict__ nbr, int W, int Ws,
                                        const double* __restrict__ bvec, const double* __restrict__ Cin,
                                        double* __restrict__ Cout, int T, int K, double gamma, int use_gamma,
@@ -466,14 +467,32 @@ __global__ void mu_sweep_sparse_kernel(const double* __restrict__ Gc, const int*
     }
   }
   if (live) {
-    for (int s_ = sub; s_ < W; s_ += Ws) {
-      const int l = max(nbr[(size_t)k * W + s_], 0);  // padding slots hold G = 0
-      DNMF_DASSERT(l < K);
+    // kMuSB list slots per round: their neighbour ids are requested together, then the kMuSB x kMuTB (G, C) pairs --
+    // two dependent memory round trips per round instead of per slot (long rows: W ~ 300 at K = 1000: 50 sweeps over
+    // 100 frames 3.78 -> 2.49 ms; rows of one round, W <= 32, run the kMuSB = 1 instantiation)
+    for (int s0 = sub; s0 < W; s0 += kMuSB * Ws) {
+      int l[kMuSB];
 #pragma unroll
-      for (int u = 0; u < kMuTB; ++u) {
-        const int t = min(t0 + u, T - 1);
-        dot[u] = fma(Gc[((size_t)t * K + k) * W + s_], Cin[(size_t)t * K + l], dot[u]);
+      for (int v = 0; v < kMuSB; ++v) {
+        const int s_ = s0 + v * Ws;
+        l[v] = s_ < W ? max(nbr[(size_t)k * W + s_], 0) : 0;  // padding slots hold G = 0
+        DNMF_DASSERT(l[v] < K);
       }
+      double g[kMuSB][kMuTB], cc[kMuSB][kMuTB];
+#pragma unroll
+      for (int v = 0; v < kMuSB; ++v) {
+        const int s_ = s0 + v * Ws;
+#pragma unroll
+        for (int u = 0; u < kMuTB; ++u) {
+          const int t = min(t0 + u, T - 1);
+          g[v][u] = s_ < W ? Gc[((size_t)t * K + k) * W + s_] : 0.0;
+          cc[v][u] = Cin[(size_t)t * K + l[v]];
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < kMuSB; ++v)   // ascending slot order: the same sum as one slot per round
+#pragma unroll
+        for (int u = 0; u < kMuTB; ++u) dot[u] = fma(g[v][u], cc[v][u], dot[u]);
     }
   }
 #pragma unroll
@@ -1018,9 +1037,14 @@ extern "C" int dnmf_mu_sweep(dnmf_ctx* c, double gamma, int use_gamma, const dou
     while (Ws < 32 && Ws < W) Ws *= 2;
     const int rows_per_block = 256 / Ws;
     const dim3 grid((unsigned)((c->T + kMuTB - 1) / kMuTB), (unsigned)((c->K + rows_per_block - 1) / rows_per_block));
-    mu_sweep_sparse_kernel<<<grid, 256, 0, st>>>(
-        c->d_Gc, c->d_mu_nbr, W, Ws, c->d_b, c->d_Cd[c->cd_cur], c->d_Cd[c->cd_cur ^ 1], c->T, c->K, gamma, use_gamma,
-        halo_prev_dev, halo_next_dev);
+    if (W > 2 * Ws)
+      mu_sweep_sparse_kernel<4><<<grid, 256, 0, st>>>(
+          c->d_Gc, c->d_mu_nbr, W, Ws, c->d_b, c->d_Cd[c->cd_cur], c->d_Cd[c->cd_cur ^ 1], c->T, c->K, gamma, use_gamma,
+          halo_prev_dev, halo_next_dev);
+    else
+      mu_sweep_sparse_kernel<1><<<grid, 256, 0, st>>>(
+          c->d_Gc, c->d_mu_nbr, W, Ws, c->d_b, c->d_Cd[c->cd_cur], c->d_Cd[c->cd_cur ^ 1], c->T, c->K, gamma, use_gamma,
+          halo_prev_dev, halo_next_dev);
   } else {
     const dim3 grid((unsigned)c->T, (unsigned)((c->K + 7) / 8));
     mu_sweep_kernel<<<grid, 256, 0, st>>>(
