@@ -500,8 +500,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
     }
   }
   __syncthreads();
+  // the finished block goes through shared memory once more (behind sQ; the slices are free as well), so that every
+  // thread can store BOTH triangles of its row from the upper one: element (row, col) = S[min][max].  The stored block
+  // is bitwise symmetric by construction and the second stage reads rows only (coalesced; reading element
+  // (min slot, max slot) column-wise cost it 8x the sectors for half of its entries).
+  float* sS = sQ + kGramRows * kQPitch;
   if (warp < kTcProducers) {
-    float* out = p.out.vals + tf * (size_t)p.out.capL * p.out.ld + (size_t)row * p.out.ld;
     for (int cb = 32 * colq; cb < npad; cb += 32 * (kTcProducers / 4)) {
       float sum[32];
       uint32_t r[32];
@@ -514,21 +518,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const __grid_con
 #pragma unroll
         for (int i = 0; i < 32; ++i) sum[i] += __uint_as_float(r[i]);
       }
-      // the cross terms, Q[row][col] + Q[col][row] first: commutative, so that the block stays bitwise symmetric
+      // the cross terms, Q[row][col] + Q[col][row]
 #pragma unroll
-      for (int i = 0; i < 32; ++i) sum[i] += sQ[row * kQPitch + cb + i] + sQ[(cb + i) * kQPitch + row];
-      if (row < L) {
+      for (int i = 0; i < 32; ++i) sS[row * kQPitch + cb + i] = sum[i] + (sQ[row * kQPitch + cb + i] + sQ[(cb + i) * kQPitch + row]);
+    }
+  }
+  __syncthreads();
+  if (warp < kTcProducers && row < L) {
+    float* out = p.out.vals + tf * (size_t)p.out.capL * p.out.ld + (size_t)row * p.out.ld;
+    for (int cb = 32 * colq; cb < npad; cb += 32 * (kTcProducers / 4)) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const int col = cb + i;
-          if (col + 3 < L) {
-            *reinterpret_cast<float4*>(out + col) = make_float4(sum[i], sum[i + 1], sum[i + 2], sum[i + 3]);
-          } else {
+      for (int i = 0; i < 32; i += 4) {
+        const int col = cb + i;
+        float v[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (col + q < L) out[col + q] = sum[i + q];
-              else if (col + q == L) out[p.out.capL] = sum[i + q];
-            }
+        for (int q = 0; q < 4; ++q) {
+          const int c = col + q;
+          v[q] = c >= row ? sS[row * kQPitch + c] : sS[c * kQPitch + row];
+        }
+        if (col + 3 < L) {
+          *reinterpret_cast<float4*>(out + col) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (col + q < L) out[col + q] = v[q];
+            else if (col + q == L) out[p.out.capL] = v[q];
           }
         }
       }

@@ -289,8 +289,9 @@ __global__ void __launch_bounds__(kMuThreads) mu_stats_kernel(const __grid_const
 // walks the tiles in ascending order, finds the ones that list k (slot_of), and adds that tile's partial row to
 // its row accumulators in shared memory (fp64), then writes the whole row G_t[k][:] and b_t[k] once.  A row has
 // one owner and tiles are visited in a fixed order: bitwise reproducible, no atomics, and exactly symmetric --
-// G_t[k][l] and G_t[l][k] both read the element (min slot, max slot) of every block (the tensor-core blocks are
-// not bitwise symmetric: the two cross terms of the 3xTF32 split arrive in swapped order).
+// every first stage stores bitwise symmetric blocks (the fused tiles and the SIMT panel mirror their off-diagonal
+// register blocks, the tensor-core panel stores both triangles from the upper one), so a row reads its own row of
+// each block: contiguous (reading element (min slot, max slot) instead cost 8x the sectors below the diagonal).
 __global__ void stats_reduce_kernel(StatsPartials sp, const int* __restrict__ frame_ids, int nt, int K,
                                     double* __restrict__ G, double* __restrict__ bvec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -325,9 +326,9 @@ __global__ void stats_reduce_kernel(StatsPartials sp, const int* __restrict__ fr
         const int j = (int)__shfl_sync(0xffffffffu, s[r], src);
         const int L = __shfl_sync(0xffffffffu, cnt[r], src);
         const size_t tf = (size_t)b * nt + tile0 + r * 32 + src;
-        const float* blk = sp.vals + tf * (size_t)sp.capL * sp.ld;
+        const float* blk = sp.vals + tf * (size_t)sp.capL * sp.ld + (size_t)j * sp.ld;  // this neuron's row of the block
         const unsigned short* ids = sp.ids + tf * sp.capL;
-        const float bj = lane == 0 ? blk[(size_t)j * sp.ld + sp.capL] : 0.f;
+        const float bj = lane == 0 ? blk[sp.capL] : 0.f;
         for (int i0 = 0; i0 < L; i0 += 128) {  // four entries per lane in flight: one memory round trip per 128 entries
           float v[4];
           int id[4];
@@ -339,7 +340,7 @@ __global__ void stats_reduce_kernel(StatsPartials sp, const int* __restrict__ fr
             if (i < L) {
               id[u] = ids[i];
               DNMF_DASSERT(id[u] < K && j < L && L <= sp.capL);
-              v[u] = i >= j ? blk[(size_t)j * sp.ld + i] : blk[(size_t)i * sp.ld + j];
+              v[u] = blk[i];
             }
           }
 #pragma unroll
@@ -347,7 +348,7 @@ __global__ void stats_reduce_kernel(StatsPartials sp, const int* __restrict__ fr
             if (i0 + u * 32 + lane < L) row[id[u]] += (double)v[u];
         }
         if (lane == 0) bsum += (double)bj;
-        __syncwarp();
+        __syncwarp();  // (four listing tiles per round with all their loads in flight measured 20 % slower: not latency-bound)
       }
     }
   }
