@@ -413,28 +413,22 @@ __global__ void mu_compact_kernel(const double* __restrict__ G, const int* __res
   const int k = (int)(row % K);
   const double* g = G + (size_t)row * K;
   const int* nb = nbr + (size_t)k * W;
-  bool bad = false;
-  for (int l = lane; l < K; l += 32) {
-    if (g[l] != 0.0) {
-      int lo = 0, hi = W - 1;  // is l in nb[] ? (-1 padding sorts last: treat as +inf)
-      bool found = false;
-      while (lo <= hi) {
-        const int mid = (lo + hi) >> 1;
-        const int v = nb[mid];
-        if (v == l) {
-          found = true;
-          break;
-        }
-        if (v < 0 || v > l) hi = mid - 1; else lo = mid + 1;
-      }
-      bad |= !found;
-    }
-  }
-  if (bad) atomicOr(violation, 1);
+  // every non-zero of the row must be one of the listed entries: the list holds distinct neurons, so it is enough that
+  // the row has as many non-zeros as its listed entries have (no search per non-zero: W ~ 300 of them at K = 1000)
+  int nnz_row = 0, nnz_list = 0;
+  for (int l = lane; l < K; l += 32) nnz_row += g[l] != 0.0 ? 1 : 0;
   for (int s_ = lane; s_ < W; s_ += 32) {
     const int l = nb[s_];
-    Gc[(size_t)row * W + s_] = l >= 0 ? g[l] : 0.0;
+    const double v = l >= 0 ? g[l] : 0.0;
+    Gc[(size_t)row * W + s_] = v;
+    nnz_list += v != 0.0 ? 1 : 0;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nnz_row += __shfl_xor_sync(0xffffffffu, nnz_row, o);
+    nnz_list += __shfl_xor_sync(0xffffffffu, nnz_list, o);
+  }
+  if (lane == 0 && nnz_row != nnz_list) atomicOr(violation, 1);
 }
 
 // Ws lanes per neuron k (the power of two covering the row length W, at most 32); one thread walks kMuTB

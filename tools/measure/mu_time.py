@@ -50,3 +50,17 @@ for flags, label in ((0, "automatic"), (4, "one launch per sweep")):
     b.record(torch.cuda.current_stream(dev))
     torch.cuda.synchronize()
     print("%s: 50 sweeps (%s) %.3f ms per %d frames" % (cfg, label, a.elapsed_time(b) / 3, T))
+e.mu_path(0)
+c = C.clone()
+for _ in range(2):
+    e.mu_stats(ids, beta)
+    e.mu_sweeps(c, None, 50)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record(torch.cuda.current_stream(dev))
+for _ in range(3):
+    e.mu_stats(ids, beta)
+    e.mu_sweeps(c, None, 50)
+b.record(torch.cuda.current_stream(dev))
+torch.cuda.synchronize()
+print("%s: trace update (statistics + compaction + 50 sweeps) %.3f ms per %d frames" % (cfg, a.elapsed_time(b) / 3, T))
