@@ -26,6 +26,21 @@ def test_library_exports_every_declared_symbol():
         assert n in lib2._signatures, n
 
 
+def test_checked_build_exists_and_says_so():
+    """`python -m dnmf_b200.build --checked` (built by __graft_entry__.build()) is the same library with device-side
+    assertions compiled in; dnmf_build_info tells the two apart, and both export every declared symbol."""
+    import dnmf_b200
+    from dnmf_b200 import build as b
+    checked = ctypes.CDLL(b.build(checked=True))
+    normal = ctypes.CDLL(b.build())
+    for lib in (checked, normal):
+        lib.dnmf_build_info.restype = ctypes.c_int
+        for n in dnmf_b200.declared_symbols():
+            assert hasattr(lib, n), n
+    assert checked.dnmf_build_info() & 1 == 1
+    assert normal.dnmf_build_info() & 1 == 0
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_no_cpu_fallback():
     import dnmf_b200
